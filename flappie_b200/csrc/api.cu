@@ -1,0 +1,901 @@
+// api.cu -- host side of libflappie_b200.so: the C ABI declared in include/flappie_b200.h.
+//
+// Holds (a) the model arena (weights unpacked from the reference's `_Mat` bundle and
+// re-laid-out for the kernels), (b) the per-stream context with grow-only HBM workspaces,
+// (c) the host planning of a ragged batch (block counts, length sort, the reference's
+// convolution edge plan) and (d) the per-read drop-ins with the reference's signatures.
+//
+// There is deliberately NO CPU implementation of any arithmetic in this file: if CUDA is
+// unavailable every entry point fails loudly (NULL / NAN / negative status + message).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/flappie_b200.h"
+#include "ffb_common.cuh"
+
+// ------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static void set_err(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    fprintf(stderr, "flappie_b200: %s\n", buf);
+}
+#define CUDA_TRY(expr, ret)                                                              \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            set_err("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return ret;                                                                  \
+        }                                                                                \
+    } while (0)
+
+extern "C" const char *ffb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *ffb_version(void) { return "flappie_b200 0.1 (sm_100a)"; }
+extern "C" int ffb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------
+// Grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+            cap = bytes;
+            return 0;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------------------------
+struct ffb_model {
+    int device = 0, kind = 0, S = 0, G = 0, nparam = 0, nbase = 0, nstate = 0, nconv = 0;
+    int conv_nf[FFB_MAX_CONV] = {0}, conv_nfilter[FFB_MAX_CONV] = {0}, conv_winlen[FFB_MAX_CONV] = {0},
+        conv_stride[FFB_MAX_CONV] = {0};
+    float *d_convWt[FFB_MAX_CONV] = {nullptr}, *d_convb[FFB_MAX_CONV] = {nullptr};
+    float *d_iWt[FFB_NLAYER] = {nullptr}, *d_b[FFB_NLAYER] = {nullptr}, *d_sWp[FFB_NLAYER] = {nullptr};
+    float *d_ffWt = nullptr, *d_ffb = nullptr;
+    int layer_in[FFB_NLAYER] = {0};
+    // conv edge plans, cached per (conv layer, T_in)
+    std::mutex mu;
+    std::map<std::pair<int, int>, ffb::ConvTail> tail_cache;
+};
+
+static inline float mat_at(const _Mat *m, size_t r, size_t c) { return m->data.f[c * m->stride + r]; }
+
+static float *upload(const std::vector<float> &h) {
+    float *d = nullptr;
+    if (cudaMalloc(&d, h.size() * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(d); return nullptr;
+    }
+    return d;
+}
+
+extern "C" void ffb_model_destroy(ffb_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (int i = 0; i < FFB_MAX_CONV; i++) { cudaFree(m->d_convWt[i]); cudaFree(m->d_convb[i]); }
+    for (int i = 0; i < FFB_NLAYER; i++) { cudaFree(m->d_iWt[i]); cudaFree(m->d_b[i]); cudaFree(m->d_sWp[i]); }
+    cudaFree(m->d_ffWt); cudaFree(m->d_ffb);
+    delete m;
+}
+
+extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *mats, int nmat,
+                                       const int *conv_stride, int nconv) {
+    if (!mats || !conv_stride) { set_err("ffb_model_create: NULL argument"); return nullptr; }
+    if (ffb_device_count() <= device) { set_err("ffb_model_create: CUDA device %d not available", device); return nullptr; }
+    const int want_conv = (kind == FFB_KIND_GRU) ? 1 : 3;
+    if ((kind != FFB_KIND_GRU && kind != FFB_KIND_LSTM) || nconv != want_conv || nmat != 2 * nconv + 3 * FFB_NLAYER + 2) {
+        set_err("ffb_model_create: kind %d expects %d convolutions and %d matrices (got %d, %d)", kind, want_conv,
+                2 * want_conv + 17, nconv, nmat);
+        return nullptr;
+    }
+    for (int i = 0; i < nmat; i++)
+        if (!mats[i] || !mats[i]->data.f) { set_err("ffb_model_create: matrix %d is NULL", i); return nullptr; }
+    CUDA_TRY(cudaSetDevice(device), nullptr);
+    ffb_model *m = new ffb_model();
+    m->device = device; m->kind = kind; m->nconv = nconv;
+    m->G = (kind == FFB_KIND_GRU) ? 3 : 4;
+    bool ok = true;
+    int nf = 1;
+    for (int i = 0; i < nconv; i++) {
+        const _Mat *W = mats[2 * i], *b = mats[2 * i + 1];
+        const int nf4 = 4 * ((nf + 3) / 4);
+        const int nfilter = (int)W->nc;
+        const int winlen = (int)((W->nr - nf + nf4) / nf4);   // nr = nf4*winlen - nf4 + nf
+        if ((size_t)(nf4 * winlen - nf4 + nf) != W->nr || b->nr != W->nc || conv_stride[i] < 1) {
+            set_err("ffb_model_create: convolution %d has inconsistent shape (nr=%zu nc=%zu nf=%d)", i, W->nr, W->nc, nf);
+            ok = false; break;
+        }
+        m->conv_nf[i] = nf; m->conv_nfilter[i] = nfilter; m->conv_winlen[i] = winlen; m->conv_stride[i] = conv_stride[i];
+        std::vector<float> Wt((size_t)winlen * nf * nfilter), bb(nfilter);
+        for (int f = 0; f < nfilter; f++) {
+            for (int k = 0; k < winlen; k++)
+                for (int n = 0; n < nf; n++) Wt[((size_t)k * nf + n) * nfilter + f] = mat_at(W, (size_t)k * nf4 + n, f);
+            bb[f] = mat_at(b, f, 0);
+        }
+        m->d_convWt[i] = upload(Wt); m->d_convb[i] = upload(bb);
+        ok = ok && m->d_convWt[i] && m->d_convb[i];
+        nf = nfilter;
+    }
+    const _Mat *const *L = mats + 2 * nconv;
+    if (ok) {
+        m->S = (int)L[1]->nr;   // sW is [S x G*S]
+        const int S = m->S, G = m->G;
+        if (!ffb_rnn_supported(kind, S)) {
+            set_err("ffb_model_create: no recurrent kernel for kind %d size %d", kind, S);
+            ok = false;
+        }
+        int in = nf;
+        for (int l = 0; ok && l < FFB_NLAYER; l++) {
+            const _Mat *iW = L[3 * l], *sW = L[3 * l + 1], *b = L[3 * l + 2];
+            if ((int)iW->nr != in || (int)iW->nc != G * S || (int)sW->nr != S || (int)sW->nc != G * S || (int)b->nr != G * S) {
+                set_err("ffb_model_create: recurrent layer %d has inconsistent shape", l);
+                ok = false; break;
+            }
+            m->layer_in[l] = in;
+            std::vector<float> iWt((size_t)in * G * S), bb(G * S), sWd((size_t)G * S * S), packed(ffb_rnn_packed_floats(kind, S));
+            for (int n = 0; n < G * S; n++) {
+                for (int k = 0; k < in; k++) iWt[(size_t)k * G * S + n] = mat_at(iW, k, n);
+                for (int k = 0; k < S; k++) sWd[(size_t)n * S + k] = mat_at(sW, k, n);
+                bb[n] = mat_at(b, n, 0);
+            }
+            ffb_rnn_pack_weights(kind, S, sWd.data(), packed.data());
+            m->d_iWt[l] = upload(iWt); m->d_b[l] = upload(bb); m->d_sWp[l] = upload(packed);
+            ok = ok && m->d_iWt[l] && m->d_b[l] && m->d_sWp[l];
+            in = S;
+        }
+    }
+    if (ok) {
+        const _Mat *FW = L[15], *Fb = L[16];
+        m->nparam = (int)FW->nc;
+        m->nbase = (int)nbase_from_flipflop_nparam(m->nparam);
+        m->nstate = 2 * m->nbase;
+        if ((int)FW->nr != m->S || (int)Fb->nr != m->nparam || m->nstate * (m->nbase + 1) != m->nparam ||
+            (m->nparam != 40 && m->nparam != 60)) {
+            set_err("ffb_model_create: output layer has unsupported shape (%zu x %zu)", FW->nr, FW->nc);
+            ok = false;
+        } else {
+            std::vector<float> Wt((size_t)m->S * m->nparam), bb(m->nparam);
+            for (int n = 0; n < m->nparam; n++) {
+                for (int k = 0; k < m->S; k++) Wt[(size_t)k * m->nparam + n] = mat_at(FW, k, n);
+                bb[n] = mat_at(Fb, n, 0);
+            }
+            m->d_ffWt = upload(Wt); m->d_ffb = upload(bb);
+            ok = m->d_ffWt && m->d_ffb;
+        }
+    }
+    if (ok && ffb_rnn_prepare(kind, m->S) != 0) {
+        set_err("ffb_model_create: recurrent kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ok = false;
+    }
+    if (!ok) {
+        if (g_err.empty()) set_err("ffb_model_create: device allocation failed");
+        ffb_model_destroy(m);
+        return nullptr;
+    }
+    return m;
+}
+
+extern "C" int ffb_model_size(const ffb_model *m) { return m ? m->S : 0; }
+extern "C" int ffb_model_nparam(const ffb_model *m) { return m ? m->nparam : 0; }
+extern "C" int ffb_model_stride(const ffb_model *m) {
+    if (!m) return 0;
+    int s = 1;
+    for (int i = 0; i < m->nconv; i++) s *= m->conv_stride[i];
+    return s;
+}
+extern "C" long ffb_model_nblock(const ffb_model *m, long nsample) {
+    if (!m) return -1;
+    long t = nsample;
+    for (int i = 0; i < m->nconv; i++) {
+        if (t < m->conv_winlen[i]) return -1;
+        t = (t + m->conv_stride[i] - 1) / m->conv_stride[i];
+    }
+    return t;
+}
+
+// ------------------------------------------------------------------------------------
+// The reference's convolution plan (src/layers.c:201-271), replayed with its own integer
+// arithmetic for the trailing columns only: which (x_start, tap_lo, ntap) terms does
+// column c receive?  Everything before `tail_col0` is the zero-padded window.
+struct Term { int x_start, tap_lo, ntap; };
+
+static bool build_conv_tail(int T, int winlen, int stride, ffb::ConvTail *out) {
+    const long padL = (winlen - 1) / 2, padR = winlen / 2;
+    const long ncol = (T + stride - 1) / stride;
+    const long ncolsL = (padL + stride - 1) / stride;          // :229
+    const long shiftX = ncolsL * stride - padL;                // :233
+    const long nstepC = (winlen + stride - 1) / stride;        // :236
+    const long nstepX = stride * nstepC;                       // :237
+    const long first = std::max(0L, ncol - FFB_CONV_TAIL);
+    std::vector<std::vector<Term>> terms((size_t)(ncol - first));
+    auto add = [&](long col, long xs, long tl, long nt) -> bool {
+        if (nt <= 0) return true;
+        if (col < 0 || col >= ncol || xs < 0 || xs + nt > T) return false;   // the reference itself would leave its matrices
+        if (col >= first) terms[(size_t)(col - first)].push_back(Term{(int)xs, (int)tl, (int)nt});
+        return true;
+    };
+    // left edge (:219-226)
+    for (long w = 0; w < padL; w += stride)
+        if (!add(w / stride, 0, padL - w, winlen - (padL - w))) return false;
+    // interior (:239-254): only windows landing in the tail are materialised
+    for (long w = 0; w < winlen; w += stride) {
+        const long nproc = (T - shiftX - w) / nstepX;          // ifloor on (int)
+        const long c_first = ncolsL + w / stride;
+        long i0 = 0;
+        if (first > c_first) i0 = (first - c_first + nstepC - 1) / nstepC;
+        for (long i = i0; i < nproc; i++)
+            if (!add(c_first + i * nstepC, shiftX + w + i * nstepX, 0, winlen)) return false;
+    }
+    // right edge (:257-271)
+    const long maxCol = (T - shiftX) / nstepX, rem = (T - shiftX) % nstepX;
+    const long colR = ncolsL + nstepC * (maxCol - 1) + rem / stride + 1;
+    const long xR = T - winlen + 1;
+    const long startR = stride - (padL + T - winlen) % stride - 1;
+    for (long w = startR; w < padR; w += stride)
+        if (!add(colR + w / stride, xR + w, 0, winlen - (w + 1))) return false;
+    // a right-edge column that lands before the window we materialised would be a plan we cannot express
+    if (colR + startR / stride < first && startR < padR) return false;
+
+    // first deviating column
+    long tail0 = ncol;
+    for (long c = first; c < ncol; c++) {
+        const auto &tv = terms[(size_t)(c - first)];
+        long xs = c * stride - padL, tl = 0, nt = winlen;
+        if (xs < 0) { tl = -xs; nt = winlen + xs; xs = 0; }
+        if (xs + nt > T) nt = T - xs;
+        const bool textbook = tv.size() == 1 && tv[0].x_start == xs && tv[0].tap_lo == tl && tv[0].ntap == nt;
+        if (!textbook) { tail0 = c; break; }
+    }
+    memset(out, 0, sizeof(*out));
+    out->tail_col0 = (int)tail0;
+    if (tail0 == first && first > 0) {
+        // the whole materialised window deviates: cannot prove earlier columns are textbook
+        return false;
+    }
+    for (long c = tail0; c < ncol; c++) {
+        const auto &tv = terms[(size_t)(c - first)];
+        if (tv.size() > 2) return false;
+        for (size_t q = 0; q < tv.size(); q++) {
+            out->x_start[c - tail0][q] = tv[q].x_start;
+            out->tap_lo[c - tail0][q] = tv[q].tap_lo;
+            out->ntap[c - tail0][q] = tv[q].ntap;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------
+struct ffb_ctx {
+    ffb_model *m = nullptr;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    // batch plan (host)
+    int64_t n_reads = 0, total_samples = 0, total_blocks = 0;
+    float temperature = 1.0f;
+    uint32_t flags = 0;
+    std::vector<int64_t> blk_off;                 // n_reads + 1
+    std::vector<int64_t> col_off[FFB_MAX_CONV + 1];   // per conv stage: column offsets (stage 0 = samples)
+    std::vector<int32_t> order;
+    int max_T[FFB_MAX_CONV + 1] = {0};
+    int n_slots = 0;
+    // device
+    DevBuf d_sig, d_c[2], d_act[2], d_xin, d_trans, d_tpost, d_fwd, d_tb, d_path, d_qpath, d_score, d_logz, d_trace;
+    DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
+    float *last_conv = nullptr;   // device pointer of last conv output within d_act/d_c
+    cudaEvent_t ev[8] = {nullptr};
+    float t_gemm_ms = 0.f, t_rnn_ms = 0.f;
+};
+
+extern "C" ffb_ctx *ffb_create(ffb_model *m, void *stream) {
+    if (!m) { set_err("ffb_create: NULL model"); return nullptr; }
+    CUDA_TRY(cudaSetDevice(m->device), nullptr);
+    ffb_ctx *c = new ffb_ctx();
+    c->m = m;
+    if (stream) {
+        c->st = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+            set_err("ffb_create: cudaStreamCreate failed");
+            delete c;
+            return nullptr;
+        }
+        c->own_stream = true;
+    }
+    for (auto &e : c->ev) cudaEventCreate(&e);
+    return c;
+}
+
+extern "C" void ffb_destroy(ffb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->m->device);
+    cudaStreamSynchronize(c->st);
+    DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
+                     &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
+                     &c->d_order};
+    for (auto *b : all) b->release();
+    for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
+    for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" int64_t ffb_total_blocks(const ffb_ctx *c) { return c ? c->total_blocks : 0; }
+extern "C" int64_t ffb_launch_count(const ffb_ctx *c) { return c ? c->launches : 0; }
+extern "C" int ffb_sync(ffb_ctx *c) {
+    if (!c) return FFB_ERR_ARG;
+    CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
+    return FFB_OK;
+}
+
+// ---- planning + H2D ------------------------------------------------------------------
+extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
+    if (!c || !b || !b->signal || !b->sig_off || b->n_reads < 0) { set_err("ffb_upload: bad arguments"); return FFB_ERR_ARG; }
+    ffb_model *m = c->m;
+    CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
+    const int64_t N = b->n_reads;
+    c->n_reads = N; c->temperature = b->temperature; c->flags = b->flags;
+    c->total_samples = b->sig_off[N] - b->sig_off[0];
+
+    // per-stage column counts: stage 0 = samples, stage i+1 = output of conv i
+    for (int s = 0; s <= m->nconv; s++) { c->col_off[s].assign(N + 1, 0); c->max_T[s] = 0; }
+    std::vector<ffb::ReadGeom> geom[FFB_MAX_CONV];
+    std::vector<ffb::ConvTail> tails[FFB_MAX_CONV];
+    std::map<int, int> tail_id[FFB_MAX_CONV];
+    for (int i = 0; i < m->nconv; i++) geom[i].resize((size_t)N);
+    for (int64_t n = 0; n < N; n++) {
+        long T = (long)(b->sig_off[n + 1] - b->sig_off[n]);
+        const bool ok = ffb_model_nblock(m, T) > 0;
+        if (!ok) T = 0;   // rejected read: zero columns everywhere (reference would underflow, layers.c:262)
+        c->col_off[0][n + 1] = c->col_off[0][n] + (b->sig_off[n + 1] - b->sig_off[n]);   // samples are uploaded as they are
+        c->max_T[0] = std::max<int>(c->max_T[0], (int)T);
+        for (int i = 0; i < m->nconv; i++) {
+            const long To = ok ? (T + m->conv_stride[i] - 1) / m->conv_stride[i] : 0;
+            ffb::ReadGeom g;
+            g.in_off = c->col_off[i][n]; g.out_off = c->col_off[i + 1][n];
+            g.T_in = (int)T; g.T_out = (int)To; g.tail_id = 0; g.pad = 0;
+            if (ok) {
+                auto it = tail_id[i].find((int)T);
+                if (it == tail_id[i].end()) {
+                    ffb::ConvTail tl;
+                    bool have = false;
+                    {
+                        std::lock_guard<std::mutex> lk(m->mu);
+                        auto ci = m->tail_cache.find({i, (int)T});
+                        if (ci != m->tail_cache.end()) { tl = ci->second; have = true; }
+                    }
+                    if (!have) {
+                        if (!build_conv_tail((int)T, m->conv_winlen[i], m->conv_stride[i], &tl)) {
+                            set_err("ffb_upload: convolution %d edge plan not expressible for T=%ld", i, T);
+                            return FFB_ERR_UNSUPPORTED;
+                        }
+                        std::lock_guard<std::mutex> lk(m->mu);
+                        m->tail_cache[{i, (int)T}] = tl;
+                    }
+                    const int id = (int)tails[i].size();
+                    tails[i].push_back(tl);
+                    it = tail_id[i].emplace((int)T, id).first;
+                }
+                g.tail_id = it->second;
+            }
+            geom[i][(size_t)n] = g;
+            c->col_off[i + 1][n + 1] = c->col_off[i + 1][n] + To;
+            c->max_T[i + 1] = std::max<int>(c->max_T[i + 1], (int)To);
+            T = To;
+        }
+    }
+    c->blk_off = c->col_off[m->nconv];
+    c->total_blocks = c->blk_off[N];
+    if (b->blk_off) memcpy(b->blk_off, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1));
+
+    // length-sorted slots for the recurrent kernel (descending, stable)
+    const int R = ffb_rnn_reads_per_cluster(m->kind, m->S);
+    c->n_slots = (int)(((N + R - 1) / R) * R);
+    c->order.assign((size_t)c->n_slots, -1);
+    {
+        std::vector<int32_t> idx((size_t)N);
+        std::iota(idx.begin(), idx.end(), 0);
+        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t bb) {
+            return (c->blk_off[a + 1] - c->blk_off[a]) > (c->blk_off[bb + 1] - c->blk_off[bb]);
+        });
+        std::copy(idx.begin(), idx.end(), c->order.begin());
+    }
+
+    // ---- device workspaces ----
+    const int64_t Tt = c->total_blocks, S = m->S, G = m->G, nr = m->nparam;
+    bool ok = true;
+    ok &= c->d_sig.reserve(sizeof(float) * (size_t)std::max<int64_t>(c->total_samples, 1)) == 0;
+    for (int i = 0; i + 1 < m->nconv; i++)
+        ok &= c->d_c[i].reserve(sizeof(float) * (size_t)std::max<int64_t>(c->col_off[i + 1][N] * m->conv_nfilter[i], 1)) == 0;
+    ok &= c->d_act[0].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    ok &= c->d_act[1].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    ok &= c->d_xin.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * G * S, 1)) == 0;
+    ok &= c->d_trans.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
+    if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
+        ok &= c->d_tpost.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
+        ok &= c->d_fwd.reserve(sizeof(float) * (size_t)std::max<int64_t>((Tt + N) * m->nstate, 1)) == 0;
+    }
+    ok &= c->d_tb.reserve(sizeof(uint64_t) * (size_t)std::max<int64_t>(Tt, 1)) == 0;
+    ok &= c->d_path.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(Tt + N, 1)) == 0;
+    ok &= c->d_qpath.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt + N, 1)) == 0;
+    ok &= c->d_score.reserve(sizeof(float) * (size_t)std::max<int64_t>(N, 1)) == 0;
+    ok &= c->d_logz.reserve(sizeof(double) * (size_t)std::max<int64_t>(N, 1)) == 0;
+    if (c->flags & FFB_FLAG_WANT_TRACE) ok &= c->d_trace.reserve((size_t)std::max<int64_t>((Tt + N) * m->nstate, 1)) == 0;
+    if (c->flags & FFB_FLAG_KEEP_LAYERS)
+        for (int l = 0; l < FFB_NLAYER; l++) ok &= c->d_keep[l].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    ok &= c->d_blkoff.reserve(sizeof(int64_t) * (size_t)(N + 1)) == 0;
+    ok &= c->d_order.reserve(sizeof(int32_t) * (size_t)std::max(c->n_slots, 1)) == 0;
+    for (int i = 0; i < m->nconv; i++) {
+        ok &= c->d_geom[i].reserve(sizeof(ffb::ReadGeom) * (size_t)std::max<int64_t>(N, 1)) == 0;
+        ok &= c->d_tails[i].reserve(sizeof(ffb::ConvTail) * std::max<size_t>(tails[i].size(), 1)) == 0;
+    }
+    if (!ok) { set_err("ffb_upload: out of device memory for %lld reads / %lld blocks", (long long)N, (long long)Tt); return FFB_ERR_NOMEM; }
+
+    // ---- H2D (signal is the only bulk input: 4 bytes per raw sample) ----
+    if (c->total_samples > 0)
+        CUDA_TRY(cudaMemcpyAsync(c->d_sig.p, b->signal + b->sig_off[0], sizeof(float) * (size_t)c->total_samples,
+                                 cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+    CUDA_TRY(cudaMemcpyAsync(c->d_blkoff.p, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+    if (c->n_slots > 0)
+        CUDA_TRY(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int32_t) * (size_t)c->n_slots, cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+    for (int i = 0; i < m->nconv; i++) {
+        if (N > 0) CUDA_TRY(cudaMemcpyAsync(c->d_geom[i].p, geom[i].data(), sizeof(ffb::ReadGeom) * (size_t)N, cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+        if (!tails[i].empty())
+            CUDA_TRY(cudaMemcpyAsync(c->d_tails[i].p, tails[i].data(), sizeof(ffb::ConvTail) * tails[i].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+    }
+    // the staging vectors above are pageable: make sure the copies have consumed them
+    CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
+    return FFB_OK;
+}
+
+// ---- all kernels of the path ------------------------------------------------------------
+#define LAUNCH(expr)                                                         \
+    do {                                                                     \
+        const int n_ = (expr);                                               \
+        if (n_ < 0) {                                                        \
+            set_err("launch failed: %s: %s", #expr, cudaGetErrorString(cudaGetLastError())); \
+            return FFB_ERR_CUDA;                                             \
+        }                                                                    \
+        c->launches += n_;                                                   \
+    } while (0)
+
+static int forward_impl(ffb_ctx *c, bool timed) {
+    ffb_model *m = c->m;
+    const int64_t N = c->n_reads, Tt = c->total_blocks;
+    const int S = m->S, G = m->G, nr = m->nparam;
+    cudaStream_t st = c->st;
+    if (N == 0 || Tt == 0) return FFB_OK;
+    if (N > 0x7fffffff) return FFB_ERR_ARG;
+    if (timed) cudaEventRecord(c->ev[0], st);
+    // ---- convolutions (features_from_raw folded into the first load) ----
+    const float *cur = c->d_sig.as<float>();
+    for (int i = 0; i < m->nconv; i++) {
+        float *out = (i + 1 == m->nconv) ? c->d_act[0].as<float>() : c->d_c[i].as<float>();
+        const int act = (m->kind == FFB_KIND_GRU) ? FFB_ACT_TANH : FFB_ACT_SWISH;   // networks.c:458 / :546-554
+        LAUNCH(ffb_launch_conv(cur, out, m->d_convWt[i], m->d_convb[i], c->d_geom[i].as<ffb::ReadGeom>(),
+                               c->d_tails[i].as<ffb::ConvTail>(), (int)N, c->col_off[i + 1][N], c->max_T[i + 1],
+                               m->conv_nf[i], m->conv_nfilter[i], m->conv_winlen[i], m->conv_stride[i], act, st));
+        cur = out;
+    }
+    c->last_conv = c->d_act[0].as<float>();
+    if (timed) cudaEventRecord(c->ev[1], st);
+    // ---- five recurrent layers, directions B,F,B,F,B (networks.c:460-483 / :557-580) ----
+    RnnBatch rb{c->d_order.as<int32_t>(), c->d_blkoff.as<int64_t>(), c->n_slots, (int)N};
+    float gemm_ms = 0.f, rnn_ms = 0.f;
+    int a = 0;
+    for (int l = 0; l < FFB_NLAYER; l++) {
+        const float *in = (l == 0) ? c->d_act[0].as<float>() : (c->flags & FFB_FLAG_KEEP_LAYERS ? c->d_keep[l - 1].as<float>() : c->d_act[a].as<float>());
+        float *out = (c->flags & FFB_FLAG_KEEP_LAYERS) ? c->d_keep[l].as<float>() : c->d_act[a ^ 1].as<float>();
+        if (timed) cudaEventRecord(c->ev[5], st);
+        LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], c->d_xin.as<float>(), Tt, G * S, m->layer_in[l], st));
+        if (timed) cudaEventRecord(c->ev[6], st);
+        LAUNCH(ffb_launch_rnn(m->kind, S, c->d_xin.as<float>(), m->d_sWp[l], out, rb, (l % 2) == 0, st));
+        if (timed) {
+            cudaEventRecord(c->ev[7], st);
+            cudaEventSynchronize(c->ev[7]);
+            float t1 = 0, t2 = 0;
+            cudaEventElapsedTime(&t1, c->ev[5], c->ev[6]);
+            cudaEventElapsedTime(&t2, c->ev[6], c->ev[7]);
+            gemm_ms += t1; rnn_ms += t2;
+        }
+        a ^= 1;
+    }
+    const float *top = (c->flags & FFB_FLAG_KEEP_LAYERS) ? c->d_keep[FFB_NLAYER - 1].as<float>() : c->d_act[a].as<float>();
+    if (timed) cudaEventRecord(c->ev[2], st);
+    // ---- globalnorm_flipflop (layers.c:1082-1106) ----
+    LAUNCH(ffb_launch_ff_tanh(top, m->d_ffWt, m->d_ffb, c->d_trans.as<float>(), Tt, nr, S, c->temperature / 5.0f, st));
+    LAUNCH(ffb_launch_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), st));
+    LAUNCH(ffb_launch_sub_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), Tt, st));
+    if (timed) cudaEventRecord(c->ev[3], st);
+    // ---- decoding (flappie.c:277-300) ----
+    const float *post = c->d_trans.as<float>();
+    if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
+        LAUNCH(ffb_launch_transpost(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_fwd.as<float>(),
+                                    c->d_tpost.as<float>(), st));
+        LAUNCH(ffb_launch_lognorm(c->d_tpost.as<float>(), Tt, nr, st));
+        post = c->d_tpost.as<float>();
+    }
+    LAUNCH(ffb_launch_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint64_t>(), c->d_path.as<int32_t>(),
+                              c->d_qpath.as<float>(), c->d_score.as<float>(), st));
+    if (c->flags & FFB_FLAG_WANT_TRACE)
+        LAUNCH(ffb_launch_trace(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_trace.as<uint8_t>(), 1, st));
+    if (timed) {
+        cudaEventRecord(c->ev[4], st);
+        cudaEventSynchronize(c->ev[4]);
+        c->t_gemm_ms = gemm_ms;
+        c->t_rnn_ms = rnn_ms;
+    }
+    return FFB_OK;
+}
+
+extern "C" int ffb_forward(ffb_ctx *c) {
+    if (!c) return FFB_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->m->device), FFB_ERR_CUDA);
+    return forward_impl(c, false);
+}
+
+extern "C" int ffb_forward_timed(ffb_ctx *c, float ms[8]) {
+    if (!c || !ms) return FFB_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->m->device), FFB_ERR_CUDA);
+    for (int i = 0; i < 8; i++) ms[i] = 0.f;
+    const int r = forward_impl(c, true);
+    if (r != FFB_OK) return r;
+    if (c->n_reads == 0 || c->total_blocks == 0) return FFB_OK;
+    float conv = 0, rec = 0, outl = 0, dec = 0, tot = 0;
+    cudaEventElapsedTime(&conv, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&rec, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&outl, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&dec, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&tot, c->ev[0], c->ev[4]);
+    ms[0] = conv; ms[1] = c->t_gemm_ms; ms[2] = c->t_rnn_ms; ms[3] = outl; ms[4] = dec; ms[5] = tot; ms[6] = rec;
+    return FFB_OK;
+}
+
+extern "C" int ffb_download(ffb_ctx *c, const ffb_batch *b) {
+    if (!c || !b) return FFB_ERR_ARG;
+    ffb_model *m = c->m;
+    CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
+    const int64_t N = c->n_reads, Tt = c->total_blocks;
+    cudaStream_t st = c->st;
+    if (N > 0 && Tt > 0) {
+        if (b->path) CUDA_TRY(cudaMemcpyAsync(b->path, c->d_path.p, sizeof(int32_t) * (size_t)(Tt + N), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        if (b->qpath) CUDA_TRY(cudaMemcpyAsync(b->qpath, c->d_qpath.p, sizeof(float) * (size_t)(Tt + N), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        if (b->score) CUDA_TRY(cudaMemcpyAsync(b->score, c->d_score.p, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        if (b->trans && (c->flags & FFB_FLAG_WANT_TRANS))
+            CUDA_TRY(cudaMemcpyAsync(b->trans, c->d_trans.p, sizeof(float) * (size_t)(Tt * m->nparam), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        if (b->tpost && (c->flags & FFB_FLAG_WANT_TRANS) && !(c->flags & FFB_FLAG_VITERBI_ONLY))
+            CUDA_TRY(cudaMemcpyAsync(b->tpost, c->d_tpost.p, sizeof(float) * (size_t)(Tt * m->nparam), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        if (b->trace && (c->flags & FFB_FLAG_WANT_TRACE))
+            CUDA_TRY(cudaMemcpyAsync(b->trace, c->d_trace.p, (size_t)((Tt + N) * m->nstate), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st), FFB_ERR_CUDA);
+    if (b->score && Tt == 0)
+        for (int64_t n = 0; n < N; n++) b->score[n] = NAN;
+    return FFB_OK;
+}
+
+extern "C" int ffb_basecall_batch(ffb_ctx *c, const ffb_batch *b) {
+    int r = ffb_upload(c, b);
+    if (r != FFB_OK) return r;
+    r = ffb_forward(c);
+    if (r != FFB_OK) return r;
+    return ffb_download(c, b);
+}
+
+extern "C" int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t bytes) {
+    if (!c || !dst) return FFB_ERR_ARG;
+    ffb_model *m = c->m;
+    CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
+    const void *src = nullptr;
+    int64_t have = 0;
+    const int64_t Tt = c->total_blocks;
+    if (what == 0) {
+        src = c->last_conv; have = Tt * m->S * (int64_t)sizeof(float);
+        if (!(c->flags & FFB_FLAG_KEEP_LAYERS)) { set_err("ffb_debug_fetch: conv output needs FFB_FLAG_KEEP_LAYERS"); return FFB_ERR_ARG; }
+    } else if (what >= 1 && what <= FFB_NLAYER) {
+        if (!(c->flags & FFB_FLAG_KEEP_LAYERS)) { set_err("ffb_debug_fetch: layers need FFB_FLAG_KEEP_LAYERS"); return FFB_ERR_ARG; }
+        src = c->d_keep[what - 1].p; have = Tt * m->S * (int64_t)sizeof(float);
+    } else if (what == 6) {
+        src = c->d_trans.p; have = Tt * m->nparam * (int64_t)sizeof(float);
+    } else if (what == 7) {
+        src = c->d_logz.p; have = c->n_reads * (int64_t)sizeof(double);
+    } else {
+        return FFB_ERR_ARG;
+    }
+    const int64_t n = std::min(have, bytes);
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)n, cudaMemcpyDeviceToHost, c->st), FFB_ERR_CUDA);
+        CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
+    }
+    return n;
+}
+
+// ---- host-side base emission (flappie.c:284-297) -------------------------------------------
+static inline char phredf_host(float p) {
+    // qscoref / phredf, util.h:285-305
+    const float p_clip = (p < 0.99999) ? p : 0.99999;
+    const float q = -(10.0f * 0.43429448190325182765) * log1pf(-p_clip);
+    char ph = roundf(33.0f + q);
+    return (ph < 126) ? ph : 126;
+}
+
+extern "C" int ffb_emit_bases(const int32_t *path, const float *qpath, int64_t nblock, int nbase, bool reverse,
+                              char *basecall, char *quality) {
+    static const char lookup[5] = {'A', 'C', 'G', 'T', 'Z'};   // decode.h:16
+    if (!path || !qpath || !basecall || !quality || nbase < 1 || nbase > 5) return -1;
+    int n = 0;
+    for (int64_t pos = 1; pos < nblock; pos++) {               // change_positions, decode.c:66-79 (npos = nblock)
+        if (path[pos] == path[pos - 1]) continue;
+        basecall[n] = lookup[path[pos] % nbase];
+        quality[n] = phredf_host(expf(qpath[pos]));
+        n++;
+    }
+    basecall[n] = 0; quality[n] = 0;
+    if (reverse) {                                             // reverse_char_array, util.c:416
+        std::reverse(basecall, basecall + n);
+        std::reverse(quality, quality + n);
+    }
+    return n;
+}
+
+// ======================================================================================
+// (1) drop-ins with the reference's signatures
+// ======================================================================================
+extern "C" size_t nbase_from_flipflop_nparam(size_t nparam) {
+    return (size_t)roundf((-1.0f + sqrtf(1 + 2 * nparam)) / 2.0f);   // layers.c:1029-1032
+}
+
+extern "C" flappie_matrix make_flappie_matrix(size_t nr, size_t nc) {
+    if (nr == 0 || nc == 0) return nullptr;
+    const size_t nrq = (nr + 3) / 4;
+    flappie_matrix mat = (flappie_matrix)malloc(sizeof(*mat));
+    if (!mat) return nullptr;
+    mat->nr = nr; mat->nrq = nrq; mat->nc = nc; mat->stride = nrq * 4;
+    void *p = nullptr;
+    if (posix_memalign(&p, 16, nrq * nc * 16) != 0) { free(mat); return nullptr; }
+    memset(p, 0, nrq * nc * 16);
+    mat->data.v = p;
+    return mat;
+}
+extern "C" flappie_matrix free_flappie_matrix(flappie_matrix mat) {
+    if (mat) { free(mat->data.v); free(mat); }
+    return nullptr;
+}
+extern "C" flappie_imatrix make_flappie_imatrix(size_t nr, size_t nc) {
+    return reinterpret_cast<flappie_imatrix>(make_flappie_matrix(nr, nc));
+}
+extern "C" flappie_imatrix free_flappie_imatrix(flappie_imatrix mat) {
+    if (mat) { free(mat->data.v); free(mat); }
+    return nullptr;
+}
+
+extern "C" enum model_type get_flappie_model_type(const char *modelstr) {
+    if (!modelstr) return FLAPPIE_MODEL_INVALID;
+    if (0 == strcmp(modelstr, "r941_native")) return FLAPPIE_MODEL_R941_NATIVE;
+    if (0 == strcmp(modelstr, "r941_rna002")) return FLAPPIE_MODEL_R941_RNA002;
+    if (0 == strcmp(modelstr, "r941_5mC")) return FLAPPIE_MODEL_R941_5mC;
+    if (0 == strcmp(modelstr, "r103_native")) return FLAPPIE_MODEL_R103_NATIVE;
+    if (0 == strcmp(modelstr, "rle_r941_native")) return RUNNIE_MODEL_R941_NATIVE;
+    // flappie <= 1.x name still used by the README and by BASELINE.json; the registry slot is
+    // shared with r941_native (bind the GRU bundle to it with ffb_register_model)
+    if (0 == strcmp(modelstr, "r10C_pcr")) return FLAPPIE_MODEL_R941_NATIVE;
+    return FLAPPIE_MODEL_INVALID;
+}
+extern "C" const char *flappie_model_string(const enum model_type model) {
+    switch (model) {
+    case FLAPPIE_MODEL_R941_NATIVE: return "r941_native";
+    case FLAPPIE_MODEL_R941_RNA002: return "r941_rna002";
+    case FLAPPIE_MODEL_R941_5mC: return "r941_5mC";
+    case FLAPPIE_MODEL_R103_NATIVE: return "r103_native";
+    case RUNNIE_MODEL_R941_NATIVE: return "rle_r941_native";
+    default: break;
+    }
+    fprintf(stderr, "Invalid model  %s:%d\n", __FILE__, __LINE__);   // reference: errx(EXIT_FAILURE, ...)
+    exit(EXIT_FAILURE);
+}
+extern "C" const char *flappie_model_description(const enum model_type model) {
+    switch (model) {
+    case FLAPPIE_MODEL_R941_NATIVE: return "R9.4.1 model for MinION.  Trained from native DNA library";
+    case FLAPPIE_MODEL_R941_RNA002: return "R9.4.1 dRNA model for MinION.  Trained from native and synthetic RNA library";
+    case FLAPPIE_MODEL_R941_5mC: return "R9.4.1 model for PromethION; 5mC aware.  Trained from native NA12878 library";
+    case FLAPPIE_MODEL_R103_NATIVE: return "R10.3 model for MinION.  Trained from native DNA library";
+    case RUNNIE_MODEL_R941_NATIVE: return "R9.4.1 run-length encoded model for MinION.  Trained from native DNA library";
+    default: break;
+    }
+    fprintf(stderr, "Invalid Flappie model  %s:%d\n", __FILE__, __LINE__);
+    exit(EXIT_FAILURE);
+}
+
+// model registry for calculate_transitions()
+static std::mutex g_reg_mu;
+static ffb_model *g_reg_model[RUNNIE_MODEL_INVALID + 1] = {nullptr};
+static ffb_ctx *g_reg_ctx[RUNNIE_MODEL_INVALID + 1] = {nullptr};
+
+extern "C" int ffb_register_model(enum model_type which, ffb_model *m) {
+    if ((int)which < 0 || (int)which >= RUNNIE_MODEL_INVALID || which == FLAPPIE_MODEL_INVALID) return FFB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    if (g_reg_ctx[which]) { ffb_destroy(g_reg_ctx[which]); g_reg_ctx[which] = nullptr; }
+    g_reg_model[which] = m;
+    return FFB_OK;
+}
+
+extern "C" flappie_matrix calculate_transitions(const raw_table signal, float temperature, enum model_type model) {
+    if (0 == signal.n || nullptr == signal.raw) return nullptr;          // networks.c:451-452
+    if ((int)model < 0 || (int)model >= RUNNIE_MODEL_INVALID || model == FLAPPIE_MODEL_INVALID) {
+        fprintf(stderr, "Invalid Flappie model  %s:%d\n", __FILE__, __LINE__);   // networks.c:98-104
+        exit(EXIT_FAILURE);
+    }
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    ffb_model *m = g_reg_model[model];
+    if (!m) { set_err("calculate_transitions: no weights registered for model %d (ffb_register_model)", (int)model); return nullptr; }
+    if (!g_reg_ctx[model]) g_reg_ctx[model] = ffb_create(m, nullptr);
+    ffb_ctx *c = g_reg_ctx[model];
+    if (!c) return nullptr;
+    if (signal.end <= signal.start) return nullptr;
+    const int64_t n = (int64_t)(signal.end - signal.start);
+    const long T = ffb_model_nblock(m, n);
+    if (T <= 0) return nullptr;
+    int64_t off[2] = {0, n};
+    std::vector<float> dense((size_t)T * m->nparam);
+    ffb_batch b;
+    memset(&b, 0, sizeof b);
+    b.signal = signal.raw + signal.start; b.sig_off = off; b.n_reads = 1; b.temperature = temperature;
+    b.flags = FFB_FLAG_VITERBI_ONLY | FFB_FLAG_WANT_TRANS;
+    b.trans = dense.data();
+    if (ffb_basecall_batch(c, &b) != FFB_OK) return nullptr;
+    flappie_matrix out = make_flappie_matrix(m->nparam, (size_t)T);
+    if (!out) return nullptr;
+    for (long t = 0; t < T; t++) memcpy(out->data.f + (size_t)t * out->stride, dense.data() + (size_t)t * m->nparam, sizeof(float) * m->nparam);
+    return out;
+}
+
+// standalone decode context (no model needed)
+struct DecodeCtx {
+    cudaStream_t st = nullptr;
+    DevBuf trans, tpost, fwd, tb, path, qpath, score, blkoff, trace;
+};
+static DecodeCtx *decode_ctx() {
+    static DecodeCtx *d = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!d) {
+        if (ffb_device_count() < 1) { set_err("no CUDA device: the flappie_b200 decode entry points have no CPU fallback"); return nullptr; }
+        d = new DecodeCtx();
+        if (cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking) != cudaSuccess) { delete d; d = nullptr; return nullptr; }
+    }
+    return d;
+}
+static std::mutex g_dec_mu;
+
+// _Mat [nr x nc] (padded columns) -> device dense [nc][nr]
+static int mat_to_device(const _Mat *mat, DevBuf &buf, cudaStream_t st) {
+    if (buf.reserve(sizeof(float) * mat->nr * mat->nc) != 0) return -1;
+    if (cudaMemcpy2DAsync(buf.p, mat->nr * sizeof(float), mat->data.f, mat->stride * sizeof(float), mat->nr * sizeof(float),
+                          mat->nc, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    return 0;
+}
+
+extern "C" float decode_crf_flipflop(const_flappie_matrix trans, bool combine_stays, int *path, float *qpath) {
+    if (!trans || !path || !qpath) return NAN;                           // decode.c:120-122
+    const int nr = (int)trans->nr;
+    const int64_t T = (int64_t)trans->nc;
+    if (nr != 40 && nr != 60) { set_err("decode_crf_flipflop: unsupported nr=%d", nr); return NAN; }
+    DecodeCtx *d = decode_ctx();
+    if (!d) return NAN;
+    std::lock_guard<std::mutex> lk(g_dec_mu);
+    int64_t off[2] = {0, T};
+    bool ok = mat_to_device(trans, d->trans, d->st) == 0;
+    ok = ok && d->tb.reserve(sizeof(uint64_t) * (size_t)T) == 0 && d->path.reserve(sizeof(int32_t) * (size_t)(T + 1)) == 0 &&
+         d->qpath.reserve(sizeof(float) * (size_t)(T + 1)) == 0 && d->score.reserve(sizeof(float)) == 0 &&
+         d->blkoff.reserve(sizeof(off)) == 0;
+    if (!ok) { set_err("decode_crf_flipflop: device allocation / copy failed"); return NAN; }
+    cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
+    if (ffb_launch_viterbi(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->tb.as<uint64_t>(), d->path.as<int32_t>(),
+                           d->qpath.as<float>(), d->score.as<float>(), d->st) < 0) return NAN;
+    float score = NAN;
+    static_assert(sizeof(int) == sizeof(int32_t), "int is 32-bit");
+    cudaMemcpyAsync(path, d->path.p, sizeof(int32_t) * (size_t)(T + 1), cudaMemcpyDeviceToHost, d->st);
+    cudaMemcpyAsync(qpath, d->qpath.p, sizeof(float) * (size_t)(T + 1), cudaMemcpyDeviceToHost, d->st);
+    cudaMemcpyAsync(&score, d->score.p, sizeof(float), cudaMemcpyDeviceToHost, d->st);
+    if (cudaStreamSynchronize(d->st) != cudaSuccess) { set_err("decode_crf_flipflop: %s", cudaGetErrorString(cudaGetLastError())); return NAN; }
+    if (combine_stays) {                                                 // decode.c:194-198
+        const int nbase = (int)nbase_from_flipflop_nparam(nr);
+        for (int64_t i = 0; i <= T; i++) path[i] = (path[i] < nbase) ? path[i] : -1;
+    }
+    return score;
+}
+
+extern "C" flappie_matrix transpost_crf_flipflop(const_flappie_matrix trans, bool return_log) {
+    if (!trans) return nullptr;
+    const int nr = (int)trans->nr;
+    const int64_t T = (int64_t)trans->nc;
+    if (nr != 40 && nr != 60) { set_err("transpost_crf_flipflop: unsupported nr=%d", nr); return nullptr; }
+    DecodeCtx *d = decode_ctx();
+    if (!d) return nullptr;
+    std::lock_guard<std::mutex> lk(g_dec_mu);
+    const int nstate = 2 * (int)nbase_from_flipflop_nparam(nr);
+    int64_t off[2] = {0, T};
+    bool ok = mat_to_device(trans, d->trans, d->st) == 0;
+    ok = ok && d->tpost.reserve(sizeof(float) * (size_t)(T * nr)) == 0 && d->fwd.reserve(sizeof(float) * (size_t)((T + 1) * nstate)) == 0 &&
+         d->blkoff.reserve(sizeof(off)) == 0;
+    if (!ok) { set_err("transpost_crf_flipflop: device allocation / copy failed"); return nullptr; }
+    cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
+    if (ffb_launch_transpost(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->fwd.as<float>(), d->tpost.as<float>(), d->st) < 0) return nullptr;
+    if (ffb_launch_lognorm(d->tpost.as<float>(), T, nr, d->st) < 0) return nullptr;
+    if (!return_log && ffb_launch_exp_inplace(d->tpost.as<float>(), T * nr, d->st) < 0) return nullptr;
+    flappie_matrix out = make_flappie_matrix(nr, (size_t)T);
+    if (!out) return nullptr;
+    cudaMemcpy2DAsync(out->data.f, out->stride * sizeof(float), d->tpost.p, nr * sizeof(float), nr * sizeof(float), (size_t)T,
+                      cudaMemcpyDeviceToHost, d->st);
+    if (cudaStreamSynchronize(d->st) != cudaSuccess) { set_err("transpost_crf_flipflop: %s", cudaGetErrorString(cudaGetLastError())); return free_flappie_matrix(out); }
+    return out;
+}
+
+extern "C" void exp_activation_inplace(flappie_matrix C) {
+    if (!C) return;
+    DecodeCtx *d = decode_ctx();
+    if (!d) return;
+    std::lock_guard<std::mutex> lk(g_dec_mu);
+    const size_t n = C->stride * C->nc;   // the reference exponentiates the padding too (layers.c:58-63)
+    if (d->trans.reserve(sizeof(float) * n) != 0) { set_err("exp_activation_inplace: device allocation failed"); return; }
+    cudaMemcpyAsync(d->trans.p, C->data.f, sizeof(float) * n, cudaMemcpyHostToDevice, d->st);
+    ffb_launch_exp_inplace(d->trans.as<float>(), (int64_t)n, d->st);
+    cudaMemcpyAsync(C->data.f, d->trans.p, sizeof(float) * n, cudaMemcpyDeviceToHost, d->st);
+    if (cudaStreamSynchronize(d->st) != cudaSuccess) set_err("exp_activation_inplace: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
+extern "C" flappie_imatrix trace_from_posterior(flappie_matrix tpost) {
+    if (!tpost) return nullptr;
+    const int nr = (int)tpost->nr;
+    const int64_t T = (int64_t)tpost->nc;
+    if (nr != 40 && nr != 60) { set_err("trace_from_posterior: unsupported nr=%d", nr); return nullptr; }
+    DecodeCtx *d = decode_ctx();
+    if (!d) return nullptr;
+    std::lock_guard<std::mutex> lk(g_dec_mu);
+    const int nstate = 2 * (int)nbase_from_flipflop_nparam(nr);
+    int64_t off[2] = {0, T};
+    bool ok = mat_to_device(tpost, d->trans, d->st) == 0 && d->trace.reserve((size_t)((T + 1) * nstate)) == 0 &&
+              d->blkoff.reserve(sizeof(off)) == 0;
+    if (!ok) { set_err("trace_from_posterior: device allocation / copy failed"); return nullptr; }
+    cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
+    if (ffb_launch_trace(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->trace.as<uint8_t>(), 0, d->st) < 0) return nullptr;
+    std::vector<uint8_t> h((size_t)((T + 1) * nstate));
+    cudaMemcpyAsync(h.data(), d->trace.p, h.size(), cudaMemcpyDeviceToHost, d->st);
+    if (cudaStreamSynchronize(d->st) != cudaSuccess) { set_err("trace_from_posterior: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
+    flappie_imatrix out = make_flappie_imatrix(nstate, (size_t)(T + 1));
+    if (!out) return nullptr;
+    for (int64_t t = 0; t <= T; t++)
+        for (int s = 0; s < nstate; s++) out->data.f[(size_t)t * out->stride + s] = h[(size_t)t * nstate + s];
+    return out;
+}

@@ -1,0 +1,534 @@
+// decode.cu -- flip-flop CRF decoding over a ragged batch: global normalisation constant,
+// Viterbi, transition posteriors (forward/backward) and the state trace.
+//
+// Replaces reference
+//   crf_manystay_partition_function + the "-= logZ" of globalnorm_manystay (src/layers.c:1035-1096)
+//   decode_crf_flipflop + trans_lookup + argmaxf/valmaxf   (src/decode.c:104-204, src/util.c:17-61)
+//   transpost_crf_flipflop + log_row_normalise_inplace      (src/decode.c:377-497, src/flappie_matrix.c:450-467)
+//   exp_activation_inplace + trace_from_posterior           (src/layers.c:56-66, src/decode.c:499-543)
+//
+// Layout: trans / tpost are [block][nr] row-major (one reference column per row),
+// nr = nstate*(nbase+1): rows b1*nstate+from for flip destination b1, then nstate entries
+// at nbase*nstate: entry f < nbase = flip f -> flop f+nbase, entry f >= nbase = flop stay.
+//
+// All scans are strictly sequential in the block index (max-plus / log-sum-exp
+// recurrences); parallelism is one WARP PER READ, lanes = (destination, source) pairs,
+// with the read's scores streamed through shared memory by cp.async double buffering.
+// fp32 additions and comparisons are done in the reference's visit order so the Viterbi
+// path is bit-exact given bit-identical input (first-max-wins ties included).
+#include "ffb_common.cuh"
+
+namespace ffb {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int DEC_CHUNK = 16;   // blocks per cp.async stage
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Stage `nblk` blocks (nr floats each, 16-byte aligned rows) of one read into smem.
+__device__ __forceinline__ void stage_chunk(float *dst, const float *src, int nblk, int nr, int lane) {
+    const int n16 = nblk * nr / 4;
+    for (int i = lane; i < n16; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+    cp_async_commit();
+}
+
+// ---------------------------------------------------------------------------------
+// Viterbi.  One warp per read.
+//   NBASE == 4: single pass, lane = b1*8 + from reads trans[lane] directly.
+//   otherwise : lanes = two 16-lane segments, segment h handles destination 2*it+h.
+// Traceback pointers: 4 bits per state packed into one 64-bit word per block.
+template <int NBASE>
+__global__ void __launch_bounds__(32)
+viterbi_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads,
+               uint64_t *__restrict__ tb, int32_t *__restrict__ path, float *__restrict__ qpath,
+               float *__restrict__ score) {
+    constexpr int NSTATE = 2 * NBASE;
+    constexpr int NR = NSTATE * (NBASE + 1);
+    __shared__ __align__(16) float stage[2][DEC_CHUNK * NR];
+    const int rd = blockIdx.x;
+    if (rd >= n_reads) return;
+    const int lane = threadIdx.x;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    int32_t *rpath = path + b0 + rd;       // T+1 entries
+    float *rqpath = qpath + b0 + rd;
+    if (T <= 0) {
+        if (lane == 0) { score[rd] = nanf(""); }
+        return;
+    }
+    const float *tr = trans + b0 * NR;
+    uint64_t *rtb = tb + b0;
+
+    // lane roles
+    const int from = (NBASE == 4) ? (lane & 7) : (lane & 15);
+    const int seg = (NBASE == 4) ? (lane >> 3) : (lane >> 4);
+    float P = 0.0f;   // score of state `from` after the previous block (calloc, decode.c:130)
+
+    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
+    stage_chunk(stage[0], tr, min(DEC_CHUNK, T), NR, lane);
+    uint64_t tbword = 0;   // lane i keeps the word of block (32*k + i)
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int c0 = ch * DEC_CHUNK;
+        const int cn = min(DEC_CHUNK, T - c0);
+        if (ch + 1 < nchunk) {
+            stage_chunk(stage[(ch + 1) & 1], tr + (int64_t)(c0 + DEC_CHUNK) * NR, min(DEC_CHUNK, T - c0 - DEC_CHUNK), NR, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float *sb = stage[ch & 1];
+        for (int i = 0; i < cn; i++) {
+            const float *col = sb + i * NR;
+            const float *flop = col + NSTATE * NBASE;
+            uint64_t nib = 0;
+            float Pnew = P;
+            // ---- flop destinations (decode.c:153-164): stay is the default, move wins on '>' ----
+            {
+                const float Pm = __shfl_sync(FULL, P, (lane - NBASE) & 31);   // prev[from - nbase] lives NBASE lanes down
+                if (from >= NBASE && from < NSTATE) {
+                    const float stay = P + flop[from];
+                    const float move = Pm + flop[from - NBASE];
+                    const bool mv = move > stay;
+                    Pnew = mv ? move : stay;
+                    if (seg == 0) nib |= (uint64_t)(mv ? from - NBASE : from) << (4 * from);
+                }
+            }
+            // ---- flip destinations (decode.c:167-180): source 0 is the default, later sources win on '>' ----
+            if constexpr (NBASE == 4) {
+                const float v = col[lane] + P;
+                float m = v;
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
+                m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+                const unsigned eq = __ballot_sync(FULL, v == m);
+                const int win = __ffs((eq >> (8 * seg)) & 0xffu) - 1;   // first max wins
+                if (from == 0) nib |= (uint64_t)win << (4 * seg);
+                const float mf = __shfl_sync(FULL, m, (from & 3) * 8);  // curr[from] for from < 4
+                if (from < NBASE) Pnew = mf;
+            } else {
+                constexpr int NIT = (NBASE + 1) / 2;
+#pragma unroll
+                for (int it = 0; it < NIT; it++) {
+                    const int b1 = 2 * it + seg;
+                    const bool valid = (from < NSTATE) && (b1 < NBASE);
+                    const float v = valid ? col[b1 * NSTATE + from] + P : -INFINITY;
+                    float m = v;
+                    m = fmaxf(m, __shfl_xor_sync(FULL, m, 1));
+                    m = fmaxf(m, __shfl_xor_sync(FULL, m, 2));
+                    m = fmaxf(m, __shfl_xor_sync(FULL, m, 4));
+                    m = fmaxf(m, __shfl_xor_sync(FULL, m, 8));
+                    const unsigned eq = __ballot_sync(FULL, valid && v == m);
+                    const int win = __ffs((eq >> (16 * seg)) & 0xffffu) - 1;
+                    if (from == 0 && b1 < NBASE) nib |= (uint64_t)win << (4 * b1);
+                    // states 2*it and 2*it+1 were just produced by segments 0 and 1
+                    const float m0 = __shfl_sync(FULL, m, 0);
+                    const float m1 = __shfl_sync(FULL, m, 16);
+                    if (from == 2 * it) Pnew = m0;
+                    if (from == 2 * it + 1 && from < NBASE) Pnew = m1;
+                }
+            }
+            P = Pnew;
+            // gather the 4-bit pointers of all states into one word
+            const unsigned lo = __reduce_or_sync(FULL, (unsigned)(nib & 0xffffffffu));
+            const unsigned hi = (NSTATE > 8) ? __reduce_or_sync(FULL, (unsigned)(nib >> 32)) : 0u;
+            const int blk = c0 + i;
+            if ((blk & 31) == lane) tbword = ((uint64_t)hi << 32) | lo;
+            if ((blk & 31) == 31 || blk == T - 1) {
+                const int base = blk & ~31;
+                if (base + lane <= blk) rtb[base + lane] = tbword;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- final state: valmaxf / argmaxf, first max wins (util.c:17-31, decode.c:184-185) ----
+    {
+        const bool holder = (seg == 0) && (from < NSTATE);
+        const float v = holder ? P : -INFINITY;
+        float m = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+        const unsigned eq = __ballot_sync(FULL, holder && v == m);
+        const int st = __ffs(eq) - 1;   // lane index == state for segment 0
+        if (lane == 0) {
+            score[rd] = m;
+            rpath[T] = st;
+        }
+        // ---- traceback (decode.c:186-191), 32 blocks per round ----
+        int state = st;
+        __syncwarp();
+        for (int hi_blk = T; hi_blk > 0; hi_blk -= 32) {
+            const int lo_blk = max(hi_blk - 32, 0);   // blocks [lo_blk, hi_blk)
+            const int myblk = lo_blk + lane;
+            const uint64_t w = (myblk < hi_blk) ? rtb[myblk] : 0ull;
+            int mine = 0;
+            for (int i = hi_blk - 1 - lo_blk; i >= 0; i--) {
+                const unsigned wl = __shfl_sync(FULL, (unsigned)(w & 0xffffffffu), i);
+                const unsigned wh = (NSTATE > 8) ? __shfl_sync(FULL, (unsigned)(w >> 32), i) : 0u;
+                const uint64_t ww = ((uint64_t)wh << 32) | wl;
+                state = (int)((ww >> (4 * state)) & 0xfull);   // path[blk] = tb[blk][path[blk+1]]
+                if (lane == i) mine = state;
+            }
+            if (myblk < hi_blk) rpath[myblk] = mine;
+        }
+    }
+    __syncwarp();
+    // ---- qpath (decode.c:190-192): score of the transition taken into block blk ----
+    for (int blk = lane; blk <= T; blk += 32) {
+        if (blk == 0) {
+            rqpath[0] = nanf("");
+        } else {
+            const int pf = rpath[blk - 1], pt = rpath[blk];
+            const int idx = (pt < NBASE) ? (pt * NSTATE + pf) : (NBASE * NSTATE + pf);   // trans_lookup
+            rqpath[blk] = tr[(int64_t)(blk - 1) * NR + idx];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// log partition function in DOUBLE (layers.c:1035-1079).  One warp per read; 16-lane
+// segments, segment h handles flip destination 2*it+h.  The flip sums use the
+// max-shifted form (equal to the reference's sequential logsumexp fold to ~1e-16
+// relative, far below the float the result is rounded to, layers.c:1089).
+template <int NBASE>
+__global__ void __launch_bounds__(32)
+logz_kernel(const float *__restrict__ C, const int64_t *__restrict__ blk_off, int n_reads, double *__restrict__ logZ) {
+    constexpr int NSTATE = 2 * NBASE;
+    constexpr int NR = NSTATE * (NBASE + 1);
+    __shared__ __align__(16) float stage[2][DEC_CHUNK * NR];
+    const int rd = blockIdx.x;
+    if (rd >= n_reads) return;
+    const int lane = threadIdx.x;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    if (T <= 0) {
+        if (lane == 0) logZ[rd] = 0.0;
+        return;
+    }
+    const float *tr = C + b0 * NR;
+    const int from = lane & 15, seg = lane >> 4;
+    double P = 0.0;   // calloc, layers.c:1041
+    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
+    stage_chunk(stage[0], tr, min(DEC_CHUNK, T), NR, lane);
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int c0 = ch * DEC_CHUNK;
+        const int cn = min(DEC_CHUNK, T - c0);
+        if (ch + 1 < nchunk) {
+            stage_chunk(stage[(ch + 1) & 1], tr + (int64_t)(c0 + DEC_CHUNK) * NR, min(DEC_CHUNK, T - c0 - DEC_CHUNK), NR, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float *sb = stage[ch & 1];
+        for (int i = 0; i < cn; i++) {
+            const float *col = sb + i * NR;
+            const float *stay = col + NSTATE * NBASE;
+            double Pnew = P;
+            const double Pm = __shfl_sync(FULL, P, (lane - NBASE) & 31);
+            if (from >= NBASE && from < NSTATE) {
+                const double x = P + (double)stay[from];
+                const double y = Pm + (double)stay[from - NBASE];
+                Pnew = fmax(x, y) + log1p(exp(-fabs(x - y)));   // util.h:280-282
+            }
+            constexpr int NIT = (NBASE + 1) / 2;
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int b1 = 2 * it + seg;
+                const bool valid = (from < NSTATE) && (b1 < NBASE);
+                const double v = valid ? (double)col[b1 * NSTATE + from] + P : -INFINITY;
+                double m = v;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+                double e = valid ? exp(v - m) : 0.0;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) e += __shfl_xor_sync(FULL, e, o);
+                const double r = m + log(e);
+                const double r0 = __shfl_sync(FULL, r, 0);
+                const double r1 = __shfl_sync(FULL, r, 16);
+                if (from == 2 * it) Pnew = r0;
+                if (from == 2 * it + 1 && from < NBASE) Pnew = r1;
+            }
+            P = Pnew;
+        }
+        __syncwarp();
+    }
+    // logZ = logsumexp over final states (layers.c:1071-1074)
+    const bool holder = (seg == 0) && (from < NSTATE);
+    const double v = holder ? P : -INFINITY;
+    double m = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) m = fmax(m, __shfl_xor_sync(FULL, m, o));
+    double e = holder ? exp(v - m) : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) e += __shfl_xor_sync(FULL, e, o);
+    if (lane == 0) logZ[rd] = m + log(e);
+}
+
+// trans[blk][*] -= (float)(logZ / T)   (layers.c:1089-1096)
+__global__ void sub_logz_kernel(float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads, int nr,
+                                const double *__restrict__ logZ) {
+    const int rd = blockIdx.y;
+    const int64_t b0 = blk_off[rd];
+    const int64_t n = (blk_off[rd + 1] - b0) * nr;
+    if (n <= 0) return;
+    const float lz = (float)(logZ[rd] / (double)(blk_off[rd + 1] - b0));
+    float *p = trans + b0 * nr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] -= lz;
+}
+
+// ---------------------------------------------------------------------------------
+// Transition posteriors.  Forward scan -> fwd[(T+1)][nstate]; backward scan emits
+// fwd + bwd + trans; a third, block-parallel kernel does the per-block log-normalisation
+// (a 39/59-term sequential logsumexp fold in the reference's order).
+// Lane = state; logsumexp folds run in the reference's source order (decode.c:396-484).
+template <int NBASE>
+__global__ void __launch_bounds__(32)
+transpost_fwd_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads,
+                     float *__restrict__ fwd) {
+    constexpr int NSTATE = 2 * NBASE;
+    constexpr int NR = NSTATE * (NBASE + 1);
+    __shared__ __align__(16) float stage[2][DEC_CHUNK * NR];
+    const int rd = blockIdx.x;
+    if (rd >= n_reads) return;
+    const int lane = threadIdx.x;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    if (T <= 0) return;
+    const float *tr = trans + b0 * NR;
+    float *rf = fwd + (b0 + rd) * NSTATE;   // (T+1) x NSTATE
+    float P = 0.0f;                          // fwd[.,0] = 0 (make_flappie_matrix memsets)
+    if (lane < NSTATE) rf[lane] = 0.0f;
+    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
+    stage_chunk(stage[0], tr, min(DEC_CHUNK, T), NR, lane);
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int c0 = ch * DEC_CHUNK;
+        const int cn = min(DEC_CHUNK, T - c0);
+        if (ch + 1 < nchunk) {
+            stage_chunk(stage[(ch + 1) & 1], tr + (int64_t)(c0 + DEC_CHUNK) * NR, min(DEC_CHUNK, T - c0 - DEC_CHUNK), NR, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float *sb = stage[ch & 1];
+        for (int i = 0; i < cn; i++) {
+            const float *col = sb + i * NR;
+            const float *flop = col + NSTATE * NBASE;
+            float cur;
+            // flop destinations: logsumexp(stay, move)  (decode.c:404-411)
+            const float Pm = __shfl_sync(FULL, P, (lane - NBASE) & 31);
+            const float fl = (lane >= NBASE && lane < NSTATE) ? logsumexpf_ref(P + flop[lane], Pm + flop[lane - NBASE]) : 0.0f;
+            // flip destinations: sequential fold over sources 0..nstate-1 (decode.c:414-422)
+            const int b1 = lane < NBASE ? lane : 0;
+            cur = col[b1 * NSTATE] + __shfl_sync(FULL, P, 0);
+#pragma unroll
+            for (int f = 1; f < NSTATE; f++) {
+                const float pf = __shfl_sync(FULL, P, f);
+                cur = logsumexpf_ref(cur, col[b1 * NSTATE + f] + pf);
+            }
+            P = (lane < NBASE) ? cur : fl;
+            if (lane < NSTATE) rf[(int64_t)(c0 + i + 1) * NSTATE + lane] = P;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NBASE>
+__global__ void __launch_bounds__(32)
+transpost_bwd_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads,
+                     const float *__restrict__ fwd, float *__restrict__ tpost) {
+    constexpr int NSTATE = 2 * NBASE;
+    constexpr int NR = NSTATE * (NBASE + 1);
+    const int rd = blockIdx.x;
+    if (rd >= n_reads) return;
+    const int lane = threadIdx.x;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    if (T <= 0) return;
+    const float *tr = trans + b0 * NR;
+    float *tp = tpost + b0 * NR;
+    const float *rf = fwd + (b0 + rd) * NSTATE;
+    float B = 0.0f;   // backward vector at block `blk` (lane = state); calloc -> 0 (decode.c:426-432)
+    __shared__ float Bs[32];
+    for (int blk = T; blk > 0; blk--) {
+        const float *col = tr + (int64_t)(blk - 1) * NR;
+        const float *f = rf + (int64_t)(blk - 1) * NSTATE;
+        float *pc = tp + (int64_t)(blk - 1) * NR;
+        Bs[lane] = B;
+        __syncwarp();
+        // ---- emit tpost = fwd[from] + bwd[to] + trans (decode.c:446-461) ----
+        for (int e = lane; e < NR; e += 32) {
+            int to, fr;
+            if (e < NBASE * NSTATE) { to = e / NSTATE; fr = e % NSTATE; }
+            else { fr = e - NBASE * NSTATE; to = fr < NBASE ? fr + NBASE : fr; }
+            pc[e] = f[fr] + Bs[to] + col[e];
+        }
+        __syncwarp();
+        // ---- update backward vector (decode.c:465-482) ----
+        float cur = 0.0f;
+        const float Bup = __shfl_sync(FULL, B, (lane + NBASE) & 31);   // prev[from + nbase]
+        if (lane < NSTATE) {
+            const float flopv = col[NBASE * NSTATE + lane];
+            cur = (lane >= NBASE) ? (B + flopv) : (Bup + flopv);
+        }
+#pragma unroll
+        for (int b1 = 0; b1 < NBASE; b1++) {
+            const float pb = __shfl_sync(FULL, B, b1);
+            if (lane < NSTATE) cur = logsumexpf_ref(cur, col[b1 * NSTATE + lane] + pb);
+        }
+        B = cur;
+    }
+}
+
+// per-block log normalisation, sequential fold in row order (flappie_matrix.c:450-467)
+__global__ void lognorm_rows_kernel(float *__restrict__ tpost, int64_t nblk, int nr) {
+    const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk >= nblk) return;
+    float *p = tpost + blk * nr;
+    float lse = p[0];
+    for (int r = 1; r < nr; r++) lse = logsumexpf_ref(lse, p[r]);
+    for (int r = 0; r < nr; r++) p[r] -= lse;
+}
+
+// trace (decode.c:499-543) from LOG posteriors: one thread per (read-local) trace row.
+template <int NBASE, bool IS_LOG>
+__global__ void trace_kernel(const float *__restrict__ tpost, const int64_t *__restrict__ blk_off, int n_reads,
+                             uint8_t *__restrict__ trace) {
+    constexpr int NSTATE = 2 * NBASE;
+    constexpr int NR = NSTATE * (NBASE + 1);
+    const int rd = blockIdx.y;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    if (T <= 0) return;
+    const float *tp = tpost + b0 * NR;
+    uint8_t *tr = trace + (b0 + rd) * NSTATE;
+    auto ex = [](float v) { return IS_LOG ? expf(v) : v; };
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row <= T; row += gridDim.x * blockDim.x) {
+        uint8_t *o = tr + (int64_t)row * NSTATE;
+        if (row == 0) {
+            // mass LEAVING each state in block 0 (decode.c:511-518)
+            for (int from = 0; from < NSTATE; from++) {
+                float sum = 0.0f;
+                for (int to = 0; to < NBASE; to++) sum += ex(tp[to * NSTATE + from]);
+                sum += ex(tp[NBASE * NSTATE + from]);
+                o[from] = (uint8_t)(int)roundf(255.0f * sum);
+            }
+        } else {
+            const float *pc = tp + (int64_t)(row - 1) * NR;
+            for (int to = 0; to < NBASE; to++) {
+                float sum = ex(pc[to * NSTATE]);
+                for (int from = 1; from < NSTATE; from++) sum += ex(pc[to * NSTATE + from]);
+                o[to] = (uint8_t)(int)roundf(255.0f * sum);
+            }
+            const float *pf = pc + NBASE * NSTATE;
+            for (int to = NBASE; to < NSTATE; to++) {
+                const float sum = ex(pf[to - NBASE]) + ex(pf[to]);
+                o[to] = (uint8_t)(int)roundf(255.0f * sum);
+            }
+        }
+    }
+}
+
+__global__ void exp_inplace_kernel(float *__restrict__ x, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = expf(x[i]);
+}
+
+}  // namespace ffb
+
+static inline int nbase_of(int nr) { return nr == 40 ? 4 : (nr == 60 ? 5 : 0); }
+#define FFB_OKL(n) (cudaGetLastError() == cudaSuccess ? (n) : -1)
+
+int ffb_launch_logz(const float *trans, const int64_t *blk_off, int n_reads, int nr, double *logZ, cudaStream_t st) {
+    if (n_reads <= 0) return 0;
+    switch (nbase_of(nr)) {
+    case 4: ffb::logz_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, logZ); break;
+    case 5: ffb::logz_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, logZ); break;
+    default: return -1;
+    }
+    return FFB_OKL(1);
+}
+
+int ffb_launch_sub_logz(float *trans, const int64_t *blk_off, int n_reads, int nr, const double *logZ,
+                        int64_t total_blocks, cudaStream_t st) {
+    if (n_reads <= 0 || total_blocks <= 0) return 0;
+    // x: chunks within a read, y: reads (y <= 65535 per launch)
+    int launches = 0;
+    for (int r0 = 0; r0 < n_reads; r0 += 65535) {
+        const int nr_reads = (n_reads - r0) < 65535 ? (n_reads - r0) : 65535;
+        dim3 grid(8, nr_reads);
+        ffb::sub_logz_kernel<<<grid, 256, 0, st>>>(trans, blk_off + r0, nr_reads, nr, logZ + r0);
+        launches++;
+    }
+    return FFB_OKL(launches);
+}
+
+int ffb_launch_viterbi(const float *trans, const int64_t *blk_off, int n_reads, int nr, uint64_t *tb_scratch,
+                       int32_t *path, float *qpath, float *score, cudaStream_t st) {
+    if (n_reads <= 0) return 0;
+    switch (nbase_of(nr)) {
+    case 4: ffb::viterbi_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, tb_scratch, path, qpath, score); break;
+    case 5: ffb::viterbi_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, tb_scratch, path, qpath, score); break;
+    default: return -1;
+    }
+    return FFB_OKL(1);
+}
+
+int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads, int nr, float *fwd_scratch,
+                         float *tpost, cudaStream_t st) {
+    if (n_reads <= 0) return 0;
+    switch (nbase_of(nr)) {
+    case 4:
+        ffb::transpost_fwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
+        ffb::transpost_bwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
+        break;
+    case 5:
+        ffb::transpost_fwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
+        ffb::transpost_bwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
+        break;
+    default: return -1;
+    }
+    return FFB_OKL(2);
+}
+
+int ffb_launch_lognorm(float *tpost, int64_t total_blocks, int nr, cudaStream_t st) {
+    if (total_blocks <= 0) return 0;
+    const int64_t grid = (total_blocks + 127) / 128;
+    ffb::lognorm_rows_kernel<<<(unsigned)grid, 128, 0, st>>>(tpost, total_blocks, nr);
+    return FFB_OKL(1);
+}
+
+int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, uint8_t *trace,
+                     int is_log, cudaStream_t st) {
+    if (n_reads <= 0) return 0;
+    int launches = 0;
+    for (int r0 = 0; r0 < n_reads; r0 += 65535) {
+        const int nrd = (n_reads - r0) < 65535 ? (n_reads - r0) : 65535;
+        dim3 grid(8, nrd);
+        // blk_off is absolute, so shifting the pointer keeps per-read addressing intact except
+        // for the "+ rd" row padding of the trace, handled by passing the shifted trace base.
+        const int nb = nbase_of(nr);
+        uint8_t *tb = trace + (int64_t)r0 * 2 * nb;
+        if (nb == 4 && is_log) ffb::trace_kernel<4, true><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        else if (nb == 4) ffb::trace_kernel<4, false><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        else if (nb == 5 && is_log) ffb::trace_kernel<5, true><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        else if (nb == 5) ffb::trace_kernel<5, false><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        else return -1;
+        launches++;
+    }
+    return FFB_OKL(launches);
+}
+
+int ffb_launch_exp_inplace(float *x, int64_t n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    ffb::exp_inplace_kernel<<<148 * 8, 256, 0, st>>>(x, n);
+    return FFB_OKL(1);
+}

@@ -1,0 +1,98 @@
+// ffb_common.cuh -- shared device helpers and internal launcher prototypes (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#define FFB_MAX_CONV 3
+#define FFB_NLAYER 5
+
+enum { FFB_ACT_TANH = 0, FFB_ACT_SWISH = 1, FFB_ACT_NONE = 2 };
+
+namespace ffb {
+
+// ---- scalar maths, same formulas as the reference (src/util.h:331-339):
+//      logisticfv(x) = 1 / (1 + exp(-x)),  tanhfv(x) = 2 * logisticfv(2x) - 1.
+// Accurate expf and IEEE division on purpose (no fast-math): the recurrence runs for
+// thousands of steps and the parity tolerance is 1e-4.
+__device__ __forceinline__ float logisticf(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float tanh_ref(float x) {
+    const float y = logisticf(x + x);
+    return (y + y) - 1.0f;
+}
+__device__ __forceinline__ float activate(float x, int act) {
+    if (act == FFB_ACT_TANH) return tanh_ref(x);
+    if (act == FFB_ACT_SWISH) return x * logisticf(x);
+    return x;
+}
+// reference src/util.h:276-278
+__device__ __forceinline__ float logsumexpf_ref(float x, float y) {
+    return fmaxf(x, y) + log1pf(expf(-fabsf(x - y)));
+}
+
+// Tail description of the reference convolution for one (T, winlen, stride): columns
+// >= tail_col0 are NOT the zero-padded textbook window; each gets up to two explicit
+// terms (x_start, tap_lo, ntap), ntap == 0 meaning "no term" (bias only).
+#define FFB_CONV_TAIL 32
+struct ConvTail {
+    int32_t tail_col0;
+    int32_t x_start[FFB_CONV_TAIL][2];
+    int32_t tap_lo[FFB_CONV_TAIL][2];
+    int32_t ntap[FFB_CONV_TAIL][2];
+};
+
+// Per-read geometry on the device.
+struct ReadGeom {
+    int64_t in_off;    // first input column of this read in the layer input
+    int64_t out_off;   // first output column
+    int32_t T_in;
+    int32_t T_out;
+    int32_t tail_id;   // index into the ConvTail table
+    int32_t pad;
+};
+
+}  // namespace ffb
+
+// ---- launchers (defined in the .cu files; all asynchronous on `st`) ----------------
+// Every launcher returns the number of kernels it launched (>=0) or -1 on launch error.
+
+// conv.cu: x [cols][nf] -> y [cols'][nfilter], weights Wt [winlen*nf][nfilter].
+int ffb_launch_conv(const float *x, float *y, const float *Wt, const float *bias, const ffb::ReadGeom *geom,
+                    const ffb::ConvTail *tails, int n_reads, int64_t total_out_cols, int max_T_out, int nf,
+                    int nfilter, int winlen, int stride, int act, cudaStream_t st);
+
+// gemm.cu: C[M][N] = A[M][K] * Wt[K][N] + bias[N]   (fp32 CUDA cores)
+int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
+                          cudaStream_t st);
+// gemm.cu: flip-flop output layer: C[M][N] = tanh(A*Wt + b) * scale  (N = 40 / 60)
+int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
+                       float scale, cudaStream_t st);
+
+// rnn.cu: one recurrent layer over a ragged batch.
+struct RnnBatch {
+    const int32_t *order;     // [n_slots] read index per slot (sorted by length), -1 = empty
+    const int64_t *blk_off;   // [n_reads+1]
+    int n_slots;              // multiple of reads-per-cluster
+    int n_reads;
+};
+int ffb_rnn_supported(int kind, int S);
+int ffb_rnn_reads_per_cluster(int kind, int S);
+size_t ffb_rnn_packed_floats(int kind, int S);
+// pack sW [G*S][S] (row per output, reference column) into the per-CTA resident layout
+void ffb_rnn_pack_weights(int kind, int S, const float *sW, float *packed);
+int ffb_launch_rnn(int kind, int S, const float *Xin, const float *sW_packed, float *Hout, const RnnBatch &rb,
+                   int backward, cudaStream_t st);
+int ffb_rnn_prepare(int kind, int S);   // one-time function attribute setup; returns 0 or error
+
+// decode.cu
+int ffb_launch_logz(const float *trans, const int64_t *blk_off, int n_reads, int nr, double *logZ, cudaStream_t st);
+int ffb_launch_sub_logz(float *trans, const int64_t *blk_off, int n_reads, int nr, const double *logZ,
+                        int64_t total_blocks, cudaStream_t st);
+int ffb_launch_viterbi(const float *trans, const int64_t *blk_off, int n_reads, int nr, uint64_t *tb_scratch,
+                       int32_t *path, float *qpath, float *score, cudaStream_t st);
+int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads, int nr, float *fwd_scratch,
+                         float *tpost, cudaStream_t st);
+int ffb_launch_lognorm(float *tpost, int64_t total_blocks, int nr, cudaStream_t st);
+int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, uint8_t *trace, int is_log,
+                     cudaStream_t st);
+int ffb_launch_exp_inplace(float *x, int64_t n, cudaStream_t st);

@@ -1,0 +1,203 @@
+/* flappie_b200.h -- C ABI of libflappie_b200.so (B200 / sm_100a flip-flop basecalling hot path)
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  Two groups of entry points:
+ *
+ *  (1) DROP-INS with the reference's exact names, signatures, ownership and error
+ *      behaviour, so that reference src/flappie.c links against this library unchanged
+ *      (calculate_post, src/flappie.c:245-316, is their only caller):
+ *        calculate_transitions        <- reference src/networks.h:36   (src/networks.c:108-111)
+ *        transpost_crf_flipflop       <- reference src/decode.h:35     (src/decode.c:377-497)
+ *        decode_crf_flipflop          <- reference src/decode.h:25     (src/decode.c:119-204)
+ *        trace_from_posterior         <- reference src/decode.h:38     (src/decode.c:499-543)
+ *        exp_activation_inplace       <- reference src/layers.h:17     (src/layers.c:56-66)
+ *        nbase_from_flipflop_nparam   <- reference src/layers.h:89     (src/layers.c:1029-1032)
+ *        get_flappie_model_type / flappie_model_string / flappie_model_description
+ *                                     <- reference src/networks.h:31-33 (src/networks.c:21-83)
+ *        make/free_flappie_matrix, make/free_flappie_imatrix
+ *                                     <- reference src/flappie_matrix.h:39-59 (results are
+ *                                        callee-allocated, caller frees; src/flappie_matrix.c:20-51,142)
+ *      NULL in -> NULL / NAN out, as RETURN_NULL_IF does in the reference
+ *      (src/flappie_stdlib.h:44).  All arithmetic runs on the GPU; there is NO CPU
+ *      fallback: without a usable CUDA device these functions warn and return NULL/NAN.
+ *
+ *  (2) The BATCHED extension (`ffb_*`) used by a rewired read loop (src/flappie.c:364-385):
+ *      upload a weight bundle once, then push thousands of whole reads per call.
+ *
+ * The structs below are layout-compatible with the reference's (`_Mat`,
+ * src/flappie_matrix.h:18-24; `raw_table`, src/flappie_structures.h:16-22) but do not
+ * need <immintrin.h>.
+ */
+#ifndef FLAPPIE_B200_H
+#define FLAPPIE_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- reference-compatible types ------------------------------------------------- */
+#ifndef FLAPPIE_MATRIX_H   /* if the reference header is already included, use its types */
+typedef struct {
+    size_t nr, nrq, nc, stride;   /* column-major, stride = 4*nrq >= nr floats per column */
+    union { void *v; float *f; } data;
+} _Mat;
+typedef struct {
+    size_t nr, nrq, nc, stride;
+    union { void *v; int32_t *f; } data;
+} _iMat;
+typedef _Mat *flappie_matrix;
+typedef _iMat *flappie_imatrix;
+typedef _Mat const *const_flappie_matrix;
+typedef _iMat const *const_flappie_imatrix;
+#endif
+
+#ifndef FLAPPIE_STRUCTURES_H
+typedef struct {
+    char *uuid;
+    size_t n;       /* untrimmed length */
+    size_t start;   /* signal is raw[start .. end), already normalised */
+    size_t end;
+    float *raw;
+} raw_table;
+#endif
+
+#ifndef NETWORKS_H
+enum model_type {   /* reference src/networks.h:18-26, same values */
+    FLAPPIE_MODEL_R941_NATIVE = 0,
+    FLAPPIE_MODEL_R941_RNA002,
+    FLAPPIE_MODEL_R941_5mC,
+    FLAPPIE_MODEL_R103_NATIVE,
+    FLAPPIE_MODEL_INVALID,
+    RUNNIE_MODEL_R941_NATIVE,
+    RUNNIE_MODEL_INVALID
+};
+#endif
+
+/* ---- (1) drop-ins ---------------------------------------------------------------- */
+flappie_matrix make_flappie_matrix(size_t nr, size_t nc);
+flappie_matrix free_flappie_matrix(flappie_matrix mat);
+flappie_imatrix make_flappie_imatrix(size_t nr, size_t nc);
+flappie_imatrix free_flappie_imatrix(flappie_imatrix mat);
+
+enum model_type get_flappie_model_type(const char *modelstr);   /* also accepts "r10C_pcr" */
+const char *flappie_model_string(const enum model_type model);
+const char *flappie_model_description(const enum model_type model);
+
+flappie_matrix calculate_transitions(const raw_table signal, float temperature, enum model_type model);
+flappie_matrix transpost_crf_flipflop(const_flappie_matrix trans, bool return_log);
+float decode_crf_flipflop(const_flappie_matrix trans, bool combine_stays, int *path, float *qpath);
+flappie_imatrix trace_from_posterior(flappie_matrix tpost);
+void exp_activation_inplace(flappie_matrix C);
+size_t nbase_from_flipflop_nparam(size_t nparam);
+
+/* ---- (2) batched extension ------------------------------------------------------- */
+
+#define FFB_KIND_GRU 0    /* guppy_model          (reference src/networks.c:150-177) */
+#define FFB_KIND_LSTM 1   /* guppy_stride5_model  (reference src/networks.c:180-215) */
+
+#define FFB_OK 0
+#define FFB_ERR_ARG -1
+#define FFB_ERR_CUDA -2
+#define FFB_ERR_NOMEM -3
+#define FFB_ERR_UNSUPPORTED -4
+
+typedef struct ffb_model ffb_model;   /* device-resident, pre-packed weight arena */
+typedef struct ffb_ctx ffb_ctx;       /* one per (device, stream): workspaces + plans */
+
+/* Number of usable CUDA devices (0 if none). */
+int ffb_device_count(void);
+const char *ffb_last_error(void);
+const char *ffb_version(void);
+
+/* Weight bundle in the reference's own field order:
+ *   kind GRU : conv_W, conv_b, {iW, sW, b} x 5 (B1,F2,B3,F4,B5), FF_W, FF_b         (20 mats)
+ *   kind LSTM: conv1_W, conv1_b, conv2_W, conv2_b, conv3_W, conv3_b, {iW,sW,b} x 5,
+ *              FF_W, FF_b                                                           (24 mats)
+ * `mats[i]` are reference `_Mat`s exactly as the generated model headers define them
+ * (convolution filters: nr = nf4*winlen - nf4 + nf).  conv_stride has 1 or 3 entries. */
+ffb_model *ffb_model_create(int device, int kind, const _Mat *const *mats, int nmat,
+                            const int *conv_stride, int nconv);
+void ffb_model_destroy(ffb_model *m);
+int ffb_model_size(const ffb_model *m);      /* S */
+int ffb_model_nparam(const ffb_model *m);    /* rows of trans: nstate*(nbase+1) */
+int ffb_model_stride(const ffb_model *m);    /* product of conv strides */
+/* blocks for a signal of `nsample` samples (iceil per convolution, reference
+ * src/layers.c:204), or -1 if shorter than a filter window (the reference's index
+ * arithmetic underflows there, src/layers.c:262). */
+long ffb_model_nblock(const ffb_model *m, long nsample);
+
+/* Bind a model to a reference enum value for the per-read drop-in calculate_transitions(). */
+int ffb_register_model(enum model_type which, ffb_model *m);
+
+/* `stream`: a cudaStream_t passed as void* (e.g. torch.cuda.current_stream().cuda_stream),
+ * or NULL to let the context create its own non-blocking stream. */
+ffb_ctx *ffb_create(ffb_model *m, void *stream);
+void ffb_destroy(ffb_ctx *c);
+
+#define FFB_FLAG_VITERBI_ONLY 1u   /* --viterbi: decode trans directly (reference src/flappie.c:278-283) */
+#define FFB_FLAG_WANT_TRACE 2u     /* compute the u8 state trace (reference src/flappie.c:299-300) */
+#define FFB_FLAG_WANT_TRANS 4u     /* copy trans (and tpost) back to the host */
+#define FFB_FLAG_KEEP_LAYERS 8u    /* keep every layer's output on the device for ffb_debug_fetch() */
+#define FFB_FLAG_FP32_SIMT 16u     /* force the fp32 CUDA-core GEMM / recurrence kernels */
+
+/* One batch of whole reads.  All pointers are HOST memory owned by the caller.
+ * signal      : concatenated normalised samples of all reads
+ * sig_off[n]  : start of read n in `signal` (n_reads+1 entries)
+ * Outputs (any may be NULL):
+ * blk_off     : n_reads+1 entries; read n owns blocks [blk_off[n], blk_off[n+1])
+ * path, qpath : sum(T_n + 1) entries; read n starts at blk_off[n] + n
+ * score       : n_reads   (NAN for a rejected read)
+ * trans,tpost : sum(T_n) * nparam floats, [block][nparam] row-major (= reference columns)
+ * trace       : sum(T_n + 1) * nstate bytes, read n starts at (blk_off[n] + n) * nstate
+ * Returns FFB_OK or a negative error; a read shorter than a filter window gets T_n = 0. */
+typedef struct {
+    const float *signal;
+    const int64_t *sig_off;
+    int64_t n_reads;
+    float temperature;
+    uint32_t flags;
+    int64_t *blk_off;
+    int32_t *path;
+    float *qpath;
+    float *score;
+    float *trans;
+    float *tpost;
+    uint8_t *trace;
+} ffb_batch;
+
+/* Upload, run the whole hot path, download, synchronise. */
+int ffb_basecall_batch(ffb_ctx *c, const ffb_batch *b);
+
+/* Split version for overlap / device-resident timing:
+ *   ffb_upload  : H2D of signal (async on the context stream) + host-side planning
+ *   ffb_forward : every kernel of the path, async, inputs and outputs stay in HBM
+ *   ffb_download: D2H of the requested outputs + stream synchronise */
+int ffb_upload(ffb_ctx *c, const ffb_batch *b);
+int ffb_forward(ffb_ctx *c);
+int ffb_download(ffb_ctx *c, const ffb_batch *b);
+int ffb_sync(ffb_ctx *c);
+
+/* Introspection for tests / bench. */
+int64_t ffb_total_blocks(const ffb_ctx *c);
+int64_t ffb_launch_count(const ffb_ctx *c);         /* kernels launched by this context so far */
+/* Time the kernels of one ffb_forward() by group with CUDA events on the context stream.
+ * ms[0]=conv ms[1]=input GEMMs ms[2]=recurrent ms[3]=output layer+logZ ms[4]=decode; returns FFB_OK. */
+int ffb_forward_timed(ffb_ctx *c, float ms[8]);
+/* what: 0 = last conv output [Ttot][S]; 1..5 = recurrent layer output [Ttot][S] (needs
+ * FFB_FLAG_KEEP_LAYERS); 6 = trans [Ttot][nparam]; 7 = logZ (double, n_reads).  Copies up to
+ * `bytes` to host `dst`; returns bytes copied or negative error. */
+int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t bytes);
+
+/* Base / quality emission of calculate_post (reference src/flappie.c:284-297,
+ * src/decode.c:66-79, src/util.h:285-305) on the host: returns the number of bases
+ * written to basecall/quality (each needs nblock+1 chars, NUL-terminated). */
+int ffb_emit_bases(const int32_t *path, const float *qpath, int64_t nblock, int nbase, bool reverse,
+                   char *basecall, char *quality);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAPPIE_B200_H */
