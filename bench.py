@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- raw-signal samples/sec basecalled (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the hot path (network forward + flip-flop decode, the default
+forward-backward + Viterbi mode of the reference CLI) over one batch of synthetic reads:
+BASELINE.json configs[1] = 1024 synthetic 4000-sample reads, r941_native, 1 GPU.
+Per-GPU work is fixed as N grows (reads shard embarrassingly, no collective on the data
+path): "scaling": "weak".
+
+  value : whole-job samples/s with the normalised signals already resident in HBM
+          (CUDA events on the library's stream around exactly K x ffb_forward()).
+  e2e   : same metric through the reference-facing C-ABI call ffb_basecall_batch() with
+          HOST buffers: H2D of the signals from pinned memory and D2H of path/qpath/score
+          inside the timed region.
+  roofline     : the recurrent-layer kernel (dominant), algorithmic flops / CUDA-event time.
+  cpu_baseline : the reference's own code (oracle/_ref, OpenBLAS, 1 thread per process,
+                 one process per core as its README recommends) on a bounded sample.
+
+`--impl reference` times only the CPU reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RAW_SAMPLES = 4000
+MODEL_CHOICES = {
+    # name -> (MODEL_TABLE key, description)
+    "r941_native_gru": ("r941_native_gru", "r941_native as in the north star / flappie 1.x: conv(19,s2,tanh) + 5 grumod S=256, 4 bases"),
+    "r941_native": ("r941_native", "r941_native @4de542f: 3 conv(swish) + 5 LSTM S=384, stride 5"),
+    "r941_5mC": ("r941_5mC", "conv + 5 grumod S=256, 5 bases"),
+    "r941_rna002": ("r941_rna002", "3 conv + 5 LSTM S=256"),
+    "r10C_pcr": ("r10C_pcr", "alias: conv + 5 grumod S=256, 4 bases"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def make_workload(model_key: str, n_reads: int, raw_len: int, seed: int):
+    """Seeded weights + reads; host signal prep (trim + med-MAD, reference flappie.c:251-259)
+    is done ONCE here, outside every timed region: it precedes the hot path."""
+    from flappie_b200.model import FlipflopModel, synthetic_reads
+    from flappie_b200.signal import prepare_read
+    fm = FlipflopModel.for_name(model_key, seed=1)
+    raws = synthetic_reads(n_reads, raw_len, seed=seed)
+    reads = [prepare_read(r) for r in raws]
+    assert all(r is not None for r in reads)
+    return fm, reads
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """One process = one core, OpenBLAS pinned to one thread (reference README.md:66-67,80-83)."""
+    model_key, read_arrays = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from flappie_b200.model import FlipflopModel
+    from oracle.pyoracle import Ref
+    r = Ref()
+    fm = FlipflopModel.for_name(model_key, seed=1)
+    rm = r.model(fm)
+    t0 = time.perf_counter()
+    nb = 0
+    for sig in read_arrays:
+        out = r.basecall(rm, sig, 1.0, False)
+        nb += len(out["basecall"]) if out else 0
+    return time.perf_counter() - t0, nb
+
+
+def cpu_reference_rate(model_key: str, reads, cores: int, reads_per_core: int):
+    """samples/s of the reference's CPU path on `cores` processes over a bounded sample."""
+    import multiprocessing as mp
+    from oracle import pyoracle
+    if not pyoracle.have_ref():
+        raise RuntimeError("oracle/_ref/libflappie_ref.so missing (build it where /root/reference exists)")
+    n = min(len(reads), cores * reads_per_core)
+    cores = min(cores, n)
+    chunks = [reads[i::cores][:reads_per_core] for i in range(cores)]
+    nread = sum(len(c) for c in chunks)
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, [(model_key, c) for c in chunks])
+    wall = time.perf_counter() - t0
+    busy = max(r[0] for r in res)
+    rate = nread * RAW_SAMPLES / busy
+    info = pyoracle.Ref().buildinfo
+    return dict(value=rate, unit="samples/s", cores=cores, kind="reference",
+                sample=f"{nread} of the workload's reads ({reads_per_core}/core), fwd-bwd + Viterbi + trace as calculate_post; "
+                       f"slowest worker {busy:.1f}s, wall {wall:.1f}s incl. process start; {info}")
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fm, reads = make_workload(MODEL_CHOICES[a.model][0], a.ref_reads_total, RAW_SAMPLES, seed=7)
+    cores = len(os.sched_getaffinity(0))
+    per_core = max(1, a.ref_reads_per_core)
+    rates = []
+    for step in range(a.warmup + a.steps):
+        cb = cpu_reference_rate(MODEL_CHOICES[a.model][0], reads, cores, per_core)
+        if step >= a.warmup:
+            rates.append(cb)
+    val = float(np.mean([c["value"] for c in rates]))
+    cb = dict(rates[-1]); cb["value"] = val
+    nread = min(len(reads), cores * per_core)
+    line = {
+        "impl": "reference", "metric": "raw-signal samples/sec basecalled", "value": val, "unit": "samples/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * nread * RAW_SAMPLES / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{a.reads} synthetic {RAW_SAMPLES}-sample reads, {a.model}; each step = bounded sample of {nread} reads on {cores} host cores"},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="r941_native_gru", choices=sorted(MODEL_CHOICES))
+    ap.add_argument("--reads", type=int, default=1024, help="reads per GPU per step")
+    ap.add_argument("--viterbi-only", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-reads-per-core", type=int, default=6)
+    ap.add_argument("--ref-reads-total", type=int, default=256)
+    a = ap.parse_args()
+
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from flappie_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = load_peaks()
+
+    model_key = MODEL_CHOICES[a.model][0]
+    # weak scaling: every rank gets its own `reads` reads (different seed per rank)
+    fm, reads = make_workload(model_key, a.reads, RAW_SAMPLES, seed=7 + rank)
+    n = len(reads)
+    lens = np.array([len(r) for r in reads], np.int64)
+    sig_off_np = np.zeros(n + 1, np.int64); np.cumsum(lens, out=sig_off_np[1:])
+    sig_pinned = torch.empty(int(sig_off_np[-1]), dtype=torch.float32).pin_memory()
+    sig_pinned.numpy()[:] = np.concatenate(reads)
+    signal_np = sig_pinned.numpy()
+
+    lib = api.Library.get()
+    model = api.Model(fm, device=local)
+    stream = torch.cuda.current_stream()
+    ctx = api.Context(model, stream=stream.cuda_stream)
+    flags = api.FLAG_VITERBI_ONLY if a.viterbi_only else 0
+    tot_blocks = sum(max(fm.nblock(int(x)), 0) for x in lens)
+    out = {
+        "blk_off": np.zeros(n + 1, np.int64),
+        "path": torch.empty(tot_blocks + n, dtype=torch.int32).pin_memory().numpy(),
+        "qpath": torch.empty(tot_blocks + n, dtype=torch.float32).pin_memory().numpy(),
+        "score": torch.empty(n, dtype=torch.float32).pin_memory().numpy(),
+    }
+    batch, out = ctx.make_batch(signal_np, sig_off_np, 1.0, flags, out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: inputs in HBM, K x forward ----
+    ctx.upload(batch)
+    for _ in range(a.warmup):
+        ctx.forward()
+    barrier()
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        ctx.forward()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    samples_per_step = n * RAW_SAMPLES * world
+    value = samples_per_step * a.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region ----
+    for _ in range(min(a.warmup, 2)):
+        ctx.lib.lib.ffb_basecall_batch(ctx.handle, batch)
+    barrier()
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        r = ctx.lib.lib.ffb_basecall_batch(ctx.handle, batch)
+        assert r == 0, lib.last_error()
+    e1.record(stream)
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), e2e_wall_ms))
+    e2e_value = samples_per_step * a.steps / (e2e_ms * 1e-3)
+    h2d = int(signal_np.nbytes + sig_off_np.nbytes + 4 * n)
+    d2h = int(out["path"].nbytes + out["qpath"].nbytes + out["score"].nbytes)
+
+    # ---- per-kernel-group timing for the roofline (one extra, untimed-for-value pass) ----
+    groups = ctx.forward_timed()
+    S, G, T = fm.size, fm.ngate, tot_blocks
+    rnn_flops = 2.0 * T * S * G * S                      # one layer's h_{t-1} * sW, all reads (algorithmic)
+    rnn_ms_per_launch = groups["rnn"] / 5.0
+    achieved_tf = rnn_flops / (rnn_ms_per_launch * 1e-3) / 1e12
+    roofline = {"kernel": "rnn_layer_kernel (recurrent layer: h*sW + gates, 5 launches/step)",
+                "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+                "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+                "note": "fp32 CUDA-core path (bit-faithful to the reference SGEMV); algorithmic flops = 2*T*S*G*S per launch",
+                "step_breakdown_ms": groups}
+
+    line = {
+        "metric": "raw-signal samples/sec basecalled", "value": value, "unit": "samples/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dev_ms / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{a.reads} synthetic {RAW_SAMPLES}-sample reads per GPU ({RAW_SAMPLES - 210} after the default trim), "
+                               f"{a.model}: {MODEL_CHOICES[a.model][1]}; random-init weights; "
+                               f"{'--viterbi' if a.viterbi_only else 'forward-backward + Viterbi (CLI default)'}",
+                   "blocks_per_gpu": int(tot_blocks), "reads_per_gpu": n,
+                   "l2": "working set per step (Xin + activations, ~8 GB) far exceeds the 126 MB L2; no flush needed",
+                   "host_prep": "trim + med-MAD normalisation done once on the host before timing (outside the hot path)",
+                   "parallelism": f"read-shard x{world}, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / a.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            cores = len(os.sched_getaffinity(0))
+            line["cpu_baseline"] = cpu_reference_rate(model_key, reads, cores, a.ref_reads_per_core)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close(); model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

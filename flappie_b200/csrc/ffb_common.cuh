@@ -64,7 +64,7 @@ int ffb_launch_conv(const float *x, float *y, const float *Wt, const float *bias
 // gemm.cu: C[M][N] = A[M][K] * Wt[K][N] + bias[N]   (fp32 CUDA cores)
 int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
                           cudaStream_t st);
-// gemm.cu: flip-flop output layer: C[M][N] = tanh(A*Wt + b) * scale  (N = 40 / 60)
+// gemm.cu: flip-flop output layer: C[M][N] = tanh(A*Wt + b) / scale  (N = 40 / 60; scale = temperature / 5)
 int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
                        float scale, cudaStream_t st);
 

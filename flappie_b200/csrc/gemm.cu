@@ -3,7 +3,7 @@
 //  * sgemm_bias : Xin = A * iW^T + b for all blocks of all reads at once; replaces
 //    reference feedforward_linear -> affine_map (src/layers.c:279, src/flappie_matrix.c:361-389,
 //    one cblas_sgemm per read per layer).
-//  * ff_tanh    : the flip-flop output layer C = tanh(A * FF_W^T + b) * (5 / temperature);
+//  * ff_tanh    : the flip-flop output layer C = tanh(A * FF_W^T + b) / (temperature / 5);
 //    replaces the affine_map + tanh_activation_inplace + shift_scale_matrix_inplace of
 //    reference globalnorm_manystay (src/layers.c:1082-1087).
 //
@@ -16,7 +16,7 @@ namespace ffb {
 // ---------------------------------------------------------------------------------
 // 128x128x8 register-blocked SGEMM, 256 threads, 8x8 outputs per thread, register
 // prefetch of the next k-slab (double buffered shared memory).
-// A [M][K] row-major, Wt [K][N] row-major, C [M][N] row-major.  N % 128 == 0, K % 8 == 0.
+// A [M][K] row-major, Wt [K][N] row-major, C [M][N] row-major.  N % 4 == 0, K % 8 == 0.
 constexpr int BM = 128, BN = 128, BK = 8;
 
 __global__ void __launch_bounds__(256)
@@ -33,6 +33,7 @@ sgemm_bias_kernel(const float *__restrict__ A, const float *__restrict__ Wt, con
     const int a_row = tid / 2, a_k = (tid % 2) * 4;
     const int b_k = tid / 32, b_n = (tid % 32) * 4;
     const bool a_ok = (m0 + a_row) < M;
+    const bool b_ok = (n0 + b_n) < N;   // N % 4 == 0: a float4 is either fully inside or fully outside
     const float *Ap = A + (m0 + a_row) * (int64_t)K + a_k;
     const float *Bp = Wt + (int64_t)b_k * N + n0 + b_n;
 
@@ -43,7 +44,8 @@ sgemm_bias_kernel(const float *__restrict__ A, const float *__restrict__ Wt, con
         for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
 
     float4 ra = a_ok ? *reinterpret_cast<const float4 *>(Ap) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 rb = *reinterpret_cast<const float4 *>(Bp);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 rb = b_ok ? *reinterpret_cast<const float4 *>(Bp) : zero4;
     As[0][a_k + 0][a_row] = ra.x; As[0][a_k + 1][a_row] = ra.y;
     As[0][a_k + 2][a_row] = ra.z; As[0][a_k + 3][a_row] = ra.w;
     *reinterpret_cast<float4 *>(&Bs[0][b_k][b_n]) = rb;
@@ -54,7 +56,7 @@ sgemm_bias_kernel(const float *__restrict__ A, const float *__restrict__ Wt, con
         const int cur = kt & 1;
         if (kt + 1 < nk) {
             ra = a_ok ? *reinterpret_cast<const float4 *>(Ap + (kt + 1) * BK) : make_float4(0.f, 0.f, 0.f, 0.f);
-            rb = *reinterpret_cast<const float4 *>(Bp + (int64_t)(kt + 1) * BK * N);
+            rb = b_ok ? *reinterpret_cast<const float4 *>(Bp + (int64_t)(kt + 1) * BK * N) : zero4;
         }
 #pragma unroll
         for (int k = 0; k < BK; k++) {
@@ -78,17 +80,20 @@ sgemm_bias_kernel(const float *__restrict__ A, const float *__restrict__ Wt, con
         }
     }
 
-    const float4 bb0 = *reinterpret_cast<const float4 *>(bias + n0 + tx * 4);
-    const float4 bb1 = *reinterpret_cast<const float4 *>(bias + n0 + tx * 4 + 64);
+    const bool c0_ok = (n0 + tx * 4) < N, c1_ok = (n0 + tx * 4 + 64) < N;
+    const float4 bb0 = c0_ok ? *reinterpret_cast<const float4 *>(bias + n0 + tx * 4) : zero4;
+    const float4 bb1 = c1_ok ? *reinterpret_cast<const float4 *>(bias + n0 + tx * 4 + 64) : zero4;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int64_t row = m0 + ty * 4 + (i < 4 ? i : 60 + i);
         if (row >= M) continue;
         float *cp = C + row * (int64_t)N + n0 + tx * 4;
-        *reinterpret_cast<float4 *>(cp) =
-            make_float4(acc[i][0] + bb0.x, acc[i][1] + bb0.y, acc[i][2] + bb0.z, acc[i][3] + bb0.w);
-        *reinterpret_cast<float4 *>(cp + 64) =
-            make_float4(acc[i][4] + bb1.x, acc[i][5] + bb1.y, acc[i][6] + bb1.z, acc[i][7] + bb1.w);
+        if (c0_ok)
+            *reinterpret_cast<float4 *>(cp) =
+                make_float4(acc[i][0] + bb0.x, acc[i][1] + bb0.y, acc[i][2] + bb0.z, acc[i][3] + bb0.w);
+        if (c1_ok)
+            *reinterpret_cast<float4 *>(cp + 64) =
+                make_float4(acc[i][4] + bb1.x, acc[i][5] + bb1.y, acc[i][6] + bb1.z, acc[i][7] + bb1.w);
     }
 }
 
@@ -134,7 +139,7 @@ ff_tanh_kernel(const float *__restrict__ A, const float *__restrict__ Wt, const 
         if (row < M) {
             float *cp = C + row * (int64_t)N + half * NH;
 #pragma unroll
-            for (int j = 0; j < NH; j++) cp[j] = tanh_ref(acc[j] + bias[half * NH + j]) * scale;
+            for (int j = 0; j < NH; j++) cp[j] = tanh_ref(acc[j] + bias[half * NH + j]) / scale;   // shift_scale_matrix_inplace: (x - 0) / scale
         }
     }
 }
@@ -145,7 +150,7 @@ int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, fl
                           cudaStream_t st) {
     using namespace ffb;
     if (M <= 0) return 0;
-    if (N % BN != 0 || K % BK != 0) return -1;
+    if (N % 4 != 0 || K % BK != 0) return -1;
     const int64_t mt = (M + BM - 1) / BM;
     // gridDim.y is limited to 65535 tiles: split M if needed
     int launches = 0;
@@ -153,7 +158,7 @@ int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, fl
     for (int64_t t0 = 0; t0 < mt; t0 += max_mt) {
         const int64_t nt = (mt - t0) < max_mt ? (mt - t0) : max_mt;
         const int64_t moff = t0 * BM;
-        dim3 grid(N / BN, (unsigned)nt);
+        dim3 grid((N + BN - 1) / BN, (unsigned)nt);
         sgemm_bias_kernel<<<grid, 256, 0, st>>>(A + moff * K, Wt, bias, C + moff * N, M - moff < nt * BM ? M - moff : nt * BM, N, K);
         launches++;
     }

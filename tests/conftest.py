@@ -46,15 +46,3 @@ def gpu_lib(lib):
     if lib.device_count() < 1:
         pytest.fail("no CUDA device visible but a gpu-marked test was selected")
     return lib
-
-
-def norm_reads(n, length, seed):
-    """Synthetic squiggles pushed through the host signal prep, as calculate_post would."""
-    from flappie_b200.model import synthetic_reads
-    from flappie_b200.signal import prepare_read
-    out = []
-    for r in synthetic_reads(n, length, seed=seed):
-        x = prepare_read(r)
-        assert x is not None
-        out.append(x)
-    return out
