@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--model", default="r941_native_gru", choices=sorted(MODEL_CHOICES))
     ap.add_argument("--reads", type=int, default=1024, help="reads per GPU per step")
     ap.add_argument("--viterbi-only", action="store_true")
+    ap.add_argument("--fp32-simt", action="store_true", help="force the fp32 CUDA-core GEMM / recurrence kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-reads-per-core", type=int, default=6)
     ap.add_argument("--ref-reads-total", type=int, default=256)
@@ -222,9 +223,10 @@ def main():
 
     lib = api.Library.get()
     model = api.Model(fm, device=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: torch.cuda.Event sees only the stream it records on
+    torch.cuda.set_stream(stream)
     ctx = api.Context(model, stream=stream.cuda_stream)
-    flags = api.FLAG_VITERBI_ONLY if a.viterbi_only else 0
+    flags = (api.FLAG_VITERBI_ONLY if a.viterbi_only else 0) | (api.FLAG_FP32_SIMT if a.fp32_simt else 0)
     tot_blocks = sum(max(fm.nblock(int(x)), 0) for x in lens)
     out = {
         "blk_off": np.zeros(n + 1, np.int64),

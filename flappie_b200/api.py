@@ -330,7 +330,8 @@ class Context:
         return b, o
 
     def basecall(self, reads: Sequence[np.ndarray], temperature: float = 1.0, viterbi_only: bool = False,
-                 want_trace: bool = False, want_trans: bool = False, keep_layers: bool = False) -> BatchResult:
+                 want_trace: bool = False, want_trans: bool = False, keep_layers: bool = False,
+                 fp32_simt: bool = False) -> BatchResult:
         """Whole hot path for a list of already-normalised reads (host numpy arrays)."""
         fm = self.model.fm
         n = len(reads)
@@ -339,7 +340,8 @@ class Context:
         np.cumsum(lens, out=sig_off[1:])
         signal = np.concatenate([np.asarray(r, np.float32) for r in reads]) if n else np.zeros(1, np.float32)
         flags = (FLAG_VITERBI_ONLY if viterbi_only else 0) | (FLAG_WANT_TRACE if want_trace else 0) | \
-                (FLAG_WANT_TRANS if want_trans else 0) | (FLAG_KEEP_LAYERS if keep_layers else 0)
+                (FLAG_WANT_TRANS if want_trans else 0) | (FLAG_KEEP_LAYERS if keep_layers else 0) | \
+                (FLAG_FP32_SIMT if fp32_simt else 0)
         b, o = self.make_batch(signal, sig_off, temperature, flags)
         self._check(self.lib.lib.ffb_basecall_batch(self.handle, ctypes.byref(b)), "ffb_basecall_batch")
         return BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),

@@ -82,6 +82,8 @@ struct ffb_model {
     float *d_convWt[FFB_MAX_CONV] = {nullptr}, *d_convb[FFB_MAX_CONV] = {nullptr};
     float *d_iWt[FFB_NLAYER] = {nullptr}, *d_b[FFB_NLAYER] = {nullptr}, *d_sWp[FFB_NLAYER] = {nullptr};
     float *d_ffWt = nullptr, *d_ffb = nullptr;
+    void *d_iW_hi[FFB_NLAYER] = {nullptr}, *d_iW_lo[FFB_NLAYER] = {nullptr};   // fp16 planes [G*S][in] for the tensor path
+    bool tc_gemm = false;
     int layer_in[FFB_NLAYER] = {0};
     // conv edge plans, cached per (conv layer, T_in)
     std::mutex mu;
@@ -103,7 +105,7 @@ extern "C" void ffb_model_destroy(ffb_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int i = 0; i < FFB_MAX_CONV; i++) { cudaFree(m->d_convWt[i]); cudaFree(m->d_convb[i]); }
-    for (int i = 0; i < FFB_NLAYER; i++) { cudaFree(m->d_iWt[i]); cudaFree(m->d_b[i]); cudaFree(m->d_sWp[i]); }
+    for (int i = 0; i < FFB_NLAYER; i++) { cudaFree(m->d_iWt[i]); cudaFree(m->d_b[i]); cudaFree(m->d_sWp[i]); cudaFree(m->d_iW_hi[i]); cudaFree(m->d_iW_lo[i]); }
     cudaFree(m->d_ffWt); cudaFree(m->d_ffb);
     delete m;
 }
@@ -171,6 +173,16 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             ffb_rnn_pack_weights(kind, S, sWd.data(), packed.data());
             m->d_iWt[l] = upload(iWt); m->d_b[l] = upload(bb); m->d_sWp[l] = upload(packed);
             ok = ok && m->d_iWt[l] && m->d_b[l] && m->d_sWp[l];
+            if (ok && ffb_gemm_tc_supported(G * S, in)) {
+                // hi/lo fp16 planes of iW in the reference's own [out][in] orientation (K-major B operand)
+                std::vector<float> iWd((size_t)G * S * in);
+                for (int n = 0; n < G * S; n++)
+                    for (int k = 0; k < in; k++) iWd[(size_t)n * in + k] = mat_at(iW, k, n);
+                float *tmp = upload(iWd);
+                ok = tmp && cudaMalloc(&m->d_iW_hi[l], iWd.size() * 2) == cudaSuccess && cudaMalloc(&m->d_iW_lo[l], iWd.size() * 2) == cudaSuccess &&
+                     ffb_launch_split_f16(tmp, m->d_iW_hi[l], m->d_iW_lo[l], (int64_t)iWd.size(), 0) >= 0 && cudaDeviceSynchronize() == cudaSuccess;
+                cudaFree(tmp);
+            }
             in = S;
         }
     }
@@ -192,6 +204,10 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             m->d_ffWt = upload(Wt); m->d_ffb = upload(bb);
             ok = m->d_ffWt && m->d_ffb;
         }
+    }
+    if (ok) {
+        m->tc_gemm = true;
+        for (int l = 0; l < FFB_NLAYER; l++) m->tc_gemm = m->tc_gemm && m->d_iW_hi[l] && m->d_iW_lo[l];
     }
     if (ok && ffb_rnn_prepare(kind, m->S) != 0) {
         set_err("ffb_model_create: recurrent kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -312,6 +328,7 @@ struct ffb_ctx {
     // device
     DevBuf d_sig, d_c[2], d_act[2], d_xin, d_trans, d_tpost, d_fwd, d_tb, d_path, d_qpath, d_score, d_logz, d_trace;
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
+    DevBuf d_ahi, d_alo;          // fp16 hi/lo planes of the current layer input (tensor path)
     float *last_conv = nullptr;   // device pointer of last conv output within d_act/d_c
     cudaEvent_t ev[8] = {nullptr};
     float t_gemm_ms = 0.f, t_rnn_ms = 0.f;
@@ -342,7 +359,7 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
-                     &c->d_order};
+                     &c->d_order, &c->d_ahi, &c->d_alo};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -441,6 +458,10 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
     ok &= c->d_act[0].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
     ok &= c->d_act[1].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
     ok &= c->d_xin.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * G * S, 1)) == 0;
+    if (m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT)) {
+        ok &= c->d_ahi.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+        ok &= c->d_alo.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    }
     ok &= c->d_trans.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
     if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
         ok &= c->d_tpost.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
@@ -518,7 +539,13 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         const float *in = (l == 0) ? c->d_act[0].as<float>() : (c->flags & FFB_FLAG_KEEP_LAYERS ? c->d_keep[l - 1].as<float>() : c->d_act[a].as<float>());
         float *out = (c->flags & FFB_FLAG_KEEP_LAYERS) ? c->d_keep[l].as<float>() : c->d_act[a ^ 1].as<float>();
         if (timed) cudaEventRecord(c->ev[5], st);
-        LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], c->d_xin.as<float>(), Tt, G * S, m->layer_in[l], st));
+        if (m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT)) {
+            LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
+            LAUNCH(ffb_launch_gemm_tc(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l], m->d_iW_lo[l], m->d_b[l], c->d_xin.as<float>(), Tt,
+                                      G * S, m->layer_in[l], st));
+        } else {
+            LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], c->d_xin.as<float>(), Tt, G * S, m->layer_in[l], st));
+        }
         if (timed) cudaEventRecord(c->ev[6], st);
         LAUNCH(ffb_launch_rnn(m->kind, S, c->d_xin.as<float>(), m->d_sWp[l], out, rb, (l % 2) == 0, st));
         if (timed) {

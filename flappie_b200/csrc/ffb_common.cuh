@@ -68,6 +68,12 @@ int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, fl
 int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
                        float scale, cudaStream_t st);
 
+// gemm_tc.cu: tcgen05 path.  Planes are fp16 [rows][K]; W planes keep the reference's [out][in] order.
+int ffb_gemm_tc_supported(int N, int K);
+int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st);
+int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                       int64_t M, int N, int K, cudaStream_t st);
+
 // rnn.cu: one recurrent layer over a ragged batch.
 struct RnnBatch {
     const int32_t *order;     // [n_slots] read index per slot (sorted by length), -1 = empty

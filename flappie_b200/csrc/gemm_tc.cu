@@ -1,0 +1,301 @@
+// gemm_tc.cu -- the input-projection GEMM on the 5th-generation tensor cores (tcgen05).
+//
+//   Xin[M][N] = A[M][K] * iW[N][K]^T + b[N]        M = all blocks of all reads (~2e6),
+//                                                   K = S, N = 3S / 4S
+// replaces reference feedforward_linear -> affine_map -> cblas_sgemm (src/layers.c:279,
+// src/flappie_matrix.c:361-389), 17-22 % of the reference's run time.
+//
+// fp32-faithful on the fp16 tensor pipe: both operands are split x = hi + lo (fp16 each,
+// tc_common.cuh) and the product is accumulated as hi*hi + hi*lo + lo*hi in fp32 in TMEM.
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 128B-swizzled boxes of A_hi/A_lo (128 x 64
+//              halfs) and W_hi/W_lo (BN x 64 halfs) into a multi-stage shared-memory ring
+//   warp 1   : MMA issuer    -- one elected thread issues tcgen05.mma (M=128, N=BN, K=16),
+//              3 products x 4 k-steps per stage, accumulators double-buffered in TMEM
+//   warps 2-5: epilogue      -- tcgen05.ld the finished accumulator, add bias, vectorised fp32
+//              stores; overlaps the MMAs of the next tile
+// Tile order is n-fastest so the n-tiles of one 128-row slab run concurrently and the slab is
+// read from HBM once.
+#include <cuda.h>
+
+#include "ffb_common.cuh"
+#include "tc_common.cuh"
+
+namespace ffb {
+using namespace tc;
+
+// ---------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) fp16 planes
+__global__ void split_f16_kernel(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(x) + i);
+        __half h[4], l[4];
+        split_f16(v.x, h[0], l[0]); split_f16(v.y, h[1], l[1]);
+        split_f16(v.z, h[2], l[2]); split_f16(v.w, h[3], l[3]);
+        reinterpret_cast<uint2 *>(hi)[i] = *reinterpret_cast<uint2 *>(h);
+        reinterpret_cast<uint2 *>(lo)[i] = *reinterpret_cast<uint2 *>(l);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Probe: D[128][N] = A[128][K] * B[N][K]^T with thread-placed NO-SWIZZLE K-major operands.
+// Validates the descriptor conventions the recurrent tensor kernel relies on
+// (LBO = rows*16 B between k-groups, SBO = 128 B between 8-row groups).
+__global__ void __launch_bounds__(128)
+umma_probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, float *__restrict__ D, int N, int K) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *As = smem;                              // K/8 k-groups x (128 rows x 16 B)
+    uint8_t *Bs = smem + (size_t)(K / 8) * 128 * 16; // K/8 k-groups x (N rows x 16 B)
+    for (int i = tid; i < 128 * (K / 8); i += 128) {
+        const int r = i % 128, kg = i / 128;
+        *reinterpret_cast<uint4 *>(As + (size_t)kg * 128 * 16 + r * 16) = *reinterpret_cast<const uint4 *>(A + (size_t)r * K + kg * 8);
+    }
+    for (int i = tid; i < N * (K / 8); i += 128) {
+        const int r = i % N, kg = i / N;
+        *reinterpret_cast<uint4 *>(Bs + (size_t)kg * N * 16 + r * 16) = *reinterpret_cast<const uint4 *>(B + (size_t)r * K + kg * 8);
+    }
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 1 && elect_one()) {
+        const uint32_t idesc = make_idesc_f16(128, N);
+        for (int ks = 0; ks < K / 16; ks++) {
+            const uint64_t ad = make_smem_desc(smem_u32(As) + ks * 2 * 128 * 16, 128 * 16, 128, LAYOUT_NONE);
+            const uint64_t bd = make_smem_desc(smem_u32(Bs) + ks * 2 * N * 16, N * 16, 128, LAYOUT_NONE);
+            umma_f16(tmem, ad, bd, idesc, ks > 0);
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tcgen05_fence_after();
+    for (int c = 0; c < N; c += 8) {
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; j++) D[(size_t)(warp * 32 + lane) * N + c + j] = v[j];
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------
+template <int BN>
+struct GemmTcCfg {
+    static constexpr int BM = 128, BK = 64;
+    static constexpr int A_BYTES = BM * BK * 2;          // one plane
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;   // + alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int THREADS = 192;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+               const float *__restrict__ bias, float *__restrict__ C, int64_t M, int N, int K) {
+    using Cfg = GemmTcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = N / BN;
+    const int64_t m_tiles = (M + Cfg::BM - 1) / Cfg::BM;
+    const int64_t ntile = m_tiles * n_tiles;
+    const int nk = K / Cfg::BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBhi); tma_prefetch_desc(&mapBlo);
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+                const int m0 = (int)(tile / n_tiles) * Cfg::BM, n0 = (int)(tile % n_tiles) * BN;
+                for (int kc = 0; kc < nk; kc++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(st, &mapAhi, &full_bar[stage], kc * Cfg::BK, m0);
+                    tma_load_2d(st + Cfg::A_BYTES, &mapAlo, &full_bar[stage], kc * Cfg::BK, m0);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES, &mapBhi, &full_bar[stage], kc * Cfg::BK, n0);
+                    tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, &full_bar[stage], kc * Cfg::BK, n0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_f16(Cfg::BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d = tmem + acc * BN;
+                for (int kc = 0; kc < nk; kc++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
+                    const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES, b_hi = st + 2 * Cfg::A_BYTES,
+                                   b_lo = st + 2 * Cfg::A_BYTES + Cfg::B_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < Cfg::BK / 16; k4++) {
+                        const uint32_t ko = k4 * 32;   // 16 halfs = 32 bytes along the swizzled row
+                        const uint64_t dah = make_smem_desc(a_hi + ko, 16, 1024, LAYOUT_SW128);
+                        const uint64_t dal = make_smem_desc(a_lo + ko, 16, 1024, LAYOUT_SW128);
+                        const uint64_t dbh = make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128);
+                        const uint64_t dbl = make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128);
+                        umma_f16(d, dah, dbh, idesc, (kc | k4) != 0);
+                        umma_f16(d, dah, dbl, idesc, 1);
+                        umma_f16(d, dal, dbh, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
+                    if (kc == nk - 1) umma_commit(&acc_full[acc]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 -> TMEM lane quadrants (warp % 4) =====
+        const int quad = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+            const int64_t m0 = (tile / n_tiles) * Cfg::BM;
+            const int n0 = (int)(tile % n_tiles) * BN;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int64_t row = m0 + quad * 32 + lane;
+            float *crow = C + row * (int64_t)N + n0;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 2
+            for (int c = 0; c < BN; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld_wait();
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bias + n0 + c + j);
+                        __stcs(reinterpret_cast<float4 *>(crow + c + j),
+                               make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w));
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+}
+
+}  // namespace ffb
+
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// fp16 [rows][cols] row-major, box = 64 cols x box_rows, 128-byte swizzle
+static bool make_map_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n % 4) return -1;
+    ffb::split_f16_kernel<<<148 * 8, 256, 0, st>>>(x, (__half *)hi, (__half *)lo, n / 4);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int ffb_gemm_tc_supported(int N, int K) { return (N % 64 == 0) && (K % 64 == 0) && K >= 64; }
+
+template <int BN>
+static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                          int64_t M, int N, int K, cudaStream_t st) {
+    using Cfg = ffb::GemmTcCfg<BN>;
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, 128) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, 128) ||
+        !make_map_f16(&mBh, Whi, (uint64_t)N, (uint64_t)K, BN) || !make_map_f16(&mBl, Wlo, (uint64_t)N, (uint64_t)K, BN))
+        return -1;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(ffb::gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+        attr_done = true;
+    }
+    const int64_t ntile = ((M + 127) / 128) * (N / BN);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(ntile < sms ? ntile : sms);
+    ffb::gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// A planes [M][K] fp16, W planes [N][K] fp16 (the reference's own [out][in] orientation)
+int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                       int64_t M, int N, int K, cudaStream_t st) {
+    if (M <= 0) return 0;
+    if (!ffb_gemm_tc_supported(N, K)) return -1;
+    if (N % 256 == 0) return launch_gemm_tc<256>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
+    if (N % 128 == 0) return launch_gemm_tc<128>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
+    return launch_gemm_tc<64>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
+}
+
+int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, cudaStream_t st) {
+    const size_t smem = (size_t)(K / 8) * (128 + N) * 16;
+    if (cudaFuncSetAttribute(ffb::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    ffb::umma_probe_kernel<<<1, 128, smem, st>>>((const __half *)A, (const __half *)B, D, N, K);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}

@@ -1,0 +1,73 @@
+// testhooks.cu -- exported-but-undeclared entry points used only by tests/ to exercise
+// individual kernels (host buffers in, host buffers out).  Not part of include/flappie_b200.h.
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <vector>
+
+#include "ffb_common.cuh"
+
+int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, cudaStream_t st);
+int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st);
+int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                       int64_t M, int N, int K, cudaStream_t st);
+
+#define TRY(x) do { if ((x) != cudaSuccess) { fprintf(stderr, "testhook: %s failed: %s\n", #x, cudaGetErrorString(cudaGetLastError())); return -1; } } while (0)
+
+// A [128][K] fp16 bits, B [N][K] fp16 bits -> D [128][N] fp32
+extern "C" int ffb_test_umma_probe(const uint16_t *A, const uint16_t *B, float *D, int N, int K) {
+    void *dA, *dB; float *dD;
+    TRY(cudaMalloc(&dA, 128 * K * 2)); TRY(cudaMalloc(&dB, (size_t)N * K * 2)); TRY(cudaMalloc(&dD, 128 * (size_t)N * 4));
+    TRY(cudaMemcpy(dA, A, 128 * K * 2, cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(dB, B, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+    TRY(cudaMemset(dD, 0, 128 * (size_t)N * 4));
+    if (ffb_launch_umma_probe(dA, dB, dD, N, K, 0) < 0) return -2;
+    TRY(cudaDeviceSynchronize());
+    TRY(cudaMemcpy(D, dD, 128 * (size_t)N * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return 0;
+}
+
+// C[M][N] = A[M][K] * W[N][K]^T + bias ; mode 0 = tcgen05 (hi/lo split), 1 = fp32 CUDA cores
+extern "C" int ffb_test_gemm(const float *A, const float *W, const float *bias, float *C, int64_t M, int N, int K, int mode,
+                             float *ms_out) {
+    float *dA, *dW, *db, *dC;
+    TRY(cudaMalloc(&dA, sizeof(float) * M * K)); TRY(cudaMalloc(&dW, sizeof(float) * (size_t)N * K));
+    TRY(cudaMalloc(&db, sizeof(float) * N)); TRY(cudaMalloc(&dC, sizeof(float) * M * N));
+    TRY(cudaMemcpy(dA, A, sizeof(float) * M * K, cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(db, bias, sizeof(float) * N, cudaMemcpyHostToDevice));
+    TRY(cudaMemset(dC, 0, sizeof(float) * M * N));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = 0;
+    if (mode == 0) {
+        TRY(cudaMemcpy(dW, W, sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice));
+        __half *ah, *al, *wh, *wl;
+        TRY(cudaMalloc(&ah, 2 * M * K)); TRY(cudaMalloc(&al, 2 * M * K));
+        TRY(cudaMalloc(&wh, 2 * (size_t)N * K)); TRY(cudaMalloc(&wl, 2 * (size_t)N * K));
+        if (ffb_launch_split_f16(dW, wh, wl, (int64_t)N * K, 0) < 0) return -2;
+        for (int rep = 0; rep < 2; rep++) {   // second pass is the timed one
+            cudaEventRecord(e0, 0);
+            if (ffb_launch_split_f16(dA, ah, al, M * K, 0) < 0) return -2;
+            rc = ffb_launch_gemm_tc(ah, al, wh, wl, db, dC, M, N, K, 0);
+            cudaEventRecord(e1, 0);
+            if (rc < 0) return -3;
+        }
+        TRY(cudaDeviceSynchronize());
+        cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+    } else {
+        std::vector<float> Wt((size_t)N * K);
+        for (int n = 0; n < N; n++) for (int k = 0; k < K; k++) Wt[(size_t)k * N + n] = W[(size_t)n * K + k];
+        TRY(cudaMemcpy(dW, Wt.data(), sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice));
+        for (int rep = 0; rep < 2; rep++) {
+            cudaEventRecord(e0, 0);
+            rc = ffb_launch_sgemm_bias(dA, dW, db, dC, M, N, K, 0);
+            cudaEventRecord(e1, 0);
+            if (rc < 0) return -3;
+        }
+        TRY(cudaDeviceSynchronize());
+    }
+    if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+    TRY(cudaMemcpy(C, dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dW); cudaFree(db); cudaFree(dC);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}

@@ -113,9 +113,9 @@ const char *ffb_last_error(void);
 const char *ffb_version(void);
 
 /* Weight bundle in the reference's own field order:
- *   kind GRU : conv_W, conv_b, {iW, sW, b} x 5 (B1,F2,B3,F4,B5), FF_W, FF_b         (20 mats)
+ *   kind GRU : conv_W, conv_b, {iW, sW, b} x 5 (B1,F2,B3,F4,B5), FF_W, FF_b         (19 mats)
  *   kind LSTM: conv1_W, conv1_b, conv2_W, conv2_b, conv3_W, conv3_b, {iW,sW,b} x 5,
- *              FF_W, FF_b                                                           (24 mats)
+ *              FF_W, FF_b                                                           (23 mats)
  * `mats[i]` are reference `_Mat`s exactly as the generated model headers define them
  * (convolution filters: nr = nf4*winlen - nf4 + nf).  conv_stride has 1 or 3 entries. */
 ffb_model *ffb_model_create(int device, int kind, const _Mat *const *mats, int nmat,

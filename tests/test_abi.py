@@ -1,0 +1,129 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the
+header declares, and refuses to compute without a GPU (no silent CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from flappie_b200 import api
+from flappie_b200.model import KIND_GRU, KIND_LSTM, FlipflopModel, Mat, conv_mat_image, mat_image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "flappie_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(\w+)\s*\([^;{]*\)\s*;", src, flags=re.M)
+    return sorted(set(n for n in names if n not in ("defined",)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = header_functions()
+    assert len(declared) >= 30
+    assert set(declared) == set(api.EXPORTS), set(declared) ^ set(api.EXPORTS)
+    for name in declared:
+        assert hasattr(lib.lib, name), name
+
+
+def test_model_registry_names(lib):
+    L = lib.lib
+    # reference src/networks.c:21-83
+    for name, val in (("r941_native", 0), ("r941_rna002", 1), ("r941_5mC", 2), ("r103_native", 3)):
+        assert L.get_flappie_model_type(name.encode()) == val
+        assert L.flappie_model_string(val).decode() == name
+        assert len(L.flappie_model_description(val)) > 10
+    assert L.get_flappie_model_type(b"r10C_pcr") == 0          # flappie-1.x alias
+    assert L.get_flappie_model_type(b"nonsense") == 4          # FLAPPIE_MODEL_INVALID
+    assert L.get_flappie_model_type(b"rle_r941_native") == 5
+    for nparam, nbase in ((40, 4), (60, 5), (12, 2)):
+        assert L.nbase_from_flipflop_nparam(nparam) == nbase
+
+
+def test_matrix_ownership_roundtrip(lib):
+    # results are callee-allocated `_Mat`s the caller frees (flappie_matrix.c:20-51,142)
+    m = lib.lib.make_flappie_matrix(10, 7)
+    assert m.contents.nr == 10 and m.contents.nrq == 3 and m.contents.stride == 12 and m.contents.nc == 7
+    buf = np.ctypeslib.as_array(m.contents.data, shape=(7, 12))
+    assert not buf.any()                                        # zero-initialised incl. padding
+    assert not lib.lib.free_flappie_matrix(m)                   # returns NULL
+    rows = np.arange(21, dtype=np.float32).reshape(3, 7)
+    assert np.array_equal(lib.rows_from_mat(lib.mat_from_rows(rows)), rows)
+    assert not lib.lib.make_flappie_matrix(0, 3)
+
+
+def test_null_in_null_out(lib):
+    # RETURN_NULL_IF semantics (flappie_stdlib.h:44)
+    assert not lib.lib.transpost_crf_flipflop(None, True)
+    assert not lib.lib.trace_from_posterior(None)
+    assert np.isnan(lib.lib.decode_crf_flipflop(None, False, None, None))
+    rt = api.RawTable(None, 0, 0, 0, None)
+    assert not lib.lib.calculate_transitions(rt, 1.0, 0)
+    assert lib.lib.ffb_basecall_batch(None, None) != 0
+    assert not lib.lib.ffb_create(None, None)
+
+
+def test_emit_bases_matches_oracle(lib, oracle):
+    rng = np.random.default_rng(4)
+    for nbase in (4, 5):
+        for _ in range(20):
+            T = int(rng.integers(2, 400))
+            path = np.repeat(rng.integers(0, 2 * nbase, size=T), rng.integers(1, 4, size=T))[:T + 1].astype(np.int32)
+            path = np.resize(path, T + 1)
+            qpath = np.log(rng.uniform(1e-4, 1.0, size=T + 1)).astype(np.float32)
+            assert lib.emit_bases(path, qpath, nbase) == oracle.emit_bases(path, qpath, nbase)
+            b, q = lib.emit_bases(path, qpath, nbase, reverse=True)
+            b2, q2 = oracle.emit_bases(path, qpath, nbase)
+            assert b == b2[::-1] and q == q2[::-1]
+    # quality clipping (util.h:285-305): p -> 1 saturates at Q50 = 'S'
+    b, q = lib.emit_bases(np.array([0, 1, 1], np.int32), np.array([np.nan, 0.0, 0.0], np.float32), 4)
+    assert b == "C" and q == "S"
+
+
+def test_mat_bundle_layout():
+    # the `_Mat` images are exactly what the generated model headers define
+    # (misc/taiyaki_flipflop5_guppy.py:38-99)
+    W = np.arange(2 * 5 * 3, dtype=np.float32).reshape(2, 5, 3)   # nfilter 2, winlen 5, nf 3
+    m, buf = conv_mat_image(W)
+    assert (m.nr, m.nrq, m.nc, m.stride) == (4 * 5 - 4 + 3, 5, 2, 20)
+    assert buf[1, 4 * 2 + 1] == W[1, 2, 1] and buf[0, 3] == 0.0   # 4th feature slot is padding
+    m, buf = mat_image(np.ones((6, 10), np.float32))
+    assert (m.nr, m.nrq, m.nc, m.stride) == (10, 3, 6, 12)
+    for kind, n in ((KIND_GRU, 19), (KIND_LSTM, 23)):
+        fm = FlipflopModel.synthetic(kind, 64, 4, seed=1)
+        mats, keep = fm.to_mat_bundle()
+        assert len(mats) == n
+        assert fm.nparam == 40 and fm.nbase == 4
+    fm = FlipflopModel.synthetic(KIND_GRU, 64, 5, seed=1)
+    assert fm.nblock(3790) == 1895 and fm.nblock(10) == -1
+    fm = FlipflopModel.synthetic(KIND_LSTM, 96, 4, seed=1)
+    assert fm.nblock(3790) == 758 and fm.stride == 5
+
+
+def test_no_silent_cpu_fallback(lib):
+    if lib.device_count() > 0:
+        pytest.skip("a GPU is present; the loud-failure path is exercised on CPU boxes")
+    fm = FlipflopModel.synthetic(KIND_GRU, 64, 4, seed=1)
+    with pytest.raises(api.FlappieB200Error):
+        api.Model(fm)
+    with pytest.raises(api.FlappieB200Error):
+        lib.decode_crf_flipflop(np.zeros((4, 40), np.float32))
+    # the raw C entry points report failure the reference's way: NULL / NAN
+    tm = lib.mat_from_rows(np.zeros((4, 40), np.float32))
+    assert not lib.lib.transpost_crf_flipflop(tm, True)
+    path = (ctypes.c_int * 8)(); q = (ctypes.c_float * 8)()
+    assert np.isnan(lib.lib.decode_crf_flipflop(tm, False, path, q))
+    lib.lib.free_flappie_matrix(tm)
+    assert "CUDA" in lib.last_error() or "device" in lib.last_error()
+
+
+def test_product_never_imports_oracle():
+    # a product path that routes through the oracle voids every parity claim
+    pkg = os.path.join(ROOT, "flappie_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in src and "flappie_oracle" not in src and "libflappie_ref" not in src, f

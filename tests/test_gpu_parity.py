@@ -91,17 +91,18 @@ MODELS = [
 ]
 
 
+@pytest.mark.parametrize("fp32_simt", [False, True])
 @pytest.mark.parametrize("name,kind,size,nbase", MODELS)
-def test_network_layers_small(gpu_lib, oracle, name, kind, size, nbase):
+def test_network_layers_small(gpu_lib, oracle, name, kind, size, nbase, fp32_simt):
     fm = FlipflopModel.synthetic(kind, size, nbase, seed=11)
     # ragged batch incl. lengths hitting every stride residue and a read that is too short
     lens = [1790, 1791, 1792, 1793, 1794, 600, 90, 2990, 10]
     reads = []
     for i, n in enumerate(lens):
-        reads.append(norm_reads(1, n + 210, seed=50 + i)[0][:n])
+        reads.append(norm_reads(1, max(n, 600) + 210, seed=50 + i)[0][:n])
     m = Model(fm)
     ctx = Context(m)
-    res = ctx.basecall(reads, viterbi_only=True, want_trans=True, keep_layers=True)
+    res = ctx.basecall(reads, viterbi_only=True, want_trans=True, keep_layers=True, fp32_simt=fp32_simt)
     conv_g = ctx.fetch_layer(0)
     layers_g = [ctx.fetch_layer(1 + l) for l in range(5)]
     for i, sig in enumerate(reads):

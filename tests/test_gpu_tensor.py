@@ -1,0 +1,80 @@
+"""GPU tests of the tcgen05 building blocks: the UMMA descriptor probe and the hi/lo-split
+tensor-core GEMM against float64 numpy and against the fp32 CUDA-core GEMM."""
+import ctypes
+from ctypes import POINTER, c_float, c_int, c_int64, c_uint16
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _hooks(gpu_lib):
+    L = gpu_lib.lib
+    L.ffb_test_umma_probe.restype = c_int
+    L.ffb_test_umma_probe.argtypes = [POINTER(c_uint16), POINTER(c_uint16), POINTER(c_float), c_int, c_int]
+    L.ffb_test_gemm.restype = c_int
+    L.ffb_test_gemm.argtypes = [POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float), c_int64, c_int,
+                                c_int, c_int, POINTER(c_float)]
+    return L
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (80, 32), (64, 256), (96, 256), (256, 64)])
+def test_umma_probe_noswizzle(gpu_lib, N, K):
+    L = _hooks(gpu_lib)
+    rng = np.random.default_rng(N + K)
+    A = rng.uniform(-1, 1, (128, K)).astype(np.float16)
+    B = rng.uniform(-1, 1, (N, K)).astype(np.float16)
+    D = np.zeros((128, N), np.float32)
+    r = L.ffb_test_umma_probe(A.view(np.uint16).ctypes.data_as(POINTER(c_uint16)),
+                              B.view(np.uint16).ctypes.data_as(POINTER(c_uint16)),
+                              D.ctypes.data_as(POINTER(c_float)), N, K)
+    assert r == 0
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    assert np.max(np.abs(D - ref)) < 1e-4 * max(1.0, K / 64)
+
+
+def gemm(L, A, W, b, mode):
+    M, K = A.shape
+    N = W.shape[0]
+    C = np.zeros((M, N), np.float32)
+    ms = c_float(0)
+    r = L.ffb_test_gemm(A.ctypes.data_as(POINTER(c_float)), W.ctypes.data_as(POINTER(c_float)),
+                        b.ctypes.data_as(POINTER(c_float)), C.ctypes.data_as(POINTER(c_float)), M, N, K, mode,
+                        ctypes.byref(ms))
+    assert r == 0
+    return C, ms.value
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 256), (333, 192, 64), (4097, 1024, 256),
+                                   (700, 1536, 384), (129, 384, 128)])
+def test_gemm_tc_matches_fp64(gpu_lib, M, N, K):
+    L = _hooks(gpu_lib)
+    rng = np.random.default_rng(M + N + K)
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    W = (rng.uniform(-1, 1, (N, K)) * 3 / np.sqrt(K)).astype(np.float32)
+    b = rng.uniform(-.3, .3, N).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T + b
+    C_tc, _ = gemm(L, A, W, b, 0)
+    C_f32, _ = gemm(L, A, W, b, 1)
+    err_tc = np.max(np.abs(C_tc - ref))
+    err_f32 = np.max(np.abs(C_f32 - ref))
+    # the split-fp16 tensor path must be as accurate as a plain fp32 GEMM (same order of error)
+    assert err_f32 < 5e-6
+    # 22-bit operands + tensor-core fp32 accumulation: within a small factor of plain fp32
+    assert err_tc < 2e-5 and err_tc < 6 * err_f32, (err_tc, err_f32)
+
+
+def test_gemm_tc_speed_report(gpu_lib):
+    L = _hooks(gpu_lib)
+    rng = np.random.default_rng(0)
+    M, N, K = 262144, 768, 256
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    W = (rng.uniform(-1, 1, (N, K)) * 3 / np.sqrt(K)).astype(np.float32)
+    b = np.zeros(N, np.float32)
+    C_tc, ms_tc = gemm(L, A, W, b, 0)
+    C_f32, ms_f32 = gemm(L, A, W, b, 1)
+    fl = 2.0 * M * N * K
+    print(f"\nGEMM {M}x{N}x{K}: tcgen05(split+gemm) {ms_tc:.3f} ms = {fl/ms_tc/1e9:.1f} TFLOP/s algorithmic; "
+          f"fp32 SIMT {ms_f32:.3f} ms = {fl/ms_f32/1e9:.1f} TFLOP/s")
+    assert np.max(np.abs(C_tc - C_f32)) < 2e-5
