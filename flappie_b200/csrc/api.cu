@@ -84,6 +84,9 @@ struct ffb_model {
     float *d_ffWt = nullptr, *d_ffb = nullptr;
     void *d_iW_hi[FFB_NLAYER] = {nullptr}, *d_iW_lo[FFB_NLAYER] = {nullptr};   // fp16 planes [G*S][in] for the tensor path
     bool tc_gemm = false;
+    void *d_sW_img[FFB_NLAYER] = {nullptr};   // per-CTA shared-memory images of sW (fp16 hi/lo) for rnn_tc
+    bool tc_rnn = false;
+    int tc_max_clusters = 0;
     int layer_in[FFB_NLAYER] = {0};
     // conv edge plans, cached per (conv layer, T_in)
     std::mutex mu;
@@ -105,7 +108,7 @@ extern "C" void ffb_model_destroy(ffb_model *m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (int i = 0; i < FFB_MAX_CONV; i++) { cudaFree(m->d_convWt[i]); cudaFree(m->d_convb[i]); }
-    for (int i = 0; i < FFB_NLAYER; i++) { cudaFree(m->d_iWt[i]); cudaFree(m->d_b[i]); cudaFree(m->d_sWp[i]); cudaFree(m->d_iW_hi[i]); cudaFree(m->d_iW_lo[i]); }
+    for (int i = 0; i < FFB_NLAYER; i++) { cudaFree(m->d_iWt[i]); cudaFree(m->d_b[i]); cudaFree(m->d_sWp[i]); cudaFree(m->d_iW_hi[i]); cudaFree(m->d_iW_lo[i]); cudaFree(m->d_sW_img[i]); }
     cudaFree(m->d_ffWt); cudaFree(m->d_ffb);
     delete m;
 }
@@ -173,6 +176,12 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             ffb_rnn_pack_weights(kind, S, sWd.data(), packed.data());
             m->d_iWt[l] = upload(iWt); m->d_b[l] = upload(bb); m->d_sWp[l] = upload(packed);
             ok = ok && m->d_iWt[l] && m->d_b[l] && m->d_sWp[l];
+            if (ok && ffb_rnn_tc_supported(kind, S)) {
+                std::vector<uint16_t> img(ffb_rnn_tc_image_halfs(kind, S));
+                ffb_rnn_tc_pack(kind, S, sWd.data(), img.data());
+                ok = cudaMalloc(&m->d_sW_img[l], img.size() * 2) == cudaSuccess &&
+                     cudaMemcpy(m->d_sW_img[l], img.data(), img.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+            }
             if (ok && ffb_gemm_tc_supported(G * S, in)) {
                 // hi/lo fp16 planes of iW in the reference's own [out][in] orientation (K-major B operand)
                 std::vector<float> iWd((size_t)G * S * in);
@@ -208,6 +217,13 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
     if (ok) {
         m->tc_gemm = true;
         for (int l = 0; l < FFB_NLAYER; l++) m->tc_gemm = m->tc_gemm && m->d_iW_hi[l] && m->d_iW_lo[l];
+    }
+    if (ok && ffb_rnn_tc_supported(kind, m->S) && m->tc_gemm) {
+        if (ffb_rnn_tc_prepare(kind, m->S) == 0) {
+            m->tc_max_clusters = ffb_rnn_tc_max_clusters(kind, m->S, ffb_rnn_tc_rmax(kind, m->S));
+            m->tc_rnn = m->tc_max_clusters > 0;
+        }
+        cudaGetLastError();
     }
     if (ok && ffb_rnn_prepare(kind, m->S) != 0) {
         set_err("ffb_model_create: recurrent kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -325,6 +341,8 @@ struct ffb_ctx {
     std::vector<int32_t> order;
     int max_T[FFB_MAX_CONV + 1] = {0};
     int n_slots = 0;
+    bool use_tc_rnn = false;
+    int R_tc = 0;
     // device
     DevBuf d_sig, d_c[2], d_act[2], d_xin, d_trans, d_tpost, d_fwd, d_tb, d_path, d_qpath, d_score, d_logz, d_trace;
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
@@ -437,7 +455,16 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
     if (b->blk_off) memcpy(b->blk_off, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1));
 
     // length-sorted slots for the recurrent kernel (descending, stable)
-    const int R = ffb_rnn_reads_per_cluster(m->kind, m->S);
+    int R = ffb_rnn_reads_per_cluster(m->kind, m->S);
+    c->use_tc_rnn = m->tc_rnn && !(c->flags & FFB_FLAG_FP32_SIMT) && getenv("FFB_NO_TC_RNN") == nullptr;
+    if (c->use_tc_rnn) {
+        // reads per cluster: fill the co-resident clusters once (one wave), N dimension multiple of 16
+        const int rmax = ffb_rnn_tc_rmax(m->kind, m->S);
+        int64_t r = (N + m->tc_max_clusters - 1) / std::max(m->tc_max_clusters, 1);
+        r = ((r + 15) / 16) * 16;
+        c->R_tc = (int)std::min<int64_t>(std::max<int64_t>(r, 16), rmax);
+        R = c->R_tc;
+    }
     c->n_slots = (int)(((N + R - 1) / R) * R);
     c->order.assign((size_t)c->n_slots, -1);
     {
@@ -534,20 +561,32 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     // ---- five recurrent layers, directions B,F,B,F,B (networks.c:460-483 / :557-580) ----
     RnnBatch rb{c->d_order.as<int32_t>(), c->d_blkoff.as<int64_t>(), c->n_slots, (int)N};
     float gemm_ms = 0.f, rnn_ms = 0.f;
-    int a = 0;
+    const bool keep = (c->flags & FFB_FLAG_KEEP_LAYERS) != 0;
+    const bool tc_gemm = m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT);
+    const bool tc_rnn = c->use_tc_rnn && tc_gemm;
+    const float *in = c->d_act[0].as<float>();   // fp32 input of the current layer (NULL when only planes exist)
     for (int l = 0; l < FFB_NLAYER; l++) {
-        const float *in = (l == 0) ? c->d_act[0].as<float>() : (c->flags & FFB_FLAG_KEEP_LAYERS ? c->d_keep[l - 1].as<float>() : c->d_act[a].as<float>());
-        float *out = (c->flags & FFB_FLAG_KEEP_LAYERS) ? c->d_keep[l].as<float>() : c->d_act[a ^ 1].as<float>();
+        const bool last = (l == FFB_NLAYER - 1);
+        float *out = keep ? c->d_keep[l].as<float>() : c->d_act[1].as<float>();
         if (timed) cudaEventRecord(c->ev[5], st);
-        if (m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT)) {
-            LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
+        if (tc_gemm) {
+            // layers fed by the tensor recurrent kernel already have their fp16 hi/lo planes
+            if (l == 0 || !tc_rnn) LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
             LAUNCH(ffb_launch_gemm_tc(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l], m->d_iW_lo[l], m->d_b[l], c->d_xin.as<float>(), Tt,
                                       G * S, m->layer_in[l], st));
         } else {
             LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], c->d_xin.as<float>(), Tt, G * S, m->layer_in[l], st));
         }
         if (timed) cudaEventRecord(c->ev[6], st);
-        LAUNCH(ffb_launch_rnn(m->kind, S, c->d_xin.as<float>(), m->d_sWp[l], out, rb, (l % 2) == 0, st));
+        if (tc_rnn) {
+            float *out_f32 = (keep || last) ? out : nullptr;
+            LAUNCH(ffb_launch_rnn_tc(m->kind, S, c->d_xin.as<float>(), m->d_sW_img[l], out_f32, last ? nullptr : c->d_ahi.p,
+                                     last ? nullptr : c->d_alo.p, rb, c->R_tc, (l % 2) == 0, st));
+        } else {
+            // the fp32 kernel ping-pongs between the two activation buffers
+            if (!keep) out = c->d_act[(l & 1) ^ 1].as<float>();
+            LAUNCH(ffb_launch_rnn(m->kind, S, c->d_xin.as<float>(), m->d_sWp[l], out, rb, (l % 2) == 0, st));
+        }
         if (timed) {
             cudaEventRecord(c->ev[7], st);
             cudaEventSynchronize(c->ev[7]);
@@ -556,9 +595,9 @@ static int forward_impl(ffb_ctx *c, bool timed) {
             cudaEventElapsedTime(&t2, c->ev[6], c->ev[7]);
             gemm_ms += t1; rnn_ms += t2;
         }
-        a ^= 1;
+        in = out;
     }
-    const float *top = (c->flags & FFB_FLAG_KEEP_LAYERS) ? c->d_keep[FFB_NLAYER - 1].as<float>() : c->d_act[a].as<float>();
+    const float *top = in;
     if (timed) cudaEventRecord(c->ev[2], st);
     // ---- globalnorm_flipflop (layers.c:1082-1106) ----
     LAUNCH(ffb_launch_ff_tanh(top, m->d_ffWt, m->d_ffb, c->d_trans.as<float>(), Tt, nr, S, c->temperature / 5.0f, st));

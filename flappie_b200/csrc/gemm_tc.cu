@@ -97,7 +97,10 @@ struct GemmTcCfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;   // + alignment slack
-    static constexpr int TMEM_COLS = 2 * BN;
+    // two accumulators per tile: the tensor core truncates on every accumulate (tests/probe_acc.py), so the
+    // 2^-11-sized cross terms get their own accumulator and are added in registers (round-to-nearest)
+    static constexpr int NBUF = (BN == 256) ? 1 : 2;
+    static constexpr int TMEM_COLS = 2 * BN * NBUF;
     static constexpr int THREADS = 192;
 };
 
@@ -120,7 +123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < Cfg::NBUF; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -159,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
-                const uint32_t d = tmem + acc * BN;
+                const uint32_t d = tmem + acc * 2 * BN, dx = d + BN;
                 for (int kc = 0; kc < nk; kc++) {
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
@@ -173,15 +176,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         const uint64_t dal = make_smem_desc(a_lo + ko, 16, 1024, LAYOUT_SW128);
                         const uint64_t dbh = make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128);
                         const uint64_t dbl = make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128);
-                        umma_f16(d, dah, dbh, idesc, (kc | k4) != 0);
-                        umma_f16(d, dah, dbl, idesc, 1);
-                        umma_f16(d, dal, dbh, idesc, 1);
+                        umma_f16(d, dah, dbh, idesc, (kc | k4) != 0);    // hi*hi
+                        umma_f16(dx, dah, dbl, idesc, (kc | k4) != 0);   // cross terms
+                        umma_f16(dx, dal, dbh, idesc, 1);
                     }
                     umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
                     if (kc == nk - 1) umma_commit(&acc_full[acc]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == Cfg::NBUF) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -195,12 +198,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             tcgen05_fence_after();
             const int64_t row = m0 + quad * 32 + lane;
             float *crow = C + row * (int64_t)N + n0;
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * BN;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN;
 #pragma unroll 2
             for (int c = 0; c < BN; c += 16) {
-                float v[16];
+                float v[16], vx[16];
                 tmem_ld16(taddr + c, v);
+                tmem_ld16(taddr + BN + c, vx);
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] += vx[j];
                 if (row < M) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -213,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == Cfg::NBUF) { acc = 0; acc_phase ^= 1; }
         }
     }
     tcgen05_fence_before();

@@ -88,6 +88,7 @@ MODELS = [
     ("gru96_4b", KIND_GRU, 96, 4),
     ("lstm96_4b", KIND_LSTM, 96, 4),
     ("lstm128_4b", KIND_LSTM, 128, 4),
+    ("gru256_4b", KIND_GRU, 256, 4),     # the shape with the tcgen05 recurrent kernel
 ]
 
 
@@ -127,7 +128,7 @@ def test_network_layers_small(gpu_lib, oracle, name, kind, size, nbase, fp32_sim
     ctx.close(); m.close()
 
 
-@pytest.mark.parametrize("name,kind,size,nbase", MODELS[:2] + MODELS[3:])
+@pytest.mark.parametrize("name,kind,size,nbase", MODELS[:2] + MODELS[3:])  # incl. gru256 (tensor path)
 def test_basecall_forward_backward_small(gpu_lib, oracle, name, kind, size, nbase):
     fm = FlipflopModel.synthetic(kind, size, nbase, seed=5)
     reads = norm_reads(6, 2000, seed=9)
