@@ -347,6 +347,7 @@ struct ffb_ctx {
     DevBuf d_sig, d_c[2], d_act[2], d_xin, d_trans, d_tpost, d_fwd, d_tb, d_path, d_qpath, d_score, d_logz, d_trace;
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
     DevBuf d_ahi, d_alo;          // fp16 hi/lo planes of the current layer input (tensor path)
+    DevBuf d_ring;                // state-exchange ring of the tensor recurrent kernel (L2-resident)
     float *last_conv = nullptr;   // device pointer of last conv output within d_act/d_c
     cudaEvent_t ev[8] = {nullptr};
     float t_gemm_ms = 0.f, t_rnn_ms = 0.f;
@@ -377,7 +378,7 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
-                     &c->d_order, &c->d_ahi, &c->d_alo};
+                     &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -458,11 +459,12 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
     int R = ffb_rnn_reads_per_cluster(m->kind, m->S);
     c->use_tc_rnn = m->tc_rnn && !(c->flags & FFB_FLAG_FP32_SIMT) && getenv("FFB_NO_TC_RNN") == nullptr;
     if (c->use_tc_rnn) {
-        // reads per cluster: fill the co-resident clusters once (one wave), N dimension multiple of 16
+        // groups of 16 reads; as few groups per cluster as still fit the batch into one wave of
+        // co-resident clusters (the layer is latency-bound: more clusters = shorter chains per SM)
         const int rmax = ffb_rnn_tc_rmax(m->kind, m->S);
-        int64_t r = (N + m->tc_max_clusters - 1) / std::max(m->tc_max_clusters, 1);
-        r = ((r + 15) / 16) * 16;
-        c->R_tc = (int)std::min<int64_t>(std::max<int64_t>(r, 16), rmax);
+        const int64_t groups = (N + 15) / 16;
+        int64_t gpc = (groups + m->tc_max_clusters - 1) / std::max(m->tc_max_clusters, 1);
+        c->R_tc = (int)std::min<int64_t>(std::max<int64_t>(gpc, 1) * 16, rmax);
         R = c->R_tc;
     }
     c->n_slots = (int)(((N + R - 1) / R) * R);
@@ -489,6 +491,8 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
         ok &= c->d_ahi.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
         ok &= c->d_alo.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
     }
+    if (c->use_tc_rnn)
+        ok &= c->d_ring.reserve(std::max<size_t>(ffb_rnn_tc_ring_bytes(m->kind, m->S, c->n_slots / std::max(c->R_tc, 1), c->R_tc), 16)) == 0;
     ok &= c->d_trans.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
     if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
         ok &= c->d_tpost.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
@@ -544,7 +548,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     const int S = m->S, G = m->G, nr = m->nparam;
     cudaStream_t st = c->st;
     if (N == 0 || Tt == 0) return FFB_OK;
-    if (N > 0x7fffffff) return FFB_ERR_ARG;
+    if (N > 0x7fffffff || Tt > 0x7fffffff) return FFB_ERR_ARG;   // kernels index blocks with 32 bits
     if (timed) cudaEventRecord(c->ev[0], st);
     // ---- convolutions (features_from_raw folded into the first load) ----
     const float *cur = c->d_sig.as<float>();
@@ -581,7 +585,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         if (tc_rnn) {
             float *out_f32 = (keep || last) ? out : nullptr;
             LAUNCH(ffb_launch_rnn_tc(m->kind, S, c->d_xin.as<float>(), m->d_sW_img[l], out_f32, last ? nullptr : c->d_ahi.p,
-                                     last ? nullptr : c->d_alo.p, rb, c->R_tc, (l % 2) == 0, st));
+                                     last ? nullptr : c->d_alo.p, rb, c->R_tc, (l % 2) == 0, c->d_ring.p, st));
         } else {
             // the fp32 kernel ping-pongs between the two activation buffers
             if (!keep) out = c->d_act[(l & 1) ^ 1].as<float>();

@@ -90,15 +90,16 @@ int ffb_launch_rnn(int kind, int S, const float *Xin, const float *sW_packed, fl
                    int backward, cudaStream_t st);
 int ffb_rnn_prepare(int kind, int S);   // one-time function attribute setup; returns 0 or error
 
-// rnn_tc.cu: tcgen05 recurrent layer (GRU S=256 at present)
+// rnn_tc.cu: tcgen05 recurrent layer (GRU / LSTM, S=256 at present); R = reads per cluster, multiple of 16
 int ffb_rnn_tc_supported(int kind, int S);
 size_t ffb_rnn_tc_image_halfs(int kind, int S);
 void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img);
 int ffb_rnn_tc_prepare(int kind, int S);
 int ffb_rnn_tc_max_clusters(int kind, int S, int R);
 int ffb_rnn_tc_rmax(int kind, int S);
+size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R);   // L2-resident state-exchange ring
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
-                      const RnnBatch &rb, int R, int backward, cudaStream_t st);
+                      const RnnBatch &rb, int R, int backward, void *ring, cudaStream_t st);
 
 // decode.cu
 int ffb_launch_logz(const float *trans, const int64_t *blk_off, int n_reads, int nr, double *logZ, cudaStream_t st);

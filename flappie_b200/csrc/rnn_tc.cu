@@ -1,105 +1,160 @@
 // rnn_tc.cu -- the recurrent hot loop on the 5th-generation tensor cores (tcgen05 + TMEM).
 //
-// Same cluster decomposition as rnn.cu (a cluster of C CTAs owns R whole reads for the whole
-// layer, CTA c owns hidden units [c*32, (c+1)*32)), but the per-step product
+// Replaces reference grumod_forward/backward + grumod_step (src/layers.c:571-715) and
+// lstm_forward/backward + lstm_step (src/layers.c:877-1026).
+//
+// Decomposition.  A thread-block cluster of C CTAs owns up to GMAX independent GROUPS of 16
+// whole reads for the whole layer; CTA c owns hidden units [c*HS, (c+1)*HS), HS = S/C = 32.
+// Per group and step the CTA computes
 //       a[gate g, hidden j][read] = sum_k sW[g*S + j][k] * h_{t-1}[read][k]
-// is one M=128 x N=R x K=S tensor-core GEMM per CTA per step:
-//   A = this CTA's slice of sW, RESIDENT in shared memory for all T steps (fp16 hi/lo planes,
-//       no-swizzle K-major).  Row order: TMEM lane quadrant q holds, for the 8 hidden units
-//       8q..8q+7, lanes [0,8) = z gate, [8,16) = r gate, [16,24) = n gate, [24,32) unused --
-//       so every warp (= quadrant = SM sub-partition) owns complete cells and the gate
-//       arithmetic is spread evenly over all four sub-partitions with warp shuffles only.
-//   B = the previous state of the cluster's R reads, fp16 hi/lo planes [read][k] K-major,
+// as one M=128 x N=16 x K=S tensor-core GEMM:
+//   A = the CTA's slice of sW, RESIDENT in shared memory for all T steps (fp16 hi/lo planes,
+//       no-swizzle K-major).  TMEM lane quadrant q holds, for the 8 hidden units 8q..8q+7,
+//       lanes [0,8) = gate 0, [8,16) = gate 1, [16,24) = gate 2, [24,32) = gate 3 (GRU: unused),
+//       so a 16-lane x 256-bit tcgen05.ld hands every thread two gates of the SAME cell and the
+//       gate arithmetic needs no shuffles.
+//   B = the previous state of the group's 16 reads, [k-group][plane hi/lo][read][8 halfs],
 //   D = fp32 in tensor memory.  fp32-faithful product: hi*hi + hi*lo + lo*hi (tc_common.cuh).
-//       The tensor core truncates (round-toward-zero) on every accumulate (measured:
-//       ~ -0.6e-7 relative per MMA, tests/probe_acc.py), so the hi*hi product is split over
-//       two K-halves into separate accumulators and the small cross terms into a third; the
-//       three are added in registers with round-to-nearest.
-// Step protocol (mbarrier based, no cluster-wide barrier on the critical path):
-//   control thread : wait h_full (every slice of h_{t-1} has landed in B) -> issue 3*S/16
-//                    tcgen05.mma -> tcgen05.commit -> acc_full; then tell every peer
-//                    "I have consumed h_{t-1}" (remote arrive on its h_empty)
-//   all 8 warps    : tcgen05.ld their quadrant/half, regroup (z, r, n) per cell with shuffles,
-//                    add the prefetched input projection Xin_t, gates, blend with the
-//                    register-resident previous state, write h_t to HBM (fp32 and/or fp16 hi/lo
-//                    planes for the next layer's tensor GEMM), stage the slice in the B layout
-//   control thread : wait h_empty (all peers consumed h_{t-1}) -> one cp.async.bulk per
-//                    plane per peer pushes the slice into every CTA's B operand through
-//                    distributed shared memory, completing bytes on the peer's h_full.
-// Gate order and arithmetic as the reference: grumod_step src/layers.c:664-715.
+//       The tensor core truncates on every accumulate (tests/probe_acc.py), so the hi*hi
+//       product is split over two K-halves into separate accumulators and the cross terms
+//       into a third; the three are added in registers with round-to-nearest.
+//
+// The layer is a chain of T dependent steps, so what bounds it is the LATENCY of one step's
+// chain (MMA -> gates -> state exchange across the cluster), not any throughput: the groups
+// are software-pipelined against each other -- each has its own barriers, its own 4 gate
+// warps (one per TMEM quadrant) and its own control warp -- so while one group's state is in
+// flight another group's MMAs and gates run.
+//
+// State exchange.  Every CTA needs all S elements of h_t of a group.  Pushing slices through
+// distributed shared memory measured 8-9 B/clk per CTA and cluster-scope fences ~1.3 us
+// (profiles/r01_exchange_microbench_*.txt); instead each CTA bulk-stores its staged slice to
+// a small L2-resident ring in global memory and issues ONE multicast bulk load that lands it
+// in the B operand of all C CTAs and signals their mbarriers (~80 B/clk, no fences).
+//
+// Step protocol of one group (all waits are CTA-scope mbarrier waits):
+//   control thread : wait h_full (all slices of h_{t-1} landed) -> arm h_full for h_t ->
+//                    3*S/16 tcgen05.mma -> commit -> acc_full; when the MMAs have retired, tell
+//                    every peer "I have consumed h_{t-1}" (remote arrive on its h_empty)
+//   4 gate warps   : prefetch Xin_t, wait acc_full, tcgen05.ld, gates, blend with the register-
+//                    resident previous state, write h_t to HBM (fp32 and/or fp16 hi/lo planes
+//                    for the next layer's tensor GEMM), stage the slice -> arrive `staged`
+//   control thread : wait staged -> bulk store slice to the ring -> wait h_empty (all peers
+//                    consumed h_{t-1}) -> multicast load ring -> B of every CTA (-> their h_full)
+// Gate order and arithmetic as the reference: grumod_step src/layers.c:664-715 (z, r, n);
+// lstm_step src/layers.c:979-1026 (i, f, g, o).
 #include "ffb_common.cuh"
 #include "tc_common.cuh"
 
 namespace ffb {
 using namespace tc;
 
-template <int S_, int C_>
-struct GruTcCfg {
-    static constexpr int S = S_, C = C_, G = 3;
-    static constexpr int HS = S / C;                 // hidden units per CTA
-    static constexpr int KG = S / 8;                 // 16-byte k-groups along K
-    static constexpr int A_RG = 15;                  // 8-row groups stored per k-group (the 16th is never read back)
-    static constexpr int LBO_A = A_RG * 128;         // bytes between k-groups of A
-    static constexpr int A_PLANE = KG * LBO_A;       // bytes per A plane
-    static constexpr int RMAX = 80;
-    static constexpr int CELLS = RMAX / 8;           // cells per thread: (R/2 reads per half) / 4 lane groups
-    static constexpr int NACC = 3;                   // hi*hi K-half 0, hi*hi K-half 1, cross terms
-    static constexpr int THREADS = 256;
+template <int S_, int C_, int NGATE_>
+struct RnnTcCfg {
+    static constexpr int S = S_, C = C_, NGATE = NGATE_;
+    static constexpr int HS = S / C;                  // hidden units per CTA
+    static constexpr int NQ = HS / 8;                 // TMEM quadrants in use = k-groups per slice
+    static constexpr int KG = S / 8;                  // 16-byte k-groups along K
+    static constexpr int NG = 16;                     // reads per group (MMA N)
+    static constexpr int GMAX = 5;                    // groups per cluster
+    static constexpr int A_RG = (NGATE == 3) ? 15 : 16;   // 8-row groups stored per k-group (GRU: the 16th is padding, aliased)
+    static constexpr int LBO_A = A_RG * 128;          // bytes between k-groups of A
+    static constexpr int A_PLANE = KG * LBO_A;        // bytes per A plane
+    static constexpr int A_BYTES = 2 * A_PLANE + 128; // + the aliased 16th row group of the last k-group
+    static constexpr int LBO_B = 2 * NG * 16;         // bytes between k-groups of B (hi and lo planes interleaved)
+    static constexpr int B_GROUP = KG * LBO_B;        // bytes of one group's B operand
+    static constexpr int SLICE = NQ * LBO_B;          // bytes of one CTA's slice of one group's state
+    static constexpr int ACC_COLS = 3 * NG;           // TMEM columns per group
+    static constexpr int WARPS_PER_GROUP = 5;         // 4 gate warps + 1 control warp
+    static constexpr int MAX_THREADS = GMAX * WARPS_PER_GROUP * 32;
     static_assert(HS == 32, "four quadrants of 8 hidden units");
-    __host__ __device__ static constexpr size_t smem_bytes(int R) {
-        return 2 * (size_t)A_PLANE + 128              // A hi / lo (+ the aliased 16th row group of the last k-group)
-               + 2 * (size_t)KG * R * 16              // B hi / lo
-               + 4 * (size_t)(HS / 8) * R * 16        // staged slice hi / lo, double buffered
-               + (size_t)R * 12 + 64;                 // per-read base row (int64) + length (int32)
+    __host__ __device__ static constexpr size_t smem_bytes(int G) {
+        return (size_t)A_BYTES + (size_t)G * (B_GROUP + SLICE) + 64;
+    }
+    __host__ __device__ static constexpr size_t ring_bytes(int n_clusters, int G) {
+        return (size_t)n_clusters * 2 * G * C * SLICE;
     }
 };
 
+__device__ __forceinline__ void bulk_store_global(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// one read of global memory, delivered to the same shared-memory offset of every CTA in `mask`,
+// completing `bytes` on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_load_multicast(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// CTA-scope remote arrive: orders nothing but the arrival itself (used for "operand consumed")
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// 16 lanes x 256 bit, two column blocks: thread t gets rows t/4 (v0,v1,v4,v5) and t/4 + 8
+// (v2,v3,v6,v7), columns 2*(t%4)+{0,1} (v0..v3) and 8 + 2*(t%4)+{0,1} (v4..v7)
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// sigma and tanh on the MUFU pipe: ex2.approx (2 ulp) + rcp.approx (1 ulp); same formulas as the
+// reference (src/util.h:331-339), errors of a few 1e-7, far below the 1e-4 parity tolerance
+__device__ __forceinline__ float fast_logistic(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float y = fast_logistic(x + x);
+    return (y + y) - 1.0f;
+}
+
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
-gru_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, float *__restrict__ Hout,
+__global__ void __launch_bounds__(Cfg::MAX_THREADS, 1)
+rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, float *__restrict__ Hout,
               __half *__restrict__ Hhi, __half *__restrict__ Hlo, const int32_t *__restrict__ order,
-              const int64_t *__restrict__ blk_off, int R, int backward) {
-    constexpr int S = Cfg::S, C = Cfg::C, HS = Cfg::HS, KG = Cfg::KG, CELLS = Cfg::CELLS;
+              const int64_t *__restrict__ blk_off, uint8_t *__restrict__ ring, int G, int backward) {
+    constexpr int S = Cfg::S, C = Cfg::C, NGATE = Cfg::NGATE, NG = Cfg::NG, GMAX = Cfg::GMAX;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t h_full, h_empty, acc_full;
+    __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
     __shared__ uint32_t tmem_slot;
 
     uint8_t *A_hi = smem;
     uint8_t *A_lo = A_hi + Cfg::A_PLANE;
-    uint8_t *B_hi = A_lo + Cfg::A_PLANE + 128;
-    const uint32_t b_plane = (uint32_t)KG * R * 16;
-    uint8_t *B_lo = B_hi + b_plane;
-    uint8_t *stg_base = B_lo + b_plane;                               // 2 buffers x {hi, lo} x [HS/8][R][16 B]
-    const uint32_t stg_plane = (uint32_t)(HS / 8) * R * 16;
-    int64_t *rd_base = reinterpret_cast<int64_t *>(stg_base + 4 * stg_plane);   // [R]
-    int32_t *rd_T = reinterpret_cast<int32_t *>(rd_base + R);                    // [R]
+    uint8_t *B_base = smem + Cfg::A_BYTES;                       // [G][KG][hi|lo][NG][16 B]
+    uint8_t *stg_base = B_base + (size_t)G * Cfg::B_GROUP;       // [G][NQ][hi|lo][NG][16 B]
 
     const uint32_t crank = cluster_ctarank();
     const int cluster_id = blockIdx.x / C;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quad = warp & 3;          // TMEM lane quadrant: hidden units 8*quad .. 8*quad+7 of this CTA
-    const int half = warp >> 2;         // which half of the reads this warp handles
-    const int Rh = R / 2;
-    const int e = lane & 7;             // hidden unit within the quadrant
-    const int sub = lane >> 3;          // this lane's cells are reads c0 + 4*ci + sub
+    const int nthreads = blockDim.x;
+    const int R = G * NG;                                        // reads per cluster
 
     // ---- one-time setup ----
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(Wimg) + (size_t)crank * (2 * Cfg::A_PLANE / 16);
         uint4 *dst = reinterpret_cast<uint4 *>(A_hi);
-        for (int i = tid; i < 2 * Cfg::A_PLANE / 16; i += Cfg::THREADS) dst[i] = src[i];
+        for (int i = tid; i < 2 * Cfg::A_PLANE / 16; i += nthreads) dst[i] = src[i];
         uint4 *bz = reinterpret_cast<uint4 *>(A_lo + Cfg::A_PLANE);   // the 128-byte tail + B: h_{-1} = 0
-        for (int i = tid; i < (int)((128 + 2 * b_plane) / 16); i += Cfg::THREADS) bz[i] = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < R; i += Cfg::THREADS) {
-            const int rd = order[cluster_id * R + i];
-            rd_base[i] = rd >= 0 ? blk_off[rd] : 0;
-            rd_T[i] = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
-        }
+        for (int i = tid; i < (int)((128 + (size_t)G * Cfg::B_GROUP) / 16); i += nthreads) bz[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        mbar_init(&h_full, 1);
-        mbar_init(&h_empty, C);
-        mbar_init(&acc_full, 1);
+        for (int g = 0; g < G; g++) {
+            mbar_init(&h_full[g], 1);
+            mbar_init(&h_empty[g], C);
+            mbar_init(&acc_full[g], 1);
+            mbar_init(&staged[g], Cfg::NQ);
+        }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
@@ -110,184 +165,206 @@ gru_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     cluster_sync_all();             // every CTA's barriers are initialised before any remote arrive / copy
     const uint32_t tmem = tmem_slot;
 
+    const int g = (warp < 4 * G) ? (warp >> 2) : (warp - 4 * G);    // this warp's group
+    // slots are sorted by length (descending): the group's first slot is its longest read
     int Tmax = 0;
     {
-        const int rd0 = order[cluster_id * R];
+        const int rd0 = order[cluster_id * R + g * NG];
         Tmax = rd0 >= 0 ? (int)(blk_off[rd0 + 1] - blk_off[rd0]) : 0;
     }
-    const int j = crank * HS + quad * 8 + e;         // global hidden index of this lane's cells
-    const uint32_t idesc = make_idesc_f16(128, (uint32_t)R);
-    const uint32_t slice_bytes = stg_plane;          // bytes pushed per plane per peer per step
-    const uint32_t step_tx = 2u * slice_bytes * C;   // bytes landing in this CTA's B per step
-    const int c0 = half * Rh;
+    uint8_t *Bg = B_base + (size_t)g * Cfg::B_GROUP;
+    uint8_t *stg = stg_base + (size_t)g * Cfg::SLICE;
+    const uint32_t acc = tmem + (uint32_t)g * Cfg::ACC_COLS;
 
-    // per-cell constants: read slot, length, base row (cells beyond Rh/4 are inactive)
-    float hprev[CELLS];
-    int cT[CELLS];
-    int64_t cbase[CELLS];
-#pragma unroll
-    for (int ci = 0; ci < CELLS; ci++) {
-        hprev[ci] = 0.0f;
-        const int rs = c0 + 4 * ci + sub;
-        const bool ok = (4 * ci + sub) < Rh;
-        cT[ci] = ok ? rd_T[rs] : 0;
-        cbase[ci] = ok ? rd_base[rs] : 0;
-    }
-
-    for (int s = 0; s < Tmax; s++) {
-        const uint32_t ph = (uint32_t)s & 1u;
-        // staging is double buffered: the bulk copies of step s may still be reading their source
-        // while step s+1 is staged; reuse at s+2 is safe because reaching it needs h_full(s+1)
-        // here, which needs every peer's MMA(s+1), which needs my step-s push to have landed
-        uint8_t *stg_hi = stg_base + (size_t)ph * 2 * stg_plane;
-        uint8_t *stg_lo = stg_hi + stg_plane;
-
-        // ---------------- control: MMA issue ----------------
-        if (warp == 0) {
-            if (elect_one()) {
-                if (s > 0) mbar_wait_cluster(&h_full, ph ^ 1u);       // h_{s-1} complete in B (phase s-1)
-                mbar_arrive_expect_tx(&h_full, step_tx);              // arm phase s: peers push h_s only after my MMA(s)
+    if (warp >= 4 * G) {
+        // =========================== control warp of group g ===========================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_f16(128, NG);
+            const uint64_t dA_hi = make_smem_desc(smem_u32(A_hi), Cfg::LBO_A, 128, LAYOUT_NONE);
+            const uint64_t dA_lo = make_smem_desc(smem_u32(A_lo), Cfg::LBO_A, 128, LAYOUT_NONE);
+            const uint64_t dB_hi = make_smem_desc(smem_u32(Bg), Cfg::LBO_B, 128, LAYOUT_NONE);
+            const uint64_t dB_lo = make_smem_desc(smem_u32(Bg) + NG * 16, Cfg::LBO_B, 128, LAYOUT_NONE);
+            uint8_t *ring_g = ring + ((((size_t)cluster_id * 2) * G + g) * C + crank) * Cfg::SLICE;   // parity 0
+            const size_t ring_par = (size_t)G * C * Cfg::SLICE;
+            for (int s = 0; s < Tmax; s++) {
+                const uint32_t ph = (uint32_t)s & 1u;
+                if (s > 0) mbar_wait(&h_full[g], ph ^ 1u);           // h_{s-1} complete in B
+                mbar_arrive_expect_tx(&h_full[g], C * Cfg::SLICE);    // arm phase s: peers push h_s only after my MMA(s)
                 tcgen05_fence_after();
-                const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo), b_hi = smem_u32(B_hi), b_lo = smem_u32(B_lo);
-                const uint32_t lbo_b = (uint32_t)R * 16;
 #pragma unroll 4
                 for (int ks = 0; ks < S / 16; ks++) {
-                    const uint64_t dah = make_smem_desc(a_hi + ks * 2 * Cfg::LBO_A, Cfg::LBO_A, 128, LAYOUT_NONE);
-                    const uint64_t dal = make_smem_desc(a_lo + ks * 2 * Cfg::LBO_A, Cfg::LBO_A, 128, LAYOUT_NONE);
-                    const uint64_t dbh = make_smem_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128, LAYOUT_NONE);
-                    const uint64_t dbl = make_smem_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128, LAYOUT_NONE);
-                    const int kh = ks / (S / 32);                                       // K-half
-                    umma_f16(tmem + kh * R, dah, dbh, idesc, (ks % (S / 32)) != 0);   // hi*hi
-                    umma_f16(tmem + 2 * R, dah, dbl, idesc, ks != 0);                 // cross terms
-                    umma_f16(tmem + 2 * R, dal, dbh, idesc, 1);
+                    const uint64_t oa = (uint64_t)((ks * 2 * Cfg::LBO_A) >> 4), ob = (uint64_t)((ks * 2 * Cfg::LBO_B) >> 4);
+                    const int kh = ks / (S / 32);                                            // K-half
+                    umma_f16(acc + kh * NG, dA_hi + oa, dB_hi + ob, idesc, (ks % (S / 32)) != 0);   // hi*hi
+                    umma_f16(acc + 2 * NG, dA_hi + oa, dB_lo + ob, idesc, ks != 0);                 // cross terms
+                    umma_f16(acc + 2 * NG, dA_lo + oa, dB_hi + ob, idesc, 1);
                 }
-                umma_commit(&acc_full);
+                umma_commit(&acc_full[g]);
+                mbar_wait(&acc_full[g], ph);
+                // the MMAs have retired: this CTA no longer reads h_{s-1}
+                for (uint32_t d = 0; d < (uint32_t)C; d++) mbar_arrive_remote_cta(&h_empty[g], d);
+                mbar_wait(&staged[g], ph);                            // the gate warps staged my slice of h_s
+                uint8_t *rg = ring_g + (size_t)ph * ring_par;
+                bulk_store_global(rg, stg, Cfg::SLICE);
+                mbar_wait(&h_empty[g], ph);                           // every peer has consumed h_{s-1}
+                asm volatile("fence.proxy.async;" ::: "memory");
+                bulk_load_multicast(Bg + crank * Cfg::SLICE, rg, Cfg::SLICE, &h_full[g], (uint16_t)((1u << C) - 1u));
             }
-            __syncwarp();
+            // drain: the last step's copies still target this CTA; nobody may exit before they have landed
+            if (Tmax > 0) mbar_wait(&h_full[g], (uint32_t)(Tmax - 1) & 1u);
         }
-
-        // ---------------- all warps: prefetch this step's input projection ----------------
-        float xz[CELLS], xr[CELLS], xn[CELLS];
+        __syncwarp();
+    } else {
+        // =========================== gate warp (group g, quadrant q) ===========================
+        const int q = warp & 3;
+        const int e = lane >> 2, cp = lane & 3;
+        const int j = crank * Cfg::HS + q * 8 + e;          // global hidden index of this thread's cells
+        // this thread's four cells: reads col(i) = (i>>1)*8 + 2*cp + (i&1) of the group
+        int cT[4];
+        int32_t cbase[4];           // first block of the read (the host guarantees total blocks < 2^31)
+        float hprev[4], cstate[4];
 #pragma unroll
-        for (int ci = 0; ci < CELLS; ci++) {
-            xz[ci] = xr[ci] = xn[ci] = 0.0f;
-            if (s < cT[ci]) {
-                const int t = backward ? (cT[ci] - 1 - s) : s;
-                const float *xp = Xin + (cbase[ci] + t) * (int64_t)(3 * S) + j;
-                xz[ci] = __ldcs(xp);
-                xr[ci] = __ldcs(xp + S);
-                xn[ci] = __ldcs(xp + 2 * S);
+        for (int i = 0; i < 4; i++) {
+            const int col = (i >> 1) * 8 + 2 * cp + (i & 1);
+            const int rd = order[cluster_id * R + g * NG + col];
+            cT[i] = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
+            cbase[i] = rd >= 0 ? (int32_t)blk_off[rd] : 0;
+            hprev[i] = 0.0f; cstate[i] = 0.0f;
+        }
+        const uint32_t t_lo = acc + ((uint32_t)(q * 32) << 16);       // lanes 32q .. 32q+15: gates 0, 1
+        const uint32_t t_hi = acc + ((uint32_t)(q * 32 + 16) << 16);  // lanes 32q+16 .. 32q+31: gates 2, 3
+        // staging: [kg_local = q][plane][read][8 halfs], this thread writes element e of its 4 reads
+        __half *st_hi = reinterpret_cast<__half *>(stg + (size_t)q * Cfg::LBO_B) + e;
+        __half *st_lo = st_hi + NG * 8;
+
+        for (int s = 0; s < Tmax; s++) {
+            const uint32_t ph = (uint32_t)s & 1u;
+            // ---- prefetch this step's input projection ----
+            float x[4][NGATE];
+            int32_t row[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int t = backward ? (cT[i] - 1 - s) : s;
+                row[i] = cbase[i] + t;
+#pragma unroll
+                for (int gt = 0; gt < NGATE; gt++) x[i][gt] = 0.0f;
+                if (s < cT[i]) {
+                    const float *xp = Xin + (int64_t)row[i] * (NGATE * S) + j;
+#pragma unroll
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xp + gt * S);
+                }
             }
-        }
-
-        mbar_wait(&acc_full, ph);
-        tcgen05_fence_after();
-        // once the MMAs have retired this CTA no longer reads h_{s-1}: tell every peer
-        if (warp == 0 && lane < C) mbar_arrive_remote(&h_empty, (uint32_t)lane);
-
-        // ---------------- TMEM -> registers, regroup (z, r, n) per cell ----------------
-        float az[CELLS], ar[CELLS], an[CELLS];
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + c0;
-#pragma unroll
-        for (int cc = 0; cc < Cfg::RMAX / 2; cc += 8) {
-            if (cc < Rh) {
-                float a0[8], a1[8], a2[8];
-                tmem_ld8(taddr + cc, a0);
-                tmem_ld8(taddr + R + cc, a1);
-                tmem_ld8(taddr + 2 * R + cc, a2);
+            mbar_wait(&acc_full[g], ph);
+            tcgen05_fence_after();
+            // ---- TMEM -> registers: a[i][gate], three partial accumulators added round-to-nearest ----
+            float a[4][4];
+            {
+                float v0[8], v1[8];
+                tmem_ld_16x256b_x2(t_lo, v0);
+                tmem_ld_16x256b_x2(t_lo + NG, v1);
                 tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const float a = (a0[q] + a1[q]) + a2[q];      // round-to-nearest sum of the partial accumulators
-                    const float tz = __shfl_sync(0xffffffffu, a, e);
-                    const float tr = __shfl_sync(0xffffffffu, a, 8 + e);
-                    const float tn = __shfl_sync(0xffffffffu, a, 16 + e);
-                    if ((q & 3) == sub) {
-                        az[(cc + q) >> 2] = tz; ar[(cc + q) >> 2] = tr; an[(cc + q) >> 2] = tn;
-                    }
+                for (int i = 0; i < 4; i++) {
+                    const int r0 = (i >> 1) * 4 + (i & 1);
+                    a[i][0] = v0[r0] + v1[r0]; a[i][1] = v0[r0 + 2] + v1[r0 + 2];
+                }
+                tmem_ld_16x256b_x2(t_hi, v0);
+                tmem_ld_16x256b_x2(t_hi + NG, v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int r0 = (i >> 1) * 4 + (i & 1);
+                    a[i][2] = v0[r0] + v1[r0]; a[i][3] = v0[r0 + 2] + v1[r0 + 2];
+                }
+                tmem_ld_16x256b_x2(t_lo + 2 * NG, v0);
+                tmem_ld_16x256b_x2(t_hi + 2 * NG, v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int r0 = (i >> 1) * 4 + (i & 1);
+                    a[i][0] += v0[r0]; a[i][1] += v0[r0 + 2];
+                    a[i][2] += v1[r0]; a[i][3] += v1[r0 + 2];
                 }
             }
-        }
-        tcgen05_fence_before();
-
-        // ---------------- cells ----------------
-        __half *shi = reinterpret_cast<__half *>(stg_hi + ((size_t)quad * R + c0 + sub) * 16) + e;
-        __half *slo = reinterpret_cast<__half *>(stg_lo + ((size_t)quad * R + c0 + sub) * 16) + e;
+            tcgen05_fence_before();
+            // ---- cells ----
 #pragma unroll
-        for (int ci = 0; ci < CELLS; ci++) {
-            if (4 * ci < Rh) {
-                const float z = logisticf(xz[ci] + az[ci]);                         // layers.c:697-699
-                const float r = logisticf(xr[ci] + ar[ci]);
-                const float hbar = tanh_ref(r * an[ci] + xn[ci]);                  // layers.c:704-709
-                const float hn = z * hprev[ci] + (1.0f - z) * hbar;               // layers.c:712-714
-                if (s < cT[ci]) {
-                    hprev[ci] = hn;
-                    const int t = backward ? (cT[ci] - 1 - s) : s;
-                    const int64_t row = cbase[ci] + t;
-                    if (Hout) __stcs(Hout + row * S + j, hn);
+            for (int i = 0; i < 4; i++) {
+                float hn;
+                if constexpr (NGATE == 3) {
+                    const float z = fast_logistic(x[i][0] + a[i][0]);                   // layers.c:697-699
+                    const float r = fast_logistic(x[i][1] + a[i][1]);
+                    const float hbar = fast_tanh(r * a[i][2] + x[i][2]);               // layers.c:704-709
+                    hn = z * hprev[i] + (1.0f - z) * hbar;                             // layers.c:712-714
+                } else {
+                    const float ig = fast_logistic(x[i][0] + a[i][0]);                  // layers.c:1013-1024
+                    const float fg = fast_logistic(x[i][1] + a[i][1]);
+                    const float gg = fast_tanh(x[i][2] + a[i][2]);
+                    const float og = fast_logistic(x[i][3] + a[i][3]);
+                    const float cn = fg * cstate[i] + ig * gg;
+                    hn = og * fast_tanh(cn);
+                    if (s < cT[i]) cstate[i] = cn;
+                }
+                if (s < cT[i]) {
+                    hprev[i] = hn;
+                    if (Hout) __stcs(Hout + (int64_t)row[i] * S + j, hn);
                     if (Hhi) {
                         __half hi, lo;
                         split_f16(hn, hi, lo);
-                        Hhi[row * S + j] = hi;
-                        Hlo[row * S + j] = lo;
+                        Hhi[(int64_t)row[i] * S + j] = hi;
+                        Hlo[(int64_t)row[i] * S + j] = lo;
                     }
                 }
                 __half shv, slv;
-                split_f16(hprev[ci], shv, slv);      // finished reads keep pushing their frozen state
-                shi[(size_t)ci * 32] = shv;           // 4 reads = 4 * 16 bytes = 32 halfs apart
-                slo[(size_t)ci * 32] = slv;
+                split_f16(hprev[i], shv, slv);       // finished reads keep pushing their frozen state
+                const int col = (i >> 1) * 8 + 2 * cp + (i & 1);
+                st_hi[col * 8] = shv;
+                st_lo[col * 8] = slv;
             }
-        }
-        fence_proxy_async_smem();      // staged slice -> visible to the bulk-copy engine
-        __syncthreads();
-
-        // ---------------- control: push the slice to every CTA of the cluster ----------------
-        if (warp == 0) {
-            if (elect_one()) {
-                mbar_wait_cluster(&h_empty, ph);      // every peer has consumed h_{s-1}
-                const uint32_t dst_off = crank * slice_bytes;
-                for (uint32_t d = 0; d < (uint32_t)C; d++) {
-                    dsmem_bulk_copy(B_hi + dst_off, stg_hi, slice_bytes, &h_full, d);
-                    dsmem_bulk_copy(B_lo + dst_off, stg_lo, slice_bytes, &h_full, d);
-                }
-            }
+            fence_proxy_async_smem();      // staged slice -> visible to the bulk-copy engine
             __syncwarp();
+            if (lane == 0) mbar_arrive(&staged[g]);
         }
     }
 
-    // drain: the last step's copies still target peers; nobody may exit before they have landed
-    if (Tmax > 0 && warp == 0 && elect_one()) mbar_wait_cluster(&h_full, (uint32_t)(Tmax - 1) & 1u);
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-using GruTc256 = GruTcCfg<256, 8>;
+using GruTc256 = RnnTcCfg<256, 8, 3>;
+using LstmTc256 = RnnTcCfg<256, 8, 4>;
 
 }  // namespace ffb
 
 // ---------------------------------------------------------------------------------------
-int ffb_rnn_tc_supported(int kind, int S) { return kind == 0 && S == 256; }
-int ffb_rnn_tc_rmax(int kind, int S) { (void)kind; (void)S; return ffb::GruTc256::RMAX; }
+int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && S == 256; }
+int ffb_rnn_tc_rmax(int kind, int S) { (void)kind; (void)S; return ffb::GruTc256::GMAX * ffb::GruTc256::NG; }
 
 size_t ffb_rnn_tc_image_halfs(int kind, int S) {
-    (void)kind; (void)S;
-    return (size_t)ffb::GruTc256::C * 2 * ffb::GruTc256::A_PLANE / 2;
+    (void)S;
+    return kind == 0 ? (size_t)ffb::GruTc256::C * 2 * ffb::GruTc256::A_PLANE / 2 : (size_t)ffb::LstmTc256::C * 2 * ffb::LstmTc256::A_PLANE / 2;
 }
 
-// sW [3S][S] (row per output) -> per-CTA shared-memory images (fp16 bit patterns):
-// [cta][plane hi/lo][k-group][row group rg = 4*quad + gate (3 = zero pad)][row e][8 halfs]
-void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img) {
-    (void)kind;
-    using Cfg = ffb::GruTc256;
+size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R) {
+    (void)S;
+    const int G = R / 16;
+    return kind == 0 ? ffb::GruTc256::ring_bytes(n_clusters, G) : ffb::LstmTc256::ring_bytes(n_clusters, G);
+}
+
+// sW [G*S][S] (row per output) -> per-CTA shared-memory images (fp16 bit patterns):
+// [cta][plane hi/lo][k-group][row group rg = 4*quad + gate][row e][8 halfs]
+template <class Cfg>
+static void pack_image(const float *sW, uint16_t *img) {
+    constexpr int S = Cfg::S;
     const size_t plane_halfs = Cfg::A_PLANE / 2;
     for (size_t i = 0; i < (size_t)Cfg::C * 2 * plane_halfs; i++) img[i] = 0;
     for (int c = 0; c < Cfg::C; c++) {
         uint16_t *hi = img + (size_t)c * 2 * plane_halfs, *lo = hi + plane_halfs;
         for (int kg = 0; kg < Cfg::KG; kg++)
-            for (int q = 0; q < 4; q++)
-                for (int g = 0; g < 3; g++)
+            for (int q = 0; q < Cfg::NQ; q++)
+                for (int g = 0; g < Cfg::NGATE; g++)
                     for (int e = 0; e < 8; e++)
                         for (int x = 0; x < 8; x++) {
                             const int jj = c * Cfg::HS + q * 8 + e;
@@ -301,20 +378,27 @@ void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img) {
                         }
     }
 }
-
-int ffb_rnn_tc_prepare(int kind, int S) {
-    if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    using Cfg = ffb::GruTc256;
-    if (cudaFuncSetAttribute(ffb::gru_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes(Cfg::RMAX)) != cudaSuccess) return -1;
-    return 0;
+void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img) {
+    (void)S;
+    if (kind == 0) pack_image<ffb::GruTc256>(sW, img); else pack_image<ffb::LstmTc256>(sW, img);
 }
 
-static void rnn_tc_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, int n_clusters, int R, cudaStream_t st) {
-    using Cfg = ffb::GruTc256;
+template <class Cfg>
+static int prepare_one() {
+    return cudaFuncSetAttribute(ffb::rnn_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)Cfg::smem_bytes(Cfg::GMAX)) == cudaSuccess ? 0 : -1;
+}
+int ffb_rnn_tc_prepare(int kind, int S) {
+    if (!ffb_rnn_tc_supported(kind, S)) return -1;
+    return kind == 0 ? prepare_one<ffb::GruTc256>() : prepare_one<ffb::LstmTc256>();
+}
+
+template <class Cfg>
+static void rnn_tc_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, int n_clusters, int G, cudaStream_t st) {
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3(n_clusters * Cfg::C);
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::smem_bytes(R);
+    cfg.blockDim = dim3(G * Cfg::WARPS_PER_GROUP * 32);
+    cfg.dynamicSmemBytes = Cfg::smem_bytes(G);
     cfg.stream = st;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = Cfg::C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -322,25 +406,37 @@ static void rnn_tc_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, in
 }
 
 // how many clusters of this kernel can be co-resident (0 on error)
-int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
-    if (!ffb_rnn_tc_supported(kind, S)) return 0;
+template <class Cfg>
+static int max_clusters_one(int G) {
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-    rnn_tc_config(cfg, attr, 64, R, 0);
+    rnn_tc_config<Cfg>(cfg, attr, 64, G, 0);
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, ffb::gru_tc_kernel<ffb::GruTc256>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, ffb::rnn_tc_kernel<Cfg>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
+    if (!ffb_rnn_tc_supported(kind, S)) return 0;
+    const int G = R / 16;
+    return kind == 0 ? max_clusters_one<ffb::GruTc256>(G) : max_clusters_one<ffb::LstmTc256>(G);
+}
 
-int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
-                      const RnnBatch &rb, int R, int backward, cudaStream_t st) {
-    if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    using Cfg = ffb::GruTc256;
-    if (R < 16 || R > Cfg::RMAX || R % 16 || rb.n_slots % R) return -1;
+template <class Cfg>
+static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo, const RnnBatch &rb, int R,
+                      int backward, void *ring, cudaStream_t st) {
+    const int G = R / Cfg::NG;
+    if (G < 1 || G > Cfg::GMAX || R % Cfg::NG || rb.n_slots % R || !ring) return -1;
     const int n_clusters = rb.n_slots / R;
     if (n_clusters == 0) return 0;
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-    rnn_tc_config(cfg, attr, n_clusters, R, st);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::gru_tc_kernel<Cfg>, Xin, (const __half *)Wimg, Hout, (__half *)Hhi,
-                                       (__half *)Hlo, rb.order, rb.blk_off, R, backward);
+    rnn_tc_config<Cfg>(cfg, attr, n_clusters, G, st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::rnn_tc_kernel<Cfg>, Xin, (const __half *)Wimg, Hout, (__half *)Hhi,
+                                       (__half *)Hlo, rb.order, rb.blk_off, (uint8_t *)ring, G, backward);
     return e == cudaSuccess ? 1 : -1;
+}
+
+int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
+                      const RnnBatch &rb, int R, int backward, void *ring, cudaStream_t st) {
+    if (!ffb_rnn_tc_supported(kind, S)) return -1;
+    return kind == 0 ? launch_one<ffb::GruTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, st)
+                     : launch_one<ffb::LstmTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, st);
 }

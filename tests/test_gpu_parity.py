@@ -88,7 +88,8 @@ MODELS = [
     ("gru96_4b", KIND_GRU, 96, 4),
     ("lstm96_4b", KIND_LSTM, 96, 4),
     ("lstm128_4b", KIND_LSTM, 128, 4),
-    ("gru256_4b", KIND_GRU, 256, 4),     # the shape with the tcgen05 recurrent kernel
+    ("gru256_4b", KIND_GRU, 256, 4),     # the shapes with the tcgen05 recurrent kernel
+    ("lstm256_4b", KIND_LSTM, 256, 4),
 ]
 
 

@@ -80,7 +80,8 @@ def test_network_golden(oracle, name):
     g = gold(f"net_{name}.npz")
     fm = FlipflopModel.synthetic(int(g["kind"]), int(g["size"]), int(g["nbase"]), seed=int(g["seed"]))
     trans, conv, layers = oracle.transitions(fm, g["signal"], 1.0, want_layers=True)
-    assert np.max(np.abs(conv - g["conv"].astype(np.float32))) < 2e-3      # stored as fp16
+    gc = g["conv"].astype(np.float32)                                     # stored as fp16: 2^-11 relative (swish is unbounded)
+    assert np.max(np.abs(conv - gc) / np.maximum(1.0, np.abs(gc))) < 2e-3
     assert np.max(np.abs(layers[0] - g["layer1"].astype(np.float32))) < 2e-3
     assert np.max(np.abs(layers[4] - g["layer5"])) < 2e-5
     assert np.max(np.abs(trans - g["trans"])) < 1e-4
