@@ -43,7 +43,7 @@ __global__ void split_f16_kernel(const float *__restrict__ x, __half *__restrict
 // Validates the descriptor conventions the recurrent tensor kernel relies on
 // (LBO = rows*16 B between k-groups, SBO = 128 B between 8-row groups).
 __global__ void __launch_bounds__(128)
-umma_probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, float *__restrict__ D, int N, int K) {
+umma_probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, float *__restrict__ D, int N, int K, int a_in_tmem) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -59,18 +59,33 @@ umma_probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, fl
         *reinterpret_cast<uint4 *>(Bs + (size_t)kg * N * 16 + r * 16) = *reinterpret_cast<const uint4 *>(B + (size_t)r * K + kg * 8);
     }
     if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
     fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = tmem_slot;
+    const uint32_t tmem_a = tmem + 256;            // A operand in tensor memory: row = lane, column c = halfs (2c, 2c+1)
+    if (a_in_tmem) {
+        const __half *arow = A + (size_t)(warp * 32 + lane) * K;
+        for (int c = 0; c < K / 2; c += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = *reinterpret_cast<const uint32_t *>(arow + 2 * (c + j));
+            tmem_st8(tmem_a + ((uint32_t)(warp * 32) << 16) + c, v);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+    }
     if (warp == 1 && elect_one()) {
         const uint32_t idesc = make_idesc_f16(128, N);
         for (int ks = 0; ks < K / 16; ks++) {
             const uint64_t ad = make_smem_desc(smem_u32(As) + ks * 2 * 128 * 16, 128 * 16, 128, LAYOUT_NONE);
             const uint64_t bd = make_smem_desc(smem_u32(Bs) + ks * 2 * N * 16, N * 16, 128, LAYOUT_NONE);
-            umma_f16(tmem, ad, bd, idesc, ks > 0);
+            if (a_in_tmem) umma_f16_ts(tmem, tmem_a + ks * 8, bd, idesc, ks > 0);
+            else umma_f16(tmem, ad, bd, idesc, ks > 0);
         }
         umma_commit(&bar);
     }
@@ -85,7 +100,7 @@ umma_probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, fl
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -299,9 +314,9 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
     return launch_gemm_tc<64>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
 }
 
-int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, cudaStream_t st) {
+int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, int a_in_tmem, cudaStream_t st) {
     const size_t smem = (size_t)(K / 8) * (128 + N) * 16;
     if (cudaFuncSetAttribute(ffb::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    ffb::umma_probe_kernel<<<1, 128, smem, st>>>((const __half *)A, (const __half *)B, D, N, K);
+    ffb::umma_probe_kernel<<<1, 128, smem, st>>>((const __half *)A, (const __half *)B, D, N, K, a_in_tmem);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -8,9 +8,12 @@
 // Per group and step the CTA computes
 //       a[gate g, hidden j][read] = sum_k sW[g*S + j][k] * h_{t-1}[read][k]
 // as one M=128 x N=16 x K=S tensor-core GEMM:
-//   A = the CTA's slice of sW, RESIDENT in shared memory for all T steps (fp16 hi/lo planes,
-//       no-swizzle K-major).  TMEM lane quadrant q holds, for the 8 hidden units 8q..8q+7,
-//       lanes [0,8) = gate 0, [8,16) = gate 1, [16,24) = gate 2, [24,32) = gate 3 (GRU: unused),
+//   A = the CTA's slice of sW, RESIDENT IN TENSOR MEMORY for all T steps (fp16 hi/lo planes,
+//       2 x 128 of the 512 TMEM columns; row = lane).  With A in shared memory every MMA re-reads
+//       128 rows x 32 B = 4 KB of it (32 clk at 128 B/clk) whatever N is, which made the N=16
+//       MMAs 4x slower than the tensor pipe; from TMEM they run at the pipe rate (8 clk).
+//       Row order: TMEM lane quadrant q holds, for the 8 hidden units 8q..8q+7,
+//       lanes [0,8) = gate 0, [8,16) = gate 1, [16,24) = gate 2, [24,32) = gate 3 (GRU: zero),
 //       so a 16-lane x 256-bit tcgen05.ld hands every thread two gates of the SAME cell and the
 //       gate arithmetic needs no shuffles.
 //   B = the previous state of the group's 16 reads, [k-group][plane hi/lo][read][8 halfs],
@@ -56,19 +59,20 @@ struct RnnTcCfg {
     static constexpr int KG = S / 8;                  // 16-byte k-groups along K
     static constexpr int NG = 16;                     // reads per group (MMA N)
     static constexpr int GMAX = 5;                    // groups per cluster
-    static constexpr int A_RG = (NGATE == 3) ? 15 : 16;   // 8-row groups stored per k-group (GRU: the 16th is padding, aliased)
-    static constexpr int LBO_A = A_RG * 128;          // bytes between k-groups of A
-    static constexpr int A_PLANE = KG * LBO_A;        // bytes per A plane
-    static constexpr int A_BYTES = 2 * A_PLANE + 128; // + the aliased 16th row group of the last k-group
+    static constexpr int A_COLS = S / 2;              // TMEM columns of one A plane (two halfs per 32-bit column)
+    static constexpr int A_PLANE = 128 * S * 2;       // bytes of one plane of the global weight image [128 rows][S halfs]
     static constexpr int LBO_B = 2 * NG * 16;         // bytes between k-groups of B (hi and lo planes interleaved)
     static constexpr int B_GROUP = KG * LBO_B;        // bytes of one group's B operand
     static constexpr int SLICE = NQ * LBO_B;          // bytes of one CTA's slice of one group's state
     static constexpr int ACC_COLS = 3 * NG;           // TMEM columns per group
+    static constexpr int ACC_COL0 = 2 * A_COLS;       // accumulators follow the two A planes
+    static constexpr int TMEM_COLS = 512;
     static constexpr int WARPS_PER_GROUP = 5;         // 4 gate warps + 1 control warp
     static constexpr int MAX_THREADS = GMAX * WARPS_PER_GROUP * 32;
     static_assert(HS == 32, "four quadrants of 8 hidden units");
+    static_assert(ACC_COL0 + GMAX * ACC_COLS <= TMEM_COLS, "tensor memory budget");
     __host__ __device__ static constexpr size_t smem_bytes(int G) {
-        return (size_t)A_BYTES + (size_t)G * (B_GROUP + SLICE) + 64;
+        return (size_t)G * (B_GROUP + SLICE) + 64;
     }
     __host__ __device__ static constexpr size_t ring_bytes(int n_clusters, int G) {
         return (size_t)n_clusters * 2 * G * C * SLICE;
@@ -129,9 +133,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
     __shared__ uint32_t tmem_slot;
 
-    uint8_t *A_hi = smem;
-    uint8_t *A_lo = A_hi + Cfg::A_PLANE;
-    uint8_t *B_base = smem + Cfg::A_BYTES;                       // [G][KG][hi|lo][NG][16 B]
+    uint8_t *B_base = smem;                                      // [G][KG][hi|lo][NG][16 B]
     uint8_t *stg_base = B_base + (size_t)G * Cfg::B_GROUP;       // [G][NQ][hi|lo][NG][16 B]
 
     const uint32_t crank = cluster_ctarank();
@@ -142,11 +144,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 
     // ---- one-time setup ----
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(Wimg) + (size_t)crank * (2 * Cfg::A_PLANE / 16);
-        uint4 *dst = reinterpret_cast<uint4 *>(A_hi);
-        for (int i = tid; i < 2 * Cfg::A_PLANE / 16; i += nthreads) dst[i] = src[i];
-        uint4 *bz = reinterpret_cast<uint4 *>(A_lo + Cfg::A_PLANE);   // the 128-byte tail + B: h_{-1} = 0
-        for (int i = tid; i < (int)((128 + (size_t)G * Cfg::B_GROUP) / 16); i += nthreads) bz[i] = make_uint4(0, 0, 0, 0);
+        uint4 *bz = reinterpret_cast<uint4 *>(B_base);            // h_{-1} = 0
+        for (int i = tid; i < (int)(((size_t)G * Cfg::B_GROUP) / 16); i += nthreads) bz[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
         for (int g = 0; g < G; g++) {
@@ -157,13 +156,32 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         }
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc(&tmem_slot, 256);
-    fence_proxy_async_smem();       // A / zeroed B were written through the generic proxy
+    if (warp == 0) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+    fence_proxy_async_smem();       // zeroed B was written through the generic proxy
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp < 4) {
+        // weight slice -> tensor memory: this thread owns TMEM lane 32*warp + lane = row of the image
+        const uint4 *src = reinterpret_cast<const uint4 *>(Wimg) + ((size_t)crank * 2 * Cfg::A_PLANE + (size_t)(warp * 32 + lane) * S * 2) / 16;
+#pragma unroll 1
+        for (int plane = 0; plane < 2; plane++) {
+            const uint4 *row = src + (size_t)plane * (Cfg::A_PLANE / 16);
+            const uint32_t tdst = tmem + ((uint32_t)(warp * 32) << 16) + plane * Cfg::A_COLS;
+#pragma unroll 4
+            for (int c = 0; c < Cfg::A_COLS; c += 8) {
+                const uint4 v0 = row[c / 4], v1 = row[c / 4 + 1];
+                const uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                tmem_st8(tdst + c, v);
+            }
+        }
+        tmem_st_wait();
+    }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     cluster_sync_all();             // every CTA's barriers are initialised before any remote arrive / copy
-    const uint32_t tmem = tmem_slot;
 
     const int g = (warp < 4 * G) ? (warp >> 2) : (warp - 4 * G);    // this warp's group
     // slots are sorted by length (descending): the group's first slot is its longest read
@@ -174,14 +192,13 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     }
     uint8_t *Bg = B_base + (size_t)g * Cfg::B_GROUP;
     uint8_t *stg = stg_base + (size_t)g * Cfg::SLICE;
-    const uint32_t acc = tmem + (uint32_t)g * Cfg::ACC_COLS;
+    const uint32_t acc = tmem + Cfg::ACC_COL0 + (uint32_t)g * Cfg::ACC_COLS;
 
     if (warp >= 4 * G) {
         // =========================== control warp of group g ===========================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_f16(128, NG);
-            const uint64_t dA_hi = make_smem_desc(smem_u32(A_hi), Cfg::LBO_A, 128, LAYOUT_NONE);
-            const uint64_t dA_lo = make_smem_desc(smem_u32(A_lo), Cfg::LBO_A, 128, LAYOUT_NONE);
+            const uint32_t tA_hi = tmem, tA_lo = tmem + Cfg::A_COLS;
             const uint64_t dB_hi = make_smem_desc(smem_u32(Bg), Cfg::LBO_B, 128, LAYOUT_NONE);
             const uint64_t dB_lo = make_smem_desc(smem_u32(Bg) + NG * 16, Cfg::LBO_B, 128, LAYOUT_NONE);
             uint8_t *ring_g = ring + ((((size_t)cluster_id * 2) * G + g) * C + crank) * Cfg::SLICE;   // parity 0
@@ -193,11 +210,12 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 tcgen05_fence_after();
 #pragma unroll 4
                 for (int ks = 0; ks < S / 16; ks++) {
-                    const uint64_t oa = (uint64_t)((ks * 2 * Cfg::LBO_A) >> 4), ob = (uint64_t)((ks * 2 * Cfg::LBO_B) >> 4);
+                    const uint32_t oa = (uint32_t)ks * 8;                                    // 16 halfs = 8 TMEM columns
+                    const uint64_t ob = (uint64_t)((ks * 2 * Cfg::LBO_B) >> 4);
                     const int kh = ks / (S / 32);                                            // K-half
-                    umma_f16(acc + kh * NG, dA_hi + oa, dB_hi + ob, idesc, (ks % (S / 32)) != 0);   // hi*hi
-                    umma_f16(acc + 2 * NG, dA_hi + oa, dB_lo + ob, idesc, ks != 0);                 // cross terms
-                    umma_f16(acc + 2 * NG, dA_lo + oa, dB_hi + ob, idesc, 1);
+                    umma_f16_ts(acc + kh * NG, tA_hi + oa, dB_hi + ob, idesc, (ks % (S / 32)) != 0);   // hi*hi
+                    umma_f16_ts(acc + 2 * NG, tA_hi + oa, dB_lo + ob, idesc, ks != 0);                 // cross terms
+                    umma_f16_ts(acc + 2 * NG, tA_lo + oa, dB_hi + ob, idesc, 1);
                 }
                 umma_commit(&acc_full[g]);
                 mbar_wait(&acc_full[g], ph);
@@ -330,7 +348,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }
 
 using GruTc256 = RnnTcCfg<256, 8, 3>;
@@ -353,8 +371,8 @@ size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R) {
     return kind == 0 ? ffb::GruTc256::ring_bytes(n_clusters, G) : ffb::LstmTc256::ring_bytes(n_clusters, G);
 }
 
-// sW [G*S][S] (row per output) -> per-CTA shared-memory images (fp16 bit patterns):
-// [cta][plane hi/lo][k-group][row group rg = 4*quad + gate][row e][8 halfs]
+// sW [G*S][S] (row per output) -> per-CTA tensor-memory images (fp16 bit patterns):
+// [cta][plane hi/lo][row = 32*quad + 8*gate + e][S halfs]; GRU rows with gate 3 are zero
 template <class Cfg>
 static void pack_image(const float *sW, uint16_t *img) {
     constexpr int S = Cfg::S;
@@ -362,20 +380,18 @@ static void pack_image(const float *sW, uint16_t *img) {
     for (size_t i = 0; i < (size_t)Cfg::C * 2 * plane_halfs; i++) img[i] = 0;
     for (int c = 0; c < Cfg::C; c++) {
         uint16_t *hi = img + (size_t)c * 2 * plane_halfs, *lo = hi + plane_halfs;
-        for (int kg = 0; kg < Cfg::KG; kg++)
-            for (int q = 0; q < Cfg::NQ; q++)
-                for (int g = 0; g < Cfg::NGATE; g++)
-                    for (int e = 0; e < 8; e++)
-                        for (int x = 0; x < 8; x++) {
-                            const int jj = c * Cfg::HS + q * 8 + e;
-                            const float w = sW[(size_t)(g * S + jj) * S + kg * 8 + x];
-                            const __half h = __float2half_rn(w);
-                            const __half l = __float2half_rn(w - __half2float(h));
-                            const int rg = 4 * q + g;
-                            const size_t off = ((size_t)kg * Cfg::LBO_A + rg * 128 + e * 16) / 2 + x;
-                            hi[off] = __half_as_ushort(h);
-                            lo[off] = __half_as_ushort(l);
-                        }
+        for (int q = 0; q < Cfg::NQ; q++)
+            for (int g = 0; g < Cfg::NGATE; g++)
+                for (int e = 0; e < 8; e++) {
+                    const int jj = c * Cfg::HS + q * 8 + e, row = 32 * q + 8 * g + e;
+                    for (int k = 0; k < S; k++) {
+                        const float w = sW[(size_t)(g * S + jj) * S + k];
+                        const __half h = __float2half_rn(w);
+                        const __half l = __float2half_rn(w - __half2float(h));
+                        hi[(size_t)row * S + k] = __half_as_ushort(h);
+                        lo[(size_t)row * S + k] = __half_as_ushort(l);
+                    }
+                }
     }
 }
 void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img) {

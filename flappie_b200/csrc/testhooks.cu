@@ -6,21 +6,26 @@
 
 #include "ffb_common.cuh"
 
-int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, cudaStream_t st);
+int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, int a_in_tmem, cudaStream_t st);
 int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st);
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                        int64_t M, int N, int K, cudaStream_t st);
 
 #define TRY(x) do { if ((x) != cudaSuccess) { fprintf(stderr, "testhook: %s failed: %s\n", #x, cudaGetErrorString(cudaGetLastError())); return -1; } } while (0)
 
+extern "C" int ffb_test_umma_probe2(const uint16_t *A, const uint16_t *B, float *D, int N, int K, int a_in_tmem);
 // A [128][K] fp16 bits, B [N][K] fp16 bits -> D [128][N] fp32
 extern "C" int ffb_test_umma_probe(const uint16_t *A, const uint16_t *B, float *D, int N, int K) {
+    return ffb_test_umma_probe2(A, B, D, N, K, 0);
+}
+// a_in_tmem = 1: A operand staged in tensor memory with tcgen05.st (the recurrent kernel's weights)
+extern "C" int ffb_test_umma_probe2(const uint16_t *A, const uint16_t *B, float *D, int N, int K, int a_in_tmem) {
     void *dA, *dB; float *dD;
     TRY(cudaMalloc(&dA, 128 * K * 2)); TRY(cudaMalloc(&dB, (size_t)N * K * 2)); TRY(cudaMalloc(&dD, 128 * (size_t)N * 4));
     TRY(cudaMemcpy(dA, A, 128 * K * 2, cudaMemcpyHostToDevice));
     TRY(cudaMemcpy(dB, B, (size_t)N * K * 2, cudaMemcpyHostToDevice));
     TRY(cudaMemset(dD, 0, 128 * (size_t)N * 4));
-    if (ffb_launch_umma_probe(dA, dB, dD, N, K, 0) < 0) return -2;
+    if (ffb_launch_umma_probe(dA, dB, dD, N, K, a_in_tmem, 0) < 0) return -2;
     TRY(cudaDeviceSynchronize());
     TRY(cudaMemcpy(D, dD, 128 * (size_t)N * 4, cudaMemcpyDeviceToHost));
     cudaFree(dA); cudaFree(dB); cudaFree(dD);

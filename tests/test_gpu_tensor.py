@@ -13,6 +13,8 @@ def _hooks(gpu_lib):
     L = gpu_lib.lib
     L.ffb_test_umma_probe.restype = c_int
     L.ffb_test_umma_probe.argtypes = [POINTER(c_uint16), POINTER(c_uint16), POINTER(c_float), c_int, c_int]
+    L.ffb_test_umma_probe2.restype = c_int
+    L.ffb_test_umma_probe2.argtypes = [POINTER(c_uint16), POINTER(c_uint16), POINTER(c_float), c_int, c_int, c_int]
     L.ffb_test_gemm.restype = c_int
     L.ffb_test_gemm.argtypes = [POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float), c_int64, c_int,
                                 c_int, c_int, POINTER(c_float)]
@@ -29,6 +31,23 @@ def test_umma_probe_noswizzle(gpu_lib, N, K):
     r = L.ffb_test_umma_probe(A.view(np.uint16).ctypes.data_as(POINTER(c_uint16)),
                               B.view(np.uint16).ctypes.data_as(POINTER(c_uint16)),
                               D.ctypes.data_as(POINTER(c_float)), N, K)
+    assert r == 0
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    assert np.max(np.abs(D - ref)) < 1e-4 * max(1.0, K / 64)
+
+
+@pytest.mark.parametrize("N,K", [(16, 16), (16, 256), (80, 64), (48, 256)])
+def test_umma_probe_a_in_tmem(gpu_lib, N, K):
+    """A operand resident in tensor memory (tcgen05.st, lane = row, column c = halfs 2c, 2c+1):
+    the layout the recurrent kernel keeps its weight slice in."""
+    L = _hooks(gpu_lib)
+    rng = np.random.default_rng(3 * N + K)
+    A = rng.uniform(-1, 1, (128, K)).astype(np.float16)
+    B = rng.uniform(-1, 1, (N, K)).astype(np.float16)
+    D = np.zeros((128, N), np.float32)
+    r = L.ffb_test_umma_probe2(A.view(np.uint16).ctypes.data_as(POINTER(c_uint16)),
+                               B.view(np.uint16).ctypes.data_as(POINTER(c_uint16)),
+                               D.ctypes.data_as(POINTER(c_float)), N, K, 1)
     assert r == 0
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     assert np.max(np.abs(D - ref)) < 1e-4 * max(1.0, K / 64)
