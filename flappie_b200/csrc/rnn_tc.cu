@@ -225,7 +225,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 uint8_t *rg = ring_g + (size_t)ph * ring_par;
                 bulk_store_global(rg, stg, Cfg::SLICE);
                 mbar_wait(&h_empty[g], ph);                           // every peer has consumed h_{s-1}
-                asm volatile("fence.proxy.async;" ::: "memory");
+                // no proxy fence: the ring was written by the async proxy (bulk store, completed by
+                // wait_group) and is read by the async proxy
                 bulk_load_multicast(Bg + crank * Cfg::SLICE, rg, Cfg::SLICE, &h_full[g], (uint16_t)((1u << C) - 1u));
             }
             // drain: the last step's copies still target this CTA; nobody may exit before they have landed
