@@ -18,6 +18,7 @@
 // Tile order is n-fastest so the n-tiles of one 128-row slab run concurrently and the slab is
 // read from HBM once.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "ffb_common.cuh"
 #include "tc_common.cuh"
@@ -242,6 +243,177 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// W-stationary variant (K <= 256, N % 128 == 0): the layout the hot layers run.
+//
+// What bounded gemm_tc_kernel above (profiles/r01_gemm_tc_v1_ncu_summary.txt: 4.3 ms, tensor pipe
+// 25 % busy): (1) one 16-byte store per thread per ROW of the tile -- 32 lines per store
+// instruction, ~27k clk of LSU time per tile; (2) BN=256 leaves no TMEM for a second accumulator,
+// so MMAs and epilogue alternate; (3) ~18 GB per launch through L2 (both operand tiles re-read).
+//
+// Here the CTA keeps ONE 128-row panel of iW (fp16 hi/lo) in tensor memory for the whole launch
+// (loaded once with tcgen05.st) and uses it as the MMA's A operand, so the product is computed
+// transposed, D[feature 128][block 64]: shared memory holds only the streamed activation tiles
+// (6 x 16 KB ring), the MMA needs no A fetch (N=64 at pipe rate), accumulators are double
+// buffered in the other half of TMEM, and the epilogue -- thread = feature -- writes its column
+// into a [block][feature] staging tile without bank conflicts, which is then stored as full
+// 512-byte rows.  CTAs are dealt panel = blockIdx % (N/128) with equal strides so the N/128
+// CTAs working on one activation tile run in step and the tile is read from HBM once.
+struct GemmWsCfg {
+    static constexpr int BF = 128;                 // features per panel (MMA M)
+    static constexpr int BB = 64;                  // blocks per tile (MMA N)
+    static constexpr int BK = 64;                  // K per pipeline stage
+    static constexpr int STAGE_BYTES = 2 * BB * BK * 2;   // hi + lo
+    static constexpr int STAGES = 6;
+    static constexpr int STG_BYTES = BB * BF * 4;  // fp32 staging tile [block][feature]
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STG_BYTES + 1024;
+    static constexpr int THREADS = 192;
+    static constexpr int KMAX = 256;
+    static constexpr int ACC_COL0 = KMAX;          // W planes: K/2 columns each, at 0 and KMAX/2
+};
+
+__global__ void __launch_bounds__(GemmWsCfg::THREADS, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+               const __half *__restrict__ Whi, const __half *__restrict__ Wlo, const float *__restrict__ bias,
+               float *__restrict__ C, int64_t M, int N, int K) {
+    using Cfg = GemmWsCfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *stg_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    __shared__ uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_panels = N / Cfg::BF;
+    const int panel = blockIdx.x % n_panels;
+    const int64_t first = blockIdx.x / n_panels, stride = gridDim.x / n_panels;   // host: gridDim % n_panels == 0
+    const int64_t n_tiles = (M + Cfg::BB - 1) / Cfg::BB;
+    const int nk = K / Cfg::BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapAlo); }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp >= 2) {
+        // panel -> tensor memory: this thread owns lane 32*quad + lane = feature row of the panel
+        const int quad = warp & 3;
+        const size_t row = (size_t)panel * Cfg::BF + quad * 32 + lane;
+#pragma unroll 1
+        for (int plane = 0; plane < 2; plane++) {
+            const uint4 *src = reinterpret_cast<const uint4 *>((plane ? Wlo : Whi) + row * K);
+            const uint32_t tdst = tmem + ((uint32_t)(quad * 32) << 16) + plane * (Cfg::KMAX / 2);
+            for (int c = 0; c < K / 2; c += 8) {
+                const uint4 v0 = src[c / 4], v1 = src[c / 4 + 1];
+                const uint32_t v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                tmem_st8(tdst + c, v);
+            }
+        }
+        tmem_st_wait();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+
+    if (warp == 0) {
+        // ===== TMA producer: activation tiles [64 blocks][64 K] hi / lo =====
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t tile = first; tile < n_tiles; tile += stride) {
+                const int m0 = (int)(tile * Cfg::BB);
+                for (int kc = 0; kc < nk; kc++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *st = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(st, &mapAhi, &full_bar[stage], kc * Cfg::BK, m0);
+                    tma_load_2d(st + Cfg::STAGE_BYTES / 2, &mapAlo, &full_bar[stage], kc * Cfg::BK, m0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D[feature][block] (+)= W_panel (TMEM) * act_tile^T (smem) =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_f16(Cfg::BF, Cfg::BB);
+            const uint32_t w_hi = tmem, w_lo = tmem + Cfg::KMAX / 2;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t tile = first; tile < n_tiles; tile += stride) {
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d = tmem + Cfg::ACC_COL0 + acc * 2 * Cfg::BB, dx = d + Cfg::BB;
+                for (int kc = 0; kc < nk; kc++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t b_hi = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES), b_lo = b_hi + Cfg::STAGE_BYTES / 2;
+#pragma unroll
+                    for (int k4 = 0; k4 < Cfg::BK / 16; k4++) {
+                        const uint32_t ko = k4 * 32;   // 16 halfs = 32 bytes along the swizzled row
+                        const uint32_t wo = (uint32_t)(kc * Cfg::BK + k4 * 16) / 2;   // TMEM column of these 16 halfs
+                        const uint64_t dbh = make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128);
+                        const uint64_t dbl = make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128);
+                        umma_f16_ts(d, w_hi + wo, dbh, idesc, (kc | k4) != 0);    // hi*hi
+                        umma_f16_ts(dx, w_hi + wo, dbl, idesc, (kc | k4) != 0);   // cross terms
+                        umma_f16_ts(dx, w_lo + wo, dbh, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
+                    if (kc == nk - 1) umma_commit(&acc_full[acc]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 -> TMEM lane quadrants (warp % 4); thread = feature =====
+        const int quad = warp & 3;
+        const int f = quad * 32 + lane;                     // feature within the panel
+        const float b = bias[panel * Cfg::BF + f];
+        const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t tile = first; tile < n_tiles; tile += stride) {
+            float *stg = reinterpret_cast<float *>(stg_base + (size_t)acc * Cfg::STG_BYTES);
+            mbar_wait(&acc_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + Cfg::ACC_COL0 + acc * 2 * Cfg::BB;
+#pragma unroll
+            for (int c = 0; c < Cfg::BB; c += 16) {
+                float v[16], vx[16];
+                tmem_ld16(taddr + c, v);
+                tmem_ld16(taddr + Cfg::BB + c, vx);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j++) stg[(c + j) * Cfg::BF + f] = (v[j] + vx[j]) + b;
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);    // accumulator drained: the next tile's MMAs may start
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile complete (epilogue warps only)
+            // full rows: 128 features = 512 B = one warp-wide float4 store
+            const int64_t m0 = tile * Cfg::BB;
+#pragma unroll 4
+            for (int r = et >> 5; r < Cfg::BB; r += 4) {
+                if (m0 + r < M) {
+                    const float4 v = *reinterpret_cast<const float4 *>(stg + r * Cfg::BF + lane * 4);
+                    __stcs(reinterpret_cast<float4 *>(C + (m0 + r) * (int64_t)N + panel * Cfg::BF + lane * 4), v);
+                }
+            }
+            // the staging buffer is reused two tiles later; the bar.sync of the next tile orders these reads
+            // before any thread can reach the writes of the tile after it
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace ffb
 
 // ---------------------------------------------------------------------------------------
@@ -304,11 +476,36 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                          int64_t M, int N, int K, cudaStream_t st) {
+    using Cfg = ffb::GemmWsCfg;
+    CUtensorMap mAh, mAl;
+    if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, Cfg::BB) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, Cfg::BB)) return -1;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(ffb::gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+        attr_done = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_panels = N / Cfg::BF;
+    const int64_t n_tiles = (M + Cfg::BB - 1) / Cfg::BB;
+    int64_t per_panel = sms / n_panels;
+    if (per_panel < 1) per_panel = 1;
+    if (per_panel > n_tiles) per_panel = n_tiles;
+    ffb::gemm_ws_kernel<<<(unsigned)(per_panel * n_panels), Cfg::THREADS, Cfg::SMEM, st>>>(
+        mAh, mAl, (const __half *)Whi, (const __half *)Wlo, bias, C, M, N, K);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 // A planes [M][K] fp16, W planes [N][K] fp16 (the reference's own [out][in] orientation)
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                        int64_t M, int N, int K, cudaStream_t st) {
     if (M <= 0) return 0;
     if (!ffb_gemm_tc_supported(N, K)) return -1;
+    if (N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX && getenv("FFB_GEMM_V1") == nullptr)
+        return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 256 == 0) return launch_gemm_tc<256>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 128 == 0) return launch_gemm_tc<128>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     return launch_gemm_tc<64>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
