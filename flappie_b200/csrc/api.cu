@@ -348,6 +348,11 @@ struct ffb_ctx {
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
     DevBuf d_ahi, d_alo;          // fp16 hi/lo planes of the current layer input (tensor path)
     DevBuf d_ring;                // state-exchange ring of the tensor recurrent kernel (L2-resident)
+    // streamed input GEMMs: layer l+1's projection runs on the SMs layer l's recurrence leaves free and consumes
+    // its output planes tile by tile (tile order + dependencies per production direction: 0 = forward, 1 = backward)
+    DevBuf d_xin2, d_tile_order[2], d_tile_dep[2], d_progress;
+    bool stream_gemm = false;
+    int n_groups = 0;
     float *last_conv = nullptr;   // device pointer of last conv output within d_act/d_c
     cudaEvent_t ev[8] = {nullptr};
     float t_gemm_ms = 0.f, t_rnn_ms = 0.f;
@@ -378,7 +383,8 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
-                     &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring};
+                     &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_tile_order[0], &c->d_tile_order[1],
+                     &c->d_tile_dep[0], &c->d_tile_dep[1], &c->d_progress};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -478,8 +484,65 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
         std::copy(idx.begin(), idx.end(), c->order.begin());
     }
 
-    // ---- device workspaces ----
+    // ---- streamed GEMM plan: when may each tile of the next layer's input be loaded? ----
     const int64_t Tt = c->total_blocks, S = m->S, G = m->G, nr = m->nparam;
+    std::vector<int32_t> tile_order[2];
+    std::vector<GemmTileDep> tile_dep[2];
+    c->stream_gemm = c->use_tc_rnn && !(c->flags & FFB_FLAG_KEEP_LAYERS) && getenv("FFB_NO_STREAM_GEMM") == nullptr &&
+                     ffb_gemm_tc_stream_supported((int)(G * S), (int)S) && Tt > 0;
+    if (c->stream_gemm) {
+        const int R16 = 16, P = FFB_RNN_PUBLISH_PERIOD;
+        c->n_groups = c->n_slots / R16;
+        std::vector<int32_t> group_of((size_t)N, -1), group_T((size_t)c->n_groups, 0);
+        for (int sl = 0; sl < c->n_slots; sl++) {
+            const int32_t rd = c->order[(size_t)sl];
+            if (rd < 0) continue;
+            group_of[(size_t)rd] = sl / R16;
+            if (sl % R16 == 0) group_T[(size_t)(sl / R16)] = (int32_t)(c->blk_off[rd + 1] - c->blk_off[rd]);
+        }
+        const int64_t TR = ffb_gemm_tc_stream_tile_rows();
+        const int64_t n_tiles = (Tt + TR - 1) / TR;
+        const int arrivals = 32;                       // gate warps per group and cluster: 8 CTAs x 4 quadrants
+        for (int dir = 0; dir < 2; dir++) {
+            tile_dep[dir].resize((size_t)n_tiles);
+            std::vector<int32_t> ready((size_t)n_tiles, 0);
+            int64_t rd = 0;
+            for (int64_t k = 0; k < n_tiles; k++) {
+                const int64_t r0 = k * TR, r1 = std::min<int64_t>(r0 + TR, Tt) - 1;
+                GemmTileDep dep; for (int d = 0; d < 4; d++) { dep.idx[d] = -1; dep.cnt[d] = 0; }
+                while (c->blk_off[rd + 1] <= r0) rd++;          // first read with a row in the tile
+                int nd = 0, worst = 0; bool overflow = false;
+                for (int64_t n = rd; n < N && c->blk_off[n] <= r1; n++) {
+                    const int64_t T = c->blk_off[n + 1] - c->blk_off[n];
+                    if (T == 0) continue;
+                    const int64_t ta = std::max<int64_t>(r0, c->blk_off[n]) - c->blk_off[n];
+                    const int64_t tb = std::min<int64_t>(r1, c->blk_off[n + 1] - 1) - c->blk_off[n];
+                    const int64_t need = dir == 0 ? tb + 1 : T - ta;      // steps of the producing layer
+                    const int32_t g = group_of[(size_t)n];
+                    const int events_total = (group_T[(size_t)g] + P - 1) / P;
+                    const int ev = (int)std::min<int64_t>((need + P - 1) / P, events_total);
+                    worst = std::max(worst, ev * P);
+                    if (nd < 4) { dep.idx[nd] = g; dep.cnt[nd] = ev * arrivals; nd++; }
+                    else overflow = true;
+                }
+                if (overflow) {
+                    // more than four reads in one tile (very short reads): wait for whole groups instead --
+                    // the last counter (index n_groups) counts CTAs that have finished the layer
+                    for (int d = 0; d < 4; d++) { dep.idx[d] = -1; dep.cnt[d] = 0; }
+                    dep.idx[0] = c->n_groups; dep.cnt[0] = (c->n_slots / std::max(c->R_tc, 1)) * 8;
+                    worst = 0x7fffffff;
+                }
+                tile_dep[dir][(size_t)k] = dep;
+                ready[(size_t)k] = worst;
+            }
+            tile_order[dir].resize((size_t)n_tiles);
+            std::iota(tile_order[dir].begin(), tile_order[dir].end(), 0);
+            std::stable_sort(tile_order[dir].begin(), tile_order[dir].end(),
+                             [&](int32_t a, int32_t b) { return ready[(size_t)a] < ready[(size_t)b]; });
+        }
+    }
+
+    // ---- device workspaces ----
     bool ok = true;
     ok &= c->d_sig.reserve(sizeof(float) * (size_t)std::max<int64_t>(c->total_samples, 1)) == 0;
     for (int i = 0; i + 1 < m->nconv; i++)
@@ -490,6 +553,14 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
     if (m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT)) {
         ok &= c->d_ahi.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
         ok &= c->d_alo.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    }
+    if (c->stream_gemm) {
+        ok &= c->d_xin2.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * G * S, 1)) == 0;
+        for (int dir = 0; dir < 2; dir++) {
+            ok &= c->d_tile_order[dir].reserve(sizeof(int32_t) * tile_order[dir].size()) == 0;
+            ok &= c->d_tile_dep[dir].reserve(sizeof(GemmTileDep) * tile_dep[dir].size()) == 0;
+        }
+        ok &= c->d_progress.reserve(sizeof(int) * (size_t)FFB_NLAYER * (c->n_groups + 1)) == 0;
     }
     if (c->use_tc_rnn)
         ok &= c->d_ring.reserve(std::max<size_t>(ffb_rnn_tc_ring_bytes(m->kind, m->S, c->n_slots / std::max(c->R_tc, 1), c->R_tc), 16)) == 0;
@@ -526,6 +597,11 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
         if (!tails[i].empty())
             CUDA_TRY(cudaMemcpyAsync(c->d_tails[i].p, tails[i].data(), sizeof(ffb::ConvTail) * tails[i].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
     }
+    if (c->stream_gemm)
+        for (int dir = 0; dir < 2; dir++) {
+            CUDA_TRY(cudaMemcpyAsync(c->d_tile_order[dir].p, tile_order[dir].data(), sizeof(int32_t) * tile_order[dir].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+            CUDA_TRY(cudaMemcpyAsync(c->d_tile_dep[dir].p, tile_dep[dir].data(), sizeof(GemmTileDep) * tile_dep[dir].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+        }
     // the staging vectors above are pageable: make sure the copies have consumed them
     CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
     return FFB_OK;
@@ -569,27 +645,47 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     const bool tc_gemm = m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT);
     const bool tc_rnn = c->use_tc_rnn && tc_gemm;
     const float *in = c->d_act[0].as<float>();   // fp32 input of the current layer (NULL when only planes exist)
+    // streamed mode: GEMM l+1 is launched behind recurrence l and eats its output planes as they appear
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, m->device);
+    const int free_sms = sm_count - (c->R_tc > 0 ? (c->n_slots / c->R_tc) * 8 : 0);
+    const bool streamed = c->stream_gemm && tc_rnn && !timed && free_sms >= (G * S) / 128;
+    const size_t prog_stride = (size_t)c->n_groups + 1;
+    if (streamed) {
+        if (cudaMemsetAsync(c->d_progress.p, 0, sizeof(int) * FFB_NLAYER * prog_stride, st) != cudaSuccess) return FFB_ERR_CUDA;
+    }
+    float *xin_buf[2] = {c->d_xin.as<float>(), streamed ? c->d_xin2.as<float>() : c->d_xin.as<float>()};
     for (int l = 0; l < FFB_NLAYER; l++) {
         const bool last = (l == FFB_NLAYER - 1);
         float *out = keep ? c->d_keep[l].as<float>() : c->d_act[1].as<float>();
+        float *xin = xin_buf[l & 1];
         if (timed) cudaEventRecord(c->ev[5], st);
         if (tc_gemm) {
-            // layers fed by the tensor recurrent kernel already have their fp16 hi/lo planes
-            if (l == 0 || !tc_rnn) LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
-            LAUNCH(ffb_launch_gemm_tc(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l], m->d_iW_lo[l], m->d_b[l], c->d_xin.as<float>(), Tt,
-                                      G * S, m->layer_in[l], st));
+            if (!streamed || l == 0) {
+                // layers fed by the tensor recurrent kernel already have their fp16 hi/lo planes
+                if (l == 0 || !tc_rnn) LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
+                LAUNCH(ffb_launch_gemm_tc(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l], m->d_iW_lo[l], m->d_b[l], xin, Tt,
+                                          G * S, m->layer_in[l], st));
+            }
         } else {
-            LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], c->d_xin.as<float>(), Tt, G * S, m->layer_in[l], st));
+            LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], xin, Tt, G * S, m->layer_in[l], st));
         }
         if (timed) cudaEventRecord(c->ev[6], st);
         if (tc_rnn) {
             float *out_f32 = (keep || last) ? out : nullptr;
-            LAUNCH(ffb_launch_rnn_tc(m->kind, S, c->d_xin.as<float>(), m->d_sW_img[l], out_f32, last ? nullptr : c->d_ahi.p,
-                                     last ? nullptr : c->d_alo.p, rb, c->R_tc, (l % 2) == 0, c->d_ring.p, st));
+            int *prog = (streamed && !last) ? c->d_progress.as<int>() + (size_t)l * prog_stride : nullptr;
+            LAUNCH(ffb_launch_rnn_tc(m->kind, S, xin, m->d_sW_img[l], out_f32, last ? nullptr : c->d_ahi.p,
+                                     last ? nullptr : c->d_alo.p, rb, c->R_tc, (l % 2) == 0, c->d_ring.p, prog, st));
+            if (streamed && !last) {
+                const int dir = (l % 2) == 0 ? 1 : 0;   // layer l runs backward for even l (networks.c:460-483)
+                LAUNCH(ffb_launch_gemm_tc_streamed(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l + 1], m->d_iW_lo[l + 1], m->d_b[l + 1],
+                                                   xin_buf[(l + 1) & 1], Tt, G * S, S, c->d_tile_order[dir].as<int32_t>(),
+                                                   c->d_tile_dep[dir].as<GemmTileDep>(), prog, free_sms, st));
+            }
         } else {
             // the fp32 kernel ping-pongs between the two activation buffers
             if (!keep) out = c->d_act[(l & 1) ^ 1].as<float>();
-            LAUNCH(ffb_launch_rnn(m->kind, S, c->d_xin.as<float>(), m->d_sWp[l], out, rb, (l % 2) == 0, st));
+            LAUNCH(ffb_launch_rnn(m->kind, S, xin, m->d_sWp[l], out, rb, (l % 2) == 0, st));
         }
         if (timed) {
             cudaEventRecord(c->ev[7], st);

@@ -68,11 +68,27 @@ int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, fl
 int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
                        float scale, cudaStream_t st);
 
+// Streaming dependencies of one GEMM tile (ffb_gemm_tc_stream_tile_rows() blocks) on the recurrent kernel that produces its rows:
+// the tile may be loaded once progress[idx[d]] >= cnt[d] for every d with idx[d] >= 0.
+struct GemmTileDep {
+    int32_t idx[4];
+    int32_t cnt[4];
+};
+#define FFB_RNN_PUBLISH_PERIOD 16   // the recurrent kernel publishes a group's progress every 16 steps
+
 // gemm_tc.cu: tcgen05 path.  Planes are fp16 [rows][K]; W planes keep the reference's [out][in] order.
 int ffb_gemm_tc_supported(int N, int K);
 int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st);
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                        int64_t M, int N, int K, cudaStream_t st);
+// Streamed variant: launched (programmatic dependent launch) right behind the recurrent kernel that is still
+// writing the A planes; tiles are taken in `tile_order` and each waits for its GemmTileDep.  `max_ctas` bounds the
+// grid to the SMs the recurrent kernel leaves free.  Returns 0 (nothing launched) when the shape is unsupported.
+int ffb_gemm_tc_stream_supported(int N, int K);
+int ffb_gemm_tc_stream_tile_rows(void);   // rows (blocks) per streamed tile
+int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                                int64_t M, int N, int K, const int32_t *tile_order, const GemmTileDep *tile_dep,
+                                const int *progress, int max_ctas, cudaStream_t st);
 
 // rnn.cu: one recurrent layer over a ragged batch.
 struct RnnBatch {
@@ -98,8 +114,10 @@ int ffb_rnn_tc_prepare(int kind, int S);
 int ffb_rnn_tc_max_clusters(int kind, int S, int R);
 int ffb_rnn_tc_rmax(int kind, int S);
 size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R);   // L2-resident state-exchange ring
+// progress (optional): one counter per group of 16 slots, +1 from each of the 32 gate warps of the cluster every
+// FFB_RNN_PUBLISH_PERIOD steps (and at the group's last step) once their fp16 output planes are globally visible
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
-                      const RnnBatch &rb, int R, int backward, void *ring, cudaStream_t st);
+                      const RnnBatch &rb, int R, int backward, void *ring, int *progress, cudaStream_t st);
 
 // decode.cu
 int ffb_launch_logz(const float *trans, const int64_t *blk_off, int n_reads, int nr, double *logZ, cudaStream_t st);

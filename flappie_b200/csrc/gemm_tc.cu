@@ -254,34 +254,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 //
 // Here the CTA keeps ONE 128-row panel of iW (fp16 hi/lo) in tensor memory for the whole launch
 // (loaded once with tcgen05.st) and uses it as the MMA's A operand, so the product is computed
-// transposed, D[feature 128][block 64]: shared memory holds only the streamed activation tiles
-// (6 x 16 KB ring), the MMA needs no A fetch (N=64 at pipe rate), accumulators are double
-// buffered in the other half of TMEM, and the epilogue -- thread = feature -- writes its column
-// into a [block][feature] staging tile without bank conflicts, which is then stored as full
-// 512-byte rows.  CTAs are dealt panel = blockIdx % (N/128) with equal strides so the N/128
-// CTAs working on one activation tile run in step and the tile is read from HBM once.
+// transposed, D[feature 128][block 128]:
+//   * shared memory holds only the streamed activation tiles (6 x 32 KB ring: the loads see ~1.5 us
+//     of latency, so bytes in flight decide the rate -- tools/microbench/tma_bench.cu);
+//   * N = 128 per MMA: consecutive MMAs into one accumulator issue ~45 clk apart whatever N is
+//     (tools/microbench/mma_rate_bench.cu), so N >= 128 (64 clk of math) is what keeps the pipe full;
+//   * ONE accumulator per tile, double buffered (2 x 128 of the 512 TMEM columns next to the panel);
+//   * the epilogue -- thread = feature, register = block -- stores straight from registers: the 32
+//     lanes of a warp write 32 consecutive features of one block row = one full 128-byte line.
+// CTAs are dealt panel = blockIdx % (N/128) with equal strides so the N/128 CTAs working on one
+// activation tile run in step and the tile is read from HBM once.
+#ifdef FFB_RNN_PROFILE
+__device__ unsigned long long ffb_gemm_prof_dev[16];
+#define GPROF_DECL unsigned long long pt_ = clock64(), pa_[8] = {0}
+#define GPROF(i) do { const unsigned long long n_ = clock64(); pa_[i] += n_ - pt_; pt_ = n_; } while (0)
+#define GPROF_FLUSH(base, n) do { if (blockIdx.x == 0) for (int i_ = 0; i_ < n; i_++) ffb_gemm_prof_dev[base + i_] += pa_[i_]; } while (0)
+#else
+#define GPROF_DECL
+#define GPROF(i)
+#define GPROF_FLUSH(base, n)
+#endif
 struct GemmWsCfg {
     static constexpr int BF = 128;                 // features per panel (MMA M)
-    static constexpr int BB = 64;                  // blocks per tile (MMA N)
+    static constexpr int BB = 128;                 // blocks per tile (MMA N)
     static constexpr int BK = 64;                  // K per pipeline stage
     static constexpr int STAGE_BYTES = 2 * BB * BK * 2;   // hi + lo
-    static constexpr int STAGES = 6;
-    static constexpr int STG_BYTES = BB * BF * 4;  // fp32 staging tile [block][feature]
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STG_BYTES + 1024;
-    static constexpr int THREADS = 192;
+    static constexpr int STAGES = 6;               // 192 KB in flight
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
+    static constexpr int EPI_WARPS = 8;            // two per TMEM lane quadrant, BB/2 columns each
+    static constexpr int THREADS = 64 + EPI_WARPS * 32;
     static constexpr int KMAX = 256;
     static constexpr int ACC_COL0 = KMAX;          // W planes: K/2 columns each, at 0 and KMAX/2
+    static constexpr int NACC = 2;                 // accumulator buffers of BB columns
 };
 
 __global__ void __launch_bounds__(GemmWsCfg::THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __half *__restrict__ Whi, const __half *__restrict__ Wlo, const float *__restrict__ bias,
-               float *__restrict__ C, int64_t M, int N, int K) {
+               float *__restrict__ C, int64_t M, int N, int K, const int32_t *__restrict__ tile_order,
+               const GemmTileDep *__restrict__ tile_dep, const int *progress) {
     using Cfg = GemmWsCfg;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *stg_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-    __shared__ uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES], acc_full[2], acc_empty[2];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
+    __shared__ uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES], acc_full[Cfg::NACC], acc_empty[Cfg::NACC];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -293,7 +308,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < Cfg::NACC; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], Cfg::EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapAlo); }
@@ -302,7 +317,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = tmem_slot;
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
         // panel -> tensor memory: this thread owns lane 32*quad + lane = feature row of the panel
         const int quad = warp & 3;
         const size_t row = (size_t)panel * Cfg::BF + quad * 32 + lane;
@@ -323,90 +338,140 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     tcgen05_fence_after();
 
     if (warp == 0) {
-        // ===== TMA producer: activation tiles [64 blocks][64 K] hi / lo =====
+        // ===== TMA producer: activation tiles [128 blocks][64 K] hi / lo =====
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t tile = first; tile < n_tiles; tile += stride) {
+            GPROF_DECL;
+            for (int64_t it = first; it < n_tiles; it += stride) {
+                const int64_t tile = tile_order ? tile_order[it] : it;
+                GPROF(0);
+                if (tile_dep) {
+                    // streamed mode: the rows of this tile are being written by the recurrent kernel of the previous
+                    // layer (generic-proxy stores, published with fence + atomic); acquire, then order the TMA
+                    // (async proxy) reads behind it
+                    const GemmTileDep dep = tile_dep[tile];
+#pragma unroll
+                    for (int d = 0; d < 4; d++) {
+                        if (dep.idx[d] < 0) continue;
+                        int seen;
+                        while (true) {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(progress + dep.idx[d]) : "memory");
+                            if (seen >= dep.cnt[d]) break;
+                            __nanosleep(256);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                }
                 const int m0 = (int)(tile * Cfg::BB);
+                GPROF(1);
                 for (int kc = 0; kc < nk; kc++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    GPROF(2);
                     uint8_t *st = smem + (size_t)stage * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(st, &mapAhi, &full_bar[stage], kc * Cfg::BK, m0);
                     tma_load_2d(st + Cfg::STAGE_BYTES / 2, &mapAlo, &full_bar[stage], kc * Cfg::BK, m0);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    GPROF(3);
                 }
             }
+            GPROF_FLUSH(0, 4);
         }
     } else if (warp == 1) {
         // ===== MMA issuer: D[feature][block] (+)= W_panel (TMEM) * act_tile^T (smem) =====
+        // ONE accumulator per tile: the tensor core truncates on every accumulate (tests/probe_acc.py), so the
+        // 2^-11-sized cross terms go in FIRST (their truncation is invisible) and the 16 full-size hi*hi products
+        // on top -- the same number of full-magnitude truncations as a dedicated hi*hi accumulator, at half the
+        // TMEM columns and half the tcgen05.ld traffic in the epilogue
         if (elect_one()) {
             const uint32_t idesc = make_idesc_f16(Cfg::BF, Cfg::BB);
             const uint32_t w_hi = tmem, w_lo = tmem + Cfg::KMAX / 2;
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            GPROF_DECL;
             for (int64_t tile = first; tile < n_tiles; tile += stride) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                GPROF(0);
                 tcgen05_fence_after();
-                const uint32_t d = tmem + Cfg::ACC_COL0 + acc * 2 * Cfg::BB, dx = d + Cfg::BB;
-                for (int kc = 0; kc < nk; kc++) {
-                    mbar_wait(&full_bar[stage], phase);
+                const uint32_t d = tmem + Cfg::ACC_COL0 + acc * Cfg::BB;
+                int s1 = stage; uint32_t p1 = phase;
+                for (int kc = 0; kc < nk; kc++) {           // pass 1: cross terms as the stages land
+                    mbar_wait(&full_bar[s1], p1);
+                    GPROF(1);
                     tcgen05_fence_after();
-                    const uint32_t b_hi = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES), b_lo = b_hi + Cfg::STAGE_BYTES / 2;
+                    const uint32_t b_hi = smem_u32(smem + (size_t)s1 * Cfg::STAGE_BYTES), b_lo = b_hi + Cfg::STAGE_BYTES / 2;
 #pragma unroll
                     for (int k4 = 0; k4 < Cfg::BK / 16; k4++) {
                         const uint32_t ko = k4 * 32;   // 16 halfs = 32 bytes along the swizzled row
                         const uint32_t wo = (uint32_t)(kc * Cfg::BK + k4 * 16) / 2;   // TMEM column of these 16 halfs
-                        const uint64_t dbh = make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128);
-                        const uint64_t dbl = make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128);
-                        umma_f16_ts(d, w_hi + wo, dbh, idesc, (kc | k4) != 0);    // hi*hi
-                        umma_f16_ts(dx, w_hi + wo, dbl, idesc, (kc | k4) != 0);   // cross terms
-                        umma_f16_ts(dx, w_lo + wo, dbh, idesc, 1);
+                        umma_f16_ts(d, w_hi + wo, make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128), idesc, (kc | k4) != 0);
+                        umma_f16_ts(d, w_lo + wo, make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128), idesc, 1);
+                    }
+                    if (++s1 == Cfg::STAGES) { s1 = 0; p1 ^= 1; }
+                    GPROF(2);
+                }
+                for (int kc = 0; kc < nk; kc++) {           // pass 2: hi*hi
+                    const uint32_t b_hi = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < Cfg::BK / 16; k4++) {
+                        const uint32_t wo = (uint32_t)(kc * Cfg::BK + k4 * 16) / 2;
+                        umma_f16_ts(d, w_hi + wo, make_smem_desc(b_hi + k4 * 32, 16, 1024, LAYOUT_SW128), idesc, 1);
                     }
                     umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
-                    if (kc == nk - 1) umma_commit(&acc_full[acc]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                umma_commit(&acc_full[acc]);
+                GPROF(2);
+                if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
             }
+            GPROF_FLUSH(4, 3);
         }
     } else {
-        // ===== epilogue warps 2..5 -> TMEM lane quadrants (warp % 4); thread = feature =====
-        const int quad = warp & 3;
+        // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4; thread = feature =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         const int f = quad * 32 + lane;                     // feature within the panel
         const float b = bias[panel * Cfg::BF + f];
-        const int et = threadIdx.x - 64;                    // 0..127 among the epilogue threads
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t tile = first; tile < n_tiles; tile += stride) {
-            float *stg = reinterpret_cast<float *>(stg_base + (size_t)acc * Cfg::STG_BYTES);
+        for (int64_t it = first; it < n_tiles; it += stride) {
+            const int64_t tile = tile_order ? tile_order[it] : it;
+#ifdef FFB_RNN_PROFILE
+            unsigned long long e0_ = clock64();
+#endif
             mbar_wait(&acc_full[acc], acc_phase);
+#ifdef FFB_RNN_PROFILE
+            unsigned long long e1_ = clock64();
+#endif
             tcgen05_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + Cfg::ACC_COL0 + acc * 2 * Cfg::BB;
+            const int c0 = half * (Cfg::BB / 2);
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + Cfg::ACC_COL0 + acc * Cfg::BB + c0;
+            const int64_t m0 = tile * Cfg::BB + c0;
+            float *crow = C + m0 * (int64_t)N + panel * Cfg::BF + f;
+            const int nrow = (int)((M - m0 < Cfg::BB / 2) ? (M - m0) : Cfg::BB / 2);   // rows of this half inside the matrix (may be <= 0)
 #pragma unroll
-            for (int c = 0; c < Cfg::BB; c += 16) {
-                float v[16], vx[16];
+            for (int c = 0; c < Cfg::BB / 2; c += 32) {
+                float v[16], w[16];
                 tmem_ld16(taddr + c, v);
-                tmem_ld16(taddr + Cfg::BB + c, vx);
+                tmem_ld16(taddr + c + 16, w);
                 tmem_ld_wait();
+                if (c + 32 <= nrow) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) stg[(c + j) * Cfg::BF + f] = (v[j] + vx[j]) + b;
+                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + j) * N, v[j] + b);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + 16 + j) * N, w[j] + b);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (c + j < nrow) __stcs(crow + (int64_t)(c + j) * N, v[j] + b);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (c + 16 + j < nrow) __stcs(crow + (int64_t)(c + 16 + j) * N, w[j] + b);
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);    // accumulator drained: the next tile's MMAs may start
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile complete (epilogue warps only)
-            // full rows: 128 features = 512 B = one warp-wide float4 store
-            const int64_t m0 = tile * Cfg::BB;
-#pragma unroll 4
-            for (int r = et >> 5; r < Cfg::BB; r += 4) {
-                if (m0 + r < M) {
-                    const float4 v = *reinterpret_cast<const float4 *>(stg + r * Cfg::BF + lane * 4);
-                    __stcs(reinterpret_cast<float4 *>(C + (m0 + r) * (int64_t)N + panel * Cfg::BF + lane * 4), v);
-                }
-            }
-            // the staging buffer is reused two tiles later; the bar.sync of the next tile orders these reads
-            // before any thread can reach the writes of the tile after it
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);    // accumulator drained: the tile after next may start
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+#ifdef FFB_RNN_PROFILE
+            if (blockIdx.x == 0 && threadIdx.x == 64) { ffb_gemm_prof_dev[8] += e1_ - e0_; ffb_gemm_prof_dev[9] += clock64() - e1_; ffb_gemm_prof_dev[10] += 1; }
+#endif
         }
     }
     tcgen05_fence_before();
@@ -477,7 +542,8 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
 }
 
 static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                          int64_t M, int N, int K, cudaStream_t st) {
+                          int64_t M, int N, int K, cudaStream_t st, const int32_t *tile_order = nullptr,
+                          const GemmTileDep *tile_dep = nullptr, const int *progress = nullptr, int max_ctas = 0) {
     using Cfg = ffb::GemmWsCfg;
     CUtensorMap mAh, mAl;
     if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, Cfg::BB) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, Cfg::BB)) return -1;
@@ -491,12 +557,52 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_panels = N / Cfg::BF;
     const int64_t n_tiles = (M + Cfg::BB - 1) / Cfg::BB;
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+    if (tile_dep && getenv("FFB_STREAM_CTAS")) sms = atoi(getenv("FFB_STREAM_CTAS"));
     int64_t per_panel = sms / n_panels;
-    if (per_panel < 1) per_panel = 1;
+    if (per_panel < 1) {
+        if (tile_dep) return 0;   // streamed mode needs every CTA co-resident with the producer
+        per_panel = 1;
+    }
     if (per_panel > n_tiles) per_panel = n_tiles;
-    ffb::gemm_ws_kernel<<<(unsigned)(per_panel * n_panels), Cfg::THREADS, Cfg::SMEM, st>>>(
-        mAh, mAl, (const __half *)Whi, (const __half *)Wlo, bias, C, M, N, K);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(per_panel * n_panels));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (tile_dep && getenv("FFB_STREAM_NO_PDL") == nullptr) {
+        // programmatic dependent launch: start as soon as every CTA of the preceding kernel (the recurrent layer
+        // that produces A) has issued griddepcontrol.launch_dependents, i.e. is resident and running
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::gemm_ws_kernel, mAh, mAl, (const __half *)Whi, (const __half *)Wlo, bias, C, M, N,
+                                       K, tile_order, tile_dep, progress);
+    return e == cudaSuccess ? 1 : -1;
+}
+
+int ffb_gemm_tc_prof(unsigned long long *out, int reset) {
+#ifdef FFB_RNN_PROFILE
+    if (out && cudaMemcpyFromSymbol(out, ffb::ffb_gemm_prof_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ffb::ffb_gemm_prof_dev, z, sizeof z); }
+    return 1;
+#else
+    (void)out; (void)reset;
+    return 0;
+#endif
+}
+
+int ffb_gemm_tc_stream_tile_rows(void) { return ffb::GemmWsCfg::BB; }
+int ffb_gemm_tc_stream_supported(int N, int K) { return ffb_gemm_tc_supported(N, K) && N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX; }
+
+int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                                int64_t M, int N, int K, const int32_t *tile_order, const GemmTileDep *tile_dep,
+                                const int *progress, int max_ctas, cudaStream_t st) {
+    if (M <= 0) return 0;
+    if (!ffb_gemm_tc_stream_supported(N, K) || !tile_order || !tile_dep || !progress) return -1;
+    return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st, tile_order, tile_dep, progress, max_ctas);
 }
 
 // A planes [M][K] fp16, W planes [N][K] fp16 (the reference's own [out][in] orientation)

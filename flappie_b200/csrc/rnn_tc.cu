@@ -123,11 +123,24 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return (y + y) - 1.0f;
 }
 
+// Optional phase timing of one control thread and one gate warp (cluster 0, CTA 0, group 0):
+// build with FFB_EXTRA_NVCC_FLAGS=-DFFB_RNN_PROFILE, read with ffb_test_rnn_prof() (testhooks.cu).
+#ifdef FFB_RNN_PROFILE
+__device__ unsigned long long ffb_rnn_prof_dev[16];
+#define PROF_DECL unsigned long long pt_ = clock64(), pa_[12] = {0}; const bool prof_ = (blockIdx.x == 0 && g == 0)
+#define PROF(i) do { const unsigned long long n_ = clock64(); pa_[i] += n_ - pt_; pt_ = n_; } while (0)
+#define PROF_FLUSH(lo, hi) do { if (prof_) for (int i_ = lo; i_ < hi; i_++) ffb_rnn_prof_dev[i_] += pa_[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_FLUSH(lo, hi)
+#endif
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS, 1)
 rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, float *__restrict__ Hout,
               __half *__restrict__ Hhi, __half *__restrict__ Hlo, const int32_t *__restrict__ order,
-              const int64_t *__restrict__ blk_off, uint8_t *__restrict__ ring, int G, int backward) {
+              const int64_t *__restrict__ blk_off, uint8_t *__restrict__ ring, int *__restrict__ progress, int G, int backward) {
     constexpr int S = Cfg::S, C = Cfg::C, NGATE = Cfg::NGATE, NG = Cfg::NG, GMAX = Cfg::GMAX;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
@@ -138,7 +151,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 
     const uint32_t crank = cluster_ctarank();
     const int cluster_id = blockIdx.x / C;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // provably warp-uniform: roles, TMEM and staging addresses stay in uniform registers
     const int nthreads = blockDim.x;
     const int R = G * NG;                                        // reads per cluster
 
@@ -182,6 +196,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     __syncthreads();
     tcgen05_fence_after();
     cluster_sync_all();             // every CTA's barriers are initialised before any remote arrive / copy
+    // this CTA is resident: a dependent grid (the next layer's streamed input GEMM) may be scheduled on the SMs
+    // this grid leaves free -- it synchronises on `progress`, not on this grid's completion
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int g = (warp < 4 * G) ? (warp >> 2) : (warp - 4 * G);    // this warp's group
     // slots are sorted by length (descending): the group's first slot is its longest read
@@ -203,32 +220,49 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             const uint64_t dB_lo = make_smem_desc(smem_u32(Bg) + NG * 16, Cfg::LBO_B, 128, LAYOUT_NONE);
             uint8_t *ring_g = ring + ((((size_t)cluster_id * 2) * G + g) * C + crank) * Cfg::SLICE;   // parity 0
             const size_t ring_par = (size_t)G * C * Cfg::SLICE;
+            PROF_DECL;
             for (int s = 0; s < Tmax; s++) {
                 const uint32_t ph = (uint32_t)s & 1u;
                 if (s > 0) mbar_wait(&h_full[g], ph ^ 1u);           // h_{s-1} complete in B
+                PROF(0);
                 mbar_arrive_expect_tx(&h_full[g], C * Cfg::SLICE);    // arm phase s: peers push h_s only after my MMA(s)
                 tcgen05_fence_after();
-#pragma unroll 4
-                for (int ks = 0; ks < S / 16; ks++) {
-                    const uint32_t oa = (uint32_t)ks * 8;                                    // 16 halfs = 8 TMEM columns
-                    const uint64_t ob = (uint64_t)((ks * 2 * Cfg::LBO_B) >> 4);
-                    const int kh = ks / (S / 32);                                            // K-half
-                    umma_f16_ts(acc + kh * NG, tA_hi + oa, dB_hi + ob, idesc, (ks % (S / 32)) != 0);   // hi*hi
-                    umma_f16_ts(acc + 2 * NG, tA_hi + oa, dB_lo + ob, idesc, ks != 0);                 // cross terms
-                    umma_f16_ts(acc + 2 * NG, tA_lo + oa, dB_hi + ob, idesc, 1);
+                // 3*S/16 MMAs as THREE independent accumulation chains of S/16, issued round-robin: back-to-back
+                // MMAs into the same accumulator are ~45 clk apart whatever N is (mma_rate_bench), different
+                // accumulators pipeline at the tensor rate.  Within a chain the 2^-11-sized cross terms go first,
+                // so each accumulator still sees only S/32 full-magnitude (truncating) accumulations.
+                //   chain 0: Whi*hlo then Whi*hhi over K-half 0     chain 1: the same over K-half 1
+                //   chain 2: Wlo*hhi over all of K
+                constexpr int KS = S / 16, KH = S / 32;
+#pragma unroll
+                for (int i = 0; i < KS; i++) {
+                    const int k0 = i < KH ? i : i - KH, k1 = k0 + KH;            // k-steps of chains 0 / 1
+                    const uint64_t ob0 = (uint64_t)((k0 * 2 * Cfg::LBO_B) >> 4), ob1 = (uint64_t)((k1 * 2 * Cfg::LBO_B) >> 4),
+                                   ob2 = (uint64_t)((i * 2 * Cfg::LBO_B) >> 4);
+                    const uint64_t b0 = (i < KH ? dB_lo : dB_hi) + ob0, b1 = (i < KH ? dB_lo : dB_hi) + ob1;
+                    umma_f16_ts(acc, tA_hi + k0 * 8, b0, idesc, i != 0);
+                    umma_f16_ts(acc + NG, tA_hi + k1 * 8, b1, idesc, i != 0);
+                    umma_f16_ts(acc + 2 * NG, tA_lo + i * 8, dB_hi + ob2, idesc, i != 0);
                 }
                 umma_commit(&acc_full[g]);
+                PROF(1);
                 mbar_wait(&acc_full[g], ph);
+                PROF(2);
                 // the MMAs have retired: this CTA no longer reads h_{s-1}
                 for (uint32_t d = 0; d < (uint32_t)C; d++) mbar_arrive_remote_cta(&h_empty[g], d);
                 mbar_wait(&staged[g], ph);                            // the gate warps staged my slice of h_s
+                PROF(3);
                 uint8_t *rg = ring_g + (size_t)ph * ring_par;
                 bulk_store_global(rg, stg, Cfg::SLICE);
+                PROF(4);
                 mbar_wait(&h_empty[g], ph);                           // every peer has consumed h_{s-1}
+                PROF(5);
                 // no proxy fence: the ring was written by the async proxy (bulk store, completed by
                 // wait_group) and is read by the async proxy
                 bulk_load_multicast(Bg + crank * Cfg::SLICE, rg, Cfg::SLICE, &h_full[g], (uint16_t)((1u << C) - 1u));
+                PROF(6);
             }
+            PROF_FLUSH(0, 7);
             // drain: the last step's copies still target this CTA; nobody may exit before they have landed
             if (Tmax > 0) mbar_wait(&h_full[g], (uint32_t)(Tmax - 1) & 1u);
         }
@@ -238,42 +272,70 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         const int q = warp & 3;
         const int e = lane >> 2, cp = lane & 3;
         const int j = crank * Cfg::HS + q * 8 + e;          // global hidden index of this thread's cells
-        // this thread's four cells: reads col(i) = (i>>1)*8 + 2*cp + (i&1) of the group
+        constexpr int XROW = NGATE * S;
+        // this thread's four cells: reads col(i) = (i>>1)*8 + 2*cp + (i&1) of the group.  Per cell a
+        // running pointer into Xin and a running output row, stepped by +-1 block per step.
         int cT[4];
-        int32_t cbase[4];           // first block of the read (the host guarantees total blocks < 2^31)
+        const float *xp[4];
+        int32_t orow[4];            // the host guarantees total blocks < 2^31
         float hprev[4], cstate[4];
+        int Tmin = 0x7fffffff;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int col = (i >> 1) * 8 + 2 * cp + (i & 1);
             const int rd = order[cluster_id * R + g * NG + col];
             cT[i] = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
-            cbase[i] = rd >= 0 ? (int32_t)blk_off[rd] : 0;
+            const int32_t base = rd >= 0 ? (int32_t)blk_off[rd] : 0;
+            orow[i] = base + ((backward && cT[i] > 0) ? cT[i] - 1 : 0);
+            xp[i] = Xin + (int64_t)orow[i] * XROW + j;
             hprev[i] = 0.0f; cstate[i] = 0.0f;
+            Tmin = min(Tmin, cT[i]);
         }
+        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, 1));   // shortest read of the group: while s < Tmin
+        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, 2));   // no cell needs a predicate
+        const int xstep = backward ? -XROW : XROW, rstep = backward ? -1 : 1;
+        // second role of the lane: after the slice is staged, copy one 16-byte chunk (8 hidden units of one
+        // read, one plane) from the staging tile to the fp16 layer output -- off the critical path
+        const int cl_read = lane & 15, cl_plane = lane >> 4;
+        int cl_T = 0;
+        int32_t cl_row = 0;
+        {
+            const int rd = order[cluster_id * R + g * NG + cl_read];
+            cl_T = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
+            cl_row = (rd >= 0 ? (int32_t)blk_off[rd] : 0) + ((backward && cl_T > 0) ? cl_T - 1 : 0);
+        }
+        __half *cl_dst = (cl_plane ? Hlo : Hhi);
+        if (cl_dst) cl_dst += crank * Cfg::HS + q * 8;
+        const uint4 *cl_src = reinterpret_cast<const uint4 *>(stg + (size_t)q * Cfg::LBO_B + cl_plane * NG * 16 + cl_read * 16);
+
         const uint32_t t_lo = acc + ((uint32_t)(q * 32) << 16);       // lanes 32q .. 32q+15: gates 0, 1
         const uint32_t t_hi = acc + ((uint32_t)(q * 32 + 16) << 16);  // lanes 32q+16 .. 32q+31: gates 2, 3
         // staging: [kg_local = q][plane][read][8 halfs], this thread writes element e of its 4 reads
         __half *st_hi = reinterpret_cast<__half *>(stg + (size_t)q * Cfg::LBO_B) + e;
         __half *st_lo = st_hi + NG * 8;
 
+#ifdef FFB_RNN_PROFILE
+        unsigned long long pt_ = clock64(), pa_[12] = {0}; const bool prof_ = (blockIdx.x == 0 && warp == 0 && lane == 0);
+#endif
         for (int s = 0; s < Tmax; s++) {
             const uint32_t ph = (uint32_t)s & 1u;
+            const bool all = s < Tmin;          // warp-uniform
             // ---- prefetch this step's input projection ----
             float x[4][NGATE];
-            int32_t row[4];
+            if (all) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int t = backward ? (cT[i] - 1 - s) : s;
-                row[i] = cbase[i] + t;
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int gt = 0; gt < NGATE; gt++) x[i][gt] = 0.0f;
-                if (s < cT[i]) {
-                    const float *xp = Xin + (int64_t)row[i] * (NGATE * S) + j;
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xp[i] + gt * S);
+            } else {
 #pragma unroll
-                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xp + gt * S);
-                }
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (s < cT[i]) ? __ldcs(xp[i] + gt * S) : 0.0f;
             }
+            PROF(8);
             mbar_wait(&acc_full[g], ph);
+            PROF(9);
             tcgen05_fence_after();
             // ---- TMEM -> registers: a[i][gate], three partial accumulators added round-to-nearest ----
             float a[4][4];
@@ -306,10 +368,11 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 }
             }
             tcgen05_fence_before();
+            PROF(10);
             // ---- cells ----
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                float hn;
+                float hn, cn = 0.0f;
                 if constexpr (NGATE == 3) {
                     const float z = fast_logistic(x[i][0] + a[i][0]);                   // layers.c:697-699
                     const float r = fast_logistic(x[i][1] + a[i][1]);
@@ -320,22 +383,15 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     const float fg = fast_logistic(x[i][1] + a[i][1]);
                     const float gg = fast_tanh(x[i][2] + a[i][2]);
                     const float og = fast_logistic(x[i][3] + a[i][3]);
-                    const float cn = fg * cstate[i] + ig * gg;
+                    cn = fg * cstate[i] + ig * gg;
                     hn = og * fast_tanh(cn);
-                    if (s < cT[i]) cstate[i] = cn;
                 }
-                if (s < cT[i]) {
+                if (all || s < cT[i]) {             // finished reads keep (and keep pushing) their frozen state
                     hprev[i] = hn;
-                    if (Hout) __stcs(Hout + (int64_t)row[i] * S + j, hn);
-                    if (Hhi) {
-                        __half hi, lo;
-                        split_f16(hn, hi, lo);
-                        Hhi[(int64_t)row[i] * S + j] = hi;
-                        Hlo[(int64_t)row[i] * S + j] = lo;
-                    }
+                    if constexpr (NGATE == 4) cstate[i] = cn;
                 }
                 __half shv, slv;
-                split_f16(hprev[i], shv, slv);       // finished reads keep pushing their frozen state
+                split_f16(hprev[i], shv, slv);
                 const int col = (i >> 1) * 8 + 2 * cp + (i & 1);
                 st_hi[col * 8] = shv;
                 st_lo[col * 8] = slv;
@@ -343,11 +399,32 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             fence_proxy_async_smem();      // staged slice -> visible to the bulk-copy engine
             __syncwarp();
             if (lane == 0) mbar_arrive(&staged[g]);
+            PROF(11);
+            // ---- layer output (not on the step's critical path) ----
+            if (cl_dst && s < cl_T) *reinterpret_cast<uint4 *>(cl_dst + (int64_t)cl_row * S) = *cl_src;
+            if (Hout) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (all || s < cT[i]) __stcs(Hout + (int64_t)orow[i] * S + j, hprev[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { xp[i] += xstep; orow[i] += rstep; }
+            cl_row += rstep;
+            // ---- publish progress for the consumer of the output planes ----
+            if (progress && (((s + 1) % FFB_RNN_PUBLISH_PERIOD) == 0 || s == Tmax - 1)) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(progress + cluster_id * G + g, 1);
+            }
         }
+        PROF_FLUSH(8, 12);
     }
 
     tcgen05_fence_before();
     __syncthreads();
+    // every gate warp fenced its last stores before its final publish: count this CTA as finished (the
+    // coarse dependency of GEMM tiles that span more than four reads)
+    if (progress && tid == 0) atomicAdd(progress + (gridDim.x / C) * G, 1);
     cluster_sync_all();
     if (warp == 0) tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }
@@ -358,6 +435,16 @@ using LstmTc256 = RnnTcCfg<256, 8, 4>;
 }  // namespace ffb
 
 // ---------------------------------------------------------------------------------------
+int ffb_rnn_tc_prof(unsigned long long *out, int reset) {
+#ifdef FFB_RNN_PROFILE
+    if (out && cudaMemcpyFromSymbol(out, ffb::ffb_rnn_prof_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(ffb::ffb_rnn_prof_dev, z, sizeof z); }
+    return 1;
+#else
+    (void)out; (void)reset;
+    return 0;
+#endif
+}
 int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && S == 256; }
 int ffb_rnn_tc_rmax(int kind, int S) { (void)kind; (void)S; return ffb::GruTc256::GMAX * ffb::GruTc256::NG; }
 
@@ -439,7 +526,7 @@ int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
 
 template <class Cfg>
 static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo, const RnnBatch &rb, int R,
-                      int backward, void *ring, cudaStream_t st) {
+                      int backward, void *ring, int *progress, cudaStream_t st) {
     const int G = R / Cfg::NG;
     if (G < 1 || G > Cfg::GMAX || R % Cfg::NG || rb.n_slots % R || !ring) return -1;
     const int n_clusters = rb.n_slots / R;
@@ -447,13 +534,13 @@ static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     rnn_tc_config<Cfg>(cfg, attr, n_clusters, G, st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::rnn_tc_kernel<Cfg>, Xin, (const __half *)Wimg, Hout, (__half *)Hhi,
-                                       (__half *)Hlo, rb.order, rb.blk_off, (uint8_t *)ring, G, backward);
+                                       (__half *)Hlo, rb.order, rb.blk_off, (uint8_t *)ring, progress, G, backward);
     return e == cudaSuccess ? 1 : -1;
 }
 
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
-                      const RnnBatch &rb, int R, int backward, void *ring, cudaStream_t st) {
+                      const RnnBatch &rb, int R, int backward, void *ring, int *progress, cudaStream_t st) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    return kind == 0 ? launch_one<ffb::GruTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, st)
-                     : launch_one<ffb::LstmTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, st);
+    return kind == 0 ? launch_one<ffb::GruTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, progress, st)
+                     : launch_one<ffb::LstmTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, progress, st);
 }

@@ -76,3 +76,9 @@ extern "C" int ffb_test_gemm(const float *A, const float *W, const float *bias, 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
 }
+
+// phase cycle counters of the tensor recurrent kernel (all zero unless built with -DFFB_RNN_PROFILE)
+int ffb_rnn_tc_prof(unsigned long long *out, int reset);
+extern "C" int ffb_test_rnn_prof(unsigned long long *out, int reset) { return ffb_rnn_tc_prof(out, reset); }
+int ffb_gemm_tc_prof(unsigned long long *out, int reset);
+extern "C" int ffb_test_gemm_prof(unsigned long long *out, int reset) { return ffb_gemm_tc_prof(out, reset); }

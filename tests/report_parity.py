@@ -28,4 +28,8 @@ for simt in (False, True):
         _, p_o, _ = orc.viterbi(trans_o)
         p_g, _ = res.read_path(i)
         same += int(np.array_equal(p_g, p_o)); nb += 1
+    if not simt:
+        res2 = ctx.basecall(reads, viterbi_only=True, want_trans=True)     # no keep_layers: the streamed-GEMM schedule
+        d2 = max(float(np.max(np.abs(res2.read_trans(i) - res.read_trans(i)))) for i in range(len(reads)))
+        print(f"streamed vs sequential schedule: max|d trans| = {d2:.3e} (same arithmetic: expect 0)", flush=True)
     print(f"{'fp32 SIMT' if simt else 'tensor   '}: layer max|d| {' '.join(f'{x:.2e}' for x in dl)}  trans {dt:.2e}  identical Viterbi paths {same}/{nb}", flush=True)
