@@ -285,17 +285,27 @@ def main():
     h2d = int(signal_np.nbytes + sig_off_np.nbytes + 4 * n)
     d2h = int(out["path"].nbytes + out["qpath"].nbytes + out["score"].nbytes)
 
-    # ---- per-kernel-group timing for the roofline (one extra, untimed-for-value pass) ----
+    # ---- per-kernel-group timing for the roofline (one extra pass, sequential schedule, CUDA events on the
+    #      library's stream around each kernel group; not part of `value`) ----
     groups = ctx.forward_timed()
     S, G, T = fm.size, fm.ngate, tot_blocks
     rnn_flops = 2.0 * T * S * G * S                      # one layer's h_{t-1} * sW, all reads (algorithmic)
     rnn_ms_per_launch = groups["rnn"] / 5.0
     achieved_tf = rnn_flops / (rnn_ms_per_launch * 1e-3) / 1e12
-    roofline = {"kernel": "rnn_layer_kernel (recurrent layer: h*sW + gates, 5 launches/step)",
+    tensor_path = not a.fp32_simt and fm.size == 256
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_rnn_tc_v3_ncu_summary.txt,
+    # ncu --set full of this command); algorithmic = Xin read 4*G*S + planes written 4*S bytes per block
+    traffic = 7.91e9 if (tensor_path and a.model == "r941_native_gru" and a.reads == 1024) else None
+    roofline = {"kernel": "rnn_tc_kernel (recurrent layer: h*sW on tcgen05 + gates, 5 launches/step)" if tensor_path
+                          else "rnn_layer_kernel (fp32 CUDA-core cluster kernel, 5 launches/step)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
-                "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
-                "note": "fp32 CUDA-core path (bit-faithful to the reference SGEMV); algorithmic flops = 2*T*S*G*S per launch",
+                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic,
+                "peak_source": f"{peaks['src']} bf16 dense sustained (kernel timed inside a long step)",
+                "algorithmic_bytes_per_launch": float(T) * (4 * G * S + 4 * S),
+                "note": "algorithmic flops = 2*blocks*S*G*S per launch; the fp32-faithful fp16 hi/lo split issues 3 MMAs per "
+                        "product and pads 96 gate rows to M=128, so raw tensor-pipe work is 4x algorithmic (GRU-256); the layer is "
+                        "T dependent steps of ~1.9 us each, i.e. bound by the latency of the step chain, not by the pipe "
+                        "(DESIGN.md 4.2)",
                 "step_breakdown_ms": groups}
 
     line = {
@@ -306,7 +316,8 @@ def main():
                                f"{a.model}: {MODEL_CHOICES[a.model][1]}; random-init weights; "
                                f"{'--viterbi' if a.viterbi_only else 'forward-backward + Viterbi (CLI default)'}",
                    "blocks_per_gpu": int(tot_blocks), "reads_per_gpu": n,
-                   "l2": "working set per step (Xin + activations, ~8 GB) far exceeds the 126 MB L2; no flush needed",
+                   "l2": "working set per step (Xin + activations, ~16 GB) far exceeds the 126 MB L2; no flush needed",
+                   "schedule": "layer l+1's input GEMM streamed behind layer l's recurrence (PDL)" if os.environ.get("FFB_NO_STREAM_GEMM") is None else "sequential kernels",
                    "host_prep": "trim + med-MAD normalisation done once on the host before timing (outside the hot path)",
                    "parallelism": f"read-shard x{world}, no collective"},
         "clocks": clocks,
