@@ -350,7 +350,7 @@ struct ffb_ctx {
     DevBuf d_ring;                // state-exchange ring of the tensor recurrent kernel (L2-resident)
     // streamed input GEMMs: layer l+1's projection runs on the SMs layer l's recurrence leaves free and consumes
     // its output planes tile by tile (tile order + dependencies per production direction: 0 = forward, 1 = backward)
-    DevBuf d_xin2, d_tile_order[2], d_tile_dep[2], d_progress;
+    DevBuf d_xin2, d_work[2], d_progress;
     bool stream_gemm = false;
     int n_groups = 0;
     float *last_conv = nullptr;   // device pointer of last conv output within d_act/d_c
@@ -383,8 +383,7 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
-                     &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_tile_order[0], &c->d_tile_order[1],
-                     &c->d_tile_dep[0], &c->d_tile_dep[1], &c->d_progress};
+                     &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -486,8 +485,7 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
 
     // ---- streamed GEMM plan: when may each tile of the next layer's input be loaded? ----
     const int64_t Tt = c->total_blocks, S = m->S, G = m->G, nr = m->nparam;
-    std::vector<int32_t> tile_order[2];
-    std::vector<GemmTileDep> tile_dep[2];
+    std::vector<GemmWork> work[2];
     c->stream_gemm = c->use_tc_rnn && !(c->flags & FFB_FLAG_KEEP_LAYERS) && getenv("FFB_NO_STREAM_GEMM") == nullptr &&
                      ffb_gemm_tc_stream_supported((int)(G * S), (int)S) && Tt > 0;
     if (c->stream_gemm) {
@@ -504,12 +502,13 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
         const int64_t n_tiles = (Tt + TR - 1) / TR;
         const int arrivals = 32;                       // gate warps per group and cluster: 8 CTAs x 4 quadrants
         for (int dir = 0; dir < 2; dir++) {
-            tile_dep[dir].resize((size_t)n_tiles);
+            work[dir].resize((size_t)n_tiles);
             std::vector<int32_t> ready((size_t)n_tiles, 0);
             int64_t rd = 0;
             for (int64_t k = 0; k < n_tiles; k++) {
                 const int64_t r0 = k * TR, r1 = std::min<int64_t>(r0 + TR, Tt) - 1;
-                GemmTileDep dep; for (int d = 0; d < 4; d++) { dep.idx[d] = -1; dep.cnt[d] = 0; }
+                GemmWork w; w.tile = (int32_t)k; w.pad = 0;
+                for (int d = 0; d < 3; d++) { w.idx[d] = -1; w.cnt[d] = 0; }
                 while (c->blk_off[rd + 1] <= r0) rd++;          // first read with a row in the tile
                 int nd = 0, worst = 0; bool overflow = false;
                 for (int64_t n = rd; n < N && c->blk_off[n] <= r1; n++) {
@@ -522,23 +521,21 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
                     const int events_total = (group_T[(size_t)g] + P - 1) / P;
                     const int ev = (int)std::min<int64_t>((need + P - 1) / P, events_total);
                     worst = std::max(worst, ev * P);
-                    if (nd < 4) { dep.idx[nd] = g; dep.cnt[nd] = ev * arrivals; nd++; }
+                    if (nd < 3) { w.idx[nd] = g; w.cnt[nd] = ev * arrivals; nd++; }
                     else overflow = true;
                 }
                 if (overflow) {
-                    // more than four reads in one tile (very short reads): wait for whole groups instead --
-                    // the last counter (index n_groups) counts CTAs that have finished the layer
-                    for (int d = 0; d < 4; d++) { dep.idx[d] = -1; dep.cnt[d] = 0; }
-                    dep.idx[0] = c->n_groups; dep.cnt[0] = (c->n_slots / std::max(c->R_tc, 1)) * 8;
+                    // more than three reads in one tile (very short reads): wait for the whole layer instead --
+                    // the counter at index n_groups counts CTAs that have finished it
+                    for (int d = 0; d < 3; d++) { w.idx[d] = -1; w.cnt[d] = 0; }
+                    w.idx[0] = c->n_groups; w.cnt[0] = (c->n_slots / std::max(c->R_tc, 1)) * 8;
                     worst = 0x7fffffff;
                 }
-                tile_dep[dir][(size_t)k] = dep;
+                work[dir][(size_t)k] = w;
                 ready[(size_t)k] = worst;
             }
-            tile_order[dir].resize((size_t)n_tiles);
-            std::iota(tile_order[dir].begin(), tile_order[dir].end(), 0);
-            std::stable_sort(tile_order[dir].begin(), tile_order[dir].end(),
-                             [&](int32_t a, int32_t b) { return ready[(size_t)a] < ready[(size_t)b]; });
+            std::stable_sort(work[dir].begin(), work[dir].end(),
+                             [&](const GemmWork &a, const GemmWork &b) { return ready[(size_t)a.tile] < ready[(size_t)b.tile]; });
         }
     }
 
@@ -556,11 +553,8 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
     }
     if (c->stream_gemm) {
         ok &= c->d_xin2.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * G * S, 1)) == 0;
-        for (int dir = 0; dir < 2; dir++) {
-            ok &= c->d_tile_order[dir].reserve(sizeof(int32_t) * tile_order[dir].size()) == 0;
-            ok &= c->d_tile_dep[dir].reserve(sizeof(GemmTileDep) * tile_dep[dir].size()) == 0;
-        }
-        ok &= c->d_progress.reserve(sizeof(int) * (size_t)FFB_NLAYER * (c->n_groups + 1)) == 0;
+        for (int dir = 0; dir < 2; dir++) ok &= c->d_work[dir].reserve(sizeof(GemmWork) * work[dir].size()) == 0;
+        ok &= c->d_progress.reserve(sizeof(int) * (size_t)FFB_NLAYER * (c->n_groups + 1 + 16)) == 0;
     }
     if (c->use_tc_rnn)
         ok &= c->d_ring.reserve(std::max<size_t>(ffb_rnn_tc_ring_bytes(m->kind, m->S, c->n_slots / std::max(c->R_tc, 1), c->R_tc), 16)) == 0;
@@ -598,10 +592,8 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
             CUDA_TRY(cudaMemcpyAsync(c->d_tails[i].p, tails[i].data(), sizeof(ffb::ConvTail) * tails[i].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
     }
     if (c->stream_gemm)
-        for (int dir = 0; dir < 2; dir++) {
-            CUDA_TRY(cudaMemcpyAsync(c->d_tile_order[dir].p, tile_order[dir].data(), sizeof(int32_t) * tile_order[dir].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
-            CUDA_TRY(cudaMemcpyAsync(c->d_tile_dep[dir].p, tile_dep[dir].data(), sizeof(GemmTileDep) * tile_dep[dir].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
-        }
+        for (int dir = 0; dir < 2; dir++)
+            CUDA_TRY(cudaMemcpyAsync(c->d_work[dir].p, work[dir].data(), sizeof(GemmWork) * work[dir].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
     // the staging vectors above are pageable: make sure the copies have consumed them
     CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
     return FFB_OK;
@@ -649,8 +641,8 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, m->device);
     const int free_sms = sm_count - (c->R_tc > 0 ? (c->n_slots / c->R_tc) * 8 : 0);
-    const bool streamed = c->stream_gemm && tc_rnn && !timed && free_sms >= (G * S) / 128;
-    const size_t prog_stride = (size_t)c->n_groups + 1;
+    const bool streamed = c->stream_gemm && tc_rnn && !timed && free_sms >= (G * S) / 128 && (G * S) / 128 <= 16;
+    const size_t prog_stride = (size_t)c->n_groups + 1 + 16;   // per layer: group counters, finished-CTA counter, 16 ticket queues
     if (streamed) {
         if (cudaMemsetAsync(c->d_progress.p, 0, sizeof(int) * FFB_NLAYER * prog_stride, st) != cudaSuccess) return FFB_ERR_CUDA;
     }
@@ -679,8 +671,8 @@ static int forward_impl(ffb_ctx *c, bool timed) {
             if (streamed && !last) {
                 const int dir = (l % 2) == 0 ? 1 : 0;   // layer l runs backward for even l (networks.c:460-483)
                 LAUNCH(ffb_launch_gemm_tc_streamed(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l + 1], m->d_iW_lo[l + 1], m->d_b[l + 1],
-                                                   xin_buf[(l + 1) & 1], Tt, G * S, S, c->d_tile_order[dir].as<int32_t>(),
-                                                   c->d_tile_dep[dir].as<GemmTileDep>(), prog, free_sms, st));
+                                                   xin_buf[(l + 1) & 1], Tt, G * S, S, c->d_work[dir].as<GemmWork>(), prog,
+                                                   prog + c->n_groups + 1, st));
             }
         } else {
             // the fp32 kernel ping-pongs between the two activation buffers

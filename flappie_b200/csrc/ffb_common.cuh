@@ -68,11 +68,14 @@ int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, fl
 int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
                        float scale, cudaStream_t st);
 
-// Streaming dependencies of one GEMM tile (ffb_gemm_tc_stream_tile_rows() blocks) on the recurrent kernel that produces its rows:
-// the tile may be loaded once progress[idx[d]] >= cnt[d] for every d with idx[d] >= 0.
-struct GemmTileDep {
-    int32_t idx[4];
-    int32_t cnt[4];
+// One work item of the streamed input GEMM: a tile (ffb_gemm_tc_stream_tile_rows() blocks) and what it waits
+// for -- the tile may be loaded once progress[idx[d]] >= cnt[d] for every d with idx[d] >= 0.  Items are
+// sorted by the step at which the producing recurrent layer completes them.
+struct GemmWork {
+    int32_t tile;
+    int32_t idx[3];
+    int32_t cnt[3];
+    int32_t pad;
 };
 #define FFB_RNN_PUBLISH_PERIOD 16   // the recurrent kernel publishes a group's progress every 16 steps
 
@@ -82,13 +85,14 @@ int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStre
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                        int64_t M, int N, int K, cudaStream_t st);
 // Streamed variant: launched (programmatic dependent launch) right behind the recurrent kernel that is still
-// writing the A planes; tiles are taken in `tile_order` and each waits for its GemmTileDep.  `max_ctas` bounds the
-// grid to the SMs the recurrent kernel leaves free.  Returns 0 (nothing launched) when the shape is unsupported.
+// writing the A planes; work items are taken from per-panel ticket queues in `work` order and each waits for its dependencies;
+// CTAs that find no free SM while the recurrence runs start when it ends and drain what is left.  Returns 0 (nothing launched) when the shape is unsupported.
 int ffb_gemm_tc_stream_supported(int N, int K);
 int ffb_gemm_tc_stream_tile_rows(void);   // rows (blocks) per streamed tile
+// progress: counters published by the recurrent kernel; queue: N/128 zeroed ticket counters (one per weight panel)
 int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                                int64_t M, int N, int K, const int32_t *tile_order, const GemmTileDep *tile_dep,
-                                const int *progress, int max_ctas, cudaStream_t st);
+                                int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue,
+                                cudaStream_t st);
 
 // rnn.cu: one recurrent layer over a ragged batch.
 struct RnnBatch {

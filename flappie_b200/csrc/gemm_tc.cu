@@ -278,9 +278,12 @@ struct GemmWsCfg {
     static constexpr int BF = 128;                 // features per panel (MMA M)
     static constexpr int BB = 128;                 // blocks per tile (MMA N)
     static constexpr int BK = 64;                  // K per pipeline stage
-    static constexpr int STAGE_BYTES = 2 * BB * BK * 2;   // hi + lo
-    static constexpr int STAGES = 6;               // 192 KB in flight
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
+    static constexpr int SLOT_BYTES = BB * BK * 2;  // one plane of one k-chunk: [128 blocks][64 halfs]
+    // Two rings.  The MMAs make two passes over a tile (cross terms first, then hi*hi): the hi plane of a k-chunk
+    // is needed in both and is held until pass 2, the lo plane only in pass 1.  The hi ring is two tiles deep so
+    // the next tile loads while this one computes; the lo ring one tile.
+    static constexpr int HI_SLOTS = 8, LO_SLOTS = 4;
+    static constexpr int SMEM = (HI_SLOTS + LO_SLOTS) * SLOT_BYTES + 1024;
     static constexpr int EPI_WARPS = 8;            // two per TMEM lane quadrant, BB/2 columns each
     static constexpr int THREADS = 64 + EPI_WARPS * 32;
     static constexpr int KMAX = 256;
@@ -291,12 +294,15 @@ struct GemmWsCfg {
 __global__ void __launch_bounds__(GemmWsCfg::THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __half *__restrict__ Whi, const __half *__restrict__ Wlo, const float *__restrict__ bias,
-               float *__restrict__ C, int64_t M, int N, int K, const int32_t *__restrict__ tile_order,
-               const GemmTileDep *__restrict__ tile_dep, const int *progress) {
+               float *__restrict__ C, int64_t M, int N, int K, const GemmWork *__restrict__ work,
+               const int *progress, int *queue) {
     using Cfg = GemmWsCfg;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
-    __shared__ uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES], acc_full[Cfg::NACC], acc_empty[Cfg::NACC];
+    __shared__ uint64_t full_hi[Cfg::HI_SLOTS], empty_hi[Cfg::HI_SLOTS], full_lo[Cfg::LO_SLOTS], empty_lo[Cfg::LO_SLOTS];
+    __shared__ uint64_t acc_full[Cfg::NACC], acc_empty[Cfg::NACC];
+    __shared__ uint64_t tile_bar[16];      // the producer announces each tile it starts (id in tile_ring, -1 = no more)
+    __shared__ int tile_ring[16];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -307,8 +313,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     const int nk = K / Cfg::BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < Cfg::HI_SLOTS; s++) { mbar_init(&full_hi[s], 1); mbar_init(&empty_hi[s], 1); }
+        for (int s = 0; s < Cfg::LO_SLOTS; s++) { mbar_init(&full_lo[s], 1); mbar_init(&empty_lo[s], 1); }
         for (int a = 0; a < Cfg::NACC; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], Cfg::EPI_WARPS); }
+        for (int t = 0; t < 16; t++) mbar_init(&tile_bar[t], 1);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapAlo); }
@@ -340,41 +348,70 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer: activation tiles [128 blocks][64 K] hi / lo =====
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0;
+            int sh = 0, sl = 0; uint32_t ph = 0, pl = 0;     // hi / lo ring positions
+            uint8_t *ring_hi = smem, *ring_lo = smem + Cfg::HI_SLOTS * Cfg::SLOT_BYTES;
+            int tcount = 0;
             GPROF_DECL;
-            for (int64_t it = first; it < n_tiles; it += stride) {
-                const int64_t tile = tile_order ? tile_order[it] : it;
-                GPROF(0);
-                if (tile_dep) {
-                    // streamed mode: the rows of this tile are being written by the recurrent kernel of the previous
-                    // layer (generic-proxy stores, published with fence + atomic); acquire, then order the TMA
-                    // (async proxy) reads behind it
-                    const GemmTileDep dep = tile_dep[tile];
-#pragma unroll
-                    for (int d = 0; d < 4; d++) {
-                        if (dep.idx[d] < 0) continue;
-                        int seen;
-                        while (true) {
-                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(progress + dep.idx[d]) : "memory");
-                            if (seen >= dep.cnt[d]) break;
-                            __nanosleep(256);
-                        }
-                    }
-                    asm volatile("fence.proxy.async.global;" ::: "memory");
-                }
+            auto announce = [&](int tile) {
+                tile_ring[tcount & 15] = tile;
+                mbar_arrive(&tile_bar[tcount & 15]);
+                tcount++;
+            };
+            auto load_tile = [&](int64_t tile) {
                 const int m0 = (int)(tile * Cfg::BB);
-                GPROF(1);
                 for (int kc = 0; kc < nk; kc++) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait(&empty_hi[sh], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_hi[sh], Cfg::SLOT_BYTES);
+                    tma_load_2d(ring_hi + (size_t)sh * Cfg::SLOT_BYTES, &mapAhi, &full_hi[sh], kc * Cfg::BK, m0);
+                    if (++sh == Cfg::HI_SLOTS) { sh = 0; ph ^= 1; }
+                    mbar_wait(&empty_lo[sl], pl ^ 1);
                     GPROF(2);
-                    uint8_t *st = smem + (size_t)stage * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(st, &mapAhi, &full_bar[stage], kc * Cfg::BK, m0);
-                    tma_load_2d(st + Cfg::STAGE_BYTES / 2, &mapAlo, &full_bar[stage], kc * Cfg::BK, m0);
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    mbar_arrive_expect_tx(&full_lo[sl], Cfg::SLOT_BYTES);
+                    tma_load_2d(ring_lo + (size_t)sl * Cfg::SLOT_BYTES, &mapAlo, &full_lo[sl], kc * Cfg::BK, m0);
+                    if (++sl == Cfg::LO_SLOTS) { sl = 0; pl ^= 1; }
                     GPROF(3);
                 }
+            };
+            if (!work) {
+                for (int64_t tile = first; tile < n_tiles; tile += stride) { announce((int)tile); load_tile(tile); }
+            } else {
+                // streamed mode: tickets from this panel's queue, in the order the recurrent kernel of the previous
+                // layer completes the tiles; its rows arrive as generic-proxy stores published with fence + atomic
+                int *q = queue + panel;
+#ifdef FFB_RNN_PROFILE
+                if (blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_gemm_prof_dev[12] = t_; ffb_gemm_prof_dev[15] = 0; }
+                if (blockIdx.x == gridDim.x - 1) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_gemm_prof_dev[14] = t_; }
+#endif
+                int64_t ticket = atomicAdd(q, 1);
+                GemmWork w = {};
+                if (ticket < n_tiles) w = work[ticket];
+                while (ticket < n_tiles) {
+                    const int64_t ticket_n = atomicAdd(q, 1);      // next ticket: its latency hides under this tile
+                    GPROF(0);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        if (w.idx[d] < 0) continue;
+                        while (true) {
+                            int seen;
+                            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(progress + w.idx[d]) : "memory");
+                            if (seen >= w.cnt[d]) break;
+                            __nanosleep(200);
+                        }
+                    }
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");           // acquire what the counters published
+                    asm volatile("fence.proxy.async.global;" ::: "memory");    // ... also for the TMA (async proxy) reads
+                    GemmWork w_n = {};
+                    if (ticket_n < n_tiles) w_n = work[ticket_n];
+                    GPROF(1);
+                    announce(w.tile);
+                    load_tile(w.tile);
+                    ticket = ticket_n; w = w_n;
+                }
             }
+            announce(-1);
+#ifdef FFB_RNN_PROFILE
+            if (work && blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_gemm_prof_dev[13] = t_; ffb_gemm_prof_dev[15] = tcount; }
+#endif
             GPROF_FLUSH(0, 4);
         }
     } else if (warp == 1) {
@@ -386,20 +423,24 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         if (elect_one()) {
             const uint32_t idesc = make_idesc_f16(Cfg::BF, Cfg::BB);
             const uint32_t w_hi = tmem, w_lo = tmem + Cfg::KMAX / 2;
-            int stage = 0; uint32_t phase = 0;
+            int sh = 0, sl = 0; uint32_t ph = 0, pl = 0;     // hi / lo ring positions
+            const uint32_t ring_hi = smem_u32(smem), ring_lo = ring_hi + Cfg::HI_SLOTS * Cfg::SLOT_BYTES;
             int acc = 0; uint32_t acc_phase = 0;
             GPROF_DECL;
-            for (int64_t tile = first; tile < n_tiles; tile += stride) {
+            for (int tc = 0;; tc++) {
+                mbar_wait(&tile_bar[tc & 15], (uint32_t)(tc >> 4) & 1u);
+                if (tile_ring[tc & 15] < 0) break;
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 GPROF(0);
                 tcgen05_fence_after();
                 const uint32_t d = tmem + Cfg::ACC_COL0 + acc * Cfg::BB;
-                int s1 = stage; uint32_t p1 = phase;
-                for (int kc = 0; kc < nk; kc++) {           // pass 1: cross terms as the stages land
-                    mbar_wait(&full_bar[s1], p1);
+                int s1 = sh;
+                for (int kc = 0; kc < nk; kc++) {           // pass 1: cross terms as the k-chunks land
+                    mbar_wait(&full_hi[s1], (s1 < sh) ? (ph ^ 1) : ph);   // s1 wrapped past the ring end: next phase
+                    mbar_wait(&full_lo[sl], pl);
                     GPROF(1);
                     tcgen05_fence_after();
-                    const uint32_t b_hi = smem_u32(smem + (size_t)s1 * Cfg::STAGE_BYTES), b_lo = b_hi + Cfg::STAGE_BYTES / 2;
+                    const uint32_t b_hi = ring_hi + (uint32_t)s1 * Cfg::SLOT_BYTES, b_lo = ring_lo + (uint32_t)sl * Cfg::SLOT_BYTES;
 #pragma unroll
                     for (int k4 = 0; k4 < Cfg::BK / 16; k4++) {
                         const uint32_t ko = k4 * 32;   // 16 halfs = 32 bytes along the swizzled row
@@ -407,18 +448,20 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         umma_f16_ts(d, w_hi + wo, make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128), idesc, (kc | k4) != 0);
                         umma_f16_ts(d, w_lo + wo, make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128), idesc, 1);
                     }
-                    if (++s1 == Cfg::STAGES) { s1 = 0; p1 ^= 1; }
+                    umma_commit(&empty_lo[sl]);                // the lo plane is done with
+                    if (++sl == Cfg::LO_SLOTS) { sl = 0; pl ^= 1; }
+                    if (++s1 == Cfg::HI_SLOTS) s1 = 0;
                     GPROF(2);
                 }
                 for (int kc = 0; kc < nk; kc++) {           // pass 2: hi*hi
-                    const uint32_t b_hi = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_hi = ring_hi + (uint32_t)sh * Cfg::SLOT_BYTES;
 #pragma unroll
                     for (int k4 = 0; k4 < Cfg::BK / 16; k4++) {
                         const uint32_t wo = (uint32_t)(kc * Cfg::BK + k4 * 16) / 2;
                         umma_f16_ts(d, w_hi + wo, make_smem_desc(b_hi + k4 * 32, 16, 1024, LAYOUT_SW128), idesc, 1);
                     }
-                    umma_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&empty_hi[sh]);                // hi slot free once these MMAs retire
+                    if (++sh == Cfg::HI_SLOTS) { sh = 0; ph ^= 1; }
                 }
                 umma_commit(&acc_full[acc]);
                 GPROF(2);
@@ -432,8 +475,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         const int f = quad * 32 + lane;                     // feature within the panel
         const float b = bias[panel * Cfg::BF + f];
         int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t it = first; it < n_tiles; it += stride) {
-            const int64_t tile = tile_order ? tile_order[it] : it;
+        for (int tc = 0;; tc++) {
+            mbar_wait(&tile_bar[tc & 15], (uint32_t)(tc >> 4) & 1u);
+            const int64_t tile = tile_ring[tc & 15];
+            if (tile < 0) break;
 #ifdef FFB_RNN_PROFILE
             unsigned long long e0_ = clock64();
 #endif
@@ -542,8 +587,8 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
 }
 
 static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                          int64_t M, int N, int K, cudaStream_t st, const int32_t *tile_order = nullptr,
-                          const GemmTileDep *tile_dep = nullptr, const int *progress = nullptr, int max_ctas = 0) {
+                          int64_t M, int N, int K, cudaStream_t st, const GemmWork *work = nullptr,
+                          const int *progress = nullptr, int *queue = nullptr) {
     using Cfg = ffb::GemmWsCfg;
     CUtensorMap mAh, mAl;
     if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, Cfg::BB) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, Cfg::BB)) return -1;
@@ -557,13 +602,9 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_panels = N / Cfg::BF;
     const int64_t n_tiles = (M + Cfg::BB - 1) / Cfg::BB;
-    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
-    if (tile_dep && getenv("FFB_STREAM_CTAS")) sms = atoi(getenv("FFB_STREAM_CTAS"));
+    if (work && getenv("FFB_STREAM_CTAS")) sms = atoi(getenv("FFB_STREAM_CTAS"));
     int64_t per_panel = sms / n_panels;
-    if (per_panel < 1) {
-        if (tile_dep) return 0;   // streamed mode needs every CTA co-resident with the producer
-        per_panel = 1;
-    }
+    if (per_panel < 1) per_panel = 1;
     if (per_panel > n_tiles) per_panel = n_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(per_panel * n_panels));
@@ -571,7 +612,7 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
-    if (tile_dep && getenv("FFB_STREAM_NO_PDL") == nullptr) {
+    if (work && getenv("FFB_STREAM_NO_PDL") == nullptr) {
         // programmatic dependent launch: start as soon as every CTA of the preceding kernel (the recurrent layer
         // that produces A) has issued griddepcontrol.launch_dependents, i.e. is resident and running
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -579,7 +620,7 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::gemm_ws_kernel, mAh, mAl, (const __half *)Whi, (const __half *)Wlo, bias, C, M, N,
-                                       K, tile_order, tile_dep, progress);
+                                       K, work, progress, queue);
     return e == cudaSuccess ? 1 : -1;
 }
 
@@ -598,11 +639,11 @@ int ffb_gemm_tc_stream_tile_rows(void) { return ffb::GemmWsCfg::BB; }
 int ffb_gemm_tc_stream_supported(int N, int K) { return ffb_gemm_tc_supported(N, K) && N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX; }
 
 int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                                int64_t M, int N, int K, const int32_t *tile_order, const GemmTileDep *tile_dep,
-                                const int *progress, int max_ctas, cudaStream_t st) {
+                                int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue,
+                                cudaStream_t st) {
     if (M <= 0) return 0;
-    if (!ffb_gemm_tc_stream_supported(N, K) || !tile_order || !tile_dep || !progress) return -1;
-    return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st, tile_order, tile_dep, progress, max_ctas);
+    if (!ffb_gemm_tc_stream_supported(N, K) || !work || !progress || !queue) return -1;
+    return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st, work, progress, queue);
 }
 
 // A planes [M][K] fp16, W planes [N][K] fp16 (the reference's own [out][in] orientation)

@@ -199,6 +199,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     // this CTA is resident: a dependent grid (the next layer's streamed input GEMM) may be scheduled on the SMs
     // this grid leaves free -- it synchronises on `progress`, not on this grid's completion
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef FFB_RNN_PROFILE
+    if (progress && blockIdx.x == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_rnn_prof_dev[12] = t_; }
+#endif
 
     const int g = (warp < 4 * G) ? (warp >> 2) : (warp - 4 * G);    // this warp's group
     // slots are sorted by length (descending): the group's first slot is its longest read
@@ -425,6 +428,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     // every gate warp fenced its last stores before its final publish: count this CTA as finished (the
     // coarse dependency of GEMM tiles that span more than four reads)
     if (progress && tid == 0) atomicAdd(progress + (gridDim.x / C) * G, 1);
+#ifdef FFB_RNN_PROFILE
+    if (progress && blockIdx.x == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_rnn_prof_dev[13] = t_; }
+#endif
     cluster_sync_all();
     if (warp == 0) tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }

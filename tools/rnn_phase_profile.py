@@ -38,3 +38,9 @@ gn = {0: "prod loop overhead", 1: "prod dependency poll + fence", 2: "prod wait 
 print(f"GEMM (CTA 0, {nt} tiles since reset, all launches):")
 for i, nm in gn.items():
     print(f"{nm:34s} {g[i] / nt:9.1f} clk/tile")
+
+if g[12]:
+    t0 = out[12]
+    print(f"timeline (us, relative to the start of recurrent layer 4 of 5): recurrence ends {(out[13]-t0)/1e3:.0f}; "
+          f"streamed GEMM of layer 5: CTA 0 starts {(int(g[12])-t0)/1e3:.0f}, last CTA starts {(int(g[14])-t0)/1e3:.0f}, "
+          f"CTA 0 ends {(int(g[13])-t0)/1e3:.0f} after {int(g[15])-1} tiles")
