@@ -528,7 +528,7 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
                     // more than three reads in one tile (very short reads): wait for the whole layer instead --
                     // the counter at index n_groups counts CTAs that have finished it
                     for (int d = 0; d < 3; d++) { w.idx[d] = -1; w.cnt[d] = 0; }
-                    w.idx[0] = c->n_groups; w.cnt[0] = (c->n_slots / std::max(c->R_tc, 1)) * 8;
+                    w.idx[0] = c->n_groups; w.cnt[0] = (c->n_slots / std::max(c->R_tc, 1)) * ffb_rnn_tc_cluster_size(m->kind, m->S);
                     worst = 0x7fffffff;
                 }
                 work[dir][(size_t)k] = w;
@@ -640,7 +640,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     // streamed mode: GEMM l+1 is launched behind recurrence l and eats its output planes as they appear
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, m->device);
-    const int free_sms = sm_count - (c->R_tc > 0 ? (c->n_slots / c->R_tc) * 8 : 0);
+    const int free_sms = sm_count - (c->R_tc > 0 ? (c->n_slots / c->R_tc) * ffb_rnn_tc_cluster_size(m->kind, m->S) : 0);
     const bool streamed = c->stream_gemm && tc_rnn && !timed && free_sms >= (G * S) / 128 && (G * S) / 128 <= 16;
     const size_t prog_stride = (size_t)c->n_groups + 1 + 16;   // per layer: group counters, finished-CTA counter, 16 ticket queues
     if (streamed) {

@@ -117,6 +117,7 @@ void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img);
 int ffb_rnn_tc_prepare(int kind, int S);
 int ffb_rnn_tc_max_clusters(int kind, int S, int R);
 int ffb_rnn_tc_rmax(int kind, int S);
+int ffb_rnn_tc_cluster_size(int kind, int S);
 size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R);   // L2-resident state-exchange ring
 // progress (optional): one counter per group of 16 slots, +1 from each of the 32 gate warps of the cluster every
 // FFB_RNN_PUBLISH_PERIOD steps (and at the group's last step) once their fp16 output planes are globally visible

@@ -45,6 +45,8 @@
 //                    consumed h_{t-1}) -> multicast load ring -> B of every CTA (-> their h_full)
 // Gate order and arithmetic as the reference: grumod_step src/layers.c:664-715 (z, r, n);
 // lstm_step src/layers.c:979-1026 (i, f, g, o).
+#include <algorithm>
+
 #include "ffb_common.cuh"
 #include "tc_common.cuh"
 
@@ -58,7 +60,8 @@ struct RnnTcCfg {
     static constexpr int NQ = HS / 8;                 // TMEM quadrants in use = k-groups per slice
     static constexpr int KG = S / 8;                  // 16-byte k-groups along K
     static constexpr int NG = 16;                     // reads per group (MMA N)
-    static constexpr int GMAX = 5;                    // groups per cluster
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int GMAX = (TMEM_COLS - S) / (3 * 16) < 5 ? (TMEM_COLS - S) / (3 * 16) : 5;   // groups per cluster: what TMEM holds next to the two weight planes
     static constexpr int A_COLS = S / 2;              // TMEM columns of one A plane (two halfs per 32-bit column)
     static constexpr int A_PLANE = 128 * S * 2;       // bytes of one plane of the global weight image [128 rows][S halfs]
     static constexpr int LBO_B = 2 * NG * 16;         // bytes between k-groups of B (hi and lo planes interleaved)
@@ -66,11 +69,11 @@ struct RnnTcCfg {
     static constexpr int SLICE = NQ * LBO_B;          // bytes of one CTA's slice of one group's state
     static constexpr int ACC_COLS = 3 * NG;           // TMEM columns per group
     static constexpr int ACC_COL0 = 2 * A_COLS;       // accumulators follow the two A planes
-    static constexpr int TMEM_COLS = 512;
     static constexpr int WARPS_PER_GROUP = 5;         // 4 gate warps + 1 control warp
     static constexpr int MAX_THREADS = GMAX * WARPS_PER_GROUP * 32;
     static_assert(HS == 32, "four quadrants of 8 hidden units");
-    static_assert(ACC_COL0 + GMAX * ACC_COLS <= TMEM_COLS, "tensor memory budget");
+    static_assert(GMAX >= 1 && ACC_COL0 + GMAX * ACC_COLS <= TMEM_COLS, "tensor memory budget");
+    static_assert(C <= 16, "cluster size");
     __host__ __device__ static constexpr size_t smem_bytes(int G) {
         return (size_t)G * (B_GROUP + SLICE) + 64;
     }
@@ -437,10 +440,19 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 
 using GruTc256 = RnnTcCfg<256, 8, 3>;
 using LstmTc256 = RnnTcCfg<256, 8, 4>;
+using GruTc384 = RnnTcCfg<384, 12, 3>;    // 12-CTA clusters (non-portable size): 32 hidden units per CTA again,
+using LstmTc384 = RnnTcCfg<384, 12, 4>;   // 2 x 192 TMEM columns of weights + 2 groups of accumulators
 
 }  // namespace ffb
 
 // ---------------------------------------------------------------------------------------
+// shape dispatch: f is a generic lambda called with a value-initialised config object
+template <class F>
+static auto tc_dispatch(int kind, int S, F &&f) {
+    if (S == 384) return kind == 0 ? f(ffb::GruTc384{}) : f(ffb::LstmTc384{});
+    return kind == 0 ? f(ffb::GruTc256{}) : f(ffb::LstmTc256{});
+}
+
 int ffb_rnn_tc_prof(unsigned long long *out, int reset) {
 #ifdef FFB_RNN_PROFILE
     if (out && cudaMemcpyFromSymbol(out, ffb::ffb_rnn_prof_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
@@ -451,18 +463,16 @@ int ffb_rnn_tc_prof(unsigned long long *out, int reset) {
     return 0;
 #endif
 }
-int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && S == 256; }
-int ffb_rnn_tc_rmax(int kind, int S) { (void)kind; (void)S; return ffb::GruTc256::GMAX * ffb::GruTc256::NG; }
+int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && (S == 256 || S == 384); }
+int ffb_rnn_tc_cluster_size(int kind, int S) { return tc_dispatch(kind, S, [](auto cfg) { return (int)decltype(cfg)::C; }); }
+int ffb_rnn_tc_rmax(int kind, int S) { return tc_dispatch(kind, S, [](auto cfg) { return (int)(decltype(cfg)::GMAX * decltype(cfg)::NG); }); }
 
 size_t ffb_rnn_tc_image_halfs(int kind, int S) {
-    (void)S;
-    return kind == 0 ? (size_t)ffb::GruTc256::C * 2 * ffb::GruTc256::A_PLANE / 2 : (size_t)ffb::LstmTc256::C * 2 * ffb::LstmTc256::A_PLANE / 2;
+    return tc_dispatch(kind, S, [](auto cfg) { using Cfg = decltype(cfg); return (size_t)Cfg::C * 2 * Cfg::A_PLANE / 2; });
 }
 
 size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R) {
-    (void)S;
-    const int G = R / 16;
-    return kind == 0 ? ffb::GruTc256::ring_bytes(n_clusters, G) : ffb::LstmTc256::ring_bytes(n_clusters, G);
+    return tc_dispatch(kind, S, [&](auto cfg) { return decltype(cfg)::ring_bytes(n_clusters, R / 16); });
 }
 
 // sW [G*S][S] (row per output) -> per-CTA tensor-memory images (fp16 bit patterns):
@@ -489,18 +499,18 @@ static void pack_image(const float *sW, uint16_t *img) {
     }
 }
 void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img) {
-    (void)S;
-    if (kind == 0) pack_image<ffb::GruTc256>(sW, img); else pack_image<ffb::LstmTc256>(sW, img);
+    tc_dispatch(kind, S, [&](auto cfg) { pack_image<decltype(cfg)>(sW, img); return 0; });
 }
 
 template <class Cfg>
 static int prepare_one() {
-    return cudaFuncSetAttribute(ffb::rnn_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)Cfg::smem_bytes(Cfg::GMAX)) == cudaSuccess ? 0 : -1;
+    if (cudaFuncSetAttribute(ffb::rnn_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes(Cfg::GMAX)) != cudaSuccess) return -1;
+    if (Cfg::C > 8 && cudaFuncSetAttribute(ffb::rnn_tc_kernel<Cfg>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -1;
+    return 0;
 }
 int ffb_rnn_tc_prepare(int kind, int S) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    return kind == 0 ? prepare_one<ffb::GruTc256>() : prepare_one<ffb::LstmTc256>();
+    return tc_dispatch(kind, S, [](auto cfg) { return prepare_one<decltype(cfg)>(); });
 }
 
 template <class Cfg>
@@ -526,8 +536,7 @@ static int max_clusters_one(int G) {
 }
 int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
     if (!ffb_rnn_tc_supported(kind, S)) return 0;
-    const int G = R / 16;
-    return kind == 0 ? max_clusters_one<ffb::GruTc256>(G) : max_clusters_one<ffb::LstmTc256>(G);
+    return tc_dispatch(kind, S, [&](auto cfg) { return max_clusters_one<decltype(cfg)>(std::min(R / 16, (int)decltype(cfg)::GMAX)); });
 }
 
 template <class Cfg>
@@ -547,6 +556,5 @@ static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
                       const RnnBatch &rb, int R, int backward, void *ring, int *progress, cudaStream_t st) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    return kind == 0 ? launch_one<ffb::GruTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, progress, st)
-                     : launch_one<ffb::LstmTc256>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, progress, st);
+    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, progress, st); });
 }

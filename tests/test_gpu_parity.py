@@ -90,6 +90,7 @@ MODELS = [
     ("lstm128_4b", KIND_LSTM, 128, 4),
     ("gru256_4b", KIND_GRU, 256, 4),     # the shapes with the tcgen05 recurrent kernel
     ("lstm256_4b", KIND_LSTM, 256, 4),
+    ("lstm384_4b", KIND_LSTM, 384, 4),   # 12-CTA clusters
 ]
 
 
