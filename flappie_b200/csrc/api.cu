@@ -693,15 +693,20 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     if (timed) cudaEventRecord(c->ev[2], st);
     // ---- globalnorm_flipflop (layers.c:1082-1106) ----
     LAUNCH(ffb_launch_ff_tanh(top, m->d_ffWt, m->d_ffb, c->d_trans.as<float>(), Tt, nr, S, c->temperature / 5.0f, st));
-    LAUNCH(ffb_launch_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), st));
-    LAUNCH(ffb_launch_sub_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), Tt, st));
+    // -logZ/T (layers.c:1035-1096) shifts every entry of a read by one constant.  The posteriors, their Viterbi
+    // path, qualities, score and trace are invariant under it (decode.cu, fb kernels), so in forward-backward
+    // mode the fp64 partition scan only runs when the caller wants `trans` itself.
+    const bool need_logz = (c->flags & FFB_FLAG_VITERBI_ONLY) || (c->flags & FFB_FLAG_WANT_TRANS) || getenv("FFB_ALWAYS_LOGZ");
+    if (need_logz) {
+        LAUNCH(ffb_launch_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), st));
+        LAUNCH(ffb_launch_sub_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), Tt, st));
+    }
     if (timed) cudaEventRecord(c->ev[3], st);
     // ---- decoding (flappie.c:277-300) ----
     const float *post = c->d_trans.as<float>();
     if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
         LAUNCH(ffb_launch_transpost(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_fwd.as<float>(),
-                                    c->d_tpost.as<float>(), st));
-        LAUNCH(ffb_launch_lognorm(c->d_tpost.as<float>(), Tt, nr, st));
+                                    c->d_tpost.as<float>(), st));   // includes the per-block log normalisation
         post = c->d_tpost.as<float>();
     }
     LAUNCH(ffb_launch_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint64_t>(), c->d_path.as<int32_t>(),
@@ -1010,7 +1015,6 @@ extern "C" flappie_matrix transpost_crf_flipflop(const_flappie_matrix trans, boo
     if (!ok) { set_err("transpost_crf_flipflop: device allocation / copy failed"); return nullptr; }
     cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
     if (ffb_launch_transpost(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->fwd.as<float>(), d->tpost.as<float>(), d->st) < 0) return nullptr;
-    if (ffb_launch_lognorm(d->tpost.as<float>(), T, nr, d->st) < 0) return nullptr;
     if (!return_log && ffb_launch_exp_inplace(d->tpost.as<float>(), T * nr, d->st) < 0) return nullptr;
     flappie_matrix out = make_flappie_matrix(nr, (size_t)T);
     if (!out) return nullptr;

@@ -388,6 +388,198 @@ transpost_bwd_kernel(const float *__restrict__ trans, const int64_t *__restrict_
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Transition posteriors, fused and shift-invariant ("fb" kernels): the production path.
+//
+// tpost[blk][e] = fwd[from, blk] + bwd[to, blk+1] + trans[blk][e], log-normalised per block
+// (decode.c:377-497, flappie_matrix.c:450-467).  Any constant added to a forward row, a
+// backward row or a block of trans cancels in that per-block normalisation, so
+//   * the scans run on running-shifted vectors (state 0 pinned to 0 every step): values stay
+//     O(10), which also makes them MORE accurate than the reference's drifting fp32 sums;
+//   * the global normalisation constant logZ/T (layers.c:1035-1096) is not needed for the
+//     posteriors at all: in forward-backward mode the fp64 partition scan and the "-= logZ/T"
+//     pass are skipped unless the caller asks for `trans` itself.
+// The reference's sequential logsumexp folds become max-shifted sums (one exp per term in
+// parallel, one log): same value to ~1e-7, an eighth of the dependent latency.
+// One warp per read.  Lane = (destination slot lane / SEG, source lane % SEG); NBASE = 4 covers
+// the 32 flip transitions in one pass, NBASE = 5 takes three passes of 2 x 16 lanes.
+template <int NBASE>
+struct FbGeom {
+    static constexpr int NSTATE = 2 * NBASE;
+    static constexpr int NR = NSTATE * (NBASE + 1);
+    static constexpr int SEG = (NSTATE <= 8) ? 8 : 16;
+    static constexpr int DPP = 32 / SEG;                       // flip destinations per pass
+    static constexpr int NPASS = (NBASE + DPP - 1) / DPP;
+};
+template <int SEG>
+__device__ __forceinline__ float seg_max(float v) {
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+template <int SEG>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+template <int NBASE>
+__global__ void __launch_bounds__(32)
+fb_fwd_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads, float *__restrict__ fwd) {
+    using Gm = FbGeom<NBASE>;
+    constexpr int NSTATE = Gm::NSTATE, NR = Gm::NR, SEG = Gm::SEG, DPP = Gm::DPP, NPASS = Gm::NPASS;
+    __shared__ __align__(16) float stage[2][DEC_CHUNK * NR];
+    const int rd = blockIdx.x;
+    if (rd >= n_reads) return;
+    const int lane = threadIdx.x;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    if (T <= 0) return;
+    const float *tr = trans + b0 * NR;
+    float *rf = fwd + (b0 + rd) * NSTATE;   // (T+1) x NSTATE, row t = forward vector before block t (shifted)
+    const int src = lane % SEG, slot = lane / SEG;
+    const bool src_ok = src < NSTATE;
+    float P = 0.0f;                          // P[src], replicated in every segment; fwd[.,0] = 0
+    if (lane < NSTATE) rf[lane] = 0.0f;
+    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
+    stage_chunk(stage[0], tr, min(DEC_CHUNK, T), NR, lane);
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int c0 = ch * DEC_CHUNK;
+        const int cn = min(DEC_CHUNK, T - c0);
+        if (ch + 1 < nchunk) {
+            stage_chunk(stage[(ch + 1) & 1], tr + (int64_t)(c0 + DEC_CHUNK) * NR, min(DEC_CHUNK, T - c0 - DEC_CHUNK), NR, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float *sb = stage[ch & 1];
+        for (int i = 0; i < cn; i++) {
+            const float *col = sb + i * NR;
+            // flop destinations src >= NBASE: logsumexp(stay, move from flip src - NBASE)   (decode.c:404-411)
+            const float fl = src_ok ? col[NBASE * NSTATE + src] : 0.0f;
+            const float x = P + fl;                                               // stay (valid where src >= NBASE)
+            const float y = __shfl_sync(FULL, x, (lane - NBASE) & 31);            // P[src-NBASE] + flop[src-NBASE]
+            const float flopv = fmaxf(x, y) + log1pf(expf(-fabsf(x - y)));
+            // flip destinations: logsumexp over all sources                            (decode.c:414-422)
+            float flipv[NPASS];
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const int b1 = p * DPP + slot;
+                const bool ok = src_ok && b1 < NBASE;
+                const float v = ok ? P + col[b1 * NSTATE + src] : -INFINITY;
+                const float m = seg_max<SEG>(v);
+                const float sum = seg_sum<SEG>(ok ? expf(v - m) : 0.0f);
+                flipv[p] = m + logf(sum);                                         // same in every lane of the segment
+            }
+            // redistribute: new P[src] = flip value of destination src (src < NBASE) or the flop value
+            float np = flopv;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const float g = __shfl_sync(FULL, flipv[p], (src % DPP) * SEG);
+                if (src < NBASE && src / DPP == p) np = g;
+            }
+            const float ref = __shfl_sync(FULL, flipv[0], 0);                     // new value of state 0: pin it to 0
+            P = src_ok ? np - ref : 0.0f;
+            if (lane < NSTATE) rf[(int64_t)(c0 + i + 1) * NSTATE + lane] = P;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NBASE>
+__global__ void __launch_bounds__(32)
+fb_bwd_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads,
+              const float *__restrict__ fwd, float *__restrict__ tpost) {
+    using Gm = FbGeom<NBASE>;
+    constexpr int NSTATE = Gm::NSTATE, NR = Gm::NR, SEG = Gm::SEG, DPP = Gm::DPP, NPASS = Gm::NPASS;
+    __shared__ __align__(16) float stage[2][DEC_CHUNK * NR];
+    const int rd = blockIdx.x;
+    if (rd >= n_reads) return;
+    const int lane = threadIdx.x;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    if (T <= 0) return;
+    const float *tr = trans + b0 * NR;
+    float *tp = tpost + b0 * NR;
+    const float *rf = fwd + (b0 + rd) * NSTATE;
+    const int src = lane % SEG, slot = lane / SEG;
+    const bool src_ok = src < NSTATE;
+    const int to_flop = src < NBASE ? src + NBASE : src;      // flop-row entry `src`: flip src -> flop src+NBASE, or flop stay
+    float B = 0.0f;                                           // bwd[src] after the current block, replicated; calloc -> 0
+    // chunks are walked from the end of the read; chunk `ch` covers blocks [ch*DEC_CHUNK, ...)
+    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
+    {
+        const int cl = nchunk - 1;
+        stage_chunk(stage[cl & 1], tr + (int64_t)cl * DEC_CHUNK * NR, T - cl * DEC_CHUNK, NR, lane);
+    }
+    float f_next = src_ok ? rf[(int64_t)(T - 1) * NSTATE + src] : 0.0f;   // forward row of the block about to be processed
+    for (int ch = nchunk - 1; ch >= 0; ch--) {
+        const int c0 = ch * DEC_CHUNK;
+        const int cn = min(DEC_CHUNK, T - c0);
+        if (ch > 0) {
+            stage_chunk(stage[(ch - 1) & 1], tr + (int64_t)(c0 - DEC_CHUNK) * NR, DEC_CHUNK, NR, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float *sb = stage[ch & 1];
+        for (int i = cn - 1; i >= 0; i--) {
+            const int blk = c0 + i;
+            const float *col = sb + i * NR;
+            const float f = f_next;
+            if (blk > 0) f_next = src_ok ? rf[(int64_t)(blk - 1) * NSTATE + src] : 0.0f;   // prefetch
+            // ---- terms: t = trans + bwd[to]; x = t + fwd[from] ----
+            const float Bto = __shfl_sync(FULL, B, to_flop);            // (shuffles stay outside divergent selects)
+            const float tfl = src_ok ? col[NBASE * NSTATE + src] + Bto : -INFINITY;   // flop row
+            float t[NPASS], x[NPASS];
+            float m = (slot == 0 && src_ok) ? tfl + f : -INFINITY;       // the flop row is counted once (segment 0)
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const int b1 = p * DPP + slot;
+                const bool ok = src_ok && b1 < NBASE;
+                const float Bb = __shfl_sync(FULL, B, b1 < NBASE ? b1 : 0);
+                t[p] = ok ? col[b1 * NSTATE + src] + Bb : -INFINITY;
+                x[p] = ok ? t[p] + f : -INFINITY;
+                m = fmaxf(m, x[p]);
+            }
+            // ---- per-block log normalisation over all NR entries (flappie_matrix.c:450-467) ----
+            m = seg_max<32>(m);
+            float sum = (slot == 0 && src_ok) ? expf(tfl + f - m) : 0.0f;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) sum += (x[p] > -INFINITY) ? expf(x[p] - m) : 0.0f;
+            sum = seg_sum<32>(sum);
+            const float lse = m + logf(sum);
+            float *pc = tp + (int64_t)blk * NR;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const int b1 = p * DPP + slot;
+                if (src_ok && b1 < NBASE) pc[b1 * NSTATE + src] = x[p] - lse;
+            }
+            if (slot == 0 && src_ok) pc[NBASE * NSTATE + src] = tfl + f - lse;
+            // ---- backward update: bwd[from = src] = logsumexp over destinations (decode.c:465-482) ----
+            float m2 = tfl;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) m2 = fmaxf(m2, t[p]);
+#pragma unroll
+            for (int o = SEG; o < 32; o <<= 1) m2 = fmaxf(m2, __shfl_xor_sync(FULL, m2, o));   // across segments: same src
+            float s2 = 0.0f;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) s2 += (t[p] > -INFINITY) ? expf(t[p] - m2) : 0.0f;
+#pragma unroll
+            for (int o = SEG; o < 32; o <<= 1) s2 += __shfl_xor_sync(FULL, s2, o);
+            s2 += src_ok ? expf(tfl - m2) : 0.0f;                        // the flop term, once per lane
+            const float nb = src_ok ? m2 + logf(s2) : 0.0f;
+            const float ref = __shfl_sync(FULL, nb, 0);                  // pin state 0 to 0
+            B = src_ok ? nb - ref : 0.0f;
+        }
+        __syncwarp();
+    }
+}
+
 // per-block log normalisation, sequential fold in row order (flappie_matrix.c:450-467)
 __global__ void lognorm_rows_kernel(float *__restrict__ tpost, int64_t nblk, int nr) {
     const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -487,18 +679,20 @@ int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads
     if (n_reads <= 0) return 0;
     switch (nbase_of(nr)) {
     case 4:
-        ffb::transpost_fwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
-        ffb::transpost_bwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
+        ffb::fb_fwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
+        ffb::fb_bwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
         break;
     case 5:
-        ffb::transpost_fwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
-        ffb::transpost_bwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
+        ffb::fb_fwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
+        ffb::fb_bwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
         break;
     default: return -1;
     }
     return FFB_OKL(2);
 }
 
+// (the fused fb_bwd_kernel already log-normalises every block; this stays for callers that hold
+// un-normalised posteriors)
 int ffb_launch_lognorm(float *tpost, int64_t total_blocks, int nr, cudaStream_t st) {
     if (total_blocks <= 0) return 0;
     const int64_t grid = (total_blocks + 127) / 128;
