@@ -620,10 +620,17 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     if (timed) cudaEventRecord(c->ev[0], st);
     // ---- convolutions (features_from_raw folded into the first load) ----
     const float *cur = c->d_sig.as<float>();
+    const bool keep = (c->flags & FFB_FLAG_KEEP_LAYERS) != 0;
+    const bool tc_gemm = m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT);
     for (int i = 0; i < m->nconv; i++) {
-        float *out = (i + 1 == m->nconv) ? c->d_act[0].as<float>() : c->d_c[i].as<float>();
+        const bool lastc = (i + 1 == m->nconv);
+        float *out = lastc ? c->d_act[0].as<float>() : c->d_c[i].as<float>();
         const int act = (m->kind == FFB_KIND_GRU) ? FFB_ACT_TANH : FFB_ACT_SWISH;   // networks.c:458 / :546-554
-        LAUNCH(ffb_launch_conv(cur, out, m->d_convWt[i], m->d_convb[i], c->d_geom[i].as<ffb::ReadGeom>(),
+        // on the tensor path the last convolution writes the fp16 hi/lo planes the first input GEMM reads
+        // (and the fp32 copy only when the caller wants to look at it)
+        const bool planes = lastc && tc_gemm;
+        LAUNCH(ffb_launch_conv(cur, (planes && !keep) ? nullptr : out, planes ? c->d_ahi.p : nullptr, planes ? c->d_alo.p : nullptr,
+                               m->d_convWt[i], m->d_convb[i], c->d_geom[i].as<ffb::ReadGeom>(),
                                c->d_tails[i].as<ffb::ConvTail>(), (int)N, c->col_off[i + 1][N], c->max_T[i + 1],
                                m->conv_nf[i], m->conv_nfilter[i], m->conv_winlen[i], m->conv_stride[i], act, st));
         cur = out;
@@ -633,8 +640,6 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     // ---- five recurrent layers, directions B,F,B,F,B (networks.c:460-483 / :557-580) ----
     RnnBatch rb{c->d_order.as<int32_t>(), c->d_blkoff.as<int64_t>(), c->n_slots, (int)N};
     float gemm_ms = 0.f, rnn_ms = 0.f;
-    const bool keep = (c->flags & FFB_FLAG_KEEP_LAYERS) != 0;
-    const bool tc_gemm = m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT);
     const bool tc_rnn = c->use_tc_rnn && tc_gemm;
     const float *in = c->d_act[0].as<float>();   // fp32 input of the current layer (NULL when only planes exist)
     // streamed mode: GEMM l+1 is launched behind recurrence l and eats its output planes as they appear
@@ -654,8 +659,8 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         if (timed) cudaEventRecord(c->ev[5], st);
         if (tc_gemm) {
             if (!streamed || l == 0) {
-                // layers fed by the tensor recurrent kernel already have their fp16 hi/lo planes
-                if (l == 0 || !tc_rnn) LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
+                // layer 0 gets its fp16 hi/lo planes from the convolution, later layers from the tensor recurrent kernel
+                if (l > 0 && !tc_rnn) LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
                 LAUNCH(ffb_launch_gemm_tc(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l], m->d_iW_lo[l], m->d_b[l], xin, Tt,
                                           G * S, m->layer_in[l], st));
             }

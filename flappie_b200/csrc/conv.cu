@@ -15,6 +15,8 @@
 // One CTA computes a tile of columns of ONE read for all filters: the input span is
 // staged once in shared memory (coalesced, zero-filled outside the read), threads map to
 // filters so weight reads (Wt[tap*nf+f][filter]) and output writes are coalesced.
+#include <cuda_fp16.h>
+
 #include "ffb_common.cuh"
 
 namespace ffb {
@@ -22,9 +24,82 @@ namespace ffb {
 constexpr int CONV_TILE_C = 16;     // output columns per thread
 constexpr int CONV_THREADS = 256;
 
+__device__ __forceinline__ void conv_store(float *y, __half *yhi, __half *ylo, int64_t idx, float v) {
+    if (y) y[idx] = v;
+    if (yhi) {
+        const __half hi = __float2half_rn(v);
+        yhi[idx] = hi;
+        ylo[idx] = __float2half_rn(v - __half2float(hi));
+    }
+}
+
+// Single-feature input (the raw signal: conv of the GRU topology, first conv of the LSTM topology): the
+// thread's whole input window lives in registers, so the inner loop is one weight load per tap and
+// CONV_TILE_C register-register FMAs.
+template <int WINLEN, int STRIDE, int ACT>
+__global__ void __launch_bounds__(1024)
+conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ yhi, __half *__restrict__ ylo,
+             const float *__restrict__ Wt, const float *__restrict__ bias, const ReadGeom *__restrict__ geom,
+             const ConvTail *__restrict__ tails, int nfilter, int groups) {
+    extern __shared__ float xs[];   // [span]
+    const ReadGeom g = geom[blockIdx.x];
+    const int cols_per_cta = groups * CONV_TILE_C;
+    const int c0 = blockIdx.y * cols_per_cta;
+    if (c0 >= g.T_out) return;
+    constexpr int padL = (WINLEN - 1) / 2;
+    constexpr int WIN = (CONV_TILE_C - 1) * STRIDE + WINLEN;    // samples one thread needs
+    const int span = (cols_per_cta - 1) * STRIDE + WINLEN;
+    const int xin0 = c0 * STRIDE - padL;
+    const float *xr = x + g.in_off;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) {
+        const int col = xin0 + i;
+        xs[i] = (col >= 0 && col < g.T_in) ? xr[col] : 0.0f;
+    }
+    __syncthreads();
+    const int f = threadIdx.x % nfilter;
+    const int grp = threadIdx.x / nfilter;
+    if (grp >= groups) return;
+    const int cbase = grp * CONV_TILE_C;
+    float xw[WIN];
+#pragma unroll
+    for (int i = 0; i < WIN; i++) xw[i] = xs[cbase * STRIDE + i];
+    float acc[CONV_TILE_C];
+    const float b = bias[f];
+#pragma unroll
+    for (int c = 0; c < CONV_TILE_C; c++) acc[c] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < WINLEN; j++) {
+        const float w = __ldg(Wt + (size_t)j * nfilter + f);
+#pragma unroll
+        for (int c = 0; c < CONV_TILE_C; c++) acc[c] = fmaf(w, xw[c * STRIDE + j], acc[c]);
+    }
+    const ConvTail *tl = tails + g.tail_id;
+    const int tail0 = tl->tail_col0;
+#pragma unroll
+    for (int c = 0; c < CONV_TILE_C; c++) {
+        const int col = c0 + cbase + c;
+        if (col >= g.T_out) break;
+        float v = acc[c];
+        if (col >= tail0) {
+            const int ti = col - tail0;
+            v = 0.0f;
+            for (int q = 0; q < 2; q++) {
+                const int nt = tl->ntap[ti][q];
+                if (nt <= 0) continue;
+                const float *wq = Wt + (size_t)tl->tap_lo[ti][q] * nfilter + f;
+                const float *xq = xr + tl->x_start[ti][q];
+                float a = 0.0f;
+                for (int j = 0; j < nt; j++) a = fmaf(__ldg(wq + (size_t)j * nfilter), __ldg(xq + j), a);
+                v += a;
+            }
+        }
+        conv_store(y, yhi, ylo, (g.out_off + col) * (int64_t)nfilter + f, fast_activate(v + b, ACT));
+    }
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(1024)
-conv_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ Wt,
+conv_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ yhi, __half *__restrict__ ylo, const float *__restrict__ Wt,
             const float *__restrict__ bias, const ReadGeom *__restrict__ geom,
             const ConvTail *__restrict__ tails, int nf, int nfilter, int winlen, int stride,
             int groups /* column groups per CTA */) {
@@ -53,14 +128,27 @@ conv_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__r
     for (int c = 0; c < CONV_TILE_C; c++) acc[c] = 0.0f;
     const int K = winlen * nf;
     const float *xsb = xs + cbase * stride * nf;
-    for (int j = 0; j < K; j++) {
-        const float w = __ldg(Wt + (size_t)j * nfilter + f);
+    if ((nf & 3) == 0) {
+        // features are contiguous per input column: four taps per 16-byte shared load
+        for (int j = 0; j < K; j += 4) {
+            const float w0 = __ldg(Wt + (size_t)j * nfilter + f), w1 = __ldg(Wt + (size_t)(j + 1) * nfilter + f),
+                        w2 = __ldg(Wt + (size_t)(j + 2) * nfilter + f), w3 = __ldg(Wt + (size_t)(j + 3) * nfilter + f);
 #pragma unroll
-        for (int c = 0; c < CONV_TILE_C; c++) acc[c] = fmaf(w, xsb[c * stride * nf + j], acc[c]);
+            for (int c = 0; c < CONV_TILE_C; c++) {
+                const float4 xv = *reinterpret_cast<const float4 *>(xsb + c * stride * nf + j);
+                acc[c] = fmaf(w0, xv.x, acc[c]); acc[c] = fmaf(w1, xv.y, acc[c]);
+                acc[c] = fmaf(w2, xv.z, acc[c]); acc[c] = fmaf(w3, xv.w, acc[c]);
+            }
+        }
+    } else {
+        for (int j = 0; j < K; j++) {
+            const float w = __ldg(Wt + (size_t)j * nfilter + f);
+#pragma unroll
+            for (int c = 0; c < CONV_TILE_C; c++) acc[c] = fmaf(w, xsb[c * stride * nf + j], acc[c]);
+        }
     }
     const ConvTail *tl = tails + g.tail_id;
     const int tail0 = tl->tail_col0;
-    float *yr = y + g.out_off * nfilter;
 #pragma unroll
     for (int c = 0; c < CONV_TILE_C; c++) {
         const int col = c0 + cbase + c;
@@ -80,15 +168,15 @@ conv_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__r
                 v += a;
             }
         }
-        yr[(int64_t)col * nfilter + f] = activate(v + b, ACT);
+        conv_store(y, yhi, ylo, (g.out_off + col) * (int64_t)nfilter + f, fast_activate(v + b, ACT));
     }
 }
 
 }  // namespace ffb
 
-int ffb_launch_conv(const float *x, float *y, const float *Wt, const float *bias, const ffb::ReadGeom *geom,
-                    const ffb::ConvTail *tails, int n_reads, int64_t total_out_cols, int max_T_out, int nf,
-                    int nfilter, int winlen, int stride, int act, cudaStream_t st) {
+int ffb_launch_conv(const float *x, float *y, void *yhi_, void *ylo_, const float *Wt, const float *bias,
+                    const ffb::ReadGeom *geom, const ffb::ConvTail *tails, int n_reads, int64_t total_out_cols,
+                    int max_T_out, int nf, int nfilter, int winlen, int stride, int act, cudaStream_t st) {
     using namespace ffb;
     (void)total_out_cols;
     if (n_reads <= 0 || max_T_out <= 0) return 0;
@@ -101,14 +189,28 @@ int ffb_launch_conv(const float *x, float *y, const float *Wt, const float *bias
         groups = CONV_THREADS / nfilter;
         threads = groups * nfilter;
     }
+    __half *yhi = (__half *)yhi_, *ylo = (__half *)ylo_;
     const int cols_per_cta = groups * CONV_TILE_C;
     const int span = (cols_per_cta - 1) * stride + winlen;
     const size_t smem = (size_t)span * nf * sizeof(float);
     dim3 grid(n_reads, (max_T_out + cols_per_cta - 1) / cols_per_cta);   // x = read, y = column tile
     if (grid.y > 65535) return -1;
+    if (nf == 1 && ((winlen == 19 && stride == 2) || (winlen == 5 && stride == 1))) {
+        auto launch1 = [&](auto kern) { kern<<<grid, threads, smem, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nfilter, groups); };
+        if (winlen == 19) {
+            if (act == FFB_ACT_TANH) launch1(conv1_kernel<19, 2, FFB_ACT_TANH>);
+            else if (act == FFB_ACT_SWISH) launch1(conv1_kernel<19, 2, FFB_ACT_SWISH>);
+            else launch1(conv1_kernel<19, 2, FFB_ACT_NONE>);
+        } else {
+            if (act == FFB_ACT_TANH) launch1(conv1_kernel<5, 1, FFB_ACT_TANH>);
+            else if (act == FFB_ACT_SWISH) launch1(conv1_kernel<5, 1, FFB_ACT_SWISH>);
+            else launch1(conv1_kernel<5, 1, FFB_ACT_NONE>);
+        }
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     auto launch = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, threads, smem, st>>>(x, y, Wt, bias, geom, tails, nf, nfilter, winlen, stride, groups);
+        kern<<<grid, threads, smem, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nf, nfilter, winlen, stride, groups);
     };
     if (act == FFB_ACT_TANH) launch(conv_kernel<FFB_ACT_TANH>);
     else if (act == FFB_ACT_SWISH) launch(conv_kernel<FFB_ACT_SWISH>);

@@ -25,6 +25,23 @@ __device__ __forceinline__ float activate(float x, int act) {
     if (act == FFB_ACT_SWISH) return x * logisticf(x);
     return x;
 }
+// MUFU versions for the throughput kernels: ex2.approx (2 ulp) + rcp.approx (1 ulp); same formulas as the
+// reference (src/util.h:331-339), errors of a few 1e-7, far below the parity tolerances (1e-5 .. 1e-4)
+__device__ __forceinline__ float fast_logistic(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float y = fast_logistic(x + x);
+    return (y + y) - 1.0f;
+}
+__device__ __forceinline__ float fast_activate(float x, int act) {
+    if (act == FFB_ACT_TANH) return fast_tanh(x);
+    if (act == FFB_ACT_SWISH) return x * fast_logistic(x);
+    return x;
+}
 // reference src/util.h:276-278
 __device__ __forceinline__ float logsumexpf_ref(float x, float y) {
     return fmaxf(x, y) + log1pf(expf(-fabsf(x - y)));
@@ -57,9 +74,10 @@ struct ReadGeom {
 // Every launcher returns the number of kernels it launched (>=0) or -1 on launch error.
 
 // conv.cu: x [cols][nf] -> y [cols'][nfilter], weights Wt [winlen*nf][nfilter].
-int ffb_launch_conv(const float *x, float *y, const float *Wt, const float *bias, const ffb::ReadGeom *geom,
-                    const ffb::ConvTail *tails, int n_reads, int64_t total_out_cols, int max_T_out, int nf,
-                    int nfilter, int winlen, int stride, int act, cudaStream_t st);
+// y (fp32) and/or the fp16 hi/lo planes yhi/ylo (x = hi + lo, for the tensor GEMM) may be NULL
+int ffb_launch_conv(const float *x, float *y, void *yhi, void *ylo, const float *Wt, const float *bias,
+                    const ffb::ReadGeom *geom, const ffb::ConvTail *tails, int n_reads, int64_t total_out_cols,
+                    int max_T_out, int nf, int nfilter, int winlen, int stride, int act, cudaStream_t st);
 
 // gemm.cu: C[M][N] = A[M][K] * Wt[K][N] + bias[N]   (fp32 CUDA cores)
 int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,

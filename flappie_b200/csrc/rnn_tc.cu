@@ -113,19 +113,6 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]
     for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// sigma and tanh on the MUFU pipe: ex2.approx (2 ulp) + rcp.approx (1 ulp); same formulas as the
-// reference (src/util.h:331-339), errors of a few 1e-7, far below the 1e-4 parity tolerance
-__device__ __forceinline__ float fast_logistic(float x) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return r;
-}
-__device__ __forceinline__ float fast_tanh(float x) {
-    const float y = fast_logistic(x + x);
-    return (y + y) - 1.0f;
-}
-
 // Optional phase timing of one control thread and one gate warp (cluster 0, CTA 0, group 0):
 // build with FFB_EXTRA_NVCC_FLAGS=-DFFB_RNN_PROFILE, read with ffb_test_rnn_prof() (testhooks.cu).
 #ifdef FFB_RNN_PROFILE
