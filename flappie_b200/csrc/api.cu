@@ -82,6 +82,9 @@ struct ffb_model {
     float *d_convWt[FFB_MAX_CONV] = {nullptr}, *d_convb[FFB_MAX_CONV] = {nullptr};
     float *d_iWt[FFB_NLAYER] = {nullptr}, *d_b[FFB_NLAYER] = {nullptr}, *d_sWp[FFB_NLAYER] = {nullptr};
     float *d_ffWt = nullptr, *d_ffb = nullptr;
+    void *d_ff_hi = nullptr, *d_ff_lo = nullptr;   // fp16 planes of FF_W [FFB_FF_TC_ROWS][S], zero-padded (tensor output layer)
+    float *d_ffb_pad = nullptr;
+    bool tc_ff = false;
     void *d_iW_hi[FFB_NLAYER] = {nullptr}, *d_iW_lo[FFB_NLAYER] = {nullptr};   // fp16 planes [G*S][in] for the tensor path
     bool tc_gemm = false;
     void *d_sW_img[FFB_NLAYER] = {nullptr};   // per-CTA shared-memory images of sW (fp16 hi/lo) for rnn_tc
@@ -110,6 +113,7 @@ extern "C" void ffb_model_destroy(ffb_model *m) {
     for (int i = 0; i < FFB_MAX_CONV; i++) { cudaFree(m->d_convWt[i]); cudaFree(m->d_convb[i]); }
     for (int i = 0; i < FFB_NLAYER; i++) { cudaFree(m->d_iWt[i]); cudaFree(m->d_b[i]); cudaFree(m->d_sWp[i]); cudaFree(m->d_iW_hi[i]); cudaFree(m->d_iW_lo[i]); cudaFree(m->d_sW_img[i]); }
     cudaFree(m->d_ffWt); cudaFree(m->d_ffb);
+    cudaFree(m->d_ff_hi); cudaFree(m->d_ff_lo); cudaFree(m->d_ffb_pad);
     delete m;
 }
 
@@ -212,6 +216,21 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             }
             m->d_ffWt = upload(Wt); m->d_ffb = upload(bb);
             ok = m->d_ffWt && m->d_ffb;
+            if (ok && ffb_ff_tc_supported(m->nparam, m->S)) {
+                // [out][in] planes like iW, zero rows beyond nparam
+                std::vector<float> Wd((size_t)FFB_FF_TC_ROWS * m->S, 0.0f), bp(FFB_FF_TC_ROWS, 0.0f);
+                for (int n = 0; n < m->nparam; n++) {
+                    for (int k = 0; k < m->S; k++) Wd[(size_t)n * m->S + k] = mat_at(FW, k, n);
+                    bp[n] = bb[n];
+                }
+                float *tmp = upload(Wd);
+                m->d_ffb_pad = upload(bp);
+                ok = tmp && m->d_ffb_pad && cudaMalloc(&m->d_ff_hi, Wd.size() * 2) == cudaSuccess &&
+                     cudaMalloc(&m->d_ff_lo, Wd.size() * 2) == cudaSuccess &&
+                     ffb_launch_split_f16(tmp, m->d_ff_hi, m->d_ff_lo, (int64_t)Wd.size(), 0) >= 0 && cudaDeviceSynchronize() == cudaSuccess;
+                cudaFree(tmp);
+                m->tc_ff = ok;
+            }
         }
     }
     if (ok) {
@@ -641,6 +660,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     RnnBatch rb{c->d_order.as<int32_t>(), c->d_blkoff.as<int64_t>(), c->n_slots, (int)N};
     float gemm_ms = 0.f, rnn_ms = 0.f;
     const bool tc_rnn = c->use_tc_rnn && tc_gemm;
+    const bool tc_ff = tc_rnn && m->tc_ff && getenv("FFB_NO_TC_FF") == nullptr;
     const float *in = c->d_act[0].as<float>();   // fp32 input of the current layer (NULL when only planes exist)
     // streamed mode: GEMM l+1 is launched behind recurrence l and eats its output planes as they appear
     int sm_count = 148;
@@ -669,10 +689,12 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         }
         if (timed) cudaEventRecord(c->ev[6], st);
         if (tc_rnn) {
-            float *out_f32 = (keep || last) ? out : nullptr;
+            // the top layer feeds the output layer: fp16 planes for the tensor version, fp32 otherwise
+            const bool planes_out = !last || tc_ff;
+            float *out_f32 = (keep || (last && !tc_ff)) ? out : nullptr;
             int *prog = (streamed && !last) ? c->d_progress.as<int>() + (size_t)l * prog_stride : nullptr;
-            LAUNCH(ffb_launch_rnn_tc(m->kind, S, xin, m->d_sW_img[l], out_f32, last ? nullptr : c->d_ahi.p,
-                                     last ? nullptr : c->d_alo.p, rb, c->R_tc, (l % 2) == 0, c->d_ring.p, prog, st));
+            LAUNCH(ffb_launch_rnn_tc(m->kind, S, xin, m->d_sW_img[l], out_f32, planes_out ? c->d_ahi.p : nullptr,
+                                     planes_out ? c->d_alo.p : nullptr, rb, c->R_tc, (l % 2) == 0, c->d_ring.p, prog, st));
             if (streamed && !last) {
                 const int dir = (l % 2) == 0 ? 1 : 0;   // layer l runs backward for even l (networks.c:460-483)
                 LAUNCH(ffb_launch_gemm_tc_streamed(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l + 1], m->d_iW_lo[l + 1], m->d_b[l + 1],
@@ -697,7 +719,11 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     const float *top = in;
     if (timed) cudaEventRecord(c->ev[2], st);
     // ---- globalnorm_flipflop (layers.c:1082-1106) ----
-    LAUNCH(ffb_launch_ff_tanh(top, m->d_ffWt, m->d_ffb, c->d_trans.as<float>(), Tt, nr, S, c->temperature / 5.0f, st));
+    if (tc_ff)
+        LAUNCH(ffb_launch_ff_tanh_tc(c->d_ahi.p, c->d_alo.p, m->d_ff_hi, m->d_ff_lo, m->d_ffb_pad, c->d_trans.as<float>(), Tt, nr, S,
+                                     c->temperature / 5.0f, st));
+    else
+        LAUNCH(ffb_launch_ff_tanh(top, m->d_ffWt, m->d_ffb, c->d_trans.as<float>(), Tt, nr, S, c->temperature / 5.0f, st));
     // -logZ/T (layers.c:1035-1096) shifts every entry of a read by one constant.  The posteriors, their Viterbi
     // path, qualities, score and trace are invariant under it (decode.cu, fb kernels), so in forward-backward
     // mode the fp64 partition scan only runs when the caller wants `trans` itself.

@@ -102,6 +102,12 @@ int ffb_gemm_tc_supported(int N, int K);
 int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st);
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                        int64_t M, int N, int K, cudaStream_t st);
+// Output layer on the same kernel family: trans[M][n_out] = tanh(A*W^T + b) / scale; W planes [FFB_FF_TC_ROWS][K] and
+// bias [FFB_FF_TC_ROWS] are zero-padded beyond n_out (n_out = 40 / 60)
+#define FFB_FF_TC_ROWS 64
+int ffb_ff_tc_supported(int n_out, int K);
+int ffb_launch_ff_tanh_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                          int64_t M, int n_out, int K, float scale, cudaStream_t st);
 // Streamed variant: launched (programmatic dependent launch) right behind the recurrent kernel that is still
 // writing the A planes; work items are taken from per-panel ticket queues in `work` order and each waits for its dependencies;
 // CTAs that find no free SM while the recurrence runs start when it ends and drain what is left.  Returns 0 (nothing launched) when the shape is unsupported.

@@ -120,11 +120,14 @@ struct GemmTcCfg {
     static constexpr int THREADS = 192;
 };
 
-template <int BN>
+// ACT = 0: C[M][N] = A*W^T + b.   ACT = 1 (flip-flop output layer, N == BN): only the first n_out columns exist,
+// C[M][n_out] = tanh(A*W^T + b) / scale -- the affine_map + tanh_activation_inplace + shift_scale_matrix_inplace of
+// reference globalnorm_manystay (src/layers.c:1082-1087); W and b are zero-padded to BN rows by the caller.
+template <int BN, int ACT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-               const float *__restrict__ bias, float *__restrict__ C, int64_t M, int N, int K) {
+               const float *__restrict__ bias, float *__restrict__ C, int64_t M, int N, int K, int n_out, float scale) {
     using Cfg = GemmTcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -213,10 +216,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             mbar_wait(&acc_full[acc], acc_phase);
             tcgen05_fence_after();
             const int64_t row = m0 + quad * 32 + lane;
-            float *crow = C + row * (int64_t)N + n0;
+            float *crow = C + row * (int64_t)(ACT ? n_out : N) + n0;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN;
 #pragma unroll 2
             for (int c = 0; c < BN; c += 16) {
+                if (ACT && c >= n_out) break;          // warp-uniform: the padded columns are never read
                 float v[16], vx[16];
                 tmem_ld16(taddr + c, v);
                 tmem_ld16(taddr + BN + c, vx);
@@ -227,8 +231,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(bias + n0 + c + j);
-                        __stcs(reinterpret_cast<float4 *>(crow + c + j),
-                               make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w));
+                        if constexpr (ACT == 0) {
+                            __stcs(reinterpret_cast<float4 *>(crow + c + j),
+                                   make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w));
+                        } else if (c + j < n_out) {        // n_out % 4 == 0
+                            // shift_scale_matrix_inplace divides: (x - 0) / scale (src/flappie_matrix.c:625-633)
+                            *reinterpret_cast<float4 *>(crow + c + j) =
+                                make_float4(tanh_ref(v[j] + b4.x) / scale, tanh_ref(v[j + 1] + b4.y) / scale,
+                                            tanh_ref(v[j + 2] + b4.z) / scale, tanh_ref(v[j + 3] + b4.w) / scale);
+                        }
                     }
                 }
             }
@@ -564,9 +575,9 @@ int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStre
 
 int ffb_gemm_tc_supported(int N, int K) { return (N % 64 == 0) && (K % 64 == 0) && K >= 64; }
 
-template <int BN>
+template <int BN, int ACT = 0>
 static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                          int64_t M, int N, int K, cudaStream_t st) {
+                          int64_t M, int N, int K, cudaStream_t st, int n_out = 0, float scale = 1.0f) {
     using Cfg = ffb::GemmTcCfg<BN>;
     CUtensorMap mAh, mAl, mBh, mBl;
     if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, 128) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, 128) ||
@@ -574,7 +585,7 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
         return -1;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(ffb::gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(ffb::gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
         attr_done = true;
     }
     const int64_t ntile = ((M + 127) / 128) * (N / BN);
@@ -582,7 +593,7 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(ntile < sms ? ntile : sms);
-    ffb::gemm_tc_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K);
+    ffb::gemm_tc_kernel<BN, ACT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K, n_out, scale);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -656,6 +667,16 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
     if (N % 256 == 0) return launch_gemm_tc<256>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 128 == 0) return launch_gemm_tc<128>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     return launch_gemm_tc<64>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
+}
+
+// Flip-flop output layer on the tensor cores: trans[M][n_out] = tanh(A * W^T + b) / scale with W planes and bias
+// zero-padded to FFB_FF_TC_ROWS rows.
+int ffb_ff_tc_supported(int n_out, int K) { return n_out % 4 == 0 && n_out > 0 && n_out <= FFB_FF_TC_ROWS && ffb_gemm_tc_supported(FFB_FF_TC_ROWS, K); }
+int ffb_launch_ff_tanh_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
+                          int64_t M, int n_out, int K, float scale, cudaStream_t st) {
+    if (M <= 0) return 0;
+    if (!ffb_ff_tc_supported(n_out, K)) return -1;
+    return launch_gemm_tc<FFB_FF_TC_ROWS, 1>(Ahi, Alo, Whi, Wlo, bias, C, M, FFB_FF_TC_ROWS, K, st, n_out, scale);
 }
 
 int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, int a_in_tmem, cudaStream_t st) {
