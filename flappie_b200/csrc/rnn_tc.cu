@@ -220,10 +220,10 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 PROF(0);
                 mbar_arrive_expect_tx(&h_full[g], C * Cfg::SLICE);    // arm phase s: peers push h_s only after my MMA(s)
                 tcgen05_fence_after();
-                // 3*S/16 MMAs as THREE independent accumulation chains of S/16, issued round-robin: back-to-back
-                // MMAs into the same accumulator are ~45 clk apart whatever N is (mma_rate_bench), different
-                // accumulators pipeline at the tensor rate.  Within a chain the 2^-11-sized cross terms go first,
-                // so each accumulator still sees only S/32 full-magnitude (truncating) accumulations.
+                // 3*S/16 MMAs into THREE accumulators -- for accuracy, not speed: N=16 MMAs with uniform-register
+                // operands issue at ~9 clk whichever accumulator they target (profiles/r01_mma_indep_microbench.txt).
+                // Within an accumulator the 2^-11-sized cross terms go first, so each one sees only S/32
+                // full-magnitude (truncating) accumulations.
                 //   chain 0: Whi*hlo then Whi*hhi over K-half 0     chain 1: the same over K-half 1
                 //   chain 2: Wlo*hhi over all of K
                 constexpr int KS = S / 16, KH = S / 32;
