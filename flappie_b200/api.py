@@ -43,6 +43,7 @@ EXPORTS = [
     "ffb_model_size", "ffb_model_nparam", "ffb_model_stride", "ffb_model_nblock", "ffb_register_model",
     "ffb_create", "ffb_destroy", "ffb_basecall_batch", "ffb_upload", "ffb_forward", "ffb_download", "ffb_sync",
     "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_emit_bases",
+    "ffb_upload_raw", "ffb_basecall_raw_batch",
 ]
 
 
@@ -68,6 +69,16 @@ class Batch(ctypes.Structure):
         ("blk_off", POINTER(c_int64)), ("path", POINTER(c_int32)), ("qpath", POINTER(c_float)),
         ("score", POINTER(c_float)), ("trans", POINTER(c_float)), ("tpost", POINTER(c_float)),
         ("trace", POINTER(c_uint8)),
+    ]
+
+
+class RawBatch(ctypes.Structure):
+    """ffb_raw_batch: raw reads + the reference CLI's trimming / normalisation options."""
+    _fields_ = [
+        ("raw", POINTER(c_float)), ("raw_off", POINTER(c_int64)), ("n_reads", c_int64),
+        ("trim_start", c_int64), ("trim_end", c_int64), ("varseg_chunk", c_int64),
+        ("varseg_thresh", c_float), ("delta", c_float),
+        ("start", POINTER(c_int64)), ("end", POINTER(c_int64)),
     ]
 
 
@@ -113,6 +124,8 @@ class Library:
         L.ffb_destroy.restype = None; L.ffb_destroy.argtypes = [c_void_p]
         for n in ("ffb_basecall_batch", "ffb_upload", "ffb_download"):
             getattr(L, n).restype = c_int; getattr(L, n).argtypes = [c_void_p, POINTER(Batch)]
+        for n in ("ffb_upload_raw", "ffb_basecall_raw_batch"):
+            getattr(L, n).restype = c_int; getattr(L, n).argtypes = [c_void_p, POINTER(RawBatch), POINTER(Batch)]
         L.ffb_forward.restype = c_int; L.ffb_forward.argtypes = [c_void_p]
         L.ffb_sync.restype = c_int; L.ffb_sync.argtypes = [c_void_p]
         L.ffb_total_blocks.restype = c_int64; L.ffb_total_blocks.argtypes = [c_void_p]
@@ -346,6 +359,50 @@ class Context:
         self._check(self.lib.lib.ffb_basecall_batch(self.handle, ctypes.byref(b)), "ffb_basecall_batch")
         return BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),
                            o.get("trace"), fm.nstate, fm.nparam)
+
+    def make_raw_batch(self, raw: np.ndarray, raw_off: np.ndarray, trim=(200, 10), segmentation=(100, 0.0),
+                       delta: float = 0.0):
+        """C `ffb_raw_batch` over caller-owned buffers; defaults = the reference CLI's (src/flappie.c:100-110)."""
+        n = raw_off.shape[0] - 1
+        assert raw.dtype == np.float32 and raw_off.dtype == np.int64
+        start = np.zeros(max(n, 1), np.int64)
+        end = np.zeros(max(n, 1), np.int64)
+        rb = RawBatch(raw.ctypes.data_as(POINTER(c_float)), raw_off.ctypes.data_as(POINTER(c_int64)), n,
+                      int(trim[0]), int(trim[1]), int(segmentation[0]), float(segmentation[1]), float(delta),
+                      start.ctypes.data_as(POINTER(c_int64)), end.ctypes.data_as(POINTER(c_int64)))
+        self._keep_raw = (raw, raw_off, start, end)
+        return rb, start, end
+
+    def basecall_raw(self, raws: Sequence[np.ndarray], temperature: float = 1.0, viterbi_only: bool = False,
+                     want_trace: bool = False, want_trans: bool = False, trim=(200, 10), segmentation=(100, 0.0),
+                     delta: float = 0.0) -> BatchResult:
+        """calculate_post from the raw signal on (reference src/flappie.c:245-316) for a list of raw reads
+        (pA floats): trimming + normalisation on the device, then the whole hot path.  The result carries
+        `start` / `end` (kept range per read)."""
+        fm = self.model.fm
+        n = len(raws)
+        lens = np.array([len(r) for r in raws], np.int64)
+        raw_off = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=raw_off[1:])
+        raw = np.concatenate([np.asarray(r, np.float32) for r in raws]) if n else np.zeros(1, np.float32)
+        flags = (FLAG_VITERBI_ONLY if viterbi_only else 0) | (FLAG_WANT_TRACE if want_trace else 0) | \
+                (FLAG_WANT_TRANS if want_trans else 0)
+        # outputs sized for the untrimmed lengths (upper bound on the block count)
+        b, o = self.make_batch(raw, raw_off, temperature, flags)
+        rb, start, end = self.make_raw_batch(raw, raw_off, trim, segmentation, delta)
+        self._check(self.lib.lib.ffb_basecall_raw_batch(self.handle, ctypes.byref(rb), ctypes.byref(b)), "ffb_basecall_raw_batch")
+        res = BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),
+                          o.get("trace"), fm.nstate, fm.nparam)
+        res.start, res.end = start[:n], end[:n]
+        return res
+
+    def fetch_signal(self, n_samples: int) -> np.ndarray:
+        """The normalised signal the network read (concatenated kept ranges of the last batch)."""
+        out = np.zeros(max(n_samples, 1), np.float32)
+        r = self.lib.lib.ffb_debug_fetch(self.handle, 8, out.ctypes.data_as(c_void_p), 4 * n_samples)
+        if r < 0:
+            raise FlappieB200Error("ffb_debug_fetch failed: " + self.lib.last_error())
+        return out[:n_samples]
 
     def upload(self, b: Batch):
         self._check(self.lib.lib.ffb_upload(self.handle, ctypes.byref(b)), "ffb_upload")

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "libflappie_b200.so")
-SOURCES = ["conv.cu", "gemm.cu", "gemm_tc.cu", "rnn.cu", "rnn_tc.cu", "decode.cu", "api.cu", "testhooks.cu"]
+SOURCES = ["conv.cu", "signal.cu", "gemm.cu", "gemm_tc.cu", "rnn.cu", "rnn_tc.cu", "decode.cu", "api.cu", "testhooks.cu"]
 HEADERS = ["ffb_common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "flappie_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]

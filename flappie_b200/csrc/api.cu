@@ -365,6 +365,7 @@ struct ffb_ctx {
     // device
     DevBuf d_sig, d_c[2], d_act[2], d_xin, d_trans, d_tpost, d_fwd, d_tb, d_path, d_qpath, d_score, d_logz, d_trace;
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
+    DevBuf d_raw, d_rawoff, d_chunkoff, d_mad, d_bounds, d_sigoff;   // device signal preparation (ffb_upload_raw)
     DevBuf d_ahi, d_alo;          // fp16 hi/lo planes of the current layer input (tensor path)
     DevBuf d_ring;                // state-exchange ring of the tensor recurrent kernel (L2-resident)
     // streamed input GEMMs: layer l+1's projection runs on the SMs layer l's recurrence leaves free and consumes
@@ -402,7 +403,8 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
-                     &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress};
+                     &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress,
+                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -420,8 +422,18 @@ extern "C" int ffb_sync(ffb_ctx *c) {
 }
 
 // ---- planning + H2D ------------------------------------------------------------------
-extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
-    if (!c || !b || !b->signal || !b->sig_off || b->n_reads < 0) { set_err("ffb_upload: bad arguments"); return FFB_ERR_ARG; }
+#define LAUNCH_RAW(expr)                                                     \
+    do {                                                                     \
+        const int n_ = (expr);                                               \
+        if (n_ < 0) {                                                        \
+            set_err("launch failed: %s: %s", #expr, cudaGetErrorString(cudaGetLastError())); \
+            return FFB_ERR_CUDA;                                             \
+        }                                                                    \
+        c->launches += n_;                                                   \
+    } while (0)
+// copy_signal = false: the normalised signal is produced on the device (ffb_upload_raw), only the plan is made here
+static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
+    if (!c || !b || (copy_signal && !b->signal) || !b->sig_off || b->n_reads < 0) { set_err("ffb_upload: bad arguments"); return FFB_ERR_ARG; }
     ffb_model *m = c->m;
     CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
     const int64_t N = b->n_reads;
@@ -599,7 +611,7 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
     if (!ok) { set_err("ffb_upload: out of device memory for %lld reads / %lld blocks", (long long)N, (long long)Tt); return FFB_ERR_NOMEM; }
 
     // ---- H2D (signal is the only bulk input: 4 bytes per raw sample) ----
-    if (c->total_samples > 0)
+    if (c->total_samples > 0 && copy_signal)
         CUDA_TRY(cudaMemcpyAsync(c->d_sig.p, b->signal + b->sig_off[0], sizeof(float) * (size_t)c->total_samples,
                                  cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
     CUDA_TRY(cudaMemcpyAsync(c->d_blkoff.p, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
@@ -615,6 +627,73 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) {
             CUDA_TRY(cudaMemcpyAsync(c->d_work[dir].p, work[dir].data(), sizeof(GemmWork) * work[dir].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
     // the staging vectors above are pageable: make sure the copies have consumed them
     CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
+    return FFB_OK;
+}
+
+extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) { return upload_impl(c, b, true); }
+
+// ---- raw reads: trimming + normalisation on the device, then the same plan -----------------------
+// (reference src/flappie.c:251-259; kernels in signal.cu)
+extern "C" int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
+    if (!c || !rb || !b || !rb->raw || !rb->raw_off || rb->n_reads < 0 || rb->n_reads != b->n_reads) {
+        set_err("ffb_upload_raw: bad arguments");
+        return FFB_ERR_ARG;
+    }
+    if (rb->varseg_chunk < 2 || rb->varseg_chunk > FFB_MAX_VARSEG_CHUNK || rb->varseg_thresh < 0.0f || rb->varseg_thresh > 1.0f ||
+        rb->trim_start < 0 || rb->trim_end < 0) {
+        set_err("ffb_upload_raw: varseg_chunk must be in [2, %d], varseg_thresh in [0, 1], trims >= 0", FFB_MAX_VARSEG_CHUNK);
+        return FFB_ERR_UNSUPPORTED;
+    }
+    ffb_model *m = c->m;
+    CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
+    const int64_t N = rb->n_reads;
+    if (N > 0x7fffffff) return FFB_ERR_ARG;
+    const int chunk = (int)rb->varseg_chunk;
+    const int64_t total_raw = rb->raw_off[N] - rb->raw_off[0];
+    std::vector<int64_t> roff((size_t)N + 1), coff((size_t)N + 1, 0);
+    for (int64_t n = 0; n <= N; n++) roff[(size_t)n] = rb->raw_off[n] - rb->raw_off[0];
+    for (int64_t n = 0; n < N; n++) {
+        if (roff[(size_t)n + 1] < roff[(size_t)n]) { set_err("ffb_upload_raw: raw_off must be non-decreasing"); return FFB_ERR_ARG; }
+        coff[(size_t)n + 1] = coff[(size_t)n] + (roff[(size_t)n + 1] - roff[(size_t)n]) / chunk;
+    }
+    const int64_t total_chunks = coff[(size_t)N];
+    bool ok = c->d_raw.reserve(sizeof(float) * (size_t)std::max<int64_t>(total_raw, 1)) == 0 &&
+              c->d_rawoff.reserve(sizeof(int64_t) * (size_t)(N + 1)) == 0 && c->d_chunkoff.reserve(sizeof(int64_t) * (size_t)(N + 1)) == 0 &&
+              c->d_mad.reserve(sizeof(float) * (size_t)std::max<int64_t>(total_chunks, 1)) == 0 &&
+              c->d_bounds.reserve(sizeof(int64_t) * 2 * (size_t)std::max<int64_t>(N, 1)) == 0 &&
+              c->d_sigoff.reserve(sizeof(int64_t) * (size_t)(N + 1)) == 0;
+    if (!ok) { set_err("ffb_upload_raw: out of device memory"); return FFB_ERR_NOMEM; }
+    cudaStream_t st = c->st;
+    std::vector<int64_t> bounds(2 * (size_t)N, 0), soff((size_t)N + 1, 0);
+    if (N > 0) {
+        if (total_raw > 0)
+            CUDA_TRY(cudaMemcpyAsync(c->d_raw.p, rb->raw + rb->raw_off[0], sizeof(float) * (size_t)total_raw, cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        CUDA_TRY(cudaMemcpyAsync(c->d_rawoff.p, roff.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        CUDA_TRY(cudaMemcpyAsync(c->d_chunkoff.p, coff.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        LAUNCH_RAW(ffb_launch_chunk_mad(c->d_raw.as<float>(), c->d_rawoff.as<int64_t>(), c->d_chunkoff.as<int64_t>(), (int)N, chunk,
+                                        total_chunks, c->d_mad.as<float>(), st));
+        LAUNCH_RAW(ffb_launch_trim_bounds(c->d_mad.as<float>(), c->d_rawoff.as<int64_t>(), c->d_chunkoff.as<int64_t>(), (int)N, chunk,
+                                          rb->varseg_thresh, rb->trim_start, rb->trim_end, c->d_bounds.as<int64_t>(), st));
+        CUDA_TRY(cudaMemcpyAsync(bounds.data(), c->d_bounds.p, sizeof(int64_t) * 2 * (size_t)N, cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        CUDA_TRY(cudaStreamSynchronize(st), FFB_ERR_CUDA);     // the plan below needs the trimmed lengths
+    }
+    for (int64_t n = 0; n < N; n++) {
+        const int64_t s = bounds[2 * (size_t)n], e = bounds[2 * (size_t)n + 1];
+        soff[(size_t)n + 1] = soff[(size_t)n] + (s < e ? e - s : 0);    // start >= end: the reference drops the read (flappie_common.c:22-25)
+        if (rb->start) rb->start[n] = s;
+        if (rb->end) rb->end[n] = e;
+    }
+    ffb_batch plan = *b;
+    plan.signal = nullptr;
+    plan.sig_off = soff.data();
+    const int r = upload_impl(c, &plan, false);
+    if (r != FFB_OK) return r;
+    if (N > 0) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_sigoff.p, soff.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        LAUNCH_RAW(ffb_launch_normalise(c->d_raw.as<float>(), c->d_rawoff.as<int64_t>(), c->d_bounds.as<int64_t>(), c->d_sigoff.as<int64_t>(),
+                                        (int)N, rb->delta, c->d_sig.as<float>(), st));
+        CUDA_TRY(cudaStreamSynchronize(st), FFB_ERR_CUDA);     // soff is a stack-lifetime staging vector
+    }
     return FFB_OK;
 }
 
@@ -807,6 +886,14 @@ extern "C" int ffb_basecall_batch(ffb_ctx *c, const ffb_batch *b) {
     return ffb_download(c, b);
 }
 
+extern "C" int ffb_basecall_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
+    int r = ffb_upload_raw(c, rb, b);
+    if (r != FFB_OK) return r;
+    r = ffb_forward(c);
+    if (r != FFB_OK) return r;
+    return ffb_download(c, b);
+}
+
 extern "C" int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t bytes) {
     if (!c || !dst) return FFB_ERR_ARG;
     ffb_model *m = c->m;
@@ -824,6 +911,8 @@ extern "C" int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t byte
         src = c->d_trans.p; have = Tt * m->nparam * (int64_t)sizeof(float);
     } else if (what == 7) {
         src = c->d_logz.p; have = c->n_reads * (int64_t)sizeof(double);
+    } else if (what == 8) {
+        src = c->d_sig.p; have = c->total_samples * (int64_t)sizeof(float);
     } else {
         return FFB_ERR_ARG;
     }

@@ -148,6 +148,15 @@ size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R);   // L2-re
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
                       const RnnBatch &rb, int R, int backward, void *ring, int *progress, cudaStream_t st);
 
+// signal.cu: trimming + normalisation of raw reads on the device (reference src/flappie.c:251-259)
+#define FFB_MAX_VARSEG_CHUNK 1024
+int ffb_launch_chunk_mad(const float *raw, const int64_t *raw_off, const int64_t *chunk_off, int n_reads, int chunk,
+                         int64_t total_chunks, float *mad, cudaStream_t st);
+int ffb_launch_trim_bounds(const float *mad, const int64_t *raw_off, const int64_t *chunk_off, int n_reads, int chunk,
+                           float perc, int64_t trim_start, int64_t trim_end, int64_t *bounds, cudaStream_t st);
+int ffb_launch_normalise(const float *raw, const int64_t *raw_off, const int64_t *bounds, const int64_t *sig_off,
+                         int n_reads, float delta, float *out, cudaStream_t st);
+
 // decode.cu
 int ffb_launch_logz(const float *trans, const int64_t *blk_off, int n_reads, int nr, double *logZ, cudaStream_t st);
 int ffb_launch_sub_logz(float *trans, const int64_t *blk_off, int n_reads, int nr, const double *logZ,

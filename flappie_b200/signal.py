@@ -18,7 +18,9 @@ def quantilef(x: np.ndarray, p: float) -> np.float32:
     idx = int(pos)
     remf = np.float32(pos - np.float32(idx))
     if idx < nx - 1:
-        return np.float32((1.0 - float(remf)) * float(space[idx]) + float(remf) * float(space[idx + 1]))
+        # C: `(1.0 - remf) * space[idx] + remf * space[idx + 1]` -- the first product is double, the second a
+        # float product that is then widened
+        return np.float32((1.0 - float(remf)) * float(space[idx]) + float(np.float32(remf * space[idx + 1])))
     return space[idx]
 
 

@@ -180,6 +180,31 @@ int ffb_forward(ffb_ctx *c);
 int ffb_download(ffb_ctx *c, const ffb_batch *b);
 int ffb_sync(ffb_ctx *c);
 
+/* Raw reads: the signal preparation of calculate_post (reference src/flappie.c:251-259) on the device --
+ * trim_and_segment_raw (src/flappie_common.c:13-81, chunk MADs + threshold quantile), then
+ * medmad_normalise_array (src/util.c:198-212), or difference_array + shift_scale_array when delta != 0
+ * (src/util.c:215-223,278-287) -- followed by the same plan as ffb_upload.
+ * raw         : concatenated raw samples (pA, as read_raw returns them), HOST memory
+ * raw_off[n]  : start of read n in `raw` (n_reads+1 entries)
+ * trim_start, trim_end, varseg_chunk, varseg_thresh, delta: the reference CLI options
+ *               (--trim 200:10, --segmentation 100:0.0, --delta 0.0; src/flappie.c:100-110)
+ * start, end  : outputs (may be NULL), n_reads entries: the kept range of each read; start >= end means the
+ *               reference would have dropped the read -- it gets T_n = 0 and score NAN.
+ * `b` supplies n_reads (must match), temperature, flags and the output pointers; its signal / sig_off are
+ * ignored.  path/qpath/trace must be sized for the UNTRIMMED lengths (an upper bound on the block count). */
+typedef struct {
+    const float *raw;
+    const int64_t *raw_off;
+    int64_t n_reads;
+    int64_t trim_start, trim_end, varseg_chunk;
+    float varseg_thresh;
+    float delta;
+    int64_t *start;
+    int64_t *end;
+} ffb_raw_batch;
+int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
+int ffb_basecall_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
+
 /* Introspection for tests / bench. */
 int64_t ffb_total_blocks(const ffb_ctx *c);
 int64_t ffb_launch_count(const ffb_ctx *c);         /* kernels launched by this context so far */
@@ -187,7 +212,8 @@ int64_t ffb_launch_count(const ffb_ctx *c);         /* kernels launched by this 
  * ms[0]=conv ms[1]=input GEMMs ms[2]=recurrent ms[3]=output layer+logZ ms[4]=decode; returns FFB_OK. */
 int ffb_forward_timed(ffb_ctx *c, float ms[8]);
 /* what: 0 = last conv output [Ttot][S]; 1..5 = recurrent layer output [Ttot][S] (needs
- * FFB_FLAG_KEEP_LAYERS); 6 = trans [Ttot][nparam]; 7 = logZ (double, n_reads).  Copies up to
+ * FFB_FLAG_KEEP_LAYERS); 6 = trans [Ttot][nparam]; 7 = logZ (double, n_reads); 8 = the normalised signal
+ * the network reads (concatenated kept ranges).  Copies up to
  * `bytes` to host `dst`; returns bytes copied or negative error. */
 int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t bytes);
 

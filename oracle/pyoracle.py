@@ -380,6 +380,19 @@ class Ref:
         self.free(tm)
         return out
 
+    def quantile(self, x, p):
+        """reference quantilef (src/util.c:100-137), one quantile"""
+        x = np.ascontiguousarray(x, np.float32)
+        q = ctypes.c_float(p)
+        self.lib.quantilef(_fp(x), ctypes.c_size_t(x.shape[0]), ctypes.byref(q), ctypes.c_size_t(1))
+        return np.float32(q.value)
+
+    def mad(self, x):
+        """reference madf (src/util.c:163-187) with the median computed inside"""
+        x = np.ascontiguousarray(x, np.float32)
+        self.lib.madf.restype = ctypes.c_float
+        return np.float32(self.lib.madf(_fp(x), ctypes.c_size_t(x.shape[0]), None))
+
     def medmad_normalise(self, x):
         x = np.array(x, np.float32, copy=True)
         self.lib.medmad_normalise_array(_fp(x), x.shape[0])

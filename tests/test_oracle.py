@@ -193,3 +193,18 @@ def test_reference_signal_fixtures(ref):
     assert mine.shape == trimmed.shape and np.max(np.abs(mine - trimmed)) < 1e-4
     assert np.max(np.abs(medmad_normalise_array(trimmed) - normalised)) < 1e-5
     assert np.max(np.abs(ref.medmad_normalise(trimmed) - normalised)) < 1e-5
+
+
+def test_host_signal_prep_vs_reference_object_code(ref):
+    """flappie_b200/signal.py (the host restatement the device kernels are tested against) versus the reference's
+    own quantilef / madf / medmad_normalise_array (src/util.c:100-212): bit-exact."""
+    from flappie_b200 import signal as hs
+    rng = np.random.default_rng(17)
+    for n in (2, 3, 40, 41, 100, 379, 3790):
+        x = rng.normal(90, 12, n).astype(np.float32)
+        if n == 100:
+            x = np.round(x)                      # ties
+        for p in (0.0, 0.05, 0.3, 0.5, 0.77, 1.0):
+            assert hs.quantilef(x, p) == ref.quantile(x, p), (n, p)
+        assert hs.madf(x) == ref.mad(x), n
+        assert np.array_equal(hs.medmad_normalise_array(x), ref.medmad_normalise(x)), n
