@@ -61,7 +61,7 @@ def make_workload(model_key: str, n_reads: int, raw_len: int, seed: int):
     raws = synthetic_reads(n_reads, raw_len, seed=seed)
     reads = [prepare_read(r) for r in raws]
     assert all(r is not None for r in reads)
-    return fm, reads
+    return fm, reads, raws
 
 
 class ClockSampler:
@@ -154,7 +154,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fm, reads = make_workload(MODEL_CHOICES[a.model][0], a.ref_reads_total, RAW_SAMPLES, seed=7)
+    fm, reads, _ = make_workload(MODEL_CHOICES[a.model][0], a.ref_reads_total, RAW_SAMPLES, seed=7)
     cores = len(os.sched_getaffinity(0))
     per_core = max(1, a.ref_reads_per_core)
     rates = []
@@ -213,7 +213,7 @@ def main():
 
     model_key = MODEL_CHOICES[a.model][0]
     # weak scaling: every rank gets its own `reads` reads (different seed per rank)
-    fm, reads = make_workload(model_key, a.reads, RAW_SAMPLES, seed=7 + rank)
+    fm, reads, raws = make_workload(model_key, a.reads, RAW_SAMPLES, seed=7 + rank)
     n = len(reads)
     lens = np.array([len(r) for r in reads], np.int64)
     sig_off_np = np.zeros(n + 1, np.int64); np.cumsum(lens, out=sig_off_np[1:])
@@ -268,22 +268,40 @@ def main():
     samples_per_step = n * RAW_SAMPLES * world
     value = samples_per_step * a.steps / (dev_ms * 1e-3)
 
-    # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region ----
+    # ---- end-to-end arm: RAW host buffers through the C ABI (ffb_basecall_raw_batch): H2D of the raw samples,
+    #      trimming + normalisation + network + decode on the device, D2H of path/qpath/score, all inside the timed region ----
+    import ctypes
+    raw_lens = np.array([len(r) for r in raws], np.int64)
+    raw_off_np = np.zeros(n + 1, np.int64); np.cumsum(raw_lens, out=raw_off_np[1:])
+    raw_pinned = torch.empty(int(raw_off_np[-1]), dtype=torch.float32).pin_memory()
+    raw_pinned.numpy()[:] = np.concatenate(raws)
+    raw_np = raw_pinned.numpy()
+    raw_blocks = sum(max(fm.nblock(int(x)), 0) for x in raw_lens)       # outputs sized for the untrimmed lengths
+    out_raw = {
+        "blk_off": np.zeros(n + 1, np.int64),
+        "path": torch.empty(raw_blocks + n, dtype=torch.int32).pin_memory().numpy(),
+        "qpath": torch.empty(raw_blocks + n, dtype=torch.float32).pin_memory().numpy(),
+        "score": torch.empty(n, dtype=torch.float32).pin_memory().numpy(),
+    }
+    batch_raw, out_raw = ctx.make_batch(raw_np, raw_off_np, 1.0, flags, out_raw)
+    rb, rstart, rend = ctx.make_raw_batch(raw_np, raw_off_np)
     for _ in range(min(a.warmup, 2)):
-        ctx.lib.lib.ffb_basecall_batch(ctx.handle, batch)
+        ctx.lib.lib.ffb_basecall_raw_batch(ctx.handle, ctypes.byref(rb), ctypes.byref(batch_raw))
+    # the device-prepared path must reproduce the host-prepared one bit for bit
+    assert np.array_equal(out_raw["blk_off"], out["blk_off"]) or not out["blk_off"].any()
     barrier()
     e0.record(stream)
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        r = ctx.lib.lib.ffb_basecall_batch(ctx.handle, batch)
+        r = ctx.lib.lib.ffb_basecall_raw_batch(ctx.handle, ctypes.byref(rb), ctypes.byref(batch_raw))
         assert r == 0, lib.last_error()
     e1.record(stream)
     barrier()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), e2e_wall_ms))
     e2e_value = samples_per_step * a.steps / (e2e_ms * 1e-3)
-    h2d = int(signal_np.nbytes + sig_off_np.nbytes + 4 * n)
-    d2h = int(out["path"].nbytes + out["qpath"].nbytes + out["score"].nbytes)
+    h2d = int(raw_np.nbytes + 3 * raw_off_np.nbytes + 4 * n)
+    d2h = int(out_raw["blk_off"][-1] + n) * 8 + 4 * n + 16 * n     # path + qpath of the blocks produced, score, trim bounds
 
     # ---- per-kernel-group timing for the roofline (one extra pass, sequential schedule, CUDA events on the
     #      library's stream around each kernel group; not part of `value`) ----
@@ -292,7 +310,7 @@ def main():
     rnn_flops = 2.0 * T * S * G * S                      # one layer's h_{t-1} * sW, all reads (algorithmic)
     rnn_ms_per_launch = groups["rnn"] / 5.0
     achieved_tf = rnn_flops / (rnn_ms_per_launch * 1e-3) / 1e12
-    tensor_path = not a.fp32_simt and fm.size == 256
+    tensor_path = not a.fp32_simt and fm.size in (256, 384)
     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_rnn_tc_v5_ncu_summary.txt,
     # ncu --set full of this command); algorithmic = Xin read 4*G*S + planes written 4*S bytes per block
     traffic = 7.94e9 if (tensor_path and a.model == "r941_native_gru" and a.reads == 1024) else None
@@ -318,7 +336,8 @@ def main():
                    "blocks_per_gpu": int(tot_blocks), "reads_per_gpu": n,
                    "l2": "working set per step (Xin + activations, ~16 GB) far exceeds the 126 MB L2; no flush needed",
                    "schedule": "layer l+1's input GEMM streamed behind layer l's recurrence (PDL)" if os.environ.get("FFB_NO_STREAM_GEMM") is None else "sequential kernels",
-                   "host_prep": "trim + med-MAD normalisation done once on the host before timing (outside the hot path)",
+                   "signal_prep": "value: normalised signal resident in HBM (prepared once, outside the timed region); "
+                                  "e2e: trimming + med-MAD normalisation on the device inside the timed region (ffb_basecall_raw_batch)",
                    "parallelism": f"read-shard x{world}, no collective"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
