@@ -69,7 +69,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_host(force or bool(jobs))
     return LIB
+
+
+HOST = os.path.join(HERE, "host")
+HOST_SOURCES = ["ffb_output.c", "ffb_weights.c", "ffb_rawio.c"]
+HOST_BIN = os.path.join(HOST, "flappie")
+HOST_LIB = os.path.join(HOST, "libffb_host.so")
+
+
+def build_host(force: bool = False) -> None:
+    """The C99 host side: the `flappie` command line and, for the tests, the same objects as a shared library."""
+    cc = shutil.which("gcc") or "gcc"
+    srcs = [os.path.join(HOST, s) for s in HOST_SOURCES]
+    deps = srcs + [os.path.join(HOST, "ffb_host.h"), os.path.join(HOST, "flappie_main.c"), LIB,
+                   os.path.join(HERE, "..", "include", "flappie_b200.h")]
+    flags = ["-std=c99", "-O2", "-Wall", "-Wextra", "-D_POSIX_C_SOURCE=200809L", "-fPIC"]
+    link = ["-L" + CSRC, "-lflappie_b200", "-Wl,-rpath,$ORIGIN/../csrc", "-lm"]
+    if force or _stale(HOST_BIN, deps):
+        r = subprocess.run([cc] + flags + ["-o", HOST_BIN, os.path.join(HOST, "flappie_main.c")] + srcs + link,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"gcc failed for the flappie command line:\n{r.stdout}\n{r.stderr}")
+    if force or _stale(HOST_LIB, deps):
+        r = subprocess.run([cc] + flags + ["-shared", "-o", HOST_LIB] + srcs + link, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"gcc failed for libffb_host.so:\n{r.stdout}\n{r.stderr}")
 
 
 if __name__ == "__main__":

@@ -196,6 +196,20 @@ class FlipflopModel:
                              [z[f"l{i}_iW"] for i in range(5)], [z[f"l{i}_sW"] for i in range(5)],
                              [z[f"l{i}_b"] for i in range(5)], z["ff_W"], z["ff_b"], str(z["name"]))
 
+    def save_bundle(self, path: str) -> None:
+        """Binary weight bundle for the C command line (flappie_b200/host/ffb_host.h): the `_Mat` images of
+        to_mat_bundle() in the reference's struct order, padded columns included."""
+        import struct
+        mats, keep = self.to_mat_bundle()
+        strides = list(self.conv_stride) + [0] * (3 - len(self.conv_stride))
+        with open(path, "wb") as fh:
+            fh.write(b"FFBW1\0\0\0")
+            fh.write(struct.pack("<6i", self.kind, len(self.conv_stride), strides[0], strides[1], strides[2], len(mats)))
+            for m in mats:
+                fh.write(struct.pack("<2Q", m.nr, m.nc))
+                fh.write(np.ctypeslib.as_array(m.data, shape=(m.nc * m.stride,)).astype("<f4").tobytes())
+        del keep
+
     # ------------------------------------------------------------------ `_Mat` bundle
     def to_mat_bundle(self):
         """Return (mats, keepalive): `mats` is the list of `_Mat` in the field order of

@@ -393,6 +393,16 @@ class Ref:
         self.lib.madf.restype = ctypes.c_float
         return np.float32(self.lib.madf(_fp(x), ctypes.c_size_t(x.shape[0]), None))
 
+    def format_record(self, fmt, path, uuid, readname, uuid_primary, prefix, score, nblock, basecall, quality, n, start, end):
+        """append one fasta / fastq / sam record to `path` with the reference's fprintf_format"""
+        L = self.lib
+        L.ffref_format.restype = c_int
+        L.ffref_format.argtypes = [c_char_p, c_char_p, c_char_p, c_char_p, c_bool, c_char_p, c_float, c_size_t, c_char_p, c_char_p,
+                                   c_size_t, c_size_t, c_size_t]
+        r = L.ffref_format(fmt.encode(), path.encode(), uuid.encode(), readname.encode(), uuid_primary, prefix.encode(),
+                           score, nblock, basecall.encode(), quality.encode() if quality is not None else None, n, start, end)
+        assert r == 0
+
     def medmad_normalise(self, x):
         x = np.array(x, np.float32, copy=True)
         self.lib.medmad_normalise_array(_fp(x), x.shape[0])

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "decode.h"
+#include "flappie_output.h"
 #include "flappie_matrix.h"
 #include "flappie_structures.h"
 #include "layers.h"
@@ -152,4 +153,26 @@ long ffref_basecall(const ffref_model *net, const float *signal, size_t n, float
     free(path);
     trans = free_flappie_matrix(trans);
     return nb;
+}
+
+
+/* One record through the reference's own writers (src/flappie_output.c:92-133) into the file `path` (appended):
+ * fmt 0 = fasta, 1 = fastq, 2 = sam -- by NAME, so the enum order of flappie_output.h does not matter here. */
+int ffref_format(const char *fmt_name, const char *path, const char *uuid, const char *readname, bool uuid_primary,
+                 const char *prefix, float score, size_t nblock, const char *basecall, const char *quality,
+                 size_t n, size_t start, size_t end) {
+    const enum flappie_outformat_type fmt = get_outformat(fmt_name);
+    if (FLAPPIE_OUTFORMAT_INVALID == fmt) return -1;
+    FILE *fp = fopen(path, "a");
+    if (NULL == fp) return -1;
+    struct _raw_basecall_info res = {0};
+    res.score = score;
+    res.rt.n = n; res.rt.start = start; res.rt.end = end;
+    res.basecall = (char *)basecall;
+    res.quality = (char *)quality;
+    res.basecall_length = strlen(basecall);
+    res.nblock = nblock;
+    fprintf_format(fmt, fp, uuid, readname, uuid_primary, prefix, res);
+    fclose(fp);
+    return 0;
 }

@@ -1,0 +1,170 @@
+"""The C99 host side (flappie_b200/host): record writers against the reference's own fprintf_format
+(src/flappie_output.c, compiled into oracle/_ref), weight bundles, raw-signal readers, and -- on the GPU -- the
+`flappie` command line end to end against the Python host over the same C ABI."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from flappie_b200.model import KIND_GRU, FlipflopModel, synthetic_reads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "flappie_b200", "host")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class ReadResult(ctypes.Structure):
+    _fields_ = [("score", ctypes.c_float), ("n", ctypes.c_size_t), ("start", ctypes.c_size_t), ("end", ctypes.c_size_t),
+                ("basecall", ctypes.c_char_p), ("quality", ctypes.c_char_p), ("basecall_length", ctypes.c_size_t),
+                ("nblock", ctypes.c_size_t)]
+
+
+@pytest.fixture(scope="module")
+def host():
+    path = os.path.join(HOST, "libffb_host.so")
+    if not os.path.exists(path):
+        from flappie_b200.build import build_host
+        build_host()
+    L = ctypes.CDLL(path)
+    L.ffb_get_outformat.restype = ctypes.c_int; L.ffb_get_outformat.argtypes = [ctypes.c_char_p]
+    L.ffb_outformat_string.restype = ctypes.c_char_p; L.ffb_outformat_string.argtypes = [ctypes.c_int]
+    L.ffb_fprintf_read.restype = None
+    L.ffb_fprintf_read.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_bool,
+                                   ctypes.c_char_p, ctypes.POINTER(ReadResult)]
+    L.ffb_read_raw_file.restype = ctypes.c_long
+    L.ffb_read_raw_file.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_float))]
+    return L
+
+
+def _libc():
+    libc = ctypes.CDLL(None)
+    libc.fopen.restype = ctypes.c_void_p; libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    libc.fclose.argtypes = [ctypes.c_void_p]
+    libc.free.argtypes = [ctypes.c_void_p]
+    return libc
+
+
+def _write_mine(host, fmt, path, uuid, readname, uuid_primary, prefix, score, nblock, basecall, quality, n, start, end):
+    libc = _libc()
+    fp = libc.fopen(path.encode(), b"a")
+    res = ReadResult(score, n, start, end, basecall.encode(), quality.encode() if quality is not None else None,
+                     len(basecall), nblock)
+    host.ffb_fprintf_read(host.ffb_get_outformat(fmt.encode()), fp, uuid.encode(), readname.encode(), uuid_primary,
+                          prefix.encode(), ctypes.byref(res))
+    libc.fclose(fp)
+
+
+RECORDS = [
+    ("0f776a08-1101-41d4-8097-89136494a46e", "read_ch1_file0.fast5", True, "", -1234.5678, 1895, "ACGTTGCA" * 30, "5678:;<=" * 30, 4000, 200, 3990),
+    ("uuid-2", "b.fast5", False, "run7_", -0.03125, 7, "ACGTZ", "!~+5I", 100, 0, 90),
+    ("u3", "c.f32", True, "p", -3e5, 24895, "A", "#", 50000, 1300, 49690),
+]
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq", "sam"])
+def test_record_writers_match_reference_bytes(host, ref, tmp_path, fmt):
+    mine, theirs = str(tmp_path / "mine.txt"), str(tmp_path / "ref.txt")
+    for rec in RECORDS:
+        _write_mine(host, fmt, mine, *rec)
+        ref.format_record(fmt, theirs, *rec)
+    a, b = open(mine, "rb").read(), open(theirs, "rb").read()
+    assert a == b and len(a) > 0
+    if fmt == "sam":            # the reference prints sequence and quality twice (src/flappie_output.c:126-131)
+        assert a.count(b"ACGTZ") == 2
+
+
+def test_outformat_names(host):
+    for i, nm in enumerate([b"fasta", b"fastq", b"sam"]):
+        assert host.ffb_get_outformat(nm) == i and host.ffb_outformat_string(i) == nm
+    assert host.ffb_get_outformat(b"bam") == 3 and host.ffb_outformat_string(3) is None
+
+
+def test_fastq_without_quality_prints_nothing(host, tmp_path):
+    p = str(tmp_path / "x.txt")
+    _write_mine(host, "fastq", p, "u", "r", True, "", -1.0, 10, "ACGT", None, 100, 0, 90)
+    assert open(p, "rb").read() == b""          # warnx + return, src/flappie_output.c:108-111
+
+
+def test_raw_readers(host, tmp_path):
+    x = np.random.default_rng(0).normal(90, 12, 1234).astype(np.float32)
+    f32 = tmp_path / "a.f32"; x.tofile(f32)
+    crp = tmp_path / "a.crp"
+    with open(crp, "w") as fh:                  # write_flappie_matrix_to_handle layout, src/test/flappie_util.c:30-55
+        fh.write(f"1\t{x.shape[0]}\n")
+        for v in x:
+            fh.write(float(v).hex() + "\n")
+    libc = _libc()
+    for path in (f32, crp):
+        ptr = ctypes.POINTER(ctypes.c_float)()
+        n = host.ffb_read_raw_file(str(path).encode(), ctypes.byref(ptr))
+        assert n == x.shape[0]
+        assert np.array_equal(np.ctypeslib.as_array(ptr, shape=(n,)), x)
+        libc.free(ptr)
+    ptr = ctypes.POINTER(ctypes.c_float)()
+    assert host.ffb_read_raw_file(b"/nonexistent/x.f32", ctypes.byref(ptr)) == -1
+    assert host.ffb_read_raw_file(b"whatever.fast5", ctypes.byref(ptr)) == -2     # needs libhdf5
+
+
+def test_reference_crp_fixture_is_readable(host):
+    path = "/root/reference/src/test/raw_signal.crp"
+    if not os.path.exists(path):
+        pytest.skip("reference fixtures not mounted")
+    ptr = ctypes.POINTER(ctypes.c_float)()
+    n = host.ffb_read_raw_file(path.encode(), ctypes.byref(ptr))
+    assert n == 37838
+    g = np.load(os.path.join(GOLD, "signal_fixture.npz"))
+    unit = np.float32(1373.41) / np.float32(8192.0)
+    head = ((np.ctypeslib.as_array(ptr, shape=(n,))[:g["raw_pa_head"].shape[0]] + np.float32(16.0)) * unit).astype(np.float32)
+    assert np.array_equal(head, g["raw_pa_head"])
+    _libc().free(ptr)
+
+
+def test_cli_refuses_without_gpu_or_weights(tmp_path):
+    exe = os.path.join(HOST, "flappie")
+    r = subprocess.run([exe, "--model", "help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "r941_native" in r.stdout and "(default)" in r.stdout
+    r = subprocess.run([exe, "--format", "bam", "x.f32"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Unrecognised output format" in r.stderr
+    r = subprocess.run([exe, "--model", "nosuch", "x.f32"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Invalid Flappie model" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt,extra", [("fastq", []), ("fasta", ["--viterbi"]), ("sam", ["--reverse", "--no-uuid", "--prefix", "x_"])])
+def test_cli_end_to_end(gpu_lib, ref, tmp_path, fmt, extra):
+    """flappie <dir of .f32 reads>: records equal, byte for byte, the reference's writers fed with the Python
+    host's results over the same C ABI (same kernels => same bits)."""
+    from flappie_b200.api import Context, Model
+    fm = FlipflopModel.synthetic(KIND_GRU, 96, 4, seed=3, name="r941_native")
+    fm.save_bundle(str(tmp_path / "r941_native.ffbw"))
+    lens = [4000, 2500, 6000, 150, 4000, 3000, 90]
+    raws = synthetic_reads(len(lens), lens, seed=31)
+    rdir = tmp_path / "reads"; rdir.mkdir()
+    names = [f"read_{i:02d}.f32" for i in range(len(lens))]
+    for nm, r in zip(names, raws):
+        r.tofile(rdir / nm)
+    out = tmp_path / f"calls.{fmt}"
+    env = dict(os.environ, FLAPPIE_B200_MODELS=str(tmp_path))
+    r = subprocess.run([os.path.join(HOST, "flappie"), "--format", fmt, "--batch", "3", "--output", str(out)] + extra + [str(rdir)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stderr.count("No basecall returned") == 2          # the 150- and 90-sample reads trim to nothing
+
+    m = Model(fm); ctx = Context(m)
+    want = str(tmp_path / "want.txt")
+    viterbi, reverse, uuid_primary = "--viterbi" in extra, "--reverse" in extra, "--no-uuid" not in extra
+    prefix = "x_" if "--prefix" in extra else ""
+    # same batches as the command line made (batch composition does not change bits, but keep it honest)
+    for b0 in range(0, len(lens), 3):
+        res = ctx.basecall_raw(raws[b0:b0 + 3], viterbi_only=viterbi)
+        for k in range(res.n_reads):
+            i = b0 + k
+            if res.nblock(k) == 0:
+                continue
+            bases, qual = gpu_lib.emit_bases(*res.read_path(k), fm.nbase, reverse=reverse)
+            ref.format_record(fmt, want, names[i][:-4], names[i], uuid_primary, prefix, float(res.score[k]), res.nblock(k), bases, qual,
+                              lens[i], int(res.start[k]), int(res.end[k]))
+    assert open(out, "rb").read() == open(want, "rb").read()
+    ctx.close(); m.close()
