@@ -16,6 +16,7 @@
 // staged once in shared memory (coalesced, zero-filled outside the read), threads map to
 // filters so weight reads (Wt[tap*nf+f][filter]) and output writes are coalesced.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "ffb_common.cuh"
 
@@ -172,6 +173,105 @@ conv_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restri
     }
 }
 
+// Many-feature input, many filters (third convolution of the LSTM topology: 16 -> S, winlen 19, stride 5 -- 90 GMAC per
+// 1024 reads, the one convolution that is FMA- and not HBM-bound): register tile of 4 filters x CONV_TILE_C columns per
+// thread, so one 16-byte weight load and one 16-byte (broadcast) window load feed 16 FMAs each.
+// Requires nf % 4 == 0 and nfilter % 4 == 0; threads = groups * nfilter / 4.
+template <int ACT>
+__global__ void __launch_bounds__(512)
+conv_f4_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ yhi, __half *__restrict__ ylo,
+               const float *__restrict__ Wt, const float *__restrict__ bias, const ReadGeom *__restrict__ geom,
+               const ConvTail *__restrict__ tails, int nf, int nfilter, int winlen, int stride, int groups) {
+    extern __shared__ float xs[];   // [span][nf]
+    const ReadGeom g = geom[blockIdx.x];
+    const int cols_per_cta = groups * CONV_TILE_C;
+    const int c0 = blockIdx.y * cols_per_cta;
+    if (c0 >= g.T_out) return;
+    const int padL = (winlen - 1) / 2;
+    const int span = (cols_per_cta - 1) * stride + winlen;
+    const int xin0 = c0 * stride - padL;
+    const float *xr = x + g.in_off * nf;
+    {
+        // nf % 4 == 0: stage whole 16-byte feature quads
+        const int nq = nf >> 2;
+        for (int i = threadIdx.x; i < span * nq; i += blockDim.x) {
+            const int col = xin0 + i / nq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col >= 0 && col < g.T_in) v = *reinterpret_cast<const float4 *>(xr + (int64_t)col * nf + 4 * (i % nq));
+            reinterpret_cast<float4 *>(xs)[i] = v;
+        }
+    }
+    __syncthreads();
+    const int fq = nfilter >> 2;                       // filter quads
+    const int f = 4 * (threadIdx.x % fq);
+    const int grp = threadIdx.x / fq;
+    if (grp >= groups) return;
+    const int cbase = grp * CONV_TILE_C;
+    float acc[CONV_TILE_C][4];
+#pragma unroll
+    for (int c = 0; c < CONV_TILE_C; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f;
+    const int K = winlen * nf;
+    const float *xsb = xs + cbase * stride * nf;
+    for (int j = 0; j < K; j += 4) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)j * nfilter + f));
+        const float4 w1 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(j + 1) * nfilter + f));
+        const float4 w2 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(j + 2) * nfilter + f));
+        const float4 w3 = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)(j + 3) * nfilter + f));
+#pragma unroll
+        for (int c = 0; c < CONV_TILE_C; c++) {
+            const float4 xv = *reinterpret_cast<const float4 *>(xsb + c * stride * nf + j);
+            // per output the taps accumulate in increasing k, like the scalar kernel
+            acc[c][0] = fmaf(w0.x, xv.x, acc[c][0]); acc[c][1] = fmaf(w0.y, xv.x, acc[c][1]);
+            acc[c][2] = fmaf(w0.z, xv.x, acc[c][2]); acc[c][3] = fmaf(w0.w, xv.x, acc[c][3]);
+            acc[c][0] = fmaf(w1.x, xv.y, acc[c][0]); acc[c][1] = fmaf(w1.y, xv.y, acc[c][1]);
+            acc[c][2] = fmaf(w1.z, xv.y, acc[c][2]); acc[c][3] = fmaf(w1.w, xv.y, acc[c][3]);
+            acc[c][0] = fmaf(w2.x, xv.z, acc[c][0]); acc[c][1] = fmaf(w2.y, xv.z, acc[c][1]);
+            acc[c][2] = fmaf(w2.z, xv.z, acc[c][2]); acc[c][3] = fmaf(w2.w, xv.z, acc[c][3]);
+            acc[c][0] = fmaf(w3.x, xv.w, acc[c][0]); acc[c][1] = fmaf(w3.y, xv.w, acc[c][1]);
+            acc[c][2] = fmaf(w3.z, xv.w, acc[c][2]); acc[c][3] = fmaf(w3.w, xv.w, acc[c][3]);
+        }
+    }
+    const ConvTail *tl = tails + g.tail_id;
+    const int tail0 = tl->tail_col0;
+    const float4 b4 = *reinterpret_cast<const float4 *>(bias + f);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int c = 0; c < CONV_TILE_C; c++) {
+        const int col = c0 + cbase + c;
+        if (col >= g.T_out) break;
+        float v[4] = {acc[c][0], acc[c][1], acc[c][2], acc[c][3]};
+        if (col >= tail0) {
+            const int ti = col - tail0;
+            v[0] = v[1] = v[2] = v[3] = 0.0f;
+            for (int q = 0; q < 2; q++) {
+                const int nt = tl->ntap[ti][q];
+                if (nt <= 0) continue;
+                const float *wq = Wt + (size_t)tl->tap_lo[ti][q] * nf * nfilter + f;
+                const float *xq = xr + (int64_t)tl->x_start[ti][q] * nf;
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int j = 0; j < nt * nf; j++) {
+                    const float4 w = __ldg(reinterpret_cast<const float4 *>(wq + (size_t)j * nfilter));
+                    const float xj = __ldg(xq + j);
+                    a[0] = fmaf(w.x, xj, a[0]); a[1] = fmaf(w.y, xj, a[1]); a[2] = fmaf(w.z, xj, a[2]); a[3] = fmaf(w.w, xj, a[3]);
+                }
+                v[0] += a[0]; v[1] += a[1]; v[2] += a[2]; v[3] += a[3];
+            }
+        }
+        const int64_t idx = (g.out_off + col) * (int64_t)nfilter + f;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = fast_activate(v[k] + bb[k], ACT);
+        if (y) *reinterpret_cast<float4 *>(y + idx) = make_float4(o[0], o[1], o[2], o[3]);
+        if (yhi) {
+            __half h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { h[k] = __float2half_rn(o[k]); l[k] = __float2half_rn(o[k] - __half2float(h[k])); }
+            *reinterpret_cast<uint2 *>(yhi + idx) = *reinterpret_cast<uint2 *>(h);
+            *reinterpret_cast<uint2 *>(ylo + idx) = *reinterpret_cast<uint2 *>(l);
+        }
+    }
+}
+
 }  // namespace ffb
 
 int ffb_launch_conv(const float *x, float *y, void *yhi_, void *ylo_, const float *Wt, const float *bias,
@@ -207,6 +307,25 @@ int ffb_launch_conv(const float *x, float *y, void *yhi_, void *ylo_, const floa
             else launch1(conv1_kernel<5, 1, FFB_ACT_NONE>);
         }
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    if ((nf & 3) == 0 && (nfilter & 3) == 0 && nfilter >= 128 && nfilter / 4 <= 512 && getenv("FFB_CONV_SCALAR") == nullptr) {
+        // 4 filters per thread; two or three column groups per CTA
+        const int fq = nfilter / 4;
+        const int groups4 = fq >= 256 ? 1 : (fq >= 128 ? 2 : 3);
+        const int threads4 = groups4 * fq;
+        const int cols4 = groups4 * CONV_TILE_C;
+        const size_t smem4 = (size_t)((cols4 - 1) * stride + winlen) * nf * sizeof(float);
+        dim3 grid4(n_reads, (max_T_out + cols4 - 1) / cols4);
+        if (grid4.y <= 65535) {
+            auto launch4 = [&](auto kern) {
+                if (smem4 > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+                kern<<<grid4, threads4, smem4, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nf, nfilter, winlen, stride, groups4);
+            };
+            if (act == FFB_ACT_TANH) launch4(conv_f4_kernel<FFB_ACT_TANH>);
+            else if (act == FFB_ACT_SWISH) launch4(conv_f4_kernel<FFB_ACT_SWISH>);
+            else launch4(conv_f4_kernel<FFB_ACT_NONE>);
+            return cudaGetLastError() == cudaSuccess ? 1 : -1;
+        }
     }
     auto launch = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -285,29 +285,36 @@ __device__ unsigned long long ffb_gemm_prof_dev[16];
 #define GPROF(i)
 #define GPROF_FLUSH(base, n)
 #endif
-struct GemmWsCfg {
+// KMAX = 256 / BB = 128 is the layout the S=256 models run.  S=384 (r941_native at this commit) needs 384 of the 512
+// tensor-memory columns for the panel, which leaves 128 for accumulators: two buffers of BB = 64 blocks.
+template <int KMAX_, int BB_>
+struct GemmWsCfgT {
     static constexpr int BF = 128;                 // features per panel (MMA M)
-    static constexpr int BB = 128;                 // blocks per tile (MMA N)
+    static constexpr int BB = BB_;                 // blocks per tile (MMA N)
     static constexpr int BK = 64;                  // K per pipeline stage
     static constexpr int SLOT_BYTES = BB * BK * 2;  // one plane of one k-chunk: [128 blocks][64 halfs]
     // Two rings.  The MMAs make two passes over a tile (cross terms first, then hi*hi): the hi plane of a k-chunk
     // is needed in both and is held until pass 2, the lo plane only in pass 1.  The hi ring is two tiles deep so
     // the next tile loads while this one computes; the lo ring one tile.
-    static constexpr int HI_SLOTS = 8, LO_SLOTS = 4;
+    static constexpr int HI_SLOTS = 2 * (KMAX_ / BK), LO_SLOTS = KMAX_ / BK;
     static constexpr int SMEM = (HI_SLOTS + LO_SLOTS) * SLOT_BYTES + 1024;
     static constexpr int EPI_WARPS = 8;            // two per TMEM lane quadrant, BB/2 columns each
     static constexpr int THREADS = 64 + EPI_WARPS * 32;
-    static constexpr int KMAX = 256;
+    static constexpr int KMAX = KMAX_;
     static constexpr int ACC_COL0 = KMAX;          // W planes: K/2 columns each, at 0 and KMAX/2
     static constexpr int NACC = 2;                 // accumulator buffers of BB columns
+    static_assert(ACC_COL0 + NACC * BB <= 512, "tensor memory budget");
+    static_assert(BB % 64 == 0 && BB <= 128, "epilogue: two column halves of 32 or 64 blocks per quadrant");
 };
+using GemmWsCfg = GemmWsCfgT<256, 128>;
+using GemmWsCfg384 = GemmWsCfgT<384, 64>;
 
-__global__ void __launch_bounds__(GemmWsCfg::THREADS, 1)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __half *__restrict__ Whi, const __half *__restrict__ Wlo, const float *__restrict__ bias,
                float *__restrict__ C, int64_t M, int N, int K, const GemmWork *__restrict__ work,
                const int *progress, int *queue) {
-    using Cfg = GemmWsCfg;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
     __shared__ uint64_t full_hi[Cfg::HI_SLOTS], empty_hi[Cfg::HI_SLOTS], full_lo[Cfg::LO_SLOTS], empty_lo[Cfg::LO_SLOTS];
@@ -597,15 +604,15 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+template <class Cfg = ffb::GemmWsCfg>
 static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                           int64_t M, int N, int K, cudaStream_t st, const GemmWork *work = nullptr,
                           const int *progress = nullptr, int *queue = nullptr) {
-    using Cfg = ffb::GemmWsCfg;
     CUtensorMap mAh, mAl;
     if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, Cfg::BB) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, Cfg::BB)) return -1;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(ffb::gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(ffb::gemm_ws_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
         attr_done = true;
     }
     int dev = 0, sms = 148;
@@ -630,7 +637,7 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::gemm_ws_kernel, mAh, mAl, (const __half *)Whi, (const __half *)Wlo, bias, C, M, N,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::gemm_ws_kernel<Cfg>, mAh, mAl, (const __half *)Whi, (const __half *)Wlo, bias, C, M, N,
                                        K, work, progress, queue);
     return e == cudaSuccess ? 1 : -1;
 }
@@ -664,6 +671,8 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
     if (!ffb_gemm_tc_supported(N, K)) return -1;
     if (N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX && getenv("FFB_GEMM_V1") == nullptr)
         return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
+    if (N % 128 == 0 && K <= ffb::GemmWsCfg384::KMAX && getenv("FFB_GEMM_V1") == nullptr)
+        return launch_gemm_ws<ffb::GemmWsCfg384>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 256 == 0) return launch_gemm_tc<256>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 128 == 0) return launch_gemm_tc<128>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     return launch_gemm_tc<64>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);

@@ -66,7 +66,7 @@ def gemm(L, A, W, b, mode):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 256), (333, 192, 64), (4097, 1024, 256),
-                                   (700, 1536, 384), (129, 384, 128)])
+                                   (700, 1536, 384), (129, 384, 128), (8300, 1536, 384), (65, 128, 320)])
 def test_gemm_tc_matches_fp64(gpu_lib, M, N, K):
     L = _hooks(gpu_lib)
     rng = np.random.default_rng(M + N + K)
