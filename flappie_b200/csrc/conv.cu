@@ -37,18 +37,25 @@ __device__ __forceinline__ void conv_store(float *y, __half *yhi, __half *ylo, i
 // Single-feature input (the raw signal: conv of the GRU topology, first conv of the LSTM topology): the
 // thread's whole input window lives in registers, so the inner loop is one weight load per tap and
 // CONV_TILE_C register-register FMAs.
+// Each thread owns FOUR adjacent filters and CONV1_C columns, so that the fp16 hi/lo planes leave as 8-byte
+// stores: with one filter per thread the 2-byte plane stores (two per output) were the kernel's bottleneck on
+// the load/store pipe, not the FMAs or the HBM write.
+constexpr int CONV1_C = 8;          // output columns per thread
+constexpr int CONV1_TILES = 4;      // column tiles one CTA walks through
+
 template <int WINLEN, int STRIDE, int ACT>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ yhi, __half *__restrict__ ylo,
              const float *__restrict__ Wt, const float *__restrict__ bias, const ReadGeom *__restrict__ geom,
              const ConvTail *__restrict__ tails, int nfilter, int groups) {
-    extern __shared__ float xs[];   // [span]
+    extern __shared__ float xs[];   // [span of CONV1_TILES tiles]
     const ReadGeom g = geom[blockIdx.x];
-    const int cols_per_cta = groups * CONV_TILE_C;
+    const int cols_per_tile = groups * CONV1_C;
+    const int cols_per_cta = cols_per_tile * CONV1_TILES;
     const int c0 = blockIdx.y * cols_per_cta;
     if (c0 >= g.T_out) return;
     constexpr int padL = (WINLEN - 1) / 2;
-    constexpr int WIN = (CONV_TILE_C - 1) * STRIDE + WINLEN;    // samples one thread needs
+    constexpr int WIN = (CONV1_C - 1) * STRIDE + WINLEN;        // samples one thread needs
     const int span = (cols_per_cta - 1) * STRIDE + WINLEN;
     const int xin0 = c0 * STRIDE - padL;
     const float *xr = x + g.in_off;
@@ -57,44 +64,72 @@ conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restr
         xs[i] = (col >= 0 && col < g.T_in) ? xr[col] : 0.0f;
     }
     __syncthreads();
-    const int f = threadIdx.x % nfilter;
-    const int grp = threadIdx.x / nfilter;
+    const int fq = nfilter >> 2;
+    const int f = 4 * (threadIdx.x % fq);
+    const int grp = threadIdx.x / fq;
     if (grp >= groups) return;
-    const int cbase = grp * CONV_TILE_C;
-    float xw[WIN];
+    // the thread's four filters: taps and bias stay in registers for all tiles
+    float4 w[WINLEN];
 #pragma unroll
-    for (int i = 0; i < WIN; i++) xw[i] = xs[cbase * STRIDE + i];
-    float acc[CONV_TILE_C];
-    const float b = bias[f];
-#pragma unroll
-    for (int c = 0; c < CONV_TILE_C; c++) acc[c] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < WINLEN; j++) {
-        const float w = __ldg(Wt + (size_t)j * nfilter + f);
-#pragma unroll
-        for (int c = 0; c < CONV_TILE_C; c++) acc[c] = fmaf(w, xw[c * STRIDE + j], acc[c]);
-    }
+    for (int j = 0; j < WINLEN; j++) w[j] = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)j * nfilter + f));
+    const float4 b4 = *reinterpret_cast<const float4 *>(bias + f);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
     const ConvTail *tl = tails + g.tail_id;
     const int tail0 = tl->tail_col0;
+#pragma unroll 1
+    for (int t = 0; t < CONV1_TILES; t++) {
+        const int cbase = t * cols_per_tile + grp * CONV1_C;
+        if (c0 + cbase >= g.T_out) break;
+        float xw[WIN];
 #pragma unroll
-    for (int c = 0; c < CONV_TILE_C; c++) {
-        const int col = c0 + cbase + c;
-        if (col >= g.T_out) break;
-        float v = acc[c];
-        if (col >= tail0) {
-            const int ti = col - tail0;
-            v = 0.0f;
-            for (int q = 0; q < 2; q++) {
-                const int nt = tl->ntap[ti][q];
-                if (nt <= 0) continue;
-                const float *wq = Wt + (size_t)tl->tap_lo[ti][q] * nfilter + f;
-                const float *xq = xr + tl->x_start[ti][q];
-                float a = 0.0f;
-                for (int j = 0; j < nt; j++) a = fmaf(__ldg(wq + (size_t)j * nfilter), __ldg(xq + j), a);
-                v += a;
+        for (int i = 0; i < WIN; i++) xw[i] = xs[cbase * STRIDE + i];
+        float acc[CONV1_C][4];
+#pragma unroll
+        for (int c = 0; c < CONV1_C; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < WINLEN; j++) {
+#pragma unroll
+            for (int c = 0; c < CONV1_C; c++) {
+                const float xv = xw[c * STRIDE + j];
+                acc[c][0] = fmaf(w[j].x, xv, acc[c][0]); acc[c][1] = fmaf(w[j].y, xv, acc[c][1]);
+                acc[c][2] = fmaf(w[j].z, xv, acc[c][2]); acc[c][3] = fmaf(w[j].w, xv, acc[c][3]);
             }
         }
-        conv_store(y, yhi, ylo, (g.out_off + col) * (int64_t)nfilter + f, fast_activate(v + b, ACT));
+#pragma unroll
+        for (int c = 0; c < CONV1_C; c++) {
+            const int col = c0 + cbase + c;
+            if (col >= g.T_out) break;
+            float v[4] = {acc[c][0], acc[c][1], acc[c][2], acc[c][3]};
+            if (col >= tail0) {
+                const int ti = col - tail0;
+                v[0] = v[1] = v[2] = v[3] = 0.0f;
+                for (int q = 0; q < 2; q++) {
+                    const int nt = tl->ntap[ti][q];
+                    if (nt <= 0) continue;
+                    const float *wq = Wt + (size_t)tl->tap_lo[ti][q] * nfilter + f;
+                    const float *xq = xr + tl->x_start[ti][q];
+                    float a[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int j = 0; j < nt; j++) {
+                        const float4 wj = __ldg(reinterpret_cast<const float4 *>(wq + (size_t)j * nfilter));
+                        const float xj = __ldg(xq + j);
+                        a[0] = fmaf(wj.x, xj, a[0]); a[1] = fmaf(wj.y, xj, a[1]); a[2] = fmaf(wj.z, xj, a[2]); a[3] = fmaf(wj.w, xj, a[3]);
+                    }
+                    v[0] += a[0]; v[1] += a[1]; v[2] += a[2]; v[3] += a[3];
+                }
+            }
+            const int64_t idx = (g.out_off + col) * (int64_t)nfilter + f;
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = fast_activate(v[k] + bb[k], ACT);
+            if (y) *reinterpret_cast<float4 *>(y + idx) = make_float4(o[0], o[1], o[2], o[3]);
+            if (yhi) {
+                __half h[4], l[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { h[k] = __float2half_rn(o[k]); l[k] = __float2half_rn(o[k] - __half2float(h[k])); }
+                *reinterpret_cast<uint2 *>(yhi + idx) = *reinterpret_cast<uint2 *>(h);
+                *reinterpret_cast<uint2 *>(ylo + idx) = *reinterpret_cast<uint2 *>(l);
+            }
+        }
     }
 }
 
@@ -295,8 +330,16 @@ int ffb_launch_conv(const float *x, float *y, void *yhi_, void *ylo_, const floa
     const size_t smem = (size_t)span * nf * sizeof(float);
     dim3 grid(n_reads, (max_T_out + cols_per_cta - 1) / cols_per_cta);   // x = read, y = column tile
     if (grid.y > 65535) return -1;
-    if (nf == 1 && ((winlen == 19 && stride == 2) || (winlen == 5 && stride == 1))) {
-        auto launch1 = [&](auto kern) { kern<<<grid, threads, smem, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nfilter, groups); };
+    if (nf == 1 && (nfilter & 3) == 0 && nfilter <= 1024 && ((winlen == 19 && stride == 2) || (winlen == 5 && stride == 1))) {
+        // four filters x CONV1_C columns per thread
+        const int fq = nfilter / 4;
+        const int groups1 = fq >= 256 ? 1 : 256 / fq;
+        const int threads1 = groups1 * fq;
+        const int cols1 = groups1 * CONV1_C * CONV1_TILES;
+        const size_t smem1 = (size_t)((cols1 - 1) * stride + winlen) * sizeof(float);
+        dim3 grid1(n_reads, (max_T_out + cols1 - 1) / cols1);
+        if (grid1.y > 65535 || smem1 > 48 * 1024) return -1;
+        auto launch1 = [&](auto kern) { kern<<<grid1, threads1, smem1, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nfilter, groups1); };
         if (winlen == 19) {
             if (act == FFB_ACT_TANH) launch1(conv1_kernel<19, 2, FFB_ACT_TANH>);
             else if (act == FFB_ACT_SWISH) launch1(conv1_kernel<19, 2, FFB_ACT_SWISH>);
