@@ -44,11 +44,12 @@ constexpr int CONV1_C = 8;          // output columns per thread
 constexpr int CONV1_TILES = 4;      // column tiles one CTA walks through
 
 template <int WINLEN, int STRIDE, int ACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ yhi, __half *__restrict__ ylo,
              const float *__restrict__ Wt, const float *__restrict__ bias, const ReadGeom *__restrict__ geom,
              const ConvTail *__restrict__ tails, int nfilter, int groups) {
-    extern __shared__ float xs[];   // [span of CONV1_TILES tiles]
+    extern __shared__ __align__(16) float xs[];   // [WINLEN][nfilter] taps, then [span of CONV1_TILES tiles] samples
+    float *ws = xs;
     const ReadGeom g = geom[blockIdx.x];
     const int cols_per_tile = groups * CONV1_C;
     const int cols_per_cta = cols_per_tile * CONV1_TILES;
@@ -59,19 +60,18 @@ conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restr
     const int span = (cols_per_cta - 1) * STRIDE + WINLEN;
     const int xin0 = c0 * STRIDE - padL;
     const float *xr = x + g.in_off;
+    float *xsig = ws + WINLEN * nfilter;
+    for (int i = threadIdx.x; i < WINLEN * nfilter; i += blockDim.x) ws[i] = Wt[i];
     for (int i = threadIdx.x; i < span; i += blockDim.x) {
         const int col = xin0 + i;
-        xs[i] = (col >= 0 && col < g.T_in) ? xr[col] : 0.0f;
+        xsig[i] = (col >= 0 && col < g.T_in) ? xr[col] : 0.0f;
     }
     __syncthreads();
     const int fq = nfilter >> 2;
     const int f = 4 * (threadIdx.x % fq);
     const int grp = threadIdx.x / fq;
     if (grp >= groups) return;
-    // the thread's four filters: taps and bias stay in registers for all tiles
-    float4 w[WINLEN];
-#pragma unroll
-    for (int j = 0; j < WINLEN; j++) w[j] = __ldg(reinterpret_cast<const float4 *>(Wt + (size_t)j * nfilter + f));
+    // the thread's four filters: one conflict-free 16-byte shared load per tap
     const float4 b4 = *reinterpret_cast<const float4 *>(bias + f);
     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
     const ConvTail *tl = tails + g.tail_id;
@@ -82,17 +82,18 @@ conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restr
         if (c0 + cbase >= g.T_out) break;
         float xw[WIN];
 #pragma unroll
-        for (int i = 0; i < WIN; i++) xw[i] = xs[cbase * STRIDE + i];
+        for (int i = 0; i < WIN; i++) xw[i] = xsig[cbase * STRIDE + i];
         float acc[CONV1_C][4];
 #pragma unroll
         for (int c = 0; c < CONV1_C; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0f;
 #pragma unroll
         for (int j = 0; j < WINLEN; j++) {
+            const float4 wj = *reinterpret_cast<const float4 *>(ws + j * nfilter + f);
 #pragma unroll
             for (int c = 0; c < CONV1_C; c++) {
                 const float xv = xw[c * STRIDE + j];
-                acc[c][0] = fmaf(w[j].x, xv, acc[c][0]); acc[c][1] = fmaf(w[j].y, xv, acc[c][1]);
-                acc[c][2] = fmaf(w[j].z, xv, acc[c][2]); acc[c][3] = fmaf(w[j].w, xv, acc[c][3]);
+                acc[c][0] = fmaf(wj.x, xv, acc[c][0]); acc[c][1] = fmaf(wj.y, xv, acc[c][1]);
+                acc[c][2] = fmaf(wj.z, xv, acc[c][2]); acc[c][3] = fmaf(wj.w, xv, acc[c][3]);
             }
         }
 #pragma unroll
@@ -336,10 +337,13 @@ int ffb_launch_conv(const float *x, float *y, void *yhi_, void *ylo_, const floa
         const int groups1 = fq >= 256 ? 1 : 256 / fq;
         const int threads1 = groups1 * fq;
         const int cols1 = groups1 * CONV1_C * CONV1_TILES;
-        const size_t smem1 = (size_t)((cols1 - 1) * stride + winlen) * sizeof(float);
+        const size_t smem1 = (size_t)((cols1 - 1) * stride + winlen + winlen * nfilter) * sizeof(float);
         dim3 grid1(n_reads, (max_T_out + cols1 - 1) / cols1);
-        if (grid1.y > 65535 || smem1 > 48 * 1024) return -1;
-        auto launch1 = [&](auto kern) { kern<<<grid1, threads1, smem1, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nfilter, groups1); };
+        if (grid1.y > 65535 || smem1 > 200 * 1024) return -1;
+        auto launch1 = [&](auto kern) {
+            if (smem1 > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            kern<<<grid1, threads1, smem1, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nfilter, groups1);
+        };
         if (winlen == 19) {
             if (act == FFB_ACT_TANH) launch1(conv1_kernel<19, 2, FFB_ACT_TANH>);
             else if (act == FFB_ACT_SWISH) launch1(conv1_kernel<19, 2, FFB_ACT_SWISH>);
