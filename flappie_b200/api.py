@@ -43,7 +43,7 @@ EXPORTS = [
     "ffb_model_size", "ffb_model_nparam", "ffb_model_stride", "ffb_model_nblock", "ffb_register_model",
     "ffb_create", "ffb_destroy", "ffb_basecall_batch", "ffb_upload", "ffb_forward", "ffb_download", "ffb_sync",
     "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_emit_bases",
-    "ffb_upload_raw", "ffb_basecall_raw_batch",
+    "ffb_upload_raw", "ffb_basecall_raw_batch", "ffb_submit_batch", "ffb_submit_raw_batch", "ffb_collect",
 ]
 
 
@@ -124,7 +124,9 @@ class Library:
         L.ffb_destroy.restype = None; L.ffb_destroy.argtypes = [c_void_p]
         for n in ("ffb_basecall_batch", "ffb_upload", "ffb_download"):
             getattr(L, n).restype = c_int; getattr(L, n).argtypes = [c_void_p, POINTER(Batch)]
-        for n in ("ffb_upload_raw", "ffb_basecall_raw_batch"):
+        for n in ("ffb_submit_batch", "ffb_collect"):
+            getattr(L, n).restype = c_int; getattr(L, n).argtypes = [c_void_p, POINTER(Batch)]
+        for n in ("ffb_upload_raw", "ffb_basecall_raw_batch", "ffb_submit_raw_batch"):
             getattr(L, n).restype = c_int; getattr(L, n).argtypes = [c_void_p, POINTER(RawBatch), POINTER(Batch)]
         L.ffb_forward.restype = c_int; L.ffb_forward.argtypes = [c_void_p]
         L.ffb_sync.restype = c_int; L.ffb_sync.argtypes = [c_void_p]
@@ -403,6 +405,16 @@ class Context:
         if r < 0:
             raise FlappieB200Error("ffb_debug_fetch failed: " + self.lib.last_error())
         return out[:n_samples]
+
+    def submit_raw(self, rb: RawBatch, b: Batch):
+        """enqueue upload + kernels + D2H for one raw batch; results are valid after collect(b)"""
+        self._check(self.lib.lib.ffb_submit_raw_batch(self.handle, ctypes.byref(rb), ctypes.byref(b)), "ffb_submit_raw_batch")
+
+    def submit(self, b: Batch):
+        self._check(self.lib.lib.ffb_submit_batch(self.handle, ctypes.byref(b)), "ffb_submit_batch")
+
+    def collect(self, b: Batch):
+        self._check(self.lib.lib.ffb_collect(self.handle, ctypes.byref(b)), "ffb_collect")
 
     def upload(self, b: Batch):
         self._check(self.lib.lib.ffb_upload(self.handle, ctypes.byref(b)), "ffb_upload")

@@ -855,10 +855,9 @@ extern "C" int ffb_forward_timed(ffb_ctx *c, float ms[8]) {
     return FFB_OK;
 }
 
-extern "C" int ffb_download(ffb_ctx *c, const ffb_batch *b) {
-    if (!c || !b) return FFB_ERR_ARG;
+// D2H of the requested outputs, enqueued on the context stream (no wait)
+static int download_enqueue(ffb_ctx *c, const ffb_batch *b) {
     ffb_model *m = c->m;
-    CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
     const int64_t N = c->n_reads, Tt = c->total_blocks;
     cudaStream_t st = c->st;
     if (N > 0 && Tt > 0) {
@@ -872,10 +871,42 @@ extern "C" int ffb_download(ffb_ctx *c, const ffb_batch *b) {
         if (b->trace && (c->flags & FFB_FLAG_WANT_TRACE))
             CUDA_TRY(cudaMemcpyAsync(b->trace, c->d_trace.p, (size_t)((Tt + N) * m->nstate), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
     }
-    CUDA_TRY(cudaStreamSynchronize(st), FFB_ERR_CUDA);
-    if (b->score && Tt == 0)
-        for (int64_t n = 0; n < N; n++) b->score[n] = NAN;
     return FFB_OK;
+}
+
+// wait for everything enqueued on the context stream; rejected-only batches get their NAN scores here
+extern "C" int ffb_collect(ffb_ctx *c, const ffb_batch *b) {
+    if (!c || !b) return FFB_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->m->device), FFB_ERR_CUDA);
+    CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
+    if (b->score && c->total_blocks == 0)
+        for (int64_t n = 0; n < c->n_reads; n++) b->score[n] = NAN;
+    return FFB_OK;
+}
+
+extern "C" int ffb_download(ffb_ctx *c, const ffb_batch *b) {
+    if (!c || !b) return FFB_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(c->m->device), FFB_ERR_CUDA);
+    const int r = download_enqueue(c, b);
+    if (r != FFB_OK) return r;
+    return ffb_collect(c, b);
+}
+
+// submit = upload + all kernels + D2H enqueued, WITHOUT waiting for the results: with two contexts (two streams) the
+// host prepares and uploads batch i+1 while the device still works on batch i; ffb_collect() waits for one of them
+extern "C" int ffb_submit_batch(ffb_ctx *c, const ffb_batch *b) {
+    int r = ffb_upload(c, b);
+    if (r != FFB_OK) return r;
+    r = ffb_forward(c);
+    if (r != FFB_OK) return r;
+    return download_enqueue(c, b);
+}
+extern "C" int ffb_submit_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
+    int r = ffb_upload_raw(c, rb, b);
+    if (r != FFB_OK) return r;
+    r = ffb_forward(c);
+    if (r != FFB_OK) return r;
+    return download_enqueue(c, b);
 }
 
 extern "C" int ffb_basecall_batch(ffb_ctx *c, const ffb_batch *b) {

@@ -205,6 +205,16 @@ typedef struct {
 int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
 int ffb_basecall_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
 
+/* Pipelined use (the `ffgpu_submit` / `ffgpu_collect` pair of SURVEY section 8b): submit = upload (or raw upload),
+ * every kernel and the D2H copies enqueued on the context's stream, returning WITHOUT waiting for the results;
+ * ffb_collect waits for that context and finalises its outputs.  With two contexts on two streams the host reads,
+ * plans and uploads batch i+1 while the device works on batch i.  Output buffers should be pinned host memory
+ * (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous; they belong to the library until
+ * ffb_collect returns. */
+int ffb_submit_batch(ffb_ctx *c, const ffb_batch *b);
+int ffb_submit_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
+int ffb_collect(ffb_ctx *c, const ffb_batch *b);
+
 /* Introspection for tests / bench. */
 int64_t ffb_total_blocks(const ffb_ctx *c);
 int64_t ffb_launch_count(const ffb_ctx *c);         /* kernels launched by this context so far */

@@ -126,3 +126,41 @@ def test_cfg4_r941_rna002_delta_reverse(gpu_lib, oracle):
         rev, rq = gpu_lib.emit_bases(*a.read_path(i), fm.nbase, reverse=True)
         assert fwd == full["basecall"] and rev == fwd[::-1] and rq == fq[::-1]
     ctx.close(); m.close()
+
+
+def test_submit_collect_pipeline_two_contexts(gpu_lib):
+    """ffb_submit_raw_batch / ffb_collect with two contexts in flight: same bits as the blocking call."""
+    import torch
+    fm = FlipflopModel.for_name("r10C_pcr", seed=1)
+    m = Model(fm)
+    batches = [synthetic_reads(24, 3000 + 500 * k, seed=40 + k) for k in range(4)]
+    blocking = Context(m)
+    want = [blocking.basecall_raw(b) for b in batches]
+    ctxs = [Context(m), Context(m)]
+    inflight, got = [], []
+
+    def prep(cx, raws):
+        lens = np.array([len(r) for r in raws], np.int64)
+        off = np.zeros(len(raws) + 1, np.int64); np.cumsum(lens, out=off[1:])
+        raw = torch.from_numpy(np.concatenate(raws)).pin_memory().numpy()
+        b, o = cx.make_batch(raw, off, 1.0, 0)
+        rb, s, e = cx.make_raw_batch(raw, off)
+        return rb, b, o, (raw, off, s, e)
+
+    for k, raws in enumerate(batches):
+        cx = ctxs[k % 2]
+        rb, b, o, keep = prep(cx, raws)
+        cx.submit_raw(rb, b)
+        inflight.append((cx, b, o, keep, rb))
+        if len(inflight) == 2:
+            pcx, pb, po, _, _ = inflight.pop(0)
+            pcx.collect(pb); got.append(po)
+    for pcx, pb, po, _, _ in inflight:
+        pcx.collect(pb); got.append(po)
+    for w, g in zip(want, got):
+        nb = int(w.blk_off[-1]) + w.n_reads
+        assert np.array_equal(w.blk_off, g["blk_off"]) and np.array_equal(w.path[:nb], g["path"][:nb])
+        assert np.array_equal(w.score, g["score"][:w.n_reads])
+    for cx in ctxs + [blocking]:
+        cx.close()
+    m.close()
