@@ -44,6 +44,7 @@ EXPORTS = [
     "ffb_create", "ffb_destroy", "ffb_basecall_batch", "ffb_upload", "ffb_forward", "ffb_download", "ffb_sync",
     "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_emit_bases",
     "ffb_upload_raw", "ffb_basecall_raw_batch", "ffb_submit_batch", "ffb_submit_raw_batch", "ffb_collect",
+    "ffb_alloc_pinned", "ffb_free_pinned",
 ]
 
 

@@ -592,7 +592,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     ok &= c->d_trans.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
     if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
         ok &= c->d_tpost.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
-        ok &= c->d_fwd.reserve(sizeof(float) * (size_t)std::max<int64_t>((Tt + N) * m->nstate, 1)) == 0;
+        ok &= c->d_fwd.reserve(2 * sizeof(float) * (size_t)std::max<int64_t>((Tt + N) * m->nstate, 1)) == 0;   // forward + backward vectors
     }
     ok &= c->d_tb.reserve(sizeof(uint64_t) * (size_t)std::max<int64_t>(Tt, 1)) == 0;
     ok &= c->d_path.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(Tt + N, 1)) == 0;
@@ -816,7 +816,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     const float *post = c->d_trans.as<float>();
     if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
         LAUNCH(ffb_launch_transpost(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_fwd.as<float>(),
-                                    c->d_tpost.as<float>(), st));   // includes the per-block log normalisation
+                                    c->d_tpost.as<float>(), Tt, st));   // includes the per-block log normalisation
         post = c->d_tpost.as<float>();
     }
     LAUNCH(ffb_launch_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint64_t>(), c->d_path.as<int32_t>(),
@@ -916,6 +916,15 @@ extern "C" int ffb_basecall_batch(ffb_ctx *c, const ffb_batch *b) {
     if (r != FFB_OK) return r;
     return ffb_download(c, b);
 }
+
+// pinned host memory for callers without the CUDA runtime (the C command line): async copies need it
+extern "C" void *ffb_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    memset(p, 0, bytes);
+    return p;
+}
+extern "C" void ffb_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int ffb_basecall_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
     int r = ffb_upload_raw(c, rb, b);
@@ -1161,11 +1170,11 @@ extern "C" flappie_matrix transpost_crf_flipflop(const_flappie_matrix trans, boo
     const int nstate = 2 * (int)nbase_from_flipflop_nparam(nr);
     int64_t off[2] = {0, T};
     bool ok = mat_to_device(trans, d->trans, d->st) == 0;
-    ok = ok && d->tpost.reserve(sizeof(float) * (size_t)(T * nr)) == 0 && d->fwd.reserve(sizeof(float) * (size_t)((T + 1) * nstate)) == 0 &&
+    ok = ok && d->tpost.reserve(sizeof(float) * (size_t)(T * nr)) == 0 && d->fwd.reserve(2 * sizeof(float) * (size_t)((T + 1) * nstate)) == 0 &&
          d->blkoff.reserve(sizeof(off)) == 0;
     if (!ok) { set_err("transpost_crf_flipflop: device allocation / copy failed"); return nullptr; }
     cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
-    if (ffb_launch_transpost(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->fwd.as<float>(), d->tpost.as<float>(), d->st) < 0) return nullptr;
+    if (ffb_launch_transpost(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->fwd.as<float>(), d->tpost.as<float>(), T, d->st) < 0) return nullptr;
     if (!return_log && ffb_launch_exp_inplace(d->tpost.as<float>(), T * nr, d->st) < 0) return nullptr;
     flappie_matrix out = make_flappie_matrix(nr, (size_t)T);
     if (!out) return nullptr;

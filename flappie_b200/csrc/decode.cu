@@ -16,6 +16,8 @@
 // with the read's scores streamed through shared memory by cp.async double buffering.
 // fp32 additions and comparisons are done in the reference's visit order so the Viterbi
 // path is bit-exact given bit-identical input (first-max-wins ties included).
+#include <cstdlib>
+
 #include "ffb_common.cuh"
 
 namespace ffb {
@@ -580,6 +582,199 @@ fb_bwd_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_o
     }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Production layout of the posteriors: the two scans are independent of each other, so they run CONCURRENTLY --
+// one CTA of two warps per read, warp 0 the forward scan, warp 1 the backward scan, each writing its running-shifted
+// state vectors -- and a third, fully block-parallel kernel (HBM-bound: 160 B read + 64 B vectors + 160 B written per
+// block) combines them, tpost[blk][e] = (trans[blk][e] + bwd[to, blk+1]) + fwd[from, blk], and log-normalises each
+// block.  Replaces fb_fwd_kernel -> fb_bwd_kernel (two dependent latency-bound scans, the second one also carrying
+// the normalisation on its chain).
+template <int NBASE>
+__device__ __forceinline__ void fb_bwd_scan(const float *__restrict__ tr, int T, float *__restrict__ rb /* (T+1) x NSTATE */,
+                                            float (*stage)[DEC_CHUNK * FbGeom<NBASE>::NR], int lane) {
+    using Gm = FbGeom<NBASE>;
+    constexpr int NSTATE = Gm::NSTATE, NR = Gm::NR, SEG = Gm::SEG, DPP = Gm::DPP, NPASS = Gm::NPASS;
+    const int src = lane % SEG, slot = lane / SEG;
+    const bool src_ok = src < NSTATE;
+    const int to_flop = src < NBASE ? src + NBASE : src;
+    float B = 0.0f;
+    if (lane < NSTATE) rb[(int64_t)T * NSTATE + lane] = 0.0f;     // bwd[., T] = 0 (the reference's calloc, decode.c:440)
+    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
+    {
+        const int cl = nchunk - 1;
+        stage_chunk(stage[cl & 1], tr + (int64_t)cl * DEC_CHUNK * NR, T - cl * DEC_CHUNK, NR, lane);
+    }
+    for (int ch = nchunk - 1; ch >= 0; ch--) {
+        const int c0 = ch * DEC_CHUNK;
+        const int cn = min(DEC_CHUNK, T - c0);
+        if (ch > 0) {
+            stage_chunk(stage[(ch - 1) & 1], tr + (int64_t)(c0 - DEC_CHUNK) * NR, DEC_CHUNK, NR, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float *sb = stage[ch & 1];
+        for (int i = cn - 1; i >= 0; i--) {
+            const float *col = sb + i * NR;
+            // t = trans + bwd[to]; bwd[from = src] = logsumexp over destinations (decode.c:465-482)
+            const float Bto = __shfl_sync(FULL, B, to_flop);
+            const float tfl = src_ok ? col[NBASE * NSTATE + src] + Bto : -INFINITY;
+            float t[NPASS];
+            float m2 = tfl;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const int b1 = p * DPP + slot;
+                const bool ok = src_ok && b1 < NBASE;
+                const float Bb = __shfl_sync(FULL, B, b1 < NBASE ? b1 : 0);
+                t[p] = ok ? col[b1 * NSTATE + src] + Bb : -INFINITY;
+                m2 = fmaxf(m2, t[p]);
+            }
+#pragma unroll
+            for (int o = SEG; o < 32; o <<= 1) m2 = fmaxf(m2, __shfl_xor_sync(FULL, m2, o));   // across segments: same src
+            float s2 = 0.0f;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) s2 += (t[p] > -INFINITY) ? expf(t[p] - m2) : 0.0f;
+#pragma unroll
+            for (int o = SEG; o < 32; o <<= 1) s2 += __shfl_xor_sync(FULL, s2, o);
+            s2 += src_ok ? expf(tfl - m2) : 0.0f;                        // the flop term, once per lane
+            const float nb = src_ok ? m2 + logf(s2) : 0.0f;
+            const float ref = __shfl_sync(FULL, nb, 0);                  // pin state 0 to 0
+            B = src_ok ? nb - ref : 0.0f;
+            if (lane < NSTATE) rb[(int64_t)(c0 + i) * NSTATE + lane] = B;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NBASE>
+__device__ __forceinline__ void fb_fwd_scan(const float *__restrict__ tr, int T, float *__restrict__ rf,
+                                            float (*stage)[DEC_CHUNK * FbGeom<NBASE>::NR], int lane) {
+    using Gm = FbGeom<NBASE>;
+    constexpr int NSTATE = Gm::NSTATE, NR = Gm::NR, SEG = Gm::SEG, DPP = Gm::DPP, NPASS = Gm::NPASS;
+    const int src = lane % SEG, slot = lane / SEG;
+    const bool src_ok = src < NSTATE;
+    float P = 0.0f;
+    if (lane < NSTATE) rf[lane] = 0.0f;
+    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
+    stage_chunk(stage[0], tr, min(DEC_CHUNK, T), NR, lane);
+    for (int ch = 0; ch < nchunk; ch++) {
+        const int c0 = ch * DEC_CHUNK;
+        const int cn = min(DEC_CHUNK, T - c0);
+        if (ch + 1 < nchunk) {
+            stage_chunk(stage[(ch + 1) & 1], tr + (int64_t)(c0 + DEC_CHUNK) * NR, min(DEC_CHUNK, T - c0 - DEC_CHUNK), NR, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const float *sb = stage[ch & 1];
+        for (int i = 0; i < cn; i++) {
+            const float *col = sb + i * NR;
+            const float fl = src_ok ? col[NBASE * NSTATE + src] : 0.0f;
+            const float x = P + fl;
+            const float y = __shfl_sync(FULL, x, (lane - NBASE) & 31);
+            const float flopv = fmaxf(x, y) + log1pf(expf(-fabsf(x - y)));
+            float flipv[NPASS];
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const int b1 = p * DPP + slot;
+                const bool ok = src_ok && b1 < NBASE;
+                const float v = ok ? P + col[b1 * NSTATE + src] : -INFINITY;
+                const float m = seg_max<SEG>(v);
+                const float sum = seg_sum<SEG>(ok ? expf(v - m) : 0.0f);
+                flipv[p] = m + logf(sum);
+            }
+            float np = flopv;
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const float g = __shfl_sync(FULL, flipv[p], (src % DPP) * SEG);
+                if (src < NBASE && src / DPP == p) np = g;
+            }
+            const float ref = __shfl_sync(FULL, flipv[0], 0);
+            P = src_ok ? np - ref : 0.0f;
+            if (lane < NSTATE) rf[(int64_t)(c0 + i + 1) * NSTATE + lane] = P;
+        }
+        __syncwarp();
+    }
+}
+
+// fwd / bwd: (T+1) x NSTATE rows per read starting at row blk_off[rd] + rd
+template <int NBASE>
+__global__ void __launch_bounds__(64)
+fb_scan2_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads, float *__restrict__ fwd,
+                float *__restrict__ bwd) {
+    using Gm = FbGeom<NBASE>;
+    __shared__ __align__(16) float stage[2][2][DEC_CHUNK * Gm::NR];
+    const int rd = blockIdx.x;
+    if (rd >= n_reads) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b0 = blk_off[rd];
+    const int T = (int)(blk_off[rd + 1] - b0);
+    if (T <= 0) return;
+    const float *tr = trans + b0 * Gm::NR;
+    if (warp == 0) fb_fwd_scan<NBASE>(tr, T, fwd + (b0 + rd) * Gm::NSTATE, stage[0], lane);
+    else fb_bwd_scan<NBASE>(tr, T, bwd + (b0 + rd) * Gm::NSTATE, stage[1], lane);
+}
+
+// one warp per block: entries e = lane, lane + 32 (< NR); per-block log normalisation (flappie_matrix.c:450-467)
+template <int NBASE>
+__global__ void __launch_bounds__(256)
+fb_combine_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads, const float *__restrict__ fwd,
+                  const float *__restrict__ bwd, float *__restrict__ tpost, int64_t total_blocks) {
+    using Gm = FbGeom<NBASE>;
+    constexpr int NSTATE = Gm::NSTATE, NR = Gm::NR;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // (from, to) of this lane's two entries
+    int from[2], to[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int e = lane + 32 * k;
+        if (e < NBASE * NSTATE) { from[k] = e % NSTATE; to[k] = e / NSTATE; }
+        else { const int j = e - NBASE * NSTATE; from[k] = j; to[k] = j < NBASE ? j + NBASE : j; }
+    }
+    // each warp walks a contiguous range of blocks: the owning read is searched once and then advances linearly
+    const int64_t per = (total_blocks + nwarp - 1) / nwarp;
+    const int64_t blk_lo = warp0 * per, blk_hi = (blk_lo + per < total_blocks) ? blk_lo + per : total_blocks;
+    if (blk_lo >= blk_hi) return;
+    int rd = 0;
+    {
+        int lo = 0, hi = n_reads;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (blk_off[mid] <= blk_lo) lo = mid; else hi = mid;
+        }
+        rd = lo;
+    }
+    // the block's scores are prefetched one iteration ahead (the loop is otherwise one HBM latency per block)
+    float cn[2];
+    cn[0] = trans[blk_lo * NR + lane];
+    cn[1] = (lane + 32 < NR) ? trans[blk_lo * NR + lane + 32] : 0.0f;
+    for (int64_t blk = blk_lo; blk < blk_hi; blk++) {
+        while (blk >= blk_off[rd + 1]) rd++;
+        const float c0v = cn[0], c1v = cn[1];
+        if (blk + 1 < blk_hi) {
+            cn[0] = trans[(blk + 1) * NR + lane];
+            cn[1] = (lane + 32 < NR) ? trans[(blk + 1) * NR + lane + 32] : 0.0f;
+        }
+        const float *f = fwd + (blk + rd) * NSTATE;            // forward vector before this block
+        const float *b = bwd + (blk + rd + 1) * NSTATE;        // backward vector after it
+        float x[2];
+        x[0] = (c0v + b[to[0]]) + f[from[0]];
+        x[1] = (lane + 32 < NR) ? (c1v + b[to[1]]) + f[from[1]] : -INFINITY;
+        float m = fmaxf(x[0], x[1]);
+        m = seg_max<32>(m);
+        float sum = expf(x[0] - m) + ((x[1] > -INFINITY) ? expf(x[1] - m) : 0.0f);
+        sum = seg_sum<32>(sum);
+        const float lse = m + logf(sum);
+        float *pc = tpost + blk * NR;
+        pc[lane] = x[0] - lse;
+        if (lane + 32 < NR) pc[lane + 32] = x[1] - lse;
+    }
+}
+
 // per-block log normalisation, sequential fold in row order (flappie_matrix.c:450-467)
 __global__ void lognorm_rows_kernel(float *__restrict__ tpost, int64_t nblk, int nr) {
     const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -674,19 +869,31 @@ int ffb_launch_viterbi(const float *trans, const int64_t *blk_off, int n_reads, 
     return FFB_OKL(1);
 }
 
+// fwd_scratch: 2 * (total_blocks + n_reads) * nstate floats (forward and backward state vectors)
 int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads, int nr, float *fwd_scratch,
-                         float *tpost, cudaStream_t st) {
-    if (n_reads <= 0) return 0;
-    switch (nbase_of(nr)) {
-    case 4:
-        ffb::fb_fwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
-        ffb::fb_bwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
-        break;
-    case 5:
-        ffb::fb_fwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
-        ffb::fb_bwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
-        break;
-    default: return -1;
+                         float *tpost, int64_t total_blocks, cudaStream_t st) {
+    if (n_reads <= 0 || total_blocks <= 0) return 0;
+    const int nbase = nbase_of(nr);
+    if (nbase != 4 && nbase != 5) return -1;
+    float *bwd_scratch = fwd_scratch + (total_blocks + n_reads) * 2 * nbase;
+    if (getenv("FFB_FB_SEQUENTIAL")) {      // the two-pass version (forward scan, then backward scan + normalisation)
+        if (nbase == 4) {
+            ffb::fb_fwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
+            ffb::fb_bwd_kernel<4><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
+        } else {
+            ffb::fb_fwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch);
+            ffb::fb_bwd_kernel<5><<<n_reads, 32, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, tpost);
+        }
+        return FFB_OKL(2);
+    }
+    const int64_t warps = (total_blocks < 148 * 64) ? total_blocks : 148 * 64;
+    const unsigned grid = (unsigned)((warps + 7) / 8);
+    if (nbase == 4) {
+        ffb::fb_scan2_kernel<4><<<n_reads, 64, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, bwd_scratch);
+        ffb::fb_combine_kernel<4><<<grid, 256, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, bwd_scratch, tpost, total_blocks);
+    } else {
+        ffb::fb_scan2_kernel<5><<<n_reads, 64, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, bwd_scratch);
+        ffb::fb_combine_kernel<5><<<grid, 256, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, bwd_scratch, tpost, total_blocks);
     }
     return FFB_OKL(2);
 }

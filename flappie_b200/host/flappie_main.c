@@ -204,8 +204,21 @@ static void pending_clear(struct pending *p) {
     p->n = 0;
 }
 
-/* calculate_post for every pending read at once, then the reference's per-read printing in input order */
-static void flush_batch(ffb_ctx *ctx, ffb_model *model, struct pending *p) {
+/* One batch in flight on one context: calculate_post for every pending read at once (submitted without waiting),
+ * then -- at collect time -- the reference's per-read printing in input order.  main() keeps two of these going, so
+ * the files of batch i+1 are read while the device works on batch i. */
+struct inflight {
+    ffb_ctx *ctx;
+    struct pending pend;
+    bool busy;
+    int64_t *blk_off, *start, *end;
+    int32_t *path;
+    float *qpath, *score;
+    ffb_batch b;
+};
+
+static void submit_batch(struct inflight *f, ffb_model *model) {
+    struct pending *p = &f->pend;
     if (p->n == 0) return;
     const int n = p->n;
     int64_t tot_blocks = 0;
@@ -213,37 +226,50 @@ static void flush_batch(ffb_ctx *ctx, ffb_model *model, struct pending *p) {
         const long t = ffb_model_nblock(model, (long)(p->raw_off[i + 1] - p->raw_off[i]));
         tot_blocks += t > 0 ? t : 0;                  /* upper bound: the kept range is shorter */
     }
-    int64_t *blk_off = calloc((size_t)n + 1, sizeof(int64_t)), *start = calloc((size_t)n, sizeof(int64_t)),
-            *end = calloc((size_t)n, sizeof(int64_t));
-    int32_t *path = calloc((size_t)(tot_blocks + n), sizeof(int32_t));
-    float *qpath = calloc((size_t)(tot_blocks + n), sizeof(float)), *score = calloc((size_t)n, sizeof(float));
-    if (!blk_off || !start || !end || !path || !qpath || !score) die("out of memory%s", "");
+    f->blk_off = calloc((size_t)n + 1, sizeof(int64_t));
+    f->start = calloc((size_t)n, sizeof(int64_t));
+    f->end = calloc((size_t)n, sizeof(int64_t));
+    /* page-locked, so that the device-to-host copies really are asynchronous */
+    f->path = ffb_alloc_pinned((size_t)(tot_blocks + n) * sizeof(int32_t));
+    f->qpath = ffb_alloc_pinned((size_t)(tot_blocks + n) * sizeof(float));
+    f->score = ffb_alloc_pinned((size_t)n * sizeof(float));
+    if (!f->blk_off || !f->start || !f->end || !f->path || !f->qpath || !f->score) die("out of memory%s", "");
     ffb_raw_batch rb = {.raw = p->raw, .raw_off = p->raw_off, .n_reads = n, .trim_start = args.trim_start, .trim_end = args.trim_end,
                         .varseg_chunk = args.varseg_chunk, .varseg_thresh = args.varseg_thresh, .delta = args.delta,
-                        .start = start, .end = end};
-    ffb_batch b = {0};
-    b.n_reads = n; b.temperature = args.temperature;
-    b.flags = args.viterbi_only ? FFB_FLAG_VITERBI_ONLY : 0;
-    b.blk_off = blk_off; b.path = path; b.qpath = qpath; b.score = score;
-    if (ffb_basecall_raw_batch(ctx, &rb, &b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
+                        .start = f->start, .end = f->end};
+    memset(&f->b, 0, sizeof f->b);
+    f->b.n_reads = n; f->b.temperature = args.temperature;
+    f->b.flags = args.viterbi_only ? FFB_FLAG_VITERBI_ONLY : 0;
+    f->b.blk_off = f->blk_off; f->b.path = f->path; f->b.qpath = f->qpath; f->b.score = f->score;
+    if (ffb_submit_raw_batch(f->ctx, &rb, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
+    f->busy = true;
+}
+
+static void collect_batch(struct inflight *f, ffb_model *model) {
+    if (!f->busy) return;
+    struct pending *p = &f->pend;
+    const int n = p->n;
+    if (ffb_collect(f->ctx, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
     const int nbase = (int)nbase_from_flipflop_nparam((size_t)ffb_model_nparam(model));
     for (int i = 0; i < n; i++) {
-        const int64_t nblock = blk_off[i + 1] - blk_off[i];
+        const int64_t nblock = f->blk_off[i + 1] - f->blk_off[i];
         if (nblock <= 0) {
             fprintf(stderr, "flappie: No basecall returned for %s\n", p->name[i]);   /* src/flappie.c:370-373 */
             continue;
         }
         char *basecall = calloc((size_t)nblock + 2, 1), *quality = calloc((size_t)nblock + 2, 1);
         if (!basecall || !quality) die("out of memory%s", "");
-        const int nb = ffb_emit_bases(path + blk_off[i] + i, qpath + blk_off[i] + i, nblock, nbase, args.reverse, basecall, quality);
-        ffb_read_result res = {.score = score[i], .n = (size_t)(p->raw_off[i + 1] - p->raw_off[i]), .start = (size_t)start[i],
-                               .end = (size_t)end[i], .basecall = basecall, .quality = quality, .basecall_length = (size_t)(nb > 0 ? nb : 0),
+        const int nb = ffb_emit_bases(f->path + f->blk_off[i] + i, f->qpath + f->blk_off[i] + i, nblock, nbase, args.reverse, basecall, quality);
+        ffb_read_result res = {.score = f->score[i], .n = (size_t)(p->raw_off[i + 1] - p->raw_off[i]), .start = (size_t)f->start[i],
+                               .end = (size_t)f->end[i], .basecall = basecall, .quality = quality, .basecall_length = (size_t)(nb > 0 ? nb : 0),
                                .nblock = (size_t)nblock};
         ffb_fprintf_read(args.outformat, args.output, p->uuid[i], p->name[i], args.uuid, args.prefix, &res);
         free(basecall); free(quality);
     }
-    free(blk_off); free(start); free(end); free(path); free(qpath); free(score);
+    free(f->blk_off); free(f->start); free(f->end);
+    ffb_free_pinned(f->path); ffb_free_pinned(f->qpath); ffb_free_pinned(f->score);
     pending_clear(p);
+    f->busy = false;
 }
 
 int main(int argc, char **argv) {
@@ -264,10 +290,13 @@ int main(int argc, char **argv) {
     ffb_model *model = ffb_bundle_to_model(&bundle, args.device);
     if (!model) die("weight bundle rejected: %s", ffb_last_error());
     ffb_bundle_free(&bundle);
-    ffb_ctx *ctx = ffb_create(model, NULL);
-    if (!ctx) die("ffb_create: %s", ffb_last_error());
-
-    struct pending pend = {0};
+    struct inflight fl[2];
+    memset(fl, 0, sizeof fl);
+    for (int k = 0; k < 2; k++) {
+        fl[k].ctx = ffb_create(model, NULL);
+        if (!fl[k].ctx) die("ffb_create: %s", ffb_last_error());
+    }
+    int cur = 0;                                    /* the batch being filled; the other one may be on the device */
     int reads_started = 0;
     for (int fn = optind; fn < argc; fn++) {
         if (args.limit > 0 && reads_started >= args.limit) continue;
@@ -294,15 +323,22 @@ int main(int argc, char **argv) {
             const long n = ffb_read_raw_file(filename, &sig);
             if (n == -2) { fprintf(stderr, "flappie: %s: fast5 input needs libhdf5, which this build does not have\n", filename); continue; }
             if (n <= 0) { fprintf(stderr, "flappie: No basecall returned for %s\n", filename); free(sig); continue; }
-            pending_add(&pend, filename, sig, n);
+            pending_add(&fl[cur].pend, filename, sig, n);
             free(sig);
-            if (pend.n >= args.batch) flush_batch(ctx, model, &pend);
+            if (fl[cur].pend.n >= args.batch) {
+                submit_batch(&fl[cur], model);
+                cur ^= 1;
+                collect_batch(&fl[cur], model);     /* the older batch: print it, then refill its slot */
+            }
         }
         globfree(&globbuf);
     }
-    flush_batch(ctx, model, &pend);
+    collect_batch(&fl[cur ^ 1], model);             /* older batch first: records stay in input order */
+    submit_batch(&fl[cur], model);
+    collect_batch(&fl[cur], model);
 
-    ffb_destroy(ctx);
+    ffb_destroy(fl[0].ctx);
+    ffb_destroy(fl[1].ctx);
     ffb_model_destroy(model);
     if (stdout != args.output) fclose(args.output);
     return EXIT_SUCCESS;

@@ -214,6 +214,9 @@ int ffb_basecall_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch 
 int ffb_submit_batch(ffb_ctx *c, const ffb_batch *b);
 int ffb_submit_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
 int ffb_collect(ffb_ctx *c, const ffb_batch *b);
+/* zero-filled page-locked host memory (NULL on failure), for callers that do not link the CUDA runtime */
+void *ffb_alloc_pinned(size_t bytes);
+void ffb_free_pinned(void *p);
 
 /* Introspection for tests / bench. */
 int64_t ffb_total_blocks(const ffb_ctx *c);
