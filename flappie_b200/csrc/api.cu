@@ -361,11 +361,14 @@ struct ffb_ctx {
     int max_T[FFB_MAX_CONV + 1] = {0};
     int n_slots = 0;
     bool use_tc_rnn = false;
-    int R_tc = 0;
+    int R_tc = 0;                 // reads per cluster of the tensor recurrent kernel = 16 * groups per cluster
+    int tc_clusters = 0;          // clusters launched; each of its R_tc/16 slots walks a list of 16-read groups
+    std::vector<int32_t> slot_off, slot_list;
     // device
     DevBuf d_sig, d_c[2], d_act[2], d_xin, d_trans, d_tpost, d_fwd, d_tb, d_path, d_qpath, d_score, d_logz, d_trace;
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
-    DevBuf d_raw, d_rawoff, d_chunkoff, d_mad, d_bounds, d_sigoff;   // device signal preparation (ffb_upload_raw)
+    DevBuf d_raw, d_rawoff, d_chunkoff, d_mad, d_bounds, d_sigoff;
+    DevBuf d_slotoff, d_slotlist;   // device signal preparation (ffb_upload_raw)
     DevBuf d_ahi, d_alo;          // fp16 hi/lo planes of the current layer input (tensor path)
     DevBuf d_ring;                // state-exchange ring of the tensor recurrent kernel (L2-resident)
     // streamed input GEMMs: layer l+1's projection runs on the SMs layer l's recurrence leaves free and consumes
@@ -404,7 +407,7 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
                      &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress,
-                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff};
+                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff, &c->d_slotoff, &c->d_slotlist};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -494,23 +497,64 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     // length-sorted slots for the recurrent kernel (descending, stable)
     int R = ffb_rnn_reads_per_cluster(m->kind, m->S);
     c->use_tc_rnn = m->tc_rnn && !(c->flags & FFB_FLAG_FP32_SIMT) && getenv("FFB_NO_TC_RNN") == nullptr;
+    std::vector<int32_t> idx((size_t)N);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t bb) {
+        return (c->blk_off[a + 1] - c->blk_off[a]) > (c->blk_off[bb + 1] - c->blk_off[bb]);
+    });
+    std::vector<int64_t> group_start;   // steps a group's slot has already run when the group begins
+    c->slot_off.clear(); c->slot_list.clear(); c->tc_clusters = 0;
     if (c->use_tc_rnn) {
-        // groups of 16 reads; as few groups per cluster as still fit the batch into one wave of
-        // co-resident clusters (the layer is latency-bound: more clusters = shorter chains per SM)
+        // GROUPS of 16 sorted reads; a cluster has G slots, each slot walks a LIST of groups one after the other.
+        // As few slots per cluster as still fit the batch into one wave of co-resident clusters (the layer is
+        // latency-bound: more clusters = shorter chains per SM); when the batch has more groups than slots, or the
+        // reads differ in length, the groups are dealt longest-first to the least-loaded slot (LPT) so every slot
+        // runs about the same number of steps -- short reads no longer idle behind the longest one.
         const int rmax = ffb_rnn_tc_rmax(m->kind, m->S);
+        const int gmax = rmax / 16;
         const int64_t groups = (N + 15) / 16;
-        int64_t gpc = (groups + m->tc_max_clusters - 1) / std::max(m->tc_max_clusters, 1);
-        c->R_tc = (int)std::min<int64_t>(std::max<int64_t>(gpc, 1) * 16, rmax);
-        R = c->R_tc;
-    }
-    c->n_slots = (int)(((N + R - 1) / R) * R);
-    c->order.assign((size_t)c->n_slots, -1);
-    {
-        std::vector<int32_t> idx((size_t)N);
-        std::iota(idx.begin(), idx.end(), 0);
-        std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t bb) {
-            return (c->blk_off[a + 1] - c->blk_off[a]) > (c->blk_off[bb + 1] - c->blk_off[bb]);
-        });
+        const int maxc = std::max(m->tc_max_clusters, 1);
+        int G, ncl;
+        if (groups <= (int64_t)maxc * gmax) {
+            const int64_t gpc = (groups + maxc - 1) / maxc;
+            G = (int)std::min<int64_t>(std::max<int64_t>(gpc, 1), gmax);
+            ncl = (int)((groups + G - 1) / G);
+        } else {
+            G = gmax;
+            ncl = std::max(1, maxc - 2);        // a few SMs stay free for the streamed input GEMM
+        }
+        if (getenv("FFB_TC_CLUSTERS")) ncl = std::max(1, std::min(atoi(getenv("FFB_TC_CLUSTERS")), maxc));
+        c->R_tc = G * 16;
+        c->tc_clusters = groups > 0 ? ncl : 0;
+        c->n_slots = (int)(groups * 16);
+        c->order.assign((size_t)c->n_slots, -1);
+        std::copy(idx.begin(), idx.end(), c->order.begin());
+        const int nslot = ncl * G;
+        std::vector<std::vector<int32_t>> lists((size_t)nslot);
+        std::vector<int64_t> load((size_t)nslot, 0);
+        group_start.assign((size_t)groups, 0);
+        for (int64_t g = 0; g < groups; g++) {          // groups are already in descending order of their longest read
+            const int32_t rd0 = c->order[(size_t)g * 16];
+            const int64_t Tg = c->blk_off[rd0 + 1] - c->blk_off[rd0];
+            int best = 0;
+            if (getenv("FFB_TC_ROUND_ROBIN")) {         // A/B: groups dealt in sorted order, as successive waves would run them
+                best = (int)(g % nslot);
+            } else {
+                for (int sl = 1; sl < nslot; sl++)
+                    if (load[(size_t)sl] < load[(size_t)best]) best = sl;
+            }
+            group_start[(size_t)g] = load[(size_t)best];
+            lists[(size_t)best].push_back((int32_t)g);
+            load[(size_t)best] += Tg;
+        }
+        c->slot_off.assign((size_t)nslot + 1, 0);
+        for (int sl = 0; sl < nslot; sl++) {
+            c->slot_off[(size_t)sl + 1] = c->slot_off[(size_t)sl] + (int32_t)lists[(size_t)sl].size();
+            c->slot_list.insert(c->slot_list.end(), lists[(size_t)sl].begin(), lists[(size_t)sl].end());
+        }
+    } else {
+        c->n_slots = (int)(((N + R - 1) / R) * R);
+        c->order.assign((size_t)c->n_slots, -1);
         std::copy(idx.begin(), idx.end(), c->order.begin());
     }
 
@@ -551,7 +595,8 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
                     const int32_t g = group_of[(size_t)n];
                     const int events_total = (group_T[(size_t)g] + P - 1) / P;
                     const int ev = (int)std::min<int64_t>((need + P - 1) / P, events_total);
-                    worst = std::max(worst, ev * P);
+                    // step (of its slot) at which the producing layer publishes this event
+                    worst = (int)std::min<int64_t>(std::max<int64_t>(worst, group_start[(size_t)g] + (int64_t)ev * P), 0x7ffffffe);
                     if (nd < 3) { w.idx[nd] = g; w.cnt[nd] = ev * arrivals; nd++; }
                     else overflow = true;
                 }
@@ -559,7 +604,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
                     // more than three reads in one tile (very short reads): wait for the whole layer instead --
                     // the counter at index n_groups counts CTAs that have finished it
                     for (int d = 0; d < 3; d++) { w.idx[d] = -1; w.cnt[d] = 0; }
-                    w.idx[0] = c->n_groups; w.cnt[0] = (c->n_slots / std::max(c->R_tc, 1)) * ffb_rnn_tc_cluster_size(m->kind, m->S);
+                    w.idx[0] = c->n_groups; w.cnt[0] = c->tc_clusters * ffb_rnn_tc_cluster_size(m->kind, m->S);
                     worst = 0x7fffffff;
                 }
                 work[dir][(size_t)k] = w;
@@ -588,7 +633,11 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
         ok &= c->d_progress.reserve(sizeof(int) * (size_t)FFB_NLAYER * (c->n_groups + 1 + 16)) == 0;
     }
     if (c->use_tc_rnn)
-        ok &= c->d_ring.reserve(std::max<size_t>(ffb_rnn_tc_ring_bytes(m->kind, m->S, c->n_slots / std::max(c->R_tc, 1), c->R_tc), 16)) == 0;
+    {
+        ok &= c->d_ring.reserve(std::max<size_t>(ffb_rnn_tc_ring_bytes(m->kind, m->S, c->tc_clusters, c->R_tc), 16)) == 0;
+        ok &= c->d_slotoff.reserve(sizeof(int32_t) * std::max<size_t>(c->slot_off.size(), 1)) == 0;
+        ok &= c->d_slotlist.reserve(sizeof(int32_t) * std::max<size_t>(c->slot_list.size(), 1)) == 0;
+    }
     ok &= c->d_trans.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
     if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
         ok &= c->d_tpost.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * nr, 1)) == 0;
@@ -617,6 +666,11 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     CUDA_TRY(cudaMemcpyAsync(c->d_blkoff.p, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
     if (c->n_slots > 0)
         CUDA_TRY(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int32_t) * (size_t)c->n_slots, cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+    if (!c->slot_off.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * c->slot_off.size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+        if (!c->slot_list.empty())
+            CUDA_TRY(cudaMemcpyAsync(c->d_slotlist.p, c->slot_list.data(), sizeof(int32_t) * c->slot_list.size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+    }
     for (int i = 0; i < m->nconv; i++) {
         if (N > 0) CUDA_TRY(cudaMemcpyAsync(c->d_geom[i].p, geom[i].data(), sizeof(ffb::ReadGeom) * (size_t)N, cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
         if (!tails[i].empty())
@@ -744,7 +798,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     // streamed mode: GEMM l+1 is launched behind recurrence l and eats its output planes as they appear
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, m->device);
-    const int free_sms = sm_count - (c->R_tc > 0 ? (c->n_slots / c->R_tc) * ffb_rnn_tc_cluster_size(m->kind, m->S) : 0);
+    const int free_sms = sm_count - c->tc_clusters * ffb_rnn_tc_cluster_size(m->kind, m->S);
     const bool streamed = c->stream_gemm && tc_rnn && !timed && free_sms >= (G * S) / 128 && (G * S) / 128 <= 16;
     const size_t prog_stride = (size_t)c->n_groups + 1 + 16;   // per layer: group counters, finished-CTA counter, 16 ticket queues
     if (streamed) {
@@ -772,8 +826,9 @@ static int forward_impl(ffb_ctx *c, bool timed) {
             const bool planes_out = !last || tc_ff;
             float *out_f32 = (keep || (last && !tc_ff)) ? out : nullptr;
             int *prog = (streamed && !last) ? c->d_progress.as<int>() + (size_t)l * prog_stride : nullptr;
+            RnnTcSched sched{c->d_slotoff.as<int32_t>(), c->d_slotlist.as<int32_t>(), c->tc_clusters, c->n_slots / 16};
             LAUNCH(ffb_launch_rnn_tc(m->kind, S, xin, m->d_sW_img[l], out_f32, planes_out ? c->d_ahi.p : nullptr,
-                                     planes_out ? c->d_alo.p : nullptr, rb, c->R_tc, (l % 2) == 0, c->d_ring.p, prog, st));
+                                     planes_out ? c->d_alo.p : nullptr, rb, sched, c->R_tc, (l % 2) == 0, c->d_ring.p, prog, st));
             if (streamed && !last) {
                 const int dir = (l % 2) == 0 ? 1 : 0;   // layer l runs backward for even l (networks.c:460-483)
                 LAUNCH(ffb_launch_gemm_tc_streamed(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l + 1], m->d_iW_lo[l + 1], m->d_b[l + 1],

@@ -143,10 +143,20 @@ int ffb_rnn_tc_max_clusters(int kind, int S, int R);
 int ffb_rnn_tc_rmax(int kind, int S);
 int ffb_rnn_tc_cluster_size(int kind, int S);
 size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R);   // L2-resident state-exchange ring
-// progress (optional): one counter per group of 16 slots, +1 from each of the 32 gate warps of the cluster every
-// FFB_RNN_PUBLISH_PERIOD steps (and at the group's last step) once their fp16 output planes are globally visible
+// Schedule of the tensor recurrent kernel: rb.order holds GROUPS of 16 reads (group k = order[16k .. 16k+15], longest
+// first); cluster c, slot g (g < R/16) runs the groups slot_list[slot_off[c*G+g] .. slot_off[c*G+g+1]) one after the other.
+struct RnnTcSched {
+    const int32_t *slot_off;    // [n_clusters * G + 1]
+    const int32_t *slot_list;   // group ids
+    int n_clusters;
+    int n_groups;
+};
+// progress (optional): one counter per GROUP, +1 from each of the 32 gate warps of the cluster every
+// FFB_RNN_PUBLISH_PERIOD steps (and at the group's last step) once their fp16 output planes are globally visible;
+// progress[n_groups] counts CTAs that have finished the layer
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
-                      const RnnBatch &rb, int R, int backward, void *ring, int *progress, cudaStream_t st);
+                      const RnnBatch &rb, const RnnTcSched &sched, int R, int backward, void *ring, int *progress,
+                      cudaStream_t st);
 
 // signal.cu: trimming + normalisation of raw reads on the device (reference src/flappie.c:251-259)
 #define FFB_MAX_VARSEG_CHUNK 1024

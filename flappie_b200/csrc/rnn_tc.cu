@@ -3,8 +3,11 @@
 // Replaces reference grumod_forward/backward + grumod_step (src/layers.c:571-715) and
 // lstm_forward/backward + lstm_step (src/layers.c:877-1026).
 //
-// Decomposition.  A thread-block cluster of C CTAs owns up to GMAX independent GROUPS of 16
-// whole reads for the whole layer; CTA c owns hidden units [c*HS, (c+1)*HS), HS = S/C = 32.
+// Decomposition.  A thread-block cluster of C CTAs has up to GMAX SLOTS; each slot works through a
+// list of GROUPS of 16 whole reads, one group after the other (the host deals the length-sorted
+// groups longest-first to the least-loaded slot, so a ragged or oversized batch keeps every slot
+// busy for about the same number of steps and the whole layer is ONE wave of co-resident clusters);
+// CTA c owns hidden units [c*HS, (c+1)*HS), HS = S/C = 32.
 // Per group and step the CTA computes
 //       a[gate g, hidden j][read] = sum_k sW[g*S + j][k] * h_{t-1}[read][k]
 // as one M=128 x N=16 x K=S tensor-core GEMM:
@@ -130,7 +133,8 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS, 1)
 rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, float *__restrict__ Hout,
               __half *__restrict__ Hhi, __half *__restrict__ Hlo, const int32_t *__restrict__ order,
-              const int64_t *__restrict__ blk_off, uint8_t *__restrict__ ring, int *__restrict__ progress, int G, int backward) {
+              const int64_t *__restrict__ blk_off, const int32_t *__restrict__ slot_off, const int32_t *__restrict__ slot_list,
+              uint8_t *__restrict__ ring, int *__restrict__ progress, int G, int n_groups, int backward) {
     constexpr int S = Cfg::S, C = Cfg::C, NGATE = Cfg::NGATE, NG = Cfg::NG, GMAX = Cfg::GMAX;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
@@ -144,7 +148,6 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);    // provably warp-uniform: roles, TMEM and staging addresses stay in uniform registers
     const int nthreads = blockDim.x;
-    const int R = G * NG;                                        // reads per cluster
 
     // ---- one-time setup ----
     {
@@ -193,16 +196,13 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     if (progress && blockIdx.x == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_rnn_prof_dev[12] = t_; }
 #endif
 
-    const int g = (warp < 4 * G) ? (warp >> 2) : (warp - 4 * G);    // this warp's group
-    // slots are sorted by length (descending): the group's first slot is its longest read
-    int Tmax = 0;
-    {
-        const int rd0 = order[cluster_id * R + g * NG];
-        Tmax = rd0 >= 0 ? (int)(blk_off[rd0 + 1] - blk_off[rd0]) : 0;
-    }
+    const int g = (warp < 4 * G) ? (warp >> 2) : (warp - 4 * G);    // this warp's slot of the cluster
+    // the slot walks a list of 16-read groups, one after the other (host: longest-first to the least-loaded slot)
+    const int sl0 = slot_off[cluster_id * G + g], sl1 = slot_off[cluster_id * G + g + 1];
     uint8_t *Bg = B_base + (size_t)g * Cfg::B_GROUP;
     uint8_t *stg = stg_base + (size_t)g * Cfg::SLICE;
     const uint32_t acc = tmem + Cfg::ACC_COL0 + (uint32_t)g * Cfg::ACC_COLS;
+    uint32_t gs = 0;                // steps this slot has run so far: barrier phases continue across groups
 
     if (warp >= 4 * G) {
         // =========================== control warp of group g ===========================
@@ -214,11 +214,20 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             uint8_t *ring_g = ring + ((((size_t)cluster_id * 2) * G + g) * C + crank) * Cfg::SLICE;   // parity 0
             const size_t ring_par = (size_t)G * C * Cfg::SLICE;
             PROF_DECL;
-            for (int s = 0; s < Tmax; s++) {
-                const uint32_t ph = (uint32_t)s & 1u;
+            for (int sl = sl0; sl < sl1; sl++) {
+            // slots are sorted by length (descending): the group's first read is its longest
+            const int rd0 = order[slot_list[sl] * NG];
+            const int Tmax = rd0 >= 0 ? (int)(blk_off[rd0 + 1] - blk_off[rd0]) : 0;
+            for (int s = 0; s < Tmax; s++, gs++) {
+                const uint32_t ph = gs & 1u;
                 if (s > 0) mbar_wait(&h_full[g], ph ^ 1u);           // h_{s-1} complete in B
                 PROF(0);
                 mbar_arrive_expect_tx(&h_full[g], C * Cfg::SLICE);    // arm phase s: peers push h_s only after my MMA(s)
+                if (s == 0) {
+                    // h_{-1} = 0: nothing to multiply (and B still holds the previous group's last state) -- the gate
+                    // warps take a = 0 for this step
+                    mbar_arrive(&acc_full[g]);
+                } else {
                 tcgen05_fence_after();
                 // 3*S/16 MMAs into THREE accumulators -- for accuracy, not speed: N=16 MMAs with uniform-register
                 // operands issue at ~9 clk whichever accumulator they target (profiles/r01_mma_indep_microbench.txt).
@@ -238,6 +247,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     umma_f16_ts(acc + 2 * NG, tA_lo + i * 8, dB_hi + ob2, idesc, i != 0);
                 }
                 umma_commit(&acc_full[g]);
+                }
                 PROF(1);
                 mbar_wait(&acc_full[g], ph);
                 PROF(2);
@@ -255,9 +265,11 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 bulk_load_multicast(Bg + crank * Cfg::SLICE, rg, Cfg::SLICE, &h_full[g], (uint16_t)((1u << C) - 1u));
                 PROF(6);
             }
+            // drain: the group's last copies still target this CTA; they must have landed before h_full is re-armed for
+            // the next group and before anybody exits
+            if (Tmax > 0) mbar_wait(&h_full[g], (gs - 1u) & 1u);
+            }
             PROF_FLUSH(0, 7);
-            // drain: the last step's copies still target this CTA; nobody may exit before they have landed
-            if (Tmax > 0) mbar_wait(&h_full[g], (uint32_t)(Tmax - 1) & 1u);
         }
         __syncwarp();
     } else {
@@ -268,35 +280,10 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         constexpr int XROW = NGATE * S;
         // this thread's four cells: reads col(i) = (i>>1)*8 + 2*cp + (i&1) of the group.  Per cell a
         // running pointer into Xin and a running output row, stepped by +-1 block per step.
-        int cT[4];
-        const float *xp[4];
-        int32_t orow[4];            // the host guarantees total blocks < 2^31
-        float hprev[4], cstate[4];
-        int Tmin = 0x7fffffff;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int col = (i >> 1) * 8 + 2 * cp + (i & 1);
-            const int rd = order[cluster_id * R + g * NG + col];
-            cT[i] = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
-            const int32_t base = rd >= 0 ? (int32_t)blk_off[rd] : 0;
-            orow[i] = base + ((backward && cT[i] > 0) ? cT[i] - 1 : 0);
-            xp[i] = Xin + (int64_t)orow[i] * XROW + j;
-            hprev[i] = 0.0f; cstate[i] = 0.0f;
-            Tmin = min(Tmin, cT[i]);
-        }
-        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, 1));   // shortest read of the group: while s < Tmin
-        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, 2));   // no cell needs a predicate
         const int xstep = backward ? -XROW : XROW, rstep = backward ? -1 : 1;
         // second role of the lane: after the slice is staged, copy one 16-byte chunk (8 hidden units of one
         // read, one plane) from the staging tile to the fp16 layer output -- off the critical path
         const int cl_read = lane & 15, cl_plane = lane >> 4;
-        int cl_T = 0;
-        int32_t cl_row = 0;
-        {
-            const int rd = order[cluster_id * R + g * NG + cl_read];
-            cl_T = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
-            cl_row = (rd >= 0 ? (int32_t)blk_off[rd] : 0) + ((backward && cl_T > 0) ? cl_T - 1 : 0);
-        }
         __half *cl_dst = (cl_plane ? Hlo : Hhi);
         if (cl_dst) cl_dst += crank * Cfg::HS + q * 8;
         const uint4 *cl_src = reinterpret_cast<const uint4 *>(stg + (size_t)q * Cfg::LBO_B + cl_plane * NG * 16 + cl_read * 16);
@@ -310,8 +297,40 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #ifdef FFB_RNN_PROFILE
         unsigned long long pt_ = clock64(), pa_[12] = {0}; const bool prof_ = (blockIdx.x == 0 && warp == 0 && lane == 0);
 #endif
-        for (int s = 0; s < Tmax; s++) {
-            const uint32_t ph = (uint32_t)s & 1u;
+        for (int sl = sl0; sl < sl1; sl++) {
+        const int grp = slot_list[sl];                      // this round's group of 16 reads
+        int cT[4];
+        const float *xp[4];
+        int32_t orow[4];            // the host guarantees total blocks < 2^31
+        float hprev[4], cstate[4];
+        int Tmin = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int col = (i >> 1) * 8 + 2 * cp + (i & 1);
+            const int rd = order[grp * NG + col];
+            cT[i] = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
+            const int32_t base = rd >= 0 ? (int32_t)blk_off[rd] : 0;
+            orow[i] = base + ((backward && cT[i] > 0) ? cT[i] - 1 : 0);
+            xp[i] = Xin + (int64_t)orow[i] * XROW + j;
+            hprev[i] = 0.0f; cstate[i] = 0.0f;
+            Tmin = min(Tmin, cT[i]);
+        }
+        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, 1));   // shortest read of the group: while s < Tmin
+        Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, 2));   // no cell needs a predicate
+        int Tmax = 0;               // the group's first read is its longest (sorted)
+        {
+            const int rd0 = order[grp * NG];
+            Tmax = rd0 >= 0 ? (int)(blk_off[rd0 + 1] - blk_off[rd0]) : 0;
+        }
+        int cl_T = 0;
+        int32_t cl_row = 0;
+        {
+            const int rd = order[grp * NG + cl_read];
+            cl_T = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
+            cl_row = (rd >= 0 ? (int32_t)blk_off[rd] : 0) + ((backward && cl_T > 0) ? cl_T - 1 : 0);
+        }
+        for (int s = 0; s < Tmax; s++, gs++) {
+            const uint32_t ph = gs & 1u;
             const bool all = s < Tmin;          // warp-uniform
             // ---- prefetch this step's input projection ----
             float x[4][NGATE];
@@ -332,7 +351,11 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             tcgen05_fence_after();
             // ---- TMEM -> registers: a[i][gate], three partial accumulators added round-to-nearest ----
             float a[4][4];
-            {
+            if (s == 0) {
+                // h_{-1} = 0 (layers.c:586 / :892 zero the initial state): no MMAs were issued for this step
+#pragma unroll
+                for (int i = 0; i < 4; i++) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.0f;
+            } else {
                 float v0[8], v1[8];
                 tmem_ld_16x256b_x2(t_lo, v0);
                 tmem_ld_16x256b_x2(t_lo + NG, v1);
@@ -407,8 +430,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             if (progress && (((s + 1) % FFB_RNN_PUBLISH_PERIOD) == 0 || s == Tmax - 1)) {
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicAdd(progress + cluster_id * G + g, 1);
+                if (lane == 0) atomicAdd(progress + grp, 1);
             }
+        }
         }
         PROF_FLUSH(8, 12);
     }
@@ -417,7 +441,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     __syncthreads();
     // every gate warp fenced its last stores before its final publish: count this CTA as finished (the
     // coarse dependency of GEMM tiles that span more than four reads)
-    if (progress && tid == 0) atomicAdd(progress + (gridDim.x / C) * G, 1);
+    if (progress && tid == 0) atomicAdd(progress + n_groups, 1);
 #ifdef FFB_RNN_PROFILE
     if (progress && blockIdx.x == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_rnn_prof_dev[13] = t_; }
 #endif
@@ -527,21 +551,22 @@ int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
 }
 
 template <class Cfg>
-static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo, const RnnBatch &rb, int R,
-                      int backward, void *ring, int *progress, cudaStream_t st) {
+static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo, const RnnBatch &rb,
+                      const RnnTcSched &sched, int R, int backward, void *ring, int *progress, cudaStream_t st) {
     const int G = R / Cfg::NG;
-    if (G < 1 || G > Cfg::GMAX || R % Cfg::NG || rb.n_slots % R || !ring) return -1;
-    const int n_clusters = rb.n_slots / R;
+    if (G < 1 || G > Cfg::GMAX || R % Cfg::NG || !ring || !sched.slot_off || !sched.slot_list) return -1;
+    const int n_clusters = sched.n_clusters;
     if (n_clusters == 0) return 0;
     cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
     rnn_tc_config<Cfg>(cfg, attr, n_clusters, G, st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::rnn_tc_kernel<Cfg>, Xin, (const __half *)Wimg, Hout, (__half *)Hhi,
-                                       (__half *)Hlo, rb.order, rb.blk_off, (uint8_t *)ring, progress, G, backward);
+                                       (__half *)Hlo, rb.order, rb.blk_off, sched.slot_off, sched.slot_list, (uint8_t *)ring, progress,
+                                       G, sched.n_groups, backward);
     return e == cudaSuccess ? 1 : -1;
 }
 
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
-                      const RnnBatch &rb, int R, int backward, void *ring, int *progress, cudaStream_t st) {
+                      const RnnBatch &rb, const RnnTcSched &sched, int R, int backward, void *ring, int *progress, cudaStream_t st) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, R, backward, ring, progress, st); });
+    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, sched, R, backward, ring, progress, st); });
 }
