@@ -31,7 +31,7 @@ FLAG_KEEP_LAYERS = 8
 FLAG_FP32_SIMT = 16
 
 # enum model_type, reference src/networks.h:18-26
-MODEL_ENUM = {"r941_native": 0, "r941_rna002": 1, "r941_5mC": 2, "r103_native": 3, "r10C_pcr": 0}
+MODEL_ENUM = {"r941_native": 0, "r941_rna002": 1, "r941_5mC": 2, "r103_native": 3, "r10C_pcr": 0, "rle_r941_native": 5}
 
 # every symbol include/flappie_b200.h declares
 EXPORTS = [
@@ -45,6 +45,7 @@ EXPORTS = [
     "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_emit_bases",
     "ffb_upload_raw", "ffb_basecall_raw_batch", "ffb_submit_batch", "ffb_submit_raw_batch", "ffb_collect",
     "ffb_alloc_pinned", "ffb_free_pinned",
+    "decode_crf_runlength", "transpost_crf_runlength", "ffb_emit_runs",
 ]
 
 
@@ -69,7 +70,7 @@ class Batch(ctypes.Structure):
         ("temperature", c_float), ("flags", c_uint32),
         ("blk_off", POINTER(c_int64)), ("path", POINTER(c_int32)), ("qpath", POINTER(c_float)),
         ("score", POINTER(c_float)), ("trans", POINTER(c_float)), ("tpost", POINTER(c_float)),
-        ("trace", POINTER(c_uint8)),
+        ("trace", POINTER(c_uint8)), ("rle_params", POINTER(c_float)),
     ]
 
 
@@ -111,6 +112,11 @@ class Library:
         L.trace_from_posterior.restype = PI; L.trace_from_posterior.argtypes = [PM]
         L.exp_activation_inplace.restype = None; L.exp_activation_inplace.argtypes = [PM]
         L.nbase_from_flipflop_nparam.restype = c_size_t; L.nbase_from_flipflop_nparam.argtypes = [c_size_t]
+        L.decode_crf_runlength.restype = c_float; L.decode_crf_runlength.argtypes = [PM, POINTER(c_int)]
+        L.transpost_crf_runlength.restype = PM; L.transpost_crf_runlength.argtypes = [PM]
+        L.ffb_emit_runs.restype = c_int64
+        L.ffb_emit_runs.argtypes = [POINTER(c_int32), POINTER(c_float), c_int64, c_int, c_char_p, POINTER(c_float),
+                                    POINTER(c_float), POINTER(c_int32)]
         L.ffb_device_count.restype = c_int
         L.ffb_last_error.restype = c_char_p
         L.ffb_version.restype = c_char_p
@@ -227,6 +233,42 @@ class Library:
             return None
         return self.rows_from_mat(out)
 
+    # ---- run-length ("runnie") drop-ins --------------------------------------------
+    def decode_crf_runlength(self, param: np.ndarray):
+        """param [T][40] -> (score, path[T]); reference src/decode.c:901-984."""
+        self.require_gpu()
+        T = param.shape[0]
+        pm = self.mat_from_rows(param)
+        path = np.zeros(T + 2, np.int32)
+        score = self.lib.decode_crf_runlength(pm, path.ctypes.data_as(POINTER(c_int)))
+        self.lib.free_flappie_matrix(pm)
+        if np.isnan(score):
+            raise FlappieB200Error("decode_crf_runlength failed: " + self.last_error())
+        return float(score), path[:T]
+
+    def transpost_crf_runlength(self, param: np.ndarray) -> np.ndarray:
+        self.require_gpu()
+        pm = self.mat_from_rows(param)
+        out = self.lib.transpost_crf_runlength(pm)
+        self.lib.free_flappie_matrix(pm)
+        if not out:
+            raise FlappieB200Error("transpost_crf_runlength failed: " + self.last_error())
+        return self.rows_from_mat(out)
+
+    def emit_runs(self, path: np.ndarray, rle_params: np.ndarray, nbase: int = 4):
+        """runnie's run loop (src/runnie.c:279-310): (bases, shape[], scale[], dwell[])"""
+        path = np.ascontiguousarray(path, np.int32)
+        rle_params = np.ascontiguousarray(rle_params, np.float32)
+        T = path.shape[0]
+        bases = ctypes.create_string_buffer(T + 2)
+        shape = np.zeros(T + 1, np.float32); scale = np.zeros(T + 1, np.float32); dwell = np.zeros(T + 1, np.int32)
+        n = self.lib.ffb_emit_runs(path.ctypes.data_as(POINTER(c_int32)), rle_params.ctypes.data_as(POINTER(c_float)), T, nbase,
+                                   bases, shape.ctypes.data_as(POINTER(c_float)), scale.ctypes.data_as(POINTER(c_float)),
+                                   dwell.ctypes.data_as(POINTER(c_int32)))
+        if n < 0:
+            raise FlappieB200Error("ffb_emit_runs: bad arguments")
+        return bases.raw[:n].decode(), shape[:n], scale[:n], dwell[:n]
+
     def emit_bases(self, path: np.ndarray, qpath: np.ndarray, nbase: int, reverse: bool = False):
         path = np.ascontiguousarray(path, np.int32)
         qpath = np.ascontiguousarray(qpath, np.float32)
@@ -250,7 +292,8 @@ class Model:
         mats, keep = fm.to_mat_bundle()
         arr = (POINTER(Mat) * len(mats))(*[ctypes.pointer(m) for m in mats])
         strides = (c_int * len(fm.conv_stride))(*fm.conv_stride)
-        self.handle = self.lib.lib.ffb_model_create(device, fm.kind, arr, len(mats), strides, len(fm.conv_stride))
+        kind = 2 if getattr(fm, "head", "flipflop") == "runlength" else fm.kind      # FFB_KIND_RUNLENGTH
+        self.handle = self.lib.lib.ffb_model_create(device, kind, arr, len(mats), strides, len(fm.conv_stride))
         del keep
         if not self.handle:
             raise FlappieB200Error("ffb_model_create failed: " + self.lib.last_error())
@@ -274,6 +317,7 @@ class BatchResult:
     def __init__(self, n_reads, blk_off, path, qpath, score, trans, tpost, trace, nstate, nparam):
         self.n_reads, self.blk_off, self.path, self.qpath, self.score = n_reads, blk_off, path, qpath, score
         self.trans, self.tpost, self.trace, self.nstate, self.nparam = trans, tpost, trace, nstate, nparam
+        self.rle_params = None
 
     def nblock(self, i: int) -> int:
         return int(self.blk_off[i + 1] - self.blk_off[i])
@@ -287,6 +331,11 @@ class BatchResult:
 
     def read_tpost(self, i: int):
         return self.tpost[int(self.blk_off[i]):int(self.blk_off[i + 1])]
+
+    def read_rle(self, i: int):
+        """run-length models: (states[T], shape/scale rows [T][8]) of read i"""
+        s = int(self.blk_off[i]) + i
+        return self.path[s:s + self.nblock(i)], self.rle_params[int(self.blk_off[i]):int(self.blk_off[i + 1])]
 
     def read_trace(self, i: int):
         s = int(self.blk_off[i]) + i
@@ -334,6 +383,8 @@ class Context:
                 o.setdefault("tpost", np.zeros((tot_blocks, fm.nparam), np.float32))
         if flags & FLAG_WANT_TRACE:
             o.setdefault("trace", np.zeros((tot_blocks + n, fm.nstate), np.uint8))
+        if getattr(fm, "head", "flipflop") == "runlength":
+            o.setdefault("rle_params", np.zeros((tot_blocks, 8), np.float32))
 
         def p(name, ct):
             a = o.get(name)
@@ -341,7 +392,7 @@ class Context:
 
         b = Batch(signal.ctypes.data_as(POINTER(c_float)), sig_off.ctypes.data_as(POINTER(c_int64)), n,
                   temperature, flags, p("blk_off", c_int64), p("path", c_int32), p("qpath", c_float),
-                  p("score", c_float), p("trans", c_float), p("tpost", c_float), p("trace", c_uint8))
+                  p("score", c_float), p("trans", c_float), p("tpost", c_float), p("trace", c_uint8), p("rle_params", c_float))
         self._keep = (signal, sig_off, o)
         return b, o
 
@@ -360,8 +411,10 @@ class Context:
                 (FLAG_FP32_SIMT if fp32_simt else 0)
         b, o = self.make_batch(signal, sig_off, temperature, flags)
         self._check(self.lib.lib.ffb_basecall_batch(self.handle, ctypes.byref(b)), "ffb_basecall_batch")
-        return BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),
-                           o.get("trace"), fm.nstate, fm.nparam)
+        res = BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),
+                          o.get("trace"), fm.nstate, fm.nparam)
+        res.rle_params = o.get("rle_params")
+        return res
 
     def make_raw_batch(self, raw: np.ndarray, raw_off: np.ndarray, trim=(200, 10), segmentation=(100, 0.0),
                        delta: float = 0.0):
@@ -397,6 +450,7 @@ class Context:
         res = BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),
                           o.get("trace"), fm.nstate, fm.nparam)
         res.start, res.end = start[:n], end[:n]
+        res.rle_params = o.get("rle_params")
         return res
 
     def fetch_signal(self, n_samples: int) -> np.ndarray:

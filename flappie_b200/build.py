@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "libflappie_b200.so")
-SOURCES = ["conv.cu", "signal.cu", "gemm.cu", "gemm_tc.cu", "rnn.cu", "rnn_tc.cu", "decode.cu", "api.cu", "testhooks.cu"]
+SOURCES = ["conv.cu", "signal.cu", "gemm.cu", "gemm_tc.cu", "rnn.cu", "rnn_tc.cu", "decode.cu", "rle.cu", "api.cu", "testhooks.cu"]
 HEADERS = ["ffb_common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "flappie_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]
@@ -92,6 +92,12 @@ def build_host(force: bool = False) -> None:
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"gcc failed for the flappie command line:\n{r.stdout}\n{r.stderr}")
+    runnie = os.path.join(HOST, "runnie")
+    if force or _stale(runnie, deps):
+        r = subprocess.run([cc] + flags + ["-DFFB_RUNNIE", "-o", runnie, os.path.join(HOST, "flappie_main.c")] + srcs + link,
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"gcc failed for the runnie command line:\n{r.stdout}\n{r.stderr}")
     if force or _stale(HOST_LIB, deps):
         r = subprocess.run([cc] + flags + ["-shared", "-o", HOST_LIB] + srcs + link, capture_output=True, text=True)
         if r.returncode != 0:

@@ -77,6 +77,7 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------
 struct ffb_model {
     int device = 0, kind = 0, S = 0, G = 0, nparam = 0, nbase = 0, nstate = 0, nconv = 0;
+    int head = 0;     // 0 = flip-flop CRF, 1 = run-length CRF (FFB_KIND_RUNLENGTH: LSTM topology, runnie head)
     int conv_nf[FFB_MAX_CONV] = {0}, conv_nfilter[FFB_MAX_CONV] = {0}, conv_winlen[FFB_MAX_CONV] = {0},
         conv_stride[FFB_MAX_CONV] = {0};
     float *d_convWt[FFB_MAX_CONV] = {nullptr}, *d_convb[FFB_MAX_CONV] = {nullptr};
@@ -121,6 +122,8 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
                                        const int *conv_stride, int nconv) {
     if (!mats || !conv_stride) { set_err("ffb_model_create: NULL argument"); return nullptr; }
     if (ffb_device_count() <= device) { set_err("ffb_model_create: CUDA device %d not available", device); return nullptr; }
+    const int head = (kind == FFB_KIND_RUNLENGTH) ? 1 : 0;
+    if (head) kind = FFB_KIND_LSTM;                      // runlength5_guppy_transitions: the LSTM stack (networks.c:675-722)
     const int want_conv = (kind == FFB_KIND_GRU) ? 1 : 3;
     if ((kind != FFB_KIND_GRU && kind != FFB_KIND_LSTM) || nconv != want_conv || nmat != 2 * nconv + 3 * FFB_NLAYER + 2) {
         set_err("ffb_model_create: kind %d expects %d convolutions and %d matrices (got %d, %d)", kind, want_conv,
@@ -131,7 +134,7 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
         if (!mats[i] || !mats[i]->data.f) { set_err("ffb_model_create: matrix %d is NULL", i); return nullptr; }
     CUDA_TRY(cudaSetDevice(device), nullptr);
     ffb_model *m = new ffb_model();
-    m->device = device; m->kind = kind; m->nconv = nconv;
+    m->device = device; m->kind = kind; m->nconv = nconv; m->head = head;
     m->G = (kind == FFB_KIND_GRU) ? 3 : 4;
     bool ok = true;
     int nf = 1;
@@ -205,7 +208,7 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
         m->nbase = (int)nbase_from_flipflop_nparam(m->nparam);
         m->nstate = 2 * m->nbase;
         if ((int)FW->nr != m->S || (int)Fb->nr != m->nparam || m->nstate * (m->nbase + 1) != m->nparam ||
-            (m->nparam != 40 && m->nparam != 60)) {
+            (m->nparam != 40 && m->nparam != 60) || (m->head && m->nparam != 40)) {
             set_err("ffb_model_create: output layer has unsupported shape (%zu x %zu)", FW->nr, FW->nc);
             ok = false;
         } else {
@@ -368,7 +371,8 @@ struct ffb_ctx {
     DevBuf d_sig, d_c[2], d_act[2], d_xin, d_trans, d_tpost, d_fwd, d_tb, d_path, d_qpath, d_score, d_logz, d_trace;
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
     DevBuf d_raw, d_rawoff, d_chunkoff, d_mad, d_bounds, d_sigoff;
-    DevBuf d_slotoff, d_slotlist;   // device signal preparation (ffb_upload_raw)
+    DevBuf d_slotoff, d_slotlist;
+    DevBuf d_rle;                 // run-length head: shape / scale rows of every block, [Ttot][8]   // device signal preparation (ffb_upload_raw)
     DevBuf d_ahi, d_alo;          // fp16 hi/lo planes of the current layer input (tensor path)
     DevBuf d_ring;                // state-exchange ring of the tensor recurrent kernel (L2-resident)
     // streamed input GEMMs: layer l+1's projection runs on the SMs layer l's recurrence leaves free and consumes
@@ -407,7 +411,7 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
                      &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress,
-                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff, &c->d_slotoff, &c->d_slotlist};
+                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff, &c->d_slotoff, &c->d_slotlist, &c->d_rle};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -651,6 +655,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     if (c->flags & FFB_FLAG_WANT_TRACE) ok &= c->d_trace.reserve((size_t)std::max<int64_t>((Tt + N) * m->nstate, 1)) == 0;
     if (c->flags & FFB_FLAG_KEEP_LAYERS)
         for (int l = 0; l < FFB_NLAYER; l++) ok &= c->d_keep[l].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    if (m->head) ok &= c->d_rle.reserve(sizeof(float) * 8 * (size_t)std::max<int64_t>(Tt, 1)) == 0;
     ok &= c->d_blkoff.reserve(sizeof(int64_t) * (size_t)(N + 1)) == 0;
     ok &= c->d_order.reserve(sizeof(int32_t) * (size_t)std::max(c->n_slots, 1)) == 0;
     for (int i = 0; i < m->nconv; i++) {
@@ -853,31 +858,50 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     const float *top = in;
     if (timed) cudaEventRecord(c->ev[2], st);
     // ---- globalnorm_flipflop (layers.c:1082-1106) ----
+    // scale: flip-flop divides tanh by temperature / 5 (layers.c:1087); the run-length head computes 5 tanhf / temperature
+    const float ff_scale = m->head ? c->temperature : c->temperature / 5.0f;
     if (tc_ff)
         LAUNCH(ffb_launch_ff_tanh_tc(c->d_ahi.p, c->d_alo.p, m->d_ff_hi, m->d_ff_lo, m->d_ffb_pad, c->d_trans.as<float>(), Tt, nr, S,
-                                     c->temperature / 5.0f, st));
+                                     ff_scale, m->head, st));
     else
-        LAUNCH(ffb_launch_ff_tanh(top, m->d_ffWt, m->d_ffb, c->d_trans.as<float>(), Tt, nr, S, c->temperature / 5.0f, st));
-    // -logZ/T (layers.c:1035-1096) shifts every entry of a read by one constant.  The posteriors, their Viterbi
-    // path, qualities, score and trace are invariant under it (decode.cu, fb kernels), so in forward-backward
-    // mode the fp64 partition scan only runs when the caller wants `trans` itself.
-    const bool need_logz = (c->flags & FFB_FLAG_VITERBI_ONLY) || (c->flags & FFB_FLAG_WANT_TRANS) || getenv("FFB_ALWAYS_LOGZ");
+        LAUNCH(ffb_launch_ff_tanh(top, m->d_ffWt, m->d_ffb, c->d_trans.as<float>(), Tt, nr, S, ff_scale, m->head, st));
+    // -logZ/T (layers.c:1035-1096) shifts every transition score of a read by one constant.  The flip-flop posteriors
+    // (running-shifted scans, per-block normalisation), their Viterbi path, qualities and trace are invariant under it,
+    // so in forward-backward mode the fp64 partition scan only runs when the caller wants `trans`.  The run-length
+    // posteriors are UNNORMALISED sums (decode.c:1096-1114): without the shift their fp32 forward values grow by
+    // ~logZ/T per block and the decoder loses its low bits, so that head always normalises.
+    const bool need_logz = m->head || (c->flags & FFB_FLAG_VITERBI_ONLY) || (c->flags & FFB_FLAG_WANT_TRANS) || getenv("FFB_ALWAYS_LOGZ");
     if (need_logz) {
-        LAUNCH(ffb_launch_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), st));
-        LAUNCH(ffb_launch_sub_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), Tt, st));
+        if (m->head) {
+            LAUNCH(ffb_launch_rle_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), st));
+        } else {
+            LAUNCH(ffb_launch_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), st));
+            LAUNCH(ffb_launch_sub_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), Tt, st));
+        }
     }
     if (timed) cudaEventRecord(c->ev[3], st);
-    // ---- decoding (flappie.c:277-300) ----
+    // ---- decoding (flappie.c:277-300 / runnie.c:271-277) ----
     const float *post = c->d_trans.as<float>();
-    if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
-        LAUNCH(ffb_launch_transpost(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_fwd.as<float>(),
-                                    c->d_tpost.as<float>(), Tt, st));   // includes the per-block log normalisation
-        post = c->d_tpost.as<float>();
+    if (m->head) {
+        if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
+            LAUNCH(ffb_launch_rle_transpost(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_fwd.as<float>(),
+                                            c->d_tpost.as<float>(), st));
+            post = c->d_tpost.as<float>();
+        }
+        LAUNCH(ffb_launch_rle_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint32_t>(), c->d_path.as<int32_t>(),
+                                      c->d_qpath.as<float>(), c->d_score.as<float>(), st));
+        LAUNCH(ffb_launch_rle_pack(c->d_trans.as<float>(), c->d_rle.as<float>(), Tt, st));
+    } else {
+        if (!(c->flags & FFB_FLAG_VITERBI_ONLY)) {
+            LAUNCH(ffb_launch_transpost(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_fwd.as<float>(),
+                                        c->d_tpost.as<float>(), Tt, st));   // includes the per-block log normalisation
+            post = c->d_tpost.as<float>();
+        }
+        LAUNCH(ffb_launch_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint64_t>(), c->d_path.as<int32_t>(),
+                                  c->d_qpath.as<float>(), c->d_score.as<float>(), st));
+        if (c->flags & FFB_FLAG_WANT_TRACE)
+            LAUNCH(ffb_launch_trace(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_trace.as<uint8_t>(), 1, st));
     }
-    LAUNCH(ffb_launch_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint64_t>(), c->d_path.as<int32_t>(),
-                              c->d_qpath.as<float>(), c->d_score.as<float>(), st));
-    if (c->flags & FFB_FLAG_WANT_TRACE)
-        LAUNCH(ffb_launch_trace(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_trace.as<uint8_t>(), 1, st));
     if (timed) {
         cudaEventRecord(c->ev[4], st);
         cudaEventSynchronize(c->ev[4]);
@@ -923,8 +947,10 @@ static int download_enqueue(ffb_ctx *c, const ffb_batch *b) {
             CUDA_TRY(cudaMemcpyAsync(b->trans, c->d_trans.p, sizeof(float) * (size_t)(Tt * m->nparam), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
         if (b->tpost && (c->flags & FFB_FLAG_WANT_TRANS) && !(c->flags & FFB_FLAG_VITERBI_ONLY))
             CUDA_TRY(cudaMemcpyAsync(b->tpost, c->d_tpost.p, sizeof(float) * (size_t)(Tt * m->nparam), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
-        if (b->trace && (c->flags & FFB_FLAG_WANT_TRACE))
+        if (b->trace && (c->flags & FFB_FLAG_WANT_TRACE) && !m->head)
             CUDA_TRY(cudaMemcpyAsync(b->trace, c->d_trace.p, (size_t)((Tt + N) * m->nstate), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        if (b->rle_params && m->head)
+            CUDA_TRY(cudaMemcpyAsync(b->rle_params, c->d_rle.p, sizeof(float) * 8 * (size_t)Tt, cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
     }
     return FFB_OK;
 }
@@ -1044,6 +1070,33 @@ extern "C" int ffb_emit_bases(const int32_t *path, const float *qpath, int64_t n
         std::reverse(basecall, basecall + n);
         std::reverse(quality, quality + n);
     }
+    return n;
+}
+
+// runnie's run loop (runnie.c:279-310): one run per block whose state is a move state (< nbase); shape / scale are taken
+// from the block where the run starts
+extern "C" int64_t ffb_emit_runs(const int32_t *path, const float *rle_params, int64_t nblock, int nbase, char *bases,
+                                 float *shape, float *scale, int32_t *dwell) {
+    static const char lookup[5] = {'A', 'C', 'G', 'T', 'Z'};
+    if (!path || !rle_params || !bases || !shape || !scale || !dwell || nbase != 4) return -1;
+    int64_t n = 0, last_blk = -1;
+    int32_t run = 1;
+    auto emit = [&]() {
+        const int base = path[last_blk];
+        bases[n] = lookup[base];
+        shape[n] = rle_params[last_blk * 2 * nbase + base];
+        scale[n] = rle_params[last_blk * 2 * nbase + nbase + base];
+        dwell[n] = run;
+        n++;
+    };
+    for (int64_t blk = 0; blk < nblock; blk++) {
+        if (path[blk] >= nbase) { run += 1; continue; }
+        if (last_blk >= 0) emit();
+        last_blk = blk;
+        run = 1;
+    }
+    if (last_blk >= 0) emit();
+    bases[n] = 0;
     return n;
 }
 
@@ -1236,6 +1289,53 @@ extern "C" flappie_matrix transpost_crf_flipflop(const_flappie_matrix trans, boo
     cudaMemcpy2DAsync(out->data.f, out->stride * sizeof(float), d->tpost.p, nr * sizeof(float), nr * sizeof(float), (size_t)T,
                       cudaMemcpyDeviceToHost, d->st);
     if (cudaStreamSynchronize(d->st) != cudaSuccess) { set_err("transpost_crf_flipflop: %s", cudaGetErrorString(cudaGetLastError())); return free_flappie_matrix(out); }
+    return out;
+}
+
+// ---- run-length drop-ins (decode.h:48-49) ----
+extern "C" float decode_crf_runlength(const_flappie_matrix param, int *path) {
+    if (!param || !path) return NAN;                                     // decode.c:902-903
+    const int nr = (int)param->nr;
+    const int64_t T = (int64_t)param->nc;
+    if (nr != 40) { set_err("decode_crf_runlength: unsupported nr=%d", nr); return NAN; }
+    DecodeCtx *d = decode_ctx();
+    if (!d) return NAN;
+    std::lock_guard<std::mutex> lk(g_dec_mu);
+    int64_t off[2] = {0, T};
+    bool ok = mat_to_device(param, d->trans, d->st) == 0;
+    ok = ok && d->tb.reserve(sizeof(uint64_t) * (size_t)std::max<int64_t>(T, 1)) == 0 && d->path.reserve(sizeof(int32_t) * (size_t)(T + 1)) == 0 &&
+         d->qpath.reserve(sizeof(float) * (size_t)(T + 1)) == 0 && d->score.reserve(sizeof(float)) == 0 && d->blkoff.reserve(sizeof(off)) == 0;
+    if (!ok) { set_err("decode_crf_runlength: device allocation / copy failed"); return NAN; }
+    cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
+    if (ffb_launch_rle_viterbi(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->tb.as<uint32_t>(), d->path.as<int32_t>(),
+                               d->qpath.as<float>(), d->score.as<float>(), d->st) < 0) return NAN;
+    float score = NAN;
+    cudaMemcpyAsync(path, d->path.p, sizeof(int32_t) * (size_t)T, cudaMemcpyDeviceToHost, d->st);
+    cudaMemcpyAsync(&score, d->score.p, sizeof(float), cudaMemcpyDeviceToHost, d->st);
+    if (cudaStreamSynchronize(d->st) != cudaSuccess) { set_err("decode_crf_runlength: %s", cudaGetErrorString(cudaGetLastError())); return NAN; }
+    return score;
+}
+
+extern "C" flappie_matrix transpost_crf_runlength(const_flappie_matrix param) {
+    if (!param) return nullptr;
+    const int nr = (int)param->nr;
+    const int64_t T = (int64_t)param->nc;
+    if (nr != 40) { set_err("transpost_crf_runlength: unsupported nr=%d", nr); return nullptr; }
+    DecodeCtx *d = decode_ctx();
+    if (!d) return nullptr;
+    std::lock_guard<std::mutex> lk(g_dec_mu);
+    int64_t off[2] = {0, T};
+    bool ok = mat_to_device(param, d->trans, d->st) == 0;
+    ok = ok && d->tpost.reserve(sizeof(float) * (size_t)(T * nr)) == 0 && d->fwd.reserve(2 * sizeof(float) * (size_t)((T + 1) * 8)) == 0 &&
+         d->blkoff.reserve(sizeof(off)) == 0;
+    if (!ok) { set_err("transpost_crf_runlength: device allocation / copy failed"); return nullptr; }
+    cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
+    if (ffb_launch_rle_transpost(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->fwd.as<float>(), d->tpost.as<float>(), d->st) < 0) return nullptr;
+    flappie_matrix out = make_flappie_matrix(nr, (size_t)T);
+    if (!out) return nullptr;
+    cudaMemcpy2DAsync(out->data.f, out->stride * sizeof(float), d->tpost.p, nr * sizeof(float), nr * sizeof(float), (size_t)T,
+                      cudaMemcpyDeviceToHost, d->st);
+    if (cudaStreamSynchronize(d->st) != cudaSuccess) { set_err("transpost_crf_runlength: %s", cudaGetErrorString(cudaGetLastError())); return free_flappie_matrix(out); }
     return out;
 }
 

@@ -43,6 +43,13 @@ __device__ __forceinline__ float fast_activate(float x, int act) {
     return x;
 }
 // reference src/util.h:276-278
+// run-length head row transforms (layers.c:1334-1346; softplusf util.h:83-85)
+__device__ __forceinline__ float softplus_ref(float x) { return log1pf(expf(-fabsf(x))) + ((x >= 0.0f) ? x : 0.f); }
+__device__ __forceinline__ float rle_head(float x, int row, float temperature) {
+    if (row < 4) return 1.0f + softplus_ref(x);
+    if (row < 8) return 1e-8f + softplus_ref(x);
+    return 5.0f * tanhf(x) / temperature;
+}
 __device__ __forceinline__ float logsumexpf_ref(float x, float y) {
     return fmaxf(x, y) + log1pf(expf(-fabsf(x - y)));
 }
@@ -83,8 +90,10 @@ int ffb_launch_conv(const float *x, float *y, void *yhi, void *ylo, const float 
 int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
                           cudaStream_t st);
 // gemm.cu: flip-flop output layer: C[M][N] = tanh(A*Wt + b) / scale  (N = 40 / 60; scale = temperature / 5)
+// head = 1: run-length head instead (globalnorm_runlengthV2, layers.c:1326-1346): rows [0,4) 1 + softplus, [4,8) 1e-8 + softplus,
+// the rest 5 tanhf(x) / scale with scale = temperature
 int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
-                       float scale, cudaStream_t st);
+                       float scale, int head, cudaStream_t st);
 
 // One work item of the streamed input GEMM: a tile (ffb_gemm_tc_stream_tile_rows() blocks) and what it waits
 // for -- the tile may be loaded once progress[idx[d]] >= cnt[d] for every d with idx[d] >= 0.  Items are
@@ -107,7 +116,7 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
 #define FFB_FF_TC_ROWS 64
 int ffb_ff_tc_supported(int n_out, int K);
 int ffb_launch_ff_tanh_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                          int64_t M, int n_out, int K, float scale, cudaStream_t st);
+                          int64_t M, int n_out, int K, float scale, int head, cudaStream_t st);
 // Streamed variant: launched (programmatic dependent launch) right behind the recurrent kernel that is still
 // writing the A planes; work items are taken from per-panel ticket queues in `work` order and each waits for its dependencies;
 // CTAs that find no free SM while the recurrence runs start when it ends and drain what is left.  Returns 0 (nothing launched) when the shape is unsupported.
@@ -166,6 +175,14 @@ int ffb_launch_trim_bounds(const float *mad, const int64_t *raw_off, const int64
                            float perc, int64_t trim_start, int64_t trim_end, int64_t *bounds, cudaStream_t st);
 int ffb_launch_normalise(const float *raw, const int64_t *raw_off, const int64_t *bounds, const int64_t *sig_off,
                          int n_reads, float delta, float *out, cudaStream_t st);
+
+// rle.cu: the run-length ("runnie") CRF head (nr = 40)
+int ffb_launch_rle_logz(float *param, const int64_t *blk_off, int n_reads, int nr, double *logZ, cudaStream_t st);   // scan + subtract
+int ffb_launch_rle_viterbi(const float *param, const int64_t *blk_off, int n_reads, int nr, uint32_t *tb_scratch,
+                           int32_t *path, float *qpath, float *score, cudaStream_t st);
+int ffb_launch_rle_transpost(const float *param, const int64_t *blk_off, int n_reads, int nr, float *fwd_scratch,
+                             float *post, cudaStream_t st);
+int ffb_launch_rle_pack(const float *param, float *out, int64_t total_blocks, cudaStream_t st);
 
 // decode.cu
 int ffb_launch_logz(const float *trans, const int64_t *blk_off, int n_reads, int nr, double *logZ, cudaStream_t st);

@@ -103,7 +103,7 @@ sgemm_bias_kernel(const float *__restrict__ A, const float *__restrict__ Wt, con
 template <int NH>   // outputs per thread = N / 2
 __global__ void __launch_bounds__(128)
 ff_tanh_kernel(const float *__restrict__ A, const float *__restrict__ Wt, const float *__restrict__ bias,
-               float *__restrict__ C, int64_t M, int K, float scale) {
+               float *__restrict__ C, int64_t M, int K, float scale, int head) {
     constexpr int N = 2 * NH;
     constexpr int KC = 32;   // k-chunk of the A tile
     extern __shared__ __align__(16) float sm[];
@@ -139,7 +139,10 @@ ff_tanh_kernel(const float *__restrict__ A, const float *__restrict__ Wt, const 
         if (row < M) {
             float *cp = C + row * (int64_t)N + half * NH;
 #pragma unroll
-            for (int j = 0; j < NH; j++) cp[j] = tanh_ref(acc[j] + bias[half * NH + j]) / scale;   // shift_scale_matrix_inplace: (x - 0) / scale
+            for (int j = 0; j < NH; j++) {
+                const float v = acc[j] + bias[half * NH + j];
+                cp[j] = head ? rle_head(v, half * NH + j, scale) : tanh_ref(v) / scale;   // shift_scale_matrix_inplace: (x - 0) / scale
+            }
         }
     }
 }
@@ -166,7 +169,7 @@ int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, fl
 }
 
 int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
-                       float scale, cudaStream_t st) {
+                       float scale, int head, cudaStream_t st) {
     using namespace ffb;
     if (M <= 0) return 0;
     const size_t smem = ((size_t)K * N + 64 * 33) * sizeof(float);
@@ -174,10 +177,10 @@ int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float
     const unsigned grid = (unsigned)(ntile < 148 * 4 ? ntile : 148 * 4);   // <= 4 CTAs per SM, multiple of 148
     if (N == 40) {
         cudaFuncSetAttribute(ff_tanh_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ff_tanh_kernel<20><<<grid, 128, smem, st>>>(A, Wt, bias, C, M, K, scale);
+        ff_tanh_kernel<20><<<grid, 128, smem, st>>>(A, Wt, bias, C, M, K, scale, head);
     } else if (N == 60) {
         cudaFuncSetAttribute(ff_tanh_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        ff_tanh_kernel<30><<<grid, 128, smem, st>>>(A, Wt, bias, C, M, K, scale);
+        ff_tanh_kernel<30><<<grid, 128, smem, st>>>(A, Wt, bias, C, M, K, scale, head);
     } else {
         return -1;
     }

@@ -235,10 +235,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                             __stcs(reinterpret_cast<float4 *>(crow + c + j),
                                    make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w));
                         } else if (c + j < n_out) {        // n_out % 4 == 0
-                            // shift_scale_matrix_inplace divides: (x - 0) / scale (src/flappie_matrix.c:625-633)
-                            *reinterpret_cast<float4 *>(crow + c + j) =
-                                make_float4(tanh_ref(v[j] + b4.x) / scale, tanh_ref(v[j + 1] + b4.y) / scale,
-                                            tanh_ref(v[j + 2] + b4.z) / scale, tanh_ref(v[j + 3] + b4.w) / scale);
+                            if constexpr (ACT == 1) {
+                                // shift_scale_matrix_inplace divides: (x - 0) / scale (src/flappie_matrix.c:625-633)
+                                *reinterpret_cast<float4 *>(crow + c + j) =
+                                    make_float4(tanh_ref(v[j] + b4.x) / scale, tanh_ref(v[j + 1] + b4.y) / scale,
+                                                tanh_ref(v[j + 2] + b4.z) / scale, tanh_ref(v[j + 3] + b4.w) / scale);
+                            } else {
+                                // run-length head (globalnorm_runlengthV2, src/layers.c:1334-1346); scale = temperature
+                                *reinterpret_cast<float4 *>(crow + c + j) =
+                                    make_float4(rle_head(v[j] + b4.x, c + j, scale), rle_head(v[j + 1] + b4.y, c + j + 1, scale),
+                                                rle_head(v[j + 2] + b4.z, c + j + 2, scale), rle_head(v[j + 3] + b4.w, c + j + 3, scale));
+                            }
                         }
                     }
                 }
@@ -682,9 +689,10 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
 // zero-padded to FFB_FF_TC_ROWS rows.
 int ffb_ff_tc_supported(int n_out, int K) { return n_out % 4 == 0 && n_out > 0 && n_out <= FFB_FF_TC_ROWS && ffb_gemm_tc_supported(FFB_FF_TC_ROWS, K); }
 int ffb_launch_ff_tanh_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                          int64_t M, int n_out, int K, float scale, cudaStream_t st) {
+                          int64_t M, int n_out, int K, float scale, int head, cudaStream_t st) {
     if (M <= 0) return 0;
     if (!ffb_ff_tc_supported(n_out, K)) return -1;
+    if (head) return launch_gemm_tc<FFB_FF_TC_ROWS, 2>(Ahi, Alo, Whi, Wlo, bias, C, M, FFB_FF_TC_ROWS, K, st, n_out, scale);
     return launch_gemm_tc<FFB_FF_TC_ROWS, 1>(Ahi, Alo, Whi, Wlo, bias, C, M, FFB_FF_TC_ROWS, K, st, n_out, scale);
 }
 

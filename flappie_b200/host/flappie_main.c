@@ -20,7 +20,17 @@
 
 #include "ffb_host.h"
 
+/* The same driver built with -DFFB_RUNNIE is `runnie` (reference src/runnie.c): run-length model, `.run` text output
+ * ("# uuid" then one "base<TAB>shape<TAB>scale<TAB>run" line per run, src/runnie.c:277-310). */
+#ifdef FFB_RUNNIE
+#define DEFAULT_MODEL RUNNIE_MODEL_R941_NATIVE
+#define DEFAULT_MODEL_NAME "rle_r941_native"
+#define PROGRAM "runnie"
+#else
 #define DEFAULT_MODEL FLAPPIE_MODEL_R941_NATIVE
+#define DEFAULT_MODEL_NAME "r941_native"
+#define PROGRAM "flappie"
+#endif
 
 struct arguments {
     float delta;
@@ -47,18 +57,22 @@ struct arguments {
 /* defaults of the reference, src/flappie.c:93-112 */
 static struct arguments args = {
     .delta = 0.0f, .trace = NULL, .outformat = FFB_OUT_FASTQ, .limit = 0, .model = DEFAULT_MODEL,
-    .model_name = "r941_native", .output = NULL, .prefix = "", .reverse = false, .temperature = 1.0f,
+    .model_name = DEFAULT_MODEL_NAME, .output = NULL, .prefix = "", .reverse = false, .temperature = 1.0f,
     .trim_start = 200, .trim_end = 10, .varseg_chunk = 100, .varseg_thresh = 0.0f, .viterbi_only = false,
     .uuid = true, .weights = NULL, .batch = 1024, .device = 0};
 
 static void die(const char *fmt, const char *arg) {
-    fprintf(stderr, "flappie: ");
+    fprintf(stderr, PROGRAM ": ");
     fprintf(stderr, fmt, arg);
     fputc('\n', stderr);
     exit(EXIT_FAILURE);
 }
 
 static void print_models(FILE *fh) {
+#ifdef FFB_RUNNIE
+    fprintf(fh, "%10s : %s  %s\n", flappie_model_string(RUNNIE_MODEL_R941_NATIVE), flappie_model_description(RUNNIE_MODEL_R941_NATIVE), "(default)");
+    return;
+#endif
     for (int mdl = 0; mdl < (int)FLAPPIE_MODEL_INVALID; mdl++)
         fprintf(fh, "%10s : %s  %s\n", flappie_model_string((enum model_type)mdl), flappie_model_description((enum model_type)mdl),
                 (DEFAULT_MODEL == mdl) ? "(default)" : "");
@@ -114,7 +128,11 @@ static void parse_args(int argc, char **argv) {
             if (0 == strcasecmp(optarg, "help")) { print_models(stdout); exit(EXIT_SUCCESS); }
             args.model = get_flappie_model_type(optarg);
             args.model_name = optarg;
+#ifdef FFB_RUNNIE
+            if (RUNNIE_MODEL_R941_NATIVE != args.model) {
+#else
             if (FLAPPIE_MODEL_INVALID == args.model || args.model >= FLAPPIE_MODEL_INVALID) {
+#endif
                 fprintf(stdout, "Invalid Flappie model \"%s\".\n", optarg);
                 print_models(stdout);
                 exit(EXIT_FAILURE);
@@ -213,7 +231,7 @@ struct inflight {
     bool busy;
     int64_t *blk_off, *start, *end;
     int32_t *path;
-    float *qpath, *score;
+    float *qpath, *score, *rle;
     ffb_batch b;
 };
 
@@ -233,6 +251,10 @@ static void submit_batch(struct inflight *f, ffb_model *model) {
     f->path = ffb_alloc_pinned((size_t)(tot_blocks + n) * sizeof(int32_t));
     f->qpath = ffb_alloc_pinned((size_t)(tot_blocks + n) * sizeof(float));
     f->score = ffb_alloc_pinned((size_t)n * sizeof(float));
+#ifdef FFB_RUNNIE
+    f->rle = ffb_alloc_pinned((size_t)(tot_blocks + 1) * 8 * sizeof(float));
+    if (!f->rle) die("out of memory%s", "");
+#endif
     if (!f->blk_off || !f->start || !f->end || !f->path || !f->qpath || !f->score) die("out of memory%s", "");
     ffb_raw_batch rb = {.raw = p->raw, .raw_off = p->raw_off, .n_reads = n, .trim_start = args.trim_start, .trim_end = args.trim_end,
                         .varseg_chunk = args.varseg_chunk, .varseg_thresh = args.varseg_thresh, .delta = args.delta,
@@ -241,6 +263,7 @@ static void submit_batch(struct inflight *f, ffb_model *model) {
     f->b.n_reads = n; f->b.temperature = args.temperature;
     f->b.flags = args.viterbi_only ? FFB_FLAG_VITERBI_ONLY : 0;
     f->b.blk_off = f->blk_off; f->b.path = f->path; f->b.qpath = f->qpath; f->b.score = f->score;
+    f->b.rle_params = f->rle;
     if (ffb_submit_raw_batch(f->ctx, &rb, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
     f->busy = true;
 }
@@ -254,9 +277,22 @@ static void collect_batch(struct inflight *f, ffb_model *model) {
     for (int i = 0; i < n; i++) {
         const int64_t nblock = f->blk_off[i + 1] - f->blk_off[i];
         if (nblock <= 0) {
-            fprintf(stderr, "flappie: No basecall returned for %s\n", p->name[i]);   /* src/flappie.c:370-373 */
+            fprintf(stderr, PROGRAM ": No basecall returned for %s\n", p->name[i]);   /* src/flappie.c:370-373 */
             continue;
         }
+#ifdef FFB_RUNNIE
+        {
+            char *bases = calloc((size_t)nblock + 2, 1);
+            float *shape = calloc((size_t)nblock + 1, sizeof(float)), *scale = calloc((size_t)nblock + 1, sizeof(float));
+            int32_t *dwell = calloc((size_t)nblock + 1, sizeof(int32_t));
+            if (!bases || !shape || !scale || !dwell) die("out of memory%s", "");
+            const int64_t nrun = ffb_emit_runs(f->path + f->blk_off[i] + i, f->rle + f->blk_off[i] * 8, nblock, nbase, bases, shape, scale, dwell);
+            fprintf(args.output, "# %s\n", p->uuid[i]);                                  /* src/runnie.c:277 */
+            for (int64_t r = 0; r < nrun; r++) fprintf(args.output, "%c\t%f\t%f\t%d\n", bases[r], shape[r], scale[r], dwell[r]);
+            free(bases); free(shape); free(scale); free(dwell);
+            continue;
+        }
+#endif
         char *basecall = calloc((size_t)nblock + 2, 1), *quality = calloc((size_t)nblock + 2, 1);
         if (!basecall || !quality) die("out of memory%s", "");
         const int nb = ffb_emit_bases(f->path + f->blk_off[i] + i, f->qpath + f->blk_off[i] + i, nblock, nbase, args.reverse, basecall, quality);
@@ -267,7 +303,8 @@ static void collect_batch(struct inflight *f, ffb_model *model) {
         free(basecall); free(quality);
     }
     free(f->blk_off); free(f->start); free(f->end);
-    ffb_free_pinned(f->path); ffb_free_pinned(f->qpath); ffb_free_pinned(f->score);
+    ffb_free_pinned(f->path); ffb_free_pinned(f->qpath); ffb_free_pinned(f->score); ffb_free_pinned(f->rle);
+    f->rle = NULL;
     pending_clear(p);
     f->busy = false;
 }
@@ -310,7 +347,7 @@ int main(int argc, char **argv) {
         const int globret = glob(pattern, 0, NULL, &globbuf);
         free(pattern);
         if (0 != globret) {
-            if (GLOB_NOMATCH == globret) fprintf(stderr, "flappie: File or directory \"%s\" does not exist or no signal files found.\n", argv[fn]);
+            if (GLOB_NOMATCH == globret) fprintf(stderr, PROGRAM ": File or directory \"%s\" does not exist or no signal files found.\n", argv[fn]);
             globfree(&globbuf);
             continue;
         }
@@ -321,8 +358,8 @@ int main(int argc, char **argv) {
             reads_started += 1;
             float *sig = NULL;
             const long n = ffb_read_raw_file(filename, &sig);
-            if (n == -2) { fprintf(stderr, "flappie: %s: fast5 input needs libhdf5, which this build does not have\n", filename); continue; }
-            if (n <= 0) { fprintf(stderr, "flappie: No basecall returned for %s\n", filename); free(sig); continue; }
+            if (n == -2) { fprintf(stderr, PROGRAM ": %s: fast5 input needs libhdf5, which this build does not have\n", filename); continue; }
+            if (n <= 0) { fprintf(stderr, PROGRAM ": No basecall returned for %s\n", filename); free(sig); continue; }
             pending_add(&fl[cur].pend, filename, sig, n);
             free(sig);
             if (fl[cur].pend.n >= args.batch) {

@@ -35,6 +35,7 @@ MODEL_TABLE = {
     "r103_native": (KIND_LSTM, 512, 4),
     "r10C_pcr": (KIND_GRU, 256, 4),
     "r941_native_gru": (KIND_GRU, 256, 4),   # north-star topology of r941_native (flappie 1.x)
+    "rle_r941_native": (KIND_LSTM, 256, 4),  # runnie: LSTM stack + run-length head (size inferred like the others)
 }
 
 
@@ -94,6 +95,7 @@ class FlipflopModel:
     ff_W: np.ndarray              # [nparam][S]
     ff_b: np.ndarray              # [nparam]
     name: str = "synthetic"
+    head: str = "flipflop"        # "runlength": the LSTM stack with runnie's head (networks.c:675-722)
 
     @property
     def size(self) -> int:
@@ -174,7 +176,10 @@ class FlipflopModel:
     @staticmethod
     def for_name(model: str, seed: int = 1) -> "FlipflopModel":
         kind, size, nbase = MODEL_TABLE[model]
-        return FlipflopModel.synthetic(kind, size, nbase, seed, name=model)
+        fm = FlipflopModel.synthetic(kind, size, nbase, seed, name=model)
+        if model.startswith("rle_"):
+            fm.head = "runlength"
+        return fm
 
     # ------------------------------------------------------------------ I/O
     def save(self, path: str) -> None:
@@ -204,7 +209,8 @@ class FlipflopModel:
         strides = list(self.conv_stride) + [0] * (3 - len(self.conv_stride))
         with open(path, "wb") as fh:
             fh.write(b"FFBW1\0\0\0")
-            fh.write(struct.pack("<6i", self.kind, len(self.conv_stride), strides[0], strides[1], strides[2], len(mats)))
+            kind = 2 if self.head == "runlength" else self.kind      # FFB_KIND_RUNLENGTH
+            fh.write(struct.pack("<6i", kind, len(self.conv_stride), strides[0], strides[1], strides[2], len(mats)))
             for m in mats:
                 fh.write(struct.pack("<2Q", m.nr, m.nc))
                 fh.write(np.ctypeslib.as_array(m.data, shape=(m.nc * m.stride,)).astype("<f4").tobytes())

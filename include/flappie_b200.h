@@ -11,6 +11,8 @@
  *        trace_from_posterior         <- reference src/decode.h:38     (src/decode.c:499-543)
  *        exp_activation_inplace       <- reference src/layers.h:17     (src/layers.c:56-66)
  *        nbase_from_flipflop_nparam   <- reference src/layers.h:89     (src/layers.c:1029-1032)
+ *        decode_crf_runlength / transpost_crf_runlength
+ *                                     <- reference src/decode.h:27,37  (src/decode.c:901-1159), runnie
  *        get_flappie_model_type / flappie_model_string / flappie_model_description
  *                                     <- reference src/networks.h:31-33 (src/networks.c:21-83)
  *        make/free_flappie_matrix, make/free_flappie_imatrix
@@ -92,11 +94,16 @@ float decode_crf_flipflop(const_flappie_matrix trans, bool combine_stays, int *p
 flappie_imatrix trace_from_posterior(flappie_matrix tpost);
 void exp_activation_inplace(flappie_matrix C);
 size_t nbase_from_flipflop_nparam(size_t nparam);
+/* run-length ("runnie") decoding, reference src/decode.h:27,37 (src/decode.c:901-1159); path has nblock entries */
+float decode_crf_runlength(const_flappie_matrix param, int *path);
+flappie_matrix transpost_crf_runlength(const_flappie_matrix param);
 
 /* ---- (2) batched extension ------------------------------------------------------- */
 
 #define FFB_KIND_GRU 0    /* guppy_model          (reference src/networks.c:150-177) */
 #define FFB_KIND_LSTM 1   /* guppy_stride5_model  (reference src/networks.c:180-215) */
+#define FFB_KIND_RUNLENGTH 2   /* the same 23-matrix bundle with the run-length ("runnie") head:
+                                * runlength5_guppy_transitions, reference src/networks.c:675-722 */
 
 #define FFB_OK 0
 #define FFB_ERR_ARG -1
@@ -166,6 +173,8 @@ typedef struct {
     float *trans;
     float *tpost;
     uint8_t *trace;
+    float *rle_params;   /* FFB_KIND_RUNLENGTH models only (may be NULL): sum(T_n) * 8 floats, [block][shape ACGT, scale ACGT];
+                          * for those models path[] holds the run-length states (T_n entries + one -1), qpath zeros */
 } ffb_batch;
 
 /* Upload, run the whole hot path, download, synchronise. */
@@ -235,6 +244,10 @@ int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t bytes);
  * written to basecall/quality (each needs nblock+1 chars, NUL-terminated). */
 int ffb_emit_bases(const int32_t *path, const float *qpath, int64_t nblock, int nbase, bool reverse,
                    char *basecall, char *quality);
+/* The run loop of runnie's calculate_post (reference src/runnie.c:279-310): returns the number of runs written to
+ * bases (NUL-terminated) / shape / scale / dwell (each needs nblock + 1 entries). */
+int64_t ffb_emit_runs(const int32_t *path, const float *rle_params, int64_t nblock, int nbase, char *bases,
+                      float *shape, float *scale, int32_t *dwell);
 
 #ifdef __cplusplus
 }

@@ -515,3 +515,192 @@ int ffo_basecall(const ffo_model *m, const float *signal, int n, float temperatu
     free(trans);
     return nb;
 }
+
+
+/* ==================================================================================
+ * Run-length ("runnie") head: reference src/layers.c:1235-1358, src/decode.c:893-1159,
+ * src/runnie.c:241-316.  Parameters per block (nbase = 4: 40 rows):
+ *   [0, nbase)        shape of the run-length distribution, 1 + softplus(x)
+ *   [nbase, 2 nbase)  scale, 1e-8 + softplus(x)
+ *   [2 nbase, nr)     transition scores 5 tanh(x) / temperature - logZ / T, indexed by
+ *                     rle_index(from, stay_from, to, stay_to).
+ * States: b < nbase = "move into base b" (emits a base), b + nbase = "stay in base b".
+ * ================================================================================== */
+
+static inline int ffo_rle_index(int base_from, int stay_from, int base_to, int nbase) {
+    /* decode.c:893-898 / layers.c:1241-1246: the destination's stay flag is implied by base_from == base_to */
+    return base_to * 2 * nbase + base_from + (stay_from ? nbase : 0);
+}
+static inline float ffo_softplusf(float x) { return log1pf(expf(-fabsf(x))) + ((x >= 0.0f) ? x : 0.f); }   /* util.h:83-85 */
+static inline double ffo_logsumexp_d(double x, double y) { return fmax(x, y) + log1p(exp(-fabs(x - y))); } /* util.h:272-274 */
+
+double ffo_runlength_partition(const float *C, int T, int nr) {
+    /* runlengthV2_partition_function, layers.c:1255-1302: double state, the stay states through the FLOAT
+     * logsumexpf (its arguments and its result are rounded to float) */
+    const int nbase = ffo_nbase_from_nparam(nr), nstate = 2 * nbase;
+    double mem[2 * 16] = {0};
+    double *curr = mem, *prev = mem + nstate;
+    for (int c = 0; c < T; c++) {
+        const float *p = C + (size_t)c * nr + nstate;
+        double *tmp = curr; curr = prev; prev = tmp;
+        for (int b1 = 0; b1 < nbase; b1++) {
+            curr[b1] = -HUGE_VAL;
+            for (int b2 = 0; b2 < nbase; b2++) {
+                if (b1 == b2) continue;
+                curr[b1] = ffo_logsumexp_d(curr[b1], prev[b2] + p[ffo_rle_index(b2, 0, b1, nbase)]);
+                curr[b1] = ffo_logsumexp_d(curr[b1], prev[b2 + nbase] + p[ffo_rle_index(b2, 1, b1, nbase)]);
+            }
+        }
+        for (int b = 0; b < nbase; b++) {
+            const float x = (float)(prev[b] + p[ffo_rle_index(b, 0, b, nbase)]);
+            const float y = (float)(prev[b + nbase] + p[ffo_rle_index(b, 1, b, nbase)]);
+            curr[b + nbase] = ffo_logsumexpf(x, y);
+        }
+    }
+    double logZ = curr[0];
+    for (int st = 1; st < nstate; st++) logZ = ffo_logsumexp_d(logZ, curr[st]);
+    return logZ;
+}
+
+void ffo_globalnorm_runlength(const float *h, int T, int S, const float *W, const float *b, int nr,
+                              float temperature, float *C, double *logZ_out) {
+    /* globalnorm_runlengthV2, layers.c:1326-1358 */
+    ffo_affine(h, T, S, W, b, nr, C);
+    const int nbase = ffo_nbase_from_nparam(nr), nrun = 2 * nbase;
+    for (int c = 0; c < T; c++) {
+        float *col = C + (size_t)c * nr;
+        for (int k = 0; k < nbase; k++) {
+            col[k] = 1.0f + ffo_softplusf(col[k]);
+            col[nbase + k] = 1e-8f + ffo_softplusf(col[nbase + k]);
+        }
+        for (int r = nrun; r < nr; r++) col[r] = 5.0f * tanhf(col[r]) / temperature;
+    }
+    const double Z = ffo_runlength_partition(C, T, nr);
+    if (logZ_out) *logZ_out = Z;
+    const float logZ = (float)(Z / (float)T);               /* :1349: double / float, then rounded to float */
+    for (int c = 0; c < T; c++)
+        for (int r = nrun; r < nr; r++) C[(size_t)c * nr + r] -= logZ;
+}
+
+float ffo_decode_crf_runlength(const float *param, int T, int nr, int *path) {
+    /* decode_crf_runlength, decode.c:901-984; path has T entries */
+    const int nbase = ffo_nbase_from_nparam(nr), nstate = 2 * nbase;
+    float mem[2 * 16] = {0};
+    char *tb = calloc((size_t)nstate * (size_t)(T > 0 ? T : 1), 1);
+    float *prev = mem, *curr = mem + nstate;
+    for (int blk = 0; blk < T; blk++) {
+        const float *p = param + (size_t)blk * nr + nstate;
+        char *tbc = tb + (size_t)blk * nstate;
+        float *tmp = prev; prev = curr; curr = tmp;
+        for (int st = 0; st < nstate; st++) curr[st] = -HUGE_VALF;
+        for (int b1 = 0; b1 < nbase; b1++) {
+            for (int b2 = 0; b2 < nbase; b2++) {
+                if (b1 == b2) continue;
+                const float mv = prev[b2] + p[ffo_rle_index(b2, 0, b1, nbase)];
+                if (mv > curr[b1]) { curr[b1] = mv; tbc[b1] = (char)b2; }
+                const float sv = prev[b2 + nbase] + p[ffo_rle_index(b2, 1, b1, nbase)];
+                if (sv > curr[b1]) { curr[b1] = sv; tbc[b1] = (char)(b2 + nbase); }
+            }
+        }
+        for (int b = 0; b < nbase; b++) {
+            const float sv = prev[b + nbase] + p[ffo_rle_index(b, 1, b, nbase)];
+            const float mv = prev[b] + p[ffo_rle_index(b, 0, b, nbase)];
+            if (sv > mv) { curr[b + nbase] = sv; tbc[b + nbase] = (char)(b + nbase); }
+            else { curr[b + nbase] = mv; tbc[b + nbase] = (char)b; }
+        }
+    }
+    int last = 0;                                           /* argmaxf: first max wins (util.c:17-31) */
+    for (int st = 1; st < nstate; st++) if (curr[st] > curr[last]) last = st;
+    const float score = curr[last];
+    for (int blk = T; blk > 0; blk--) {
+        const int from = tb[(size_t)(blk - 1) * nstate + last];
+        path[blk - 1] = last;
+        last = from;
+    }
+    free(tb);
+    return score;
+}
+
+int ffo_transpost_crf_runlength(const float *param, int T, int nr, float *post) {
+    /* transpost_crf_runlength, decode.c:1013-1159: UNNORMALISED log posteriors fwd + bwd + score; the shape and
+     * scale rows are copied through */
+    const int nbase = ffo_nbase_from_nparam(nr), nstate = 2 * nbase;
+    float *fwd = calloc((size_t)nstate * (size_t)(T + 1), sizeof(float));
+    if (!fwd) return -1;
+    for (int blk = 0; blk < T; blk++) {
+        const float *p = param + (size_t)blk * nr + nstate;
+        const float *prev = fwd + (size_t)blk * nstate;
+        float *curr = fwd + (size_t)(blk + 1) * nstate;
+        for (int b1 = 0; b1 < nbase; b1++) {
+            curr[b1] = -HUGE_VALF;
+            for (int b2 = 0; b2 < nbase; b2++) {
+                if (b1 == b2) continue;
+                const float sv = prev[b2 + nbase] + p[ffo_rle_index(b2, 1, b1, nbase)];
+                const float mv = prev[b2] + p[ffo_rle_index(b2, 0, b1, nbase)];
+                curr[b1] = ffo_logsumexpf(curr[b1], ffo_logsumexpf(sv, mv));
+            }
+        }
+        for (int b = 0; b < nbase; b++) {
+            const float sv = prev[b + nbase] + p[ffo_rle_index(b, 1, b, nbase)];
+            const float mv = prev[b] + p[ffo_rle_index(b, 0, b, nbase)];
+            curr[b + nbase] = ffo_logsumexpf(sv, mv);
+        }
+    }
+    float mem[2 * 16] = {0};
+    float *prev = mem, *curr = mem + nstate;
+    for (int blk = T; blk > 0; blk--) {
+        const float *f = fwd + (size_t)(blk - 1) * nstate;
+        const float *p = param + (size_t)(blk - 1) * nr + nstate;
+        float *q = post + (size_t)(blk - 1) * nr + nstate;
+        float *tmp = curr; curr = prev; prev = tmp;
+        for (int b1 = 0; b1 < nbase; b1++) {
+            curr[b1] = -HUGE_VALF;
+            curr[b1 + nbase] = -HUGE_VALF;
+            for (int b2 = 0; b2 < nbase; b2++) {
+                if (b1 == b2) continue;
+                const int mi = ffo_rle_index(b1, 0, b2, nbase);
+                curr[b1] = ffo_logsumexpf(curr[b1], prev[b2] + p[mi]);
+                q[mi] = f[b1] + prev[b2] + p[mi];
+                const int si = ffo_rle_index(b1, 1, b2, nbase);
+                curr[b1 + nbase] = ffo_logsumexpf(curr[b1 + nbase], prev[b2] + p[si]);
+                q[si] = f[b1 + nbase] + prev[b2] + p[si];
+            }
+        }
+        for (int b = 0; b < nbase; b++) {
+            const int i = ffo_rle_index(b, 0, b, nbase);
+            curr[b] = ffo_logsumexpf(curr[b], prev[b + nbase] + p[i]);
+            q[i] = f[b] + p[i] + prev[b + nbase];
+        }
+        for (int b = 0; b < nbase; b++) {
+            const int i = ffo_rle_index(b, 1, b, nbase);
+            curr[b + nbase] = ffo_logsumexpf(curr[b + nbase], prev[b + nbase] + p[i]);
+            q[i] = f[b + nbase] + p[i] + prev[b + nbase];
+        }
+        for (int k = 0; k < nstate; k++) post[(size_t)(blk - 1) * nr + k] = param[(size_t)(blk - 1) * nr + k];
+    }
+    free(fwd);
+    return 0;
+}
+
+int ffo_emit_runs(const int *path, const float *post, int T, int nr, char *bases, float *shape, float *scale, int *dwell) {
+    /* the run loop of runnie's calculate_post, runnie.c:279-310: one run per block whose state is a move state */
+    static const char lookup[5] = {'A', 'C', 'G', 'T', 'Z'};
+    const int nbase = ffo_nbase_from_nparam(nr);
+    int n = 0, run = 1, last_blk = -1;
+    for (int blk = 0; blk < T; blk++) {
+        if (path[blk] >= nbase) { run += 1; continue; }
+        if (last_blk >= 0) {
+            const int base = path[last_blk];
+            bases[n] = lookup[base]; shape[n] = post[(size_t)last_blk * nr + base];
+            scale[n] = post[(size_t)last_blk * nr + nbase + base]; dwell[n] = run; n++;
+        }
+        last_blk = blk;
+        run = 1;
+    }
+    if (last_blk >= 0) {
+        const int base = path[last_blk];
+        bases[n] = lookup[base]; shape[n] = post[(size_t)last_blk * nr + base];
+        scale[n] = post[(size_t)last_blk * nr + nbase + base]; dwell[n] = run; n++;
+    }
+    return n;
+}

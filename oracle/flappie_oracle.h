@@ -116,4 +116,12 @@ int ffo_basecall(const ffo_model *m, const float *signal, int n, float temperatu
 #ifdef __cplusplus
 }
 #endif
+/* ---- run-length ("runnie") head: layers.c:1235-1358, decode.c:893-1159, runnie.c:279-310 ---- */
+double ffo_runlength_partition(const float *C, int T, int nr);
+void ffo_globalnorm_runlength(const float *h, int T, int S, const float *W, const float *b, int nr,
+                              float temperature, float *C, double *logZ_out);
+float ffo_decode_crf_runlength(const float *param, int T, int nr, int *path);      /* path: T entries */
+int ffo_transpost_crf_runlength(const float *param, int T, int nr, float *post);
+int ffo_emit_runs(const int *path, const float *post, int T, int nr, char *bases, float *shape, float *scale, int *dwell);
+
 #endif

@@ -167,6 +167,52 @@ class Oracle:
         n = self.lib.ffo_emit_bases(path.ctypes.data_as(POINTER(c_int)), _fp(qpath), nblock, nbase, bc, ql)
         return bc.raw[:n].decode(), ql.raw[:n].decode()
 
+    # -- run-length ("runnie") head ----------------------------------------------
+    def globalnorm_runlength(self, h, W, b, temperature=1.0):
+        h = np.ascontiguousarray(h, np.float32); W = np.ascontiguousarray(W, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        out = np.zeros((h.shape[0], W.shape[0]), np.float32)
+        logz = c_double(0)
+        self.lib.ffo_globalnorm_runlength.argtypes = [_f32p, c_int, c_int, _f32p, _f32p, c_int, c_float, _f32p, POINTER(c_double)]
+        self.lib.ffo_globalnorm_runlength(_fp(h), h.shape[0], h.shape[1], _fp(W), _fp(b), W.shape[0], temperature,
+                                          _fp(out), ctypes.byref(logz))
+        return out, logz.value
+
+    def rle_viterbi(self, param):
+        param = np.ascontiguousarray(param, np.float32)
+        T, nr = param.shape
+        path = np.zeros(max(T, 1), np.int32)
+        self.lib.ffo_decode_crf_runlength.restype = c_float
+        self.lib.ffo_decode_crf_runlength.argtypes = [_f32p, c_int, c_int, POINTER(c_int)]
+        score = self.lib.ffo_decode_crf_runlength(_fp(param), T, nr, path.ctypes.data_as(POINTER(c_int)))
+        return score, path[:T]
+
+    def rle_transpost(self, param):
+        param = np.ascontiguousarray(param, np.float32)
+        out = np.zeros_like(param)
+        self.lib.ffo_transpost_crf_runlength.argtypes = [_f32p, c_int, c_int, _f32p]
+        self.lib.ffo_transpost_crf_runlength(_fp(param), param.shape[0], param.shape[1], _fp(out))
+        return out
+
+    def emit_runs(self, path, post):
+        """runnie's run loop (runnie.c:279-310) -> (bases str, shape[], scale[], dwell[])"""
+        path = np.ascontiguousarray(path, np.int32); post = np.ascontiguousarray(post, np.float32)
+        T, nr = post.shape
+        bases = ctypes.create_string_buffer(T + 1)
+        shape = np.zeros(max(T, 1), np.float32); scale = np.zeros(max(T, 1), np.float32); dwell = np.zeros(max(T, 1), np.int32)
+        self.lib.ffo_emit_runs.restype = c_int
+        self.lib.ffo_emit_runs.argtypes = [POINTER(c_int), _f32p, c_int, c_int, c_char_p, _f32p, _f32p, POINTER(c_int)]
+        n = self.lib.ffo_emit_runs(path.ctypes.data_as(POINTER(c_int)), _fp(post), T, nr, bases, _fp(shape), _fp(scale),
+                                   dwell.ctypes.data_as(POINTER(c_int)))
+        return bases.raw[:n].decode(), shape[:n], scale[:n], dwell[:n]
+
+    def runlength_transitions(self, m, signal, temperature=1.0):
+        """runlength5_guppy_transitions (networks.c:675-722): the LSTM stack of the model, then globalnorm_runlengthV2"""
+        r = self.transitions(m, signal, temperature, want_layers=True)
+        if r is None:
+            return None
+        return self.globalnorm_runlength(r[2][4], m.ff_W, m.ff_b, temperature)[0]
+
     # -- whole model ------------------------------------------------------------
     def _model(self, m):
         om = _OModel()
@@ -392,6 +438,38 @@ class Ref:
         x = np.ascontiguousarray(x, np.float32)
         self.lib.madf.restype = ctypes.c_float
         return np.float32(self.lib.madf(_fp(x), ctypes.c_size_t(x.shape[0]), None))
+
+    # -- run-length head: the reference's own object code -------------------------
+    def globalnorm_runlength(self, h, W, b, temperature=1.0):
+        L = self.lib
+        L.globalnorm_runlengthV2.restype = self.P
+        L.globalnorm_runlengthV2.argtypes = [self.P, self.P, self.P, c_float, self.P]
+        hm, Wm, bm = self.mat(h), self.mat(W), self.mat(np.asarray(b, np.float32).reshape(1, -1))
+        out = L.globalnorm_runlengthV2(hm, Wm, bm, temperature, None)
+        res = self.dense(out)
+        self.free(hm, Wm, bm)
+        return res
+
+    def rle_viterbi(self, param):
+        L = self.lib
+        L.decode_crf_runlength.restype = c_float
+        L.decode_crf_runlength.argtypes = [self.P, POINTER(c_int)]
+        T = param.shape[0]
+        pm = self.mat(param)
+        path = np.zeros(T + 2, np.int32)
+        score = L.decode_crf_runlength(pm, path.ctypes.data_as(POINTER(c_int)))
+        self.free(pm)
+        return score, path[:T]
+
+    def rle_transpost(self, param):
+        L = self.lib
+        L.transpost_crf_runlength.restype = self.P
+        L.transpost_crf_runlength.argtypes = [self.P]
+        pm = self.mat(param)
+        out = L.transpost_crf_runlength(pm)
+        res = self.dense(out)
+        self.free(pm)
+        return res
 
     def format_record(self, fmt, path, uuid, readname, uuid_primary, prefix, score, nblock, basecall, quality, n, start, end):
         """append one fasta / fastq / sam record to `path` with the reference's fprintf_format"""

@@ -168,3 +168,39 @@ def test_cli_end_to_end(gpu_lib, ref, tmp_path, fmt, extra):
                               lens[i], int(res.start[k]), int(res.end[k]))
     assert open(out, "rb").read() == open(want, "rb").read()
     ctx.close(); m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["--viterbi"]])
+def test_runnie_cli_end_to_end(gpu_lib, tmp_path, extra):
+    """runnie <dir of .f32 reads>: the `.run` text (reference src/runnie.c:277-310) equals the Python host's results
+    over the same C ABI, printed with the same format."""
+    from flappie_b200.api import Context, Model
+    from flappie_b200.model import KIND_LSTM
+    fm = FlipflopModel.synthetic(KIND_LSTM, 96, 4, seed=3, name="rle_r941_native")
+    fm.head = "runlength"
+    fm.save_bundle(str(tmp_path / "rle_r941_native.ffbw"))
+    lens = [4000, 2500, 6000, 150, 3000]
+    raws = synthetic_reads(len(lens), lens, seed=33)
+    rdir = tmp_path / "reads"; rdir.mkdir()
+    names = [f"read_{i:02d}.f32" for i in range(len(lens))]
+    for nm, r in zip(names, raws):
+        r.tofile(rdir / nm)
+    out = tmp_path / "calls.run"
+    env = dict(os.environ, FLAPPIE_B200_MODELS=str(tmp_path))
+    r = subprocess.run([os.path.join(HOST, "runnie"), "--batch", "2", "--output", str(out)] + extra + [str(rdir)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    m = Model(fm); ctx = Context(m)
+    want = []
+    for b0 in range(0, len(lens), 2):
+        res = ctx.basecall_raw(raws[b0:b0 + 2], viterbi_only="--viterbi" in extra)
+        for k in range(res.n_reads):
+            if res.nblock(k) == 0:
+                continue
+            st, rle = res.read_rle(k)
+            bases, shape, scale, dwell = gpu_lib.emit_runs(st, rle)
+            want.append("# %s\n" % names[b0 + k][:-4])
+            want += ["%s\t%f\t%f\t%d\n" % (c, float(sh), float(sc), int(d)) for c, sh, sc, d in zip(bases, shape, scale, dwell)]
+    assert open(out).read() == "".join(want) and len(want) > 50
+    ctx.close(); m.close()

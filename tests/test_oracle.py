@@ -208,3 +208,33 @@ def test_host_signal_prep_vs_reference_object_code(ref):
             assert hs.quantilef(x, p) == ref.quantile(x, p), (n, p)
         assert hs.madf(x) == ref.mad(x), n
         assert np.array_equal(hs.medmad_normalise_array(x), ref.medmad_normalise(x)), n
+
+
+def test_runlength_head_oracle_vs_reference_object_code(oracle, ref):
+    """The run-length ("runnie") head restated in oracle/flappie_oracle.c against the reference's own
+    globalnorm_runlengthV2 / decode_crf_runlength / transpost_crf_runlength (layers.c:1255-1358, decode.c:901-1159)."""
+    rng = np.random.default_rng(23)
+    for T in (1, 2, 57, 400):
+        S, nr = 32, 40
+        h = rng.uniform(-1, 1, (T, S)).astype(np.float32)
+        W = (rng.normal(size=(nr, S)) * 0.4).astype(np.float32)
+        b = (rng.normal(size=nr) * 0.2).astype(np.float32)
+        for temperature in (1.0, 0.7):
+            p_o, _ = oracle.globalnorm_runlength(h, W, b, temperature)
+            p_r = ref.globalnorm_runlength(h, W, b, temperature)
+            assert p_o.shape == p_r.shape == (T, nr)
+            assert np.max(np.abs(p_o - p_r)) < 2e-5          # OpenBLAS vs increasing-k summation in the affine map
+        s_o, path_o = oracle.rle_viterbi(p_r)                 # shared input: integers and the score bit-exact
+        s_r, path_r = ref.rle_viterbi(p_r)
+        assert np.array_equal(path_o, path_r) and s_o == s_r
+        post_o, post_r = oracle.rle_transpost(p_r), ref.rle_transpost(p_r)
+        assert np.array_equal(post_o, post_r)                 # same libm, same fold order
+        s_o, path_o = oracle.rle_viterbi(post_r)
+        s_r, path_r = ref.rle_viterbi(post_r)
+        assert np.array_equal(path_o, path_r) and s_o == s_r
+        bases, shape, scale, dwell = oracle.emit_runs(path_o, post_r)
+        assert len(bases) == int(np.sum(path_o < 4)) and int(dwell.sum()) <= T
+        assert np.all(shape >= 1.0) and np.all(scale > 0.0)
+    # quantised scores: ties resolved in the reference's visit order
+    q = rng.integers(-2, 3, size=(300, 40)).astype(np.float32)
+    assert np.array_equal(oracle.rle_viterbi(q)[1], ref.rle_viterbi(q)[1])
