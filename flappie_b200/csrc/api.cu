@@ -77,6 +77,7 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------
 struct ffb_model {
     int device = 0, kind = 0, S = 0, G = 0, nparam = 0, nbase = 0, nstate = 0, nconv = 0;
+    bool simt_rnn = true;   // the fp32 CUDA-core recurrence exists for this size
     int head = 0;     // 0 = flip-flop CRF, 1 = run-length CRF (FFB_KIND_RUNLENGTH: LSTM topology, runnie head)
     int conv_nf[FFB_MAX_CONV] = {0}, conv_nfilter[FFB_MAX_CONV] = {0}, conv_winlen[FFB_MAX_CONV] = {0},
         conv_stride[FFB_MAX_CONV] = {0};
@@ -162,10 +163,11 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
     if (ok) {
         m->S = (int)L[1]->nr;   // sW is [S x G*S]
         const int S = m->S, G = m->G;
-        if (!ffb_rnn_supported(kind, S)) {
+        if (!ffb_rnn_supported(kind, S) && !ffb_rnn_tc_supported(kind, S)) {
             set_err("ffb_model_create: no recurrent kernel for kind %d size %d", kind, S);
             ok = false;
         }
+        m->simt_rnn = ffb_rnn_supported(kind, S) != 0;    // S = 512 has the tensor kernel only
         int in = nf;
         for (int l = 0; ok && l < FFB_NLAYER; l++) {
             const _Mat *iW = L[3 * l], *sW = L[3 * l + 1], *b = L[3 * l + 2];
@@ -174,13 +176,13 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
                 ok = false; break;
             }
             m->layer_in[l] = in;
-            std::vector<float> iWt((size_t)in * G * S), bb(G * S), sWd((size_t)G * S * S), packed(ffb_rnn_packed_floats(kind, S));
+            std::vector<float> iWt((size_t)in * G * S), bb(G * S), sWd((size_t)G * S * S), packed(m->simt_rnn ? ffb_rnn_packed_floats(kind, S) : 1);
             for (int n = 0; n < G * S; n++) {
                 for (int k = 0; k < in; k++) iWt[(size_t)k * G * S + n] = mat_at(iW, k, n);
                 for (int k = 0; k < S; k++) sWd[(size_t)n * S + k] = mat_at(sW, k, n);
                 bb[n] = mat_at(b, n, 0);
             }
-            ffb_rnn_pack_weights(kind, S, sWd.data(), packed.data());
+            if (m->simt_rnn) ffb_rnn_pack_weights(kind, S, sWd.data(), packed.data());
             m->d_iWt[l] = upload(iWt); m->d_b[l] = upload(bb); m->d_sWp[l] = upload(packed);
             ok = ok && m->d_iWt[l] && m->d_b[l] && m->d_sWp[l];
             if (ok && ffb_rnn_tc_supported(kind, S)) {
@@ -247,7 +249,11 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
         }
         cudaGetLastError();
     }
-    if (ok && ffb_rnn_prepare(kind, m->S) != 0) {
+    if (ok && !m->simt_rnn && !m->tc_rnn) {
+        set_err("ffb_model_create: size %d needs the tensor recurrent kernel, which could not be set up", m->S);
+        ok = false;
+    }
+    if (ok && m->simt_rnn && ffb_rnn_prepare(kind, m->S) != 0) {
         set_err("ffb_model_create: recurrent kernel setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         ok = false;
     }
@@ -499,8 +505,12 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     if (b->blk_off) memcpy(b->blk_off, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1));
 
     // length-sorted slots for the recurrent kernel (descending, stable)
-    int R = ffb_rnn_reads_per_cluster(m->kind, m->S);
+    int R = m->simt_rnn ? ffb_rnn_reads_per_cluster(m->kind, m->S) : 16;
     c->use_tc_rnn = m->tc_rnn && !(c->flags & FFB_FLAG_FP32_SIMT) && getenv("FFB_NO_TC_RNN") == nullptr;
+    if (!c->use_tc_rnn && !m->simt_rnn) {
+        set_err("ffb_upload: size %d has no fp32 CUDA-core recurrence (FFB_FLAG_FP32_SIMT / FFB_NO_TC_RNN not available)", m->S);
+        return FFB_ERR_UNSUPPORTED;
+    }
     std::vector<int32_t> idx((size_t)N);
     std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t bb) {

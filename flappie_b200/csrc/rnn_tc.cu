@@ -56,29 +56,38 @@
 namespace ffb {
 using namespace tc;
 
-template <int S_, int C_, int NGATE_>
+// LO_SMEM: the lo plane of the weight slice lives in SHARED memory instead of tensor memory (S = 512: the two planes
+// of a 128 x 512 slice would fill all 512 TMEM columns).  Its MMAs (Wlo * hhi) then fetch A from shared memory
+// (~32 clk each instead of 9), which S = 512 pays for a third of its MMAs.
+template <int S_, int C_, int NGATE_, bool LO_SMEM_ = false>
 struct RnnTcCfg {
     static constexpr int S = S_, C = C_, NGATE = NGATE_;
+    static constexpr bool LO_SMEM = LO_SMEM_;
     static constexpr int HS = S / C;                  // hidden units per CTA
     static constexpr int NQ = HS / 8;                 // TMEM quadrants in use = k-groups per slice
     static constexpr int KG = S / 8;                  // 16-byte k-groups along K
     static constexpr int NG = 16;                     // reads per group (MMA N)
     static constexpr int TMEM_COLS = 512;
-    static constexpr int GMAX = (TMEM_COLS - S) / (3 * 16) < 5 ? (TMEM_COLS - S) / (3 * 16) : 5;   // groups per cluster: what TMEM holds next to the two weight planes
     static constexpr int A_COLS = S / 2;              // TMEM columns of one A plane (two halfs per 32-bit column)
     static constexpr int A_PLANE = 128 * S * 2;       // bytes of one plane of the global weight image [128 rows][S halfs]
+    static constexpr int A_SMEM = LO_SMEM ? A_PLANE : 0;   // shared-memory copy of the lo plane, [k-group][128 rows][16 B]
+    static constexpr int ACC_COL0_ = LO_SMEM ? A_COLS : 2 * A_COLS;
+    // groups per cluster: what TMEM holds next to the weight plane(s) -- and, with the lo plane in shared memory, what
+    // fits next to it there
+    static constexpr int GMAX_T = (TMEM_COLS - ACC_COL0_) / (3 * 16) < 5 ? (TMEM_COLS - ACC_COL0_) / (3 * 16) : 5;
+    static constexpr int GMAX = LO_SMEM ? (GMAX_T < 2 ? GMAX_T : 2) : GMAX_T;
     static constexpr int LBO_B = 2 * NG * 16;         // bytes between k-groups of B (hi and lo planes interleaved)
     static constexpr int B_GROUP = KG * LBO_B;        // bytes of one group's B operand
     static constexpr int SLICE = NQ * LBO_B;          // bytes of one CTA's slice of one group's state
     static constexpr int ACC_COLS = 3 * NG;           // TMEM columns per group
-    static constexpr int ACC_COL0 = 2 * A_COLS;       // accumulators follow the two A planes
+    static constexpr int ACC_COL0 = ACC_COL0_;        // accumulators follow the A plane(s)
     static constexpr int WARPS_PER_GROUP = 5;         // 4 gate warps + 1 control warp
     static constexpr int MAX_THREADS = GMAX * WARPS_PER_GROUP * 32;
     static_assert(HS == 32, "four quadrants of 8 hidden units");
     static_assert(GMAX >= 1 && ACC_COL0 + GMAX * ACC_COLS <= TMEM_COLS, "tensor memory budget");
     static_assert(C <= 16, "cluster size");
     __host__ __device__ static constexpr size_t smem_bytes(int G) {
-        return (size_t)G * (B_GROUP + SLICE) + 64;
+        return (size_t)A_SMEM + (size_t)G * (B_GROUP + SLICE) + 64;
     }
     __host__ __device__ static constexpr size_t ring_bytes(int n_clusters, int G) {
         return (size_t)n_clusters * 2 * G * C * SLICE;
@@ -140,7 +149,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
     __shared__ uint32_t tmem_slot;
 
-    uint8_t *B_base = smem;                                      // [G][KG][hi|lo][NG][16 B]
+    uint8_t *A_lo_smem = smem;                                   // LO_SMEM only: [KG][128 rows][16 B]
+    uint8_t *B_base = smem + Cfg::A_SMEM;                        // [G][KG][hi|lo][NG][16 B]
     uint8_t *stg_base = B_base + (size_t)G * Cfg::B_GROUP;       // [G][NQ][hi|lo][NG][16 B]
 
     const uint32_t crank = cluster_ctarank();
@@ -163,8 +173,16 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         }
         fence_barrier_init();
     }
+    if constexpr (Cfg::LO_SMEM) {
+        // lo plane -> shared memory in the no-swizzle K-major operand layout: k-group kg, row r at (kg * 128 + r) * 16 B
+        const uint4 *lo = reinterpret_cast<const uint4 *>(Wimg) + ((size_t)crank * 2 * Cfg::A_PLANE + Cfg::A_PLANE) / 16;
+        for (int i = tid; i < 128 * Cfg::KG; i += nthreads) {
+            const int kg = i % Cfg::KG, r = i / Cfg::KG;         // consecutive threads read consecutive 16-byte chunks of a row
+            reinterpret_cast<uint4 *>(A_lo_smem)[kg * 128 + r] = lo[(size_t)r * Cfg::KG + kg];
+        }
+    }
     if (warp == 0) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
-    fence_proxy_async_smem();       // zeroed B was written through the generic proxy
+    fence_proxy_async_smem();       // zeroed B (and the lo plane) were written through the generic proxy
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -173,7 +191,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         // weight slice -> tensor memory: this thread owns TMEM lane 32*warp + lane = row of the image
         const uint4 *src = reinterpret_cast<const uint4 *>(Wimg) + ((size_t)crank * 2 * Cfg::A_PLANE + (size_t)(warp * 32 + lane) * S * 2) / 16;
 #pragma unroll 1
-        for (int plane = 0; plane < 2; plane++) {
+        for (int plane = 0; plane < (Cfg::LO_SMEM ? 1 : 2); plane++) {
             const uint4 *row = src + (size_t)plane * (Cfg::A_PLANE / 16);
             const uint32_t tdst = tmem + ((uint32_t)(warp * 32) << 16) + plane * Cfg::A_COLS;
 #pragma unroll 4
@@ -211,6 +229,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             const uint32_t tA_hi = tmem, tA_lo = tmem + Cfg::A_COLS;
             const uint64_t dB_hi = make_smem_desc(smem_u32(Bg), Cfg::LBO_B, 128, LAYOUT_NONE);
             const uint64_t dB_lo = make_smem_desc(smem_u32(Bg) + NG * 16, Cfg::LBO_B, 128, LAYOUT_NONE);
+            const uint64_t dA_lo = make_smem_desc(smem_u32(A_lo_smem), 128 * 16, 128, LAYOUT_NONE);   // LO_SMEM only
             uint8_t *ring_g = ring + ((((size_t)cluster_id * 2) * G + g) * C + crank) * Cfg::SLICE;   // parity 0
             const size_t ring_par = (size_t)G * C * Cfg::SLICE;
             PROF_DECL;
@@ -244,7 +263,10 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     const uint64_t b0 = (i < KH ? dB_lo : dB_hi) + ob0, b1 = (i < KH ? dB_lo : dB_hi) + ob1;
                     umma_f16_ts(acc, tA_hi + k0 * 8, b0, idesc, i != 0);
                     umma_f16_ts(acc + NG, tA_hi + k1 * 8, b1, idesc, i != 0);
-                    umma_f16_ts(acc + 2 * NG, tA_lo + i * 8, dB_hi + ob2, idesc, i != 0);
+                    if constexpr (Cfg::LO_SMEM)
+                        umma_f16(acc + 2 * NG, dA_lo + (uint64_t)((i * 2 * 128 * 16) >> 4), dB_hi + ob2, idesc, i != 0);
+                    else
+                        umma_f16_ts(acc + 2 * NG, tA_lo + i * 8, dB_hi + ob2, idesc, i != 0);
                 }
                 umma_commit(&acc_full[g]);
                 }
@@ -453,6 +475,8 @@ using GruTc256 = RnnTcCfg<256, 8, 3>;
 using LstmTc256 = RnnTcCfg<256, 8, 4>;
 using GruTc384 = RnnTcCfg<384, 12, 3>;    // 12-CTA clusters (non-portable size): 32 hidden units per CTA again,
 using LstmTc384 = RnnTcCfg<384, 12, 4>;   // 2 x 192 TMEM columns of weights + 2 groups of accumulators
+using GruTc512 = RnnTcCfg<512, 16, 3, true>;    // r103_native: 16-CTA clusters, hi plane in tensor memory (256 columns),
+using LstmTc512 = RnnTcCfg<512, 16, 4, true>;   // lo plane in shared memory (128 KB), 2 groups
 
 }  // namespace ffb
 
@@ -461,6 +485,7 @@ using LstmTc384 = RnnTcCfg<384, 12, 4>;   // 2 x 192 TMEM columns of weights + 2
 template <class F>
 static auto tc_dispatch(int kind, int S, F &&f) {
     if (S == 384) return kind == 0 ? f(ffb::GruTc384{}) : f(ffb::LstmTc384{});
+    if (S == 512) return kind == 0 ? f(ffb::GruTc512{}) : f(ffb::LstmTc512{});
     return kind == 0 ? f(ffb::GruTc256{}) : f(ffb::LstmTc256{});
 }
 
@@ -474,7 +499,7 @@ int ffb_rnn_tc_prof(unsigned long long *out, int reset) {
     return 0;
 #endif
 }
-int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && (S == 256 || S == 384); }
+int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && (S == 256 || S == 384 || S == 512); }
 int ffb_rnn_tc_cluster_size(int kind, int S) { return tc_dispatch(kind, S, [](auto cfg) { return (int)decltype(cfg)::C; }); }
 int ffb_rnn_tc_rmax(int kind, int S) { return tc_dispatch(kind, S, [](auto cfg) { return (int)(decltype(cfg)::GMAX * decltype(cfg)::NG); }); }
 
