@@ -535,7 +535,9 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
             ncl = (int)((groups + G - 1) / G);
         } else {
             G = gmax;
-            ncl = std::max(1, maxc - 2);        // a few SMs stay free for the streamed input GEMM
+            // a few SMs stay free for the streamed input GEMM -- where that exists (K <= 256)
+            const bool can_stream = ffb_gemm_tc_stream_supported(m->G * m->S, m->S) != 0;
+            ncl = std::max(1, maxc - (can_stream ? 2 : 0));
         }
         if (getenv("FFB_TC_CLUSTERS")) ncl = std::max(1, std::min(atoi(getenv("FFB_TC_CLUSTERS")), maxc));
         c->R_tc = G * 16;

@@ -59,9 +59,12 @@ using namespace tc;
 // LO_SMEM: the lo plane of the weight slice lives in SHARED memory instead of tensor memory (S = 512: the two planes
 // of a 128 x 512 slice would fill all 512 TMEM columns).  Its MMAs (Wlo * hhi) then fetch A from shared memory
 // (~32 clk each instead of 9), which S = 512 pays for a third of its MMAs.
-template <int S_, int C_, int NGATE_, bool LO_SMEM_ = false>
+// NACC: accumulators per group.  3 (default): Whi*hhi split over the two K-halves + one for the cross terms.  2: all of
+// Whi*hhi in one accumulator (S/16 truncating full-magnitude accumulations instead of S/32) + the cross terms -- used
+// where the third accumulator would cost a whole slot of the cluster (S = 384: 4 slots instead of 2).
+template <int S_, int C_, int NGATE_, bool LO_SMEM_ = false, int NACC_ = 3>
 struct RnnTcCfg {
-    static constexpr int S = S_, C = C_, NGATE = NGATE_;
+    static constexpr int S = S_, C = C_, NGATE = NGATE_, NACC = NACC_;
     static constexpr bool LO_SMEM = LO_SMEM_;
     static constexpr int HS = S / C;                  // hidden units per CTA
     static constexpr int NQ = HS / 8;                 // TMEM quadrants in use = k-groups per slice
@@ -74,12 +77,12 @@ struct RnnTcCfg {
     static constexpr int ACC_COL0_ = LO_SMEM ? A_COLS : 2 * A_COLS;
     // groups per cluster: what TMEM holds next to the weight plane(s) -- and, with the lo plane in shared memory, what
     // fits next to it there
-    static constexpr int GMAX_T = (TMEM_COLS - ACC_COL0_) / (3 * 16) < 5 ? (TMEM_COLS - ACC_COL0_) / (3 * 16) : 5;
+    static constexpr int GMAX_T = (TMEM_COLS - ACC_COL0_) / (NACC * 16) < 5 ? (TMEM_COLS - ACC_COL0_) / (NACC * 16) : 5;
     static constexpr int GMAX = LO_SMEM ? (GMAX_T < 2 ? GMAX_T : 2) : GMAX_T;
     static constexpr int LBO_B = 2 * NG * 16;         // bytes between k-groups of B (hi and lo planes interleaved)
     static constexpr int B_GROUP = KG * LBO_B;        // bytes of one group's B operand
     static constexpr int SLICE = NQ * LBO_B;          // bytes of one CTA's slice of one group's state
-    static constexpr int ACC_COLS = 3 * NG;           // TMEM columns per group
+    static constexpr int ACC_COLS = NACC * NG;        // TMEM columns per group
     static constexpr int ACC_COL0 = ACC_COL0_;        // accumulators follow the A plane(s)
     static constexpr int WARPS_PER_GROUP = 5;         // 4 gate warps + 1 control warp
     static constexpr int MAX_THREADS = GMAX * WARPS_PER_GROUP * 32;
@@ -255,6 +258,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 //   chain 0: Whi*hlo then Whi*hhi over K-half 0     chain 1: the same over K-half 1
                 //   chain 2: Wlo*hhi over all of K
                 constexpr int KS = S / 16, KH = S / 32;
+                if constexpr (Cfg::NACC == 3) {
 #pragma unroll
                 for (int i = 0; i < KS; i++) {
                     const int k0 = i < KH ? i : i - KH, k1 = k0 + KH;            // k-steps of chains 0 / 1
@@ -267,6 +271,16 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                         umma_f16(acc + 2 * NG, dA_lo + (uint64_t)((i * 2 * 128 * 16) >> 4), dB_hi + ob2, idesc, i != 0);
                     else
                         umma_f16_ts(acc + 2 * NG, tA_lo + i * 8, dB_hi + ob2, idesc, i != 0);
+                }
+                } else {
+                    // two accumulators: acc 0 = Whi*hhi over all of K, acc 1 = Whi*hlo + Wlo*hhi
+#pragma unroll
+                for (int i = 0; i < KS; i++) {
+                    const uint64_t ob = (uint64_t)((i * 2 * Cfg::LBO_B) >> 4);
+                    umma_f16_ts(acc + NG, tA_hi + i * 8, dB_lo + ob, idesc, i != 0);
+                    umma_f16_ts(acc + NG, tA_lo + i * 8, dB_hi + ob, idesc, 1);
+                    umma_f16_ts(acc, tA_hi + i * 8, dB_hi + ob, idesc, i != 0);
+                }
                 }
                 umma_commit(&acc_full[g]);
                 }
@@ -377,7 +391,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 // h_{-1} = 0 (layers.c:586 / :892 zero the initial state): no MMAs were issued for this step
 #pragma unroll
                 for (int i = 0; i < 4; i++) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.0f;
-            } else {
+            } else if constexpr (Cfg::NACC == 3) {
                 float v0[8], v1[8];
                 tmem_ld_16x256b_x2(t_lo, v0);
                 tmem_ld_16x256b_x2(t_lo + NG, v1);
@@ -403,6 +417,19 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     const int r0 = (i >> 1) * 4 + (i & 1);
                     a[i][0] += v0[r0]; a[i][1] += v0[r0 + 2];
                     a[i][2] += v1[r0]; a[i][3] += v1[r0 + 2];
+                }
+            } else {
+                float v0[8], v1[8], v2[8], v3[8];
+                tmem_ld_16x256b_x2(t_lo, v0);
+                tmem_ld_16x256b_x2(t_lo + NG, v1);
+                tmem_ld_16x256b_x2(t_hi, v2);
+                tmem_ld_16x256b_x2(t_hi + NG, v3);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int r0 = (i >> 1) * 4 + (i & 1);
+                    a[i][0] = v0[r0] + v1[r0]; a[i][1] = v0[r0 + 2] + v1[r0 + 2];
+                    a[i][2] = v2[r0] + v3[r0]; a[i][3] = v2[r0 + 2] + v3[r0 + 2];
                 }
             }
             tcgen05_fence_before();
@@ -473,8 +500,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 
 using GruTc256 = RnnTcCfg<256, 8, 3>;
 using LstmTc256 = RnnTcCfg<256, 8, 4>;
-using GruTc384 = RnnTcCfg<384, 12, 3>;    // 12-CTA clusters (non-portable size): 32 hidden units per CTA again,
-using LstmTc384 = RnnTcCfg<384, 12, 4>;   // 2 x 192 TMEM columns of weights + 2 groups of accumulators
+using GruTc384 = RnnTcCfg<384, 12, 3, false, 2>;    // 12-CTA clusters (non-portable size): 32 hidden units per CTA again,
+using LstmTc384 = RnnTcCfg<384, 12, 4, false, 2>;   // 2 x 192 TMEM columns of weights + 4 groups of 2 accumulators
 using GruTc512 = RnnTcCfg<512, 16, 3, true>;    // r103_native: 16-CTA clusters, hi plane in tensor memory (256 columns),
 using LstmTc512 = RnnTcCfg<512, 16, 4, true>;   // lo plane in shared memory (128 KB), 2 groups
 
