@@ -85,9 +85,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken inside [t0, t1] (perf_counter); nvidia-smi needs a moment to start on an 8-GPU
+        box, so the sampler is started before the warm-up and, if the timed window itself caught no sample, the samples
+        taken under the warm-up load (same kernels) stand in -- the summary says which."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -96,9 +99,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        window = "timed region"
+        rows = [r for t, r in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.15)]
+        if not rows:
+            rows = [r for t, r in self.rows]
+            window = "warm-up + timed region (no sample fell inside the timed region)"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
             except (ValueError, IndexError):
@@ -107,7 +115,7 @@ class ClockSampler:
                 if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -253,18 +261,19 @@ def main():
 
     # ---- device-resident arm: inputs in HBM, K x forward ----
     ctx.upload(batch)
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(a.warmup):
         ctx.forward()
     barrier()
     l0 = ctx.launch_count()
-    sampler = ClockSampler(local); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(a.steps):
         ctx.forward()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(tw0, time.perf_counter())
     launches = ctx.launch_count() - l0
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     samples_per_step = n * RAW_SAMPLES * world
