@@ -539,6 +539,10 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
             const bool can_stream = ffb_gemm_tc_stream_supported(m->G * m->S, m->S) != 0;
             ncl = std::max(1, maxc - (can_stream ? 2 : 0));
         }
+        if (getenv("FFB_TC_SLOTS")) {             // experiments: slots per cluster
+            G = std::max(1, std::min(atoi(getenv("FFB_TC_SLOTS")), gmax));
+            ncl = (int)std::min<int64_t>((groups + G - 1) / G, maxc);
+        }
         if (getenv("FFB_TC_CLUSTERS")) ncl = std::max(1, std::min(atoi(getenv("FFB_TC_CLUSTERS")), maxc));
         c->R_tc = G * 16;
         c->tc_clusters = groups > 0 ? ncl : 0;

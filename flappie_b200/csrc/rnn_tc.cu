@@ -77,7 +77,10 @@ struct RnnTcCfg {
     static constexpr int ACC_COL0_ = LO_SMEM ? A_COLS : 2 * A_COLS;
     // groups per cluster: what TMEM holds next to the weight plane(s) -- and, with the lo plane in shared memory, what
     // fits next to it there
-    static constexpr int GMAX_T = (TMEM_COLS - ACC_COL0_) / (NACC * 16) < 5 ? (TMEM_COLS - ACC_COL0_) / (NACC * 16) : 5;
+    // 5 slots x 5 warps = 800 threads leave 72 registers per thread; 6 slots (960 threads, 64 registers, spills in the
+    // gate warps) measured slower: 34.9 vs 34.2 ms per step at S=256 although 16 more SMs went to the streamed GEMM
+    static constexpr int GCAP = 5;
+    static constexpr int GMAX_T = (TMEM_COLS - ACC_COL0_) / (NACC * 16) < GCAP ? (TMEM_COLS - ACC_COL0_) / (NACC * 16) : GCAP;
     static constexpr int GMAX = LO_SMEM ? (GMAX_T < 2 ? GMAX_T : 2) : GMAX_T;
     static constexpr int LBO_B = 2 * NG * 16;         // bytes between k-groups of B (hi and lo planes interleaved)
     static constexpr int B_GROUP = KG * LBO_B;        // bytes of one group's B operand
