@@ -117,6 +117,11 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
 int ffb_ff_tc_supported(int n_out, int K);
 int ffb_launch_ff_tanh_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                           int64_t M, int n_out, int K, float scale, int head, cudaStream_t st);
+// Strided convolution on the tensor cores: A = the im2col view of fp16 hi/lo planes (row r = K elements from element
+// r * hop), W planes [N][K] zero-padded in K, output = swish(. + b) as planes [M][N] (+ fp32 C if non-NULL)
+int ffb_conv_tc_supported(int N, int K);
+int ffb_launch_conv_gemm_tc(const void *Xhi, const void *Xlo, int64_t hop, const void *Whi, const void *Wlo, const float *bias,
+                            float *C, void *Chi, void *Clo, int64_t M, int N, int K, cudaStream_t st);
 // Streamed variant: launched (programmatic dependent launch) right behind the recurrent kernel that is still
 // writing the A planes; work items are taken from per-panel ticket queues in `work` order and each waits for its dependencies;
 // CTAs that find no free SM while the recurrence runs start when it ends and drain what is left.  Returns 0 (nothing launched) when the shape is unsupported.

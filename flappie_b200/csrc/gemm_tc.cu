@@ -127,7 +127,8 @@ template <int BN, int ACT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-               const float *__restrict__ bias, float *__restrict__ C, int64_t M, int N, int K, int n_out, float scale) {
+               const float *__restrict__ bias, float *__restrict__ C, int64_t M, int N, int K, int n_out, float scale,
+               __half *__restrict__ Chi, __half *__restrict__ Clo) {
     using Cfg = GemmTcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -216,11 +217,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             mbar_wait(&acc_full[acc], acc_phase);
             tcgen05_fence_after();
             const int64_t row = m0 + quad * 32 + lane;
-            float *crow = C + row * (int64_t)(ACT ? n_out : N) + n0;
+            float *crow = C + row * (int64_t)((ACT == 1 || ACT == 2) ? n_out : N) + n0;
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN;
 #pragma unroll 2
             for (int c = 0; c < BN; c += 16) {
-                if (ACT && c >= n_out) break;          // warp-uniform: the padded columns are never read
+                if ((ACT == 1 || ACT == 2) && c >= n_out) break;          // warp-uniform: the padded columns are never read
                 float v[16], vx[16];
                 tmem_ld16(taddr + c, v);
                 tmem_ld16(taddr + BN + c, vx);
@@ -234,6 +235,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         if constexpr (ACT == 0) {
                             __stcs(reinterpret_cast<float4 *>(crow + c + j),
                                    make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w));
+                        } else if constexpr (ACT == 3) {
+                            // convolution as a GEMM over the im2col view: swish(x + b) (src/layers.c:24-31), written as
+                            // the fp16 hi/lo planes the next GEMM reads
+                            const float o[4] = {fast_activate(v[j] + b4.x, FFB_ACT_SWISH), fast_activate(v[j + 1] + b4.y, FFB_ACT_SWISH),
+                                                fast_activate(v[j + 2] + b4.z, FFB_ACT_SWISH), fast_activate(v[j + 3] + b4.w, FFB_ACT_SWISH)};
+                            __half h[4], l[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) split_f16(o[q], h[q], l[q]);
+                            const int64_t idx = row * (int64_t)N + n0 + c + j;
+                            *reinterpret_cast<uint2 *>(Chi + idx) = *reinterpret_cast<uint2 *>(h);
+                            *reinterpret_cast<uint2 *>(Clo + idx) = *reinterpret_cast<uint2 *>(l);
+                            if (C) *reinterpret_cast<float4 *>(crow + c + j) = make_float4(o[0], o[1], o[2], o[3]);
                         } else if (c + j < n_out) {        // n_out % 4 == 0
                             if constexpr (ACT == 1) {
                                 // shift_scale_matrix_inplace divides: (x - 0) / scale (src/flappie_matrix.c:625-633)
@@ -568,11 +581,13 @@ static PFN_encodeTiled get_encode() {
 }
 
 // fp16 [rows][cols] row-major, box = 64 cols x box_rows, 128-byte swizzle
-static bool make_map_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// row_stride (elements) < cols describes OVERLAPPING rows: row r starts row_stride elements after row r-1 -- the im2col
+// view of a strided convolution (window = cols elements, hop = row_stride), read straight from the activation planes
+static bool make_map_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint64_t row_stride = 0) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 2};
+    cuuint64_t strides[1] = {(row_stride ? row_stride : cols) * 2};
     cuuint32_t box[2] = {64, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
@@ -591,10 +606,12 @@ int ffb_gemm_tc_supported(int N, int K) { return (N % 64 == 0) && (K % 64 == 0) 
 
 template <int BN, int ACT = 0>
 static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                          int64_t M, int N, int K, cudaStream_t st, int n_out = 0, float scale = 1.0f) {
+                          int64_t M, int N, int K, cudaStream_t st, int n_out = 0, float scale = 1.0f,
+                          int64_t a_row_stride = 0, void *Chi = nullptr, void *Clo = nullptr) {
     using Cfg = ffb::GemmTcCfg<BN>;
     CUtensorMap mAh, mAl, mBh, mBl;
-    if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, 128) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, 128) ||
+    if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, 128, (uint64_t)a_row_stride) ||
+        !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, 128, (uint64_t)a_row_stride) ||
         !make_map_f16(&mBh, Whi, (uint64_t)N, (uint64_t)K, BN) || !make_map_f16(&mBl, Wlo, (uint64_t)N, (uint64_t)K, BN))
         return -1;
     static bool attr_done = false;
@@ -607,7 +624,8 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(ntile < sms ? ntile : sms);
-    ffb::gemm_tc_kernel<BN, ACT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K, n_out, scale);
+    ffb::gemm_tc_kernel<BN, ACT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K, n_out, scale,
+                                                                         (__half *)Chi, (__half *)Clo);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -694,6 +712,17 @@ int ffb_launch_ff_tanh_tc(const void *Ahi, const void *Alo, const void *Whi, con
     if (!ffb_ff_tc_supported(n_out, K)) return -1;
     if (head) return launch_gemm_tc<FFB_FF_TC_ROWS, 2>(Ahi, Alo, Whi, Wlo, bias, C, M, FFB_FF_TC_ROWS, K, st, n_out, scale);
     return launch_gemm_tc<FFB_FF_TC_ROWS, 1>(Ahi, Alo, Whi, Wlo, bias, C, M, FFB_FF_TC_ROWS, K, st, n_out, scale);
+}
+
+// Convolution as a GEMM over the im2col VIEW of the input planes: row r of A is the window of K = winlen * nf (padded to
+// a multiple of 64 with zero weights) elements starting at element r * hop of the planes.  Output: swish(A * W^T + b) as
+// fp16 hi/lo planes [M][N] (and fp32 C if non-NULL).  N % 128 == 0.
+int ffb_conv_tc_supported(int N, int K) { return N % 128 == 0 && K % 64 == 0 && K >= 64; }
+int ffb_launch_conv_gemm_tc(const void *Xhi, const void *Xlo, int64_t hop, const void *Whi, const void *Wlo, const float *bias,
+                            float *C, void *Chi, void *Clo, int64_t M, int N, int K, cudaStream_t st) {
+    if (M <= 0) return 0;
+    if (!ffb_conv_tc_supported(N, K) || hop <= 0 || (hop * 2) % 16 != 0 || !Chi || !Clo) return -1;
+    return launch_gemm_tc<128, 3>(Xhi, Xlo, Whi, Wlo, bias, C, M, N, K, st, 0, 1.0f, hop, Chi, Clo);
 }
 
 int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, int a_in_tmem, cudaStream_t st) {

@@ -82,3 +82,35 @@ int ffb_rnn_tc_prof(unsigned long long *out, int reset);
 extern "C" int ffb_test_rnn_prof(unsigned long long *out, int reset) { return ffb_rnn_tc_prof(out, reset); }
 int ffb_gemm_tc_prof(unsigned long long *out, int reset);
 extern "C" int ffb_test_gemm_prof(unsigned long long *out, int reset) { return ffb_gemm_tc_prof(out, reset); }
+
+
+// im2col-view GEMM probe: x [nx] fp32 (flat activations), W [N][K], bias [N]; row r of A = x[r*hop .. r*hop + K).
+// Outputs swish(A W^T + b) reconstructed from the hi/lo planes, [M][N] fp32.
+int ffb_launch_conv_gemm_tc(const void *Xhi, const void *Xlo, int64_t hop, const void *Whi, const void *Wlo, const float *bias,
+                            float *C, void *Chi, void *Clo, int64_t M, int N, int K, cudaStream_t st);
+extern "C" int ffb_test_conv_gemm(const float *x, int64_t nx, int64_t hop, const float *W, const float *bias, float *out,
+                                  int64_t M, int N, int K) {
+    float *dx, *dW, *db, *dC;
+    __half *xh, *xl, *wh, *wl, *ch, *cl;
+    TRY(cudaMalloc(&dx, sizeof(float) * nx)); TRY(cudaMalloc(&dW, sizeof(float) * (size_t)N * K)); TRY(cudaMalloc(&db, sizeof(float) * N));
+    TRY(cudaMalloc(&dC, sizeof(float) * M * N));
+    TRY(cudaMalloc(&xh, 2 * nx)); TRY(cudaMalloc(&xl, 2 * nx)); TRY(cudaMalloc(&wh, 2 * (size_t)N * K)); TRY(cudaMalloc(&wl, 2 * (size_t)N * K));
+    TRY(cudaMalloc(&ch, 2 * M * N)); TRY(cudaMalloc(&cl, 2 * M * N));
+    TRY(cudaMemcpy(dx, x, sizeof(float) * nx, cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(dW, W, sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice));
+    TRY(cudaMemcpy(db, bias, sizeof(float) * N, cudaMemcpyHostToDevice));
+    if (ffb_launch_split_f16(dx, xh, xl, nx, 0) < 0 || ffb_launch_split_f16(dW, wh, wl, (int64_t)N * K, 0) < 0) return -2;
+    if (ffb_launch_conv_gemm_tc(xh, xl, hop, wh, wl, db, dC, ch, cl, M, N, K, 0) < 0) return -3;
+    TRY(cudaDeviceSynchronize());
+    std::vector<__half> hh((size_t)M * N), hl((size_t)M * N);
+    std::vector<float> c32((size_t)M * N);
+    TRY(cudaMemcpy(hh.data(), ch, 2 * M * N, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(hl.data(), cl, 2 * M * N, cudaMemcpyDeviceToHost));
+    TRY(cudaMemcpy(c32.data(), dC, sizeof(float) * M * N, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < (size_t)M * N; i++) {
+        out[i] = __half2float(hh[i]) + __half2float(hl[i]);
+        if (fabsf(out[i] - c32[i]) > 1e-6f * fmaxf(1.0f, fabsf(c32[i]))) return -4;     // planes must reproduce the fp32 value to 22 bits
+    }
+    cudaFree(dx); cudaFree(dW); cudaFree(db); cudaFree(dC); cudaFree(xh); cudaFree(xl); cudaFree(wh); cudaFree(wl); cudaFree(ch); cudaFree(cl);
+    return 0;
+}

@@ -97,3 +97,26 @@ def test_gemm_tc_speed_report(gpu_lib):
     print(f"\nGEMM {M}x{N}x{K}: tcgen05(split+gemm) {ms_tc:.3f} ms = {fl/ms_tc/1e9:.1f} TFLOP/s algorithmic; "
           f"fp32 SIMT {ms_f32:.3f} ms = {fl/ms_f32/1e9:.1f} TFLOP/s")
     assert np.max(np.abs(C_tc - C_f32)) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,hop", [(300, 128, 320, 80), (1000, 384, 320, 80), (257, 256, 64, 16)])
+def test_conv_gemm_im2col_view(gpu_lib, M, N, K, hop):
+    """The tensor-core convolution reads its A operand through an OVERLAPPING-row tensor map (row r = K elements from
+    element r * hop of the activation planes): compare with an explicit im2col in float64."""
+    L = _hooks(gpu_lib)
+    L.ffb_test_conv_gemm.restype = c_int
+    L.ffb_test_conv_gemm.argtypes = [POINTER(c_float), ctypes.c_int64, ctypes.c_int64, POINTER(c_float), POINTER(c_float),
+                                     POINTER(c_float), ctypes.c_int64, c_int, c_int]
+    rng = np.random.default_rng(M + N)
+    nx = (M - 1) * hop + K
+    x = rng.uniform(-1, 1, nx).astype(np.float32)
+    W = (rng.uniform(-1, 1, (N, K)) * 2 / np.sqrt(K)).astype(np.float32)
+    b = rng.uniform(-.3, .3, N).astype(np.float32)
+    out = np.zeros((M, N), np.float32)
+    r = L.ffb_test_conv_gemm(x.ctypes.data_as(POINTER(c_float)), nx, hop, W.ctypes.data_as(POINTER(c_float)),
+                             b.ctypes.data_as(POINTER(c_float)), out.ctypes.data_as(POINTER(c_float)), M, N, K)
+    assert r == 0
+    A = np.lib.stride_tricks.as_strided(x, shape=(M, K), strides=(4 * hop, 4)).astype(np.float64)
+    z = A @ W.astype(np.float64).T + b
+    ref = z / (1.0 + np.exp(-z))                                   # swish
+    assert np.max(np.abs(out - ref)) < 2e-5
