@@ -29,6 +29,7 @@ FLAG_WANT_TRACE = 2
 FLAG_WANT_TRANS = 4
 FLAG_KEEP_LAYERS = 8
 FLAG_FP32_SIMT = 16
+FLAG_FP32_CONV = 32
 
 # enum model_type, reference src/networks.h:18-26
 MODEL_ENUM = {"r941_native": 0, "r941_rna002": 1, "r941_5mC": 2, "r103_native": 3, "r10C_pcr": 0, "rle_r941_native": 5}

@@ -77,6 +77,10 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------
 struct ffb_model {
     int device = 0, kind = 0, S = 0, G = 0, nparam = 0, nbase = 0, nstate = 0, nconv = 0;
+    // last convolution of the LSTM topology on the tensor cores: W [nfilter][Kp] fp16 planes (K = winlen * nf, zero-padded to Kp)
+    void *d_c3_hi = nullptr, *d_c3_lo = nullptr;
+    int c3_kp = 0;
+    bool tc_conv3 = false;
     bool simt_rnn = true;   // the fp32 CUDA-core recurrence exists for this size
     int head = 0;     // 0 = flip-flop CRF, 1 = run-length CRF (FFB_KIND_RUNLENGTH: LSTM topology, runnie head)
     int conv_nf[FFB_MAX_CONV] = {0}, conv_nfilter[FFB_MAX_CONV] = {0}, conv_winlen[FFB_MAX_CONV] = {0},
@@ -116,6 +120,7 @@ extern "C" void ffb_model_destroy(ffb_model *m) {
     for (int i = 0; i < FFB_NLAYER; i++) { cudaFree(m->d_iWt[i]); cudaFree(m->d_b[i]); cudaFree(m->d_sWp[i]); cudaFree(m->d_iW_hi[i]); cudaFree(m->d_iW_lo[i]); cudaFree(m->d_sW_img[i]); }
     cudaFree(m->d_ffWt); cudaFree(m->d_ffb);
     cudaFree(m->d_ff_hi); cudaFree(m->d_ff_lo); cudaFree(m->d_ffb_pad);
+    cudaFree(m->d_c3_hi); cudaFree(m->d_c3_lo);
     delete m;
 }
 
@@ -157,6 +162,21 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
         }
         m->d_convWt[i] = upload(Wt); m->d_convb[i] = upload(bb);
         ok = ok && m->d_convWt[i] && m->d_convb[i];
+        if (ok && nconv == 3 && i == 2) {
+            // im2col weight planes [filter][k = tap * nf + feature], zero beyond winlen * nf
+            const int K = winlen * nf, Kp = 64 * ((K + 63) / 64);
+            if (ffb_conv_tc_supported(nfilter, Kp) && (nf * conv_stride[i] * 2) % 16 == 0 && getenv("FFB_NO_TC_CONV") == nullptr) {
+                std::vector<float> Wd((size_t)nfilter * Kp, 0.0f);
+                for (int f = 0; f < nfilter; f++)
+                    for (int k = 0; k < K; k++) Wd[(size_t)f * Kp + k] = Wt[(size_t)k * nfilter + f];
+                float *tmp = upload(Wd);
+                const bool okc = tmp && cudaMalloc(&m->d_c3_hi, Wd.size() * 2) == cudaSuccess && cudaMalloc(&m->d_c3_lo, Wd.size() * 2) == cudaSuccess &&
+                                 ffb_launch_split_f16(tmp, m->d_c3_hi, m->d_c3_lo, (int64_t)Wd.size(), 0) >= 0 && cudaDeviceSynchronize() == cudaSuccess;
+                cudaFree(tmp);
+                if (okc) { m->tc_conv3 = true; m->c3_kp = Kp; }
+                else cudaGetLastError();
+            }
+        }
         nf = nfilter;
     }
     const _Mat *const *L = mats + 2 * nconv;
@@ -378,6 +398,9 @@ struct ffb_ctx {
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
     DevBuf d_raw, d_rawoff, d_chunkoff, d_mad, d_bounds, d_sigoff;
     DevBuf d_slotoff, d_slotlist;
+    DevBuf d_c2hi, d_c2lo;        // tensor-core convolution: fp16 planes of its input in the slot layout (see forward_impl)
+    int conv3_fix = 0;            // columns at either end of a read the CUDA-core kernel recomputes
+    bool use_tc_conv3 = false;
     DevBuf d_rle;                 // run-length head: shape / scale rows of every block, [Ttot][8]   // device signal preparation (ffb_upload_raw)
     DevBuf d_ahi, d_alo;          // fp16 hi/lo planes of the current layer input (tensor path)
     DevBuf d_ring;                // state-exchange ring of the tensor recurrent kernel (L2-resident)
@@ -417,7 +440,7 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
                      &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress,
-                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff, &c->d_slotoff, &c->d_slotlist, &c->d_rle};
+                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff, &c->d_slotoff, &c->d_slotlist, &c->d_rle, &c->d_c2hi, &c->d_c2lo};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -469,7 +492,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
             const long To = ok ? (T + m->conv_stride[i] - 1) / m->conv_stride[i] : 0;
             ffb::ReadGeom g;
             g.in_off = c->col_off[i][n]; g.out_off = c->col_off[i + 1][n];
-            g.T_in = (int)T; g.T_out = (int)To; g.tail_id = 0; g.pad = 0;
+            g.T_in = (int)T; g.T_out = (int)To; g.tail_id = 0; g.pad = 0; g.plane_off = g.out_off;
             if (ok) {
                 auto it = tail_id[i].find((int)T);
                 if (it == tail_id[i].end()) {
@@ -503,6 +526,21 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     c->blk_off = c->col_off[m->nconv];
     c->total_blocks = c->blk_off[N];
     if (b->blk_off) memcpy(b->blk_off, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1));
+    // tensor-core last convolution: its input planes use a SLOT layout -- read n's columns start at column
+    // stride * blk_off[n], so that output block r (of the whole batch) is the window starting stride * r - padL columns
+    // into the planes and ONE overlapping-row tensor map describes the im2col matrix of the batch
+    c->use_tc_conv3 = m->tc_conv3 && m->tc_gemm && !(c->flags & (FFB_FLAG_FP32_SIMT | FFB_FLAG_FP32_CONV)) && c->total_blocks > 0;
+    c->conv3_fix = 0;
+    if (c->use_tc_conv3) {
+        const int last = m->nconv - 1;
+        int fix = 2;                                   // windows of the first / last two columns reach into a neighbouring read
+        for (int64_t n = 0; n < N; n++) {
+            geom[last - 1][(size_t)n].plane_off = (int64_t)m->conv_stride[last] * c->blk_off[n];
+            const ffb::ReadGeom &g = geom[last][(size_t)n];
+            if (g.T_out > 0) fix = std::max(fix, g.T_out - tails[last][(size_t)g.tail_id].tail_col0);   // the reference's edge plan
+        }
+        c->conv3_fix = 16 * ((fix + 15) / 16);
+    }
 
     // length-sorted slots for the recurrent kernel (descending, stable)
     int R = m->simt_rnn ? ffb_rnn_reads_per_cluster(m->kind, m->S) : 16;
@@ -671,6 +709,13 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     if (c->flags & FFB_FLAG_WANT_TRACE) ok &= c->d_trace.reserve((size_t)std::max<int64_t>((Tt + N) * m->nstate, 1)) == 0;
     if (c->flags & FFB_FLAG_KEEP_LAYERS)
         for (int l = 0; l < FFB_NLAYER; l++) ok &= c->d_keep[l].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    if (c->use_tc_conv3) {
+        const int last = m->nconv - 1;
+        const size_t halfs = (size_t)((m->conv_winlen[last] - 1) / 2) * m->conv_nf[last] +
+                             (size_t)m->conv_stride[last] * (size_t)Tt * m->conv_nf[last] + (size_t)m->c3_kp + 64;
+        ok &= c->d_c2hi.reserve(2 * halfs) == 0;
+        ok &= c->d_c2lo.reserve(2 * halfs) == 0;
+    }
     if (m->head) ok &= c->d_rle.reserve(sizeof(float) * 8 * (size_t)std::max<int64_t>(Tt, 1)) == 0;
     ok &= c->d_blkoff.reserve(sizeof(int64_t) * (size_t)(N + 1)) == 0;
     ok &= c->d_order.reserve(sizeof(int32_t) * (size_t)std::max(c->n_slots, 1)) == 0;
@@ -761,6 +806,7 @@ extern "C" int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_bat
     ffb_batch plan = *b;
     plan.signal = nullptr;
     plan.sig_off = soff.data();
+    if (rb->delta != 0.0f) plan.flags |= FFB_FLAG_FP32_CONV;      // unnormalised delta samples: see flappie_b200.h
     const int r = upload_impl(c, &plan, false);
     if (r != FFB_OK) return r;
     if (N > 0) {
@@ -802,10 +848,31 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         // on the tensor path the last convolution writes the fp16 hi/lo planes the first input GEMM reads
         // (and the fp32 copy only when the caller wants to look at it)
         const bool planes = lastc && tc_gemm;
-        LAUNCH(ffb_launch_conv(cur, (planes && !keep) ? nullptr : out, planes ? c->d_ahi.p : nullptr, planes ? c->d_alo.p : nullptr,
-                               m->d_convWt[i], m->d_convb[i], c->d_geom[i].as<ffb::ReadGeom>(),
-                               c->d_tails[i].as<ffb::ConvTail>(), (int)N, c->col_off[i + 1][N], c->max_T[i + 1],
-                               m->conv_nf[i], m->conv_nfilter[i], m->conv_winlen[i], m->conv_stride[i], act, st));
+        if (lastc && c->use_tc_conv3) {
+            // the convolution itself on the tensor cores (im2col view of the previous convolution's planes) ...
+            LAUNCH(ffb_launch_conv_gemm_tc(c->d_c2hi.p, c->d_c2lo.p, (int64_t)m->conv_stride[i] * m->conv_nf[i], m->d_c3_hi, m->d_c3_lo,
+                                           m->d_convb[i], keep ? out : nullptr, c->d_ahi.p, c->d_alo.p, Tt, m->conv_nfilter[i], m->c3_kp, st));
+            // ... and the columns it cannot know about -- windows reaching into a neighbouring read, the reference's
+            // right-edge plan -- once more on the CUDA cores from the fp32 input
+            LAUNCH(ffb_launch_conv(cur, keep ? out : nullptr, c->d_ahi.p, c->d_alo.p, m->d_convWt[i], m->d_convb[i],
+                                   c->d_geom[i].as<ffb::ReadGeom>(), c->d_tails[i].as<ffb::ConvTail>(), (int)N, c->col_off[i + 1][N],
+                                   c->max_T[i + 1], m->conv_nf[i], m->conv_nfilter[i], m->conv_winlen[i], m->conv_stride[i], act,
+                                   c->conv3_fix, st));
+        } else {
+            void *yhi = planes ? c->d_ahi.p : nullptr, *ylo = planes ? c->d_alo.p : nullptr;
+            float *y = (planes && !keep) ? nullptr : out;
+            if (i + 2 == m->nconv && c->use_tc_conv3) {
+                // input of the tensor-core convolution: fp32 (for its fix-up pass) AND zero-initialised planes in the slot layout
+                const size_t front = (size_t)((m->conv_winlen[i + 1] - 1) / 2) * m->conv_nf[i + 1];
+                if (cudaMemsetAsync(c->d_c2hi.p, 0, c->d_c2hi.cap, st) != cudaSuccess || cudaMemsetAsync(c->d_c2lo.p, 0, c->d_c2lo.cap, st) != cudaSuccess)
+                    return FFB_ERR_CUDA;
+                yhi = (uint16_t *)c->d_c2hi.p + front; ylo = (uint16_t *)c->d_c2lo.p + front;
+                y = out;
+            }
+            LAUNCH(ffb_launch_conv(cur, y, yhi, ylo, m->d_convWt[i], m->d_convb[i], c->d_geom[i].as<ffb::ReadGeom>(),
+                                   c->d_tails[i].as<ffb::ConvTail>(), (int)N, c->col_off[i + 1][N], c->max_T[i + 1],
+                                   m->conv_nf[i], m->conv_nfilter[i], m->conv_winlen[i], m->conv_stride[i], act, 0, st));
+        }
         cur = out;
     }
     c->last_conv = c->d_act[0].as<float>();

@@ -25,12 +25,12 @@ namespace ffb {
 constexpr int CONV_TILE_C = 16;     // output columns per thread
 constexpr int CONV_THREADS = 256;
 
-__device__ __forceinline__ void conv_store(float *y, __half *yhi, __half *ylo, int64_t idx, float v) {
+__device__ __forceinline__ void conv_store(float *y, __half *yhi, __half *ylo, int64_t idx, int64_t pidx, float v) {
     if (y) y[idx] = v;
     if (yhi) {
         const __half hi = __float2half_rn(v);
-        yhi[idx] = hi;
-        ylo[idx] = __float2half_rn(v - __half2float(hi));
+        yhi[pidx] = hi;
+        ylo[pidx] = __float2half_rn(v - __half2float(hi));
     }
 }
 
@@ -118,7 +118,7 @@ conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restr
                     v[0] += a[0]; v[1] += a[1]; v[2] += a[2]; v[3] += a[3];
                 }
             }
-            const int64_t idx = (g.out_off + col) * (int64_t)nfilter + f;
+            const int64_t idx = (g.out_off + col) * (int64_t)nfilter + f, pidx = (g.plane_off + col) * (int64_t)nfilter + f;
             float o[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) o[k] = fast_activate(v[k] + bb[k], ACT);
@@ -127,8 +127,8 @@ conv1_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restr
                 __half h[4], l[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) { h[k] = __float2half_rn(o[k]); l[k] = __float2half_rn(o[k] - __half2float(h[k])); }
-                *reinterpret_cast<uint2 *>(yhi + idx) = *reinterpret_cast<uint2 *>(h);
-                *reinterpret_cast<uint2 *>(ylo + idx) = *reinterpret_cast<uint2 *>(l);
+                *reinterpret_cast<uint2 *>(yhi + pidx) = *reinterpret_cast<uint2 *>(h);
+                *reinterpret_cast<uint2 *>(ylo + pidx) = *reinterpret_cast<uint2 *>(l);
             }
         }
     }
@@ -205,7 +205,7 @@ conv_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restri
                 v += a;
             }
         }
-        conv_store(y, yhi, ylo, (g.out_off + col) * (int64_t)nfilter + f, fast_activate(v + b, ACT));
+        conv_store(y, yhi, ylo, (g.out_off + col) * (int64_t)nfilter + f, (g.plane_off + col) * (int64_t)nfilter + f, fast_activate(v + b, ACT));
     }
 }
 
@@ -217,12 +217,18 @@ template <int ACT>
 __global__ void __launch_bounds__(512)
 conv_f4_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__restrict__ yhi, __half *__restrict__ ylo,
                const float *__restrict__ Wt, const float *__restrict__ bias, const ReadGeom *__restrict__ geom,
-               const ConvTail *__restrict__ tails, int nf, int nfilter, int winlen, int stride, int groups) {
+               const ConvTail *__restrict__ tails, int nf, int nfilter, int winlen, int stride, int groups, int fix_cols) {
     extern __shared__ float xs[];   // [span][nf]
     const ReadGeom g = geom[blockIdx.x];
     const int cols_per_cta = groups * CONV_TILE_C;
-    const int c0 = blockIdx.y * cols_per_cta;
-    if (c0 >= g.T_out) return;
+    int c0 = blockIdx.y * cols_per_cta, col_end = g.T_out;
+    if (fix_cols > 0) {
+        // only the head [0, fix_cols) and the tail [T_out - fix_cols, T_out) of the read: half of gridDim.y each
+        const int half = gridDim.y >> 1;
+        if ((int)blockIdx.y < half) { col_end = min(fix_cols, g.T_out); }
+        else { c0 = max(0, g.T_out - fix_cols) + ((int)blockIdx.y - half) * cols_per_cta; }
+    }
+    if (c0 >= col_end) return;
     const int padL = (winlen - 1) / 2;
     const int span = (cols_per_cta - 1) * stride + winlen;
     const int xin0 = c0 * stride - padL;
@@ -274,7 +280,7 @@ conv_f4_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__res
 #pragma unroll
     for (int c = 0; c < CONV_TILE_C; c++) {
         const int col = c0 + cbase + c;
-        if (col >= g.T_out) break;
+        if (col >= col_end) break;
         float v[4] = {acc[c][0], acc[c][1], acc[c][2], acc[c][3]};
         if (col >= tail0) {
             const int ti = col - tail0;
@@ -293,7 +299,7 @@ conv_f4_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__res
                 v[0] += a[0]; v[1] += a[1]; v[2] += a[2]; v[3] += a[3];
             }
         }
-        const int64_t idx = (g.out_off + col) * (int64_t)nfilter + f;
+        const int64_t idx = (g.out_off + col) * (int64_t)nfilter + f, pidx = (g.plane_off + col) * (int64_t)nfilter + f;
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) o[k] = fast_activate(v[k] + bb[k], ACT);
@@ -302,8 +308,8 @@ conv_f4_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__res
             __half h[4], l[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) { h[k] = __float2half_rn(o[k]); l[k] = __float2half_rn(o[k] - __half2float(h[k])); }
-            *reinterpret_cast<uint2 *>(yhi + idx) = *reinterpret_cast<uint2 *>(h);
-            *reinterpret_cast<uint2 *>(ylo + idx) = *reinterpret_cast<uint2 *>(l);
+            *reinterpret_cast<uint2 *>(yhi + pidx) = *reinterpret_cast<uint2 *>(h);
+            *reinterpret_cast<uint2 *>(ylo + pidx) = *reinterpret_cast<uint2 *>(l);
         }
     }
 }
@@ -312,7 +318,7 @@ conv_f4_kernel(const float *__restrict__ x, float *__restrict__ y, __half *__res
 
 int ffb_launch_conv(const float *x, float *y, void *yhi_, void *ylo_, const float *Wt, const float *bias,
                     const ffb::ReadGeom *geom, const ffb::ConvTail *tails, int n_reads, int64_t total_out_cols,
-                    int max_T_out, int nf, int nfilter, int winlen, int stride, int act, cudaStream_t st) {
+                    int max_T_out, int nf, int nfilter, int winlen, int stride, int act, int fix_cols, cudaStream_t st) {
     using namespace ffb;
     (void)total_out_cols;
     if (n_reads <= 0 || max_T_out <= 0) return 0;
@@ -355,18 +361,19 @@ int ffb_launch_conv(const float *x, float *y, void *yhi_, void *ylo_, const floa
         }
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
-    if ((nf & 3) == 0 && (nfilter & 3) == 0 && nfilter >= 128 && nfilter / 4 <= 512 && getenv("FFB_CONV_SCALAR") == nullptr) {
-        // 4 filters per thread; two or three column groups per CTA
+    if (fix_cols > 0 && !((nf & 3) == 0 && (nfilter & 3) == 0 && nfilter >= 128 && nfilter / 4 <= 512)) return -1;
+    if ((nf & 3) == 0 && (nfilter & 3) == 0 && nfilter >= 128 && nfilter / 4 <= 512 && (fix_cols > 0 || getenv("FFB_CONV_SCALAR") == nullptr)) {
+        // 4 filters per thread; two or three column groups per CTA (one for the narrow fix-up launches)
         const int fq = nfilter / 4;
-        const int groups4 = fq >= 256 ? 1 : (fq >= 128 ? 2 : 3);
+        const int groups4 = fix_cols > 0 ? 1 : (fq >= 256 ? 1 : (fq >= 128 ? 2 : 3));
         const int threads4 = groups4 * fq;
         const int cols4 = groups4 * CONV_TILE_C;
         const size_t smem4 = (size_t)((cols4 - 1) * stride + winlen) * nf * sizeof(float);
-        dim3 grid4(n_reads, (max_T_out + cols4 - 1) / cols4);
+        dim3 grid4(n_reads, fix_cols > 0 ? 2 * ((fix_cols + cols4 - 1) / cols4) : (max_T_out + cols4 - 1) / cols4);
         if (grid4.y <= 65535) {
             auto launch4 = [&](auto kern) {
                 if (smem4 > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
-                kern<<<grid4, threads4, smem4, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nf, nfilter, winlen, stride, groups4);
+                kern<<<grid4, threads4, smem4, st>>>(x, y, yhi, ylo, Wt, bias, geom, tails, nf, nfilter, winlen, stride, groups4, fix_cols);
             };
             if (act == FFB_ACT_TANH) launch4(conv_f4_kernel<FFB_ACT_TANH>);
             else if (act == FFB_ACT_SWISH) launch4(conv_f4_kernel<FFB_ACT_SWISH>);

@@ -73,6 +73,7 @@ struct ReadGeom {
     int32_t T_out;
     int32_t tail_id;   // index into the ConvTail table
     int32_t pad;
+    int64_t plane_off; // first output column in the fp16 hi/lo planes (== out_off except for the input of a tensor-core convolution)
 };
 
 }  // namespace ffb
@@ -82,9 +83,12 @@ struct ReadGeom {
 
 // conv.cu: x [cols][nf] -> y [cols'][nfilter], weights Wt [winlen*nf][nfilter].
 // y (fp32) and/or the fp16 hi/lo planes yhi/ylo (x = hi + lo, for the tensor GEMM) may be NULL
+// fix_cols > 0: only the first and the last fix_cols columns of every read are computed (the columns a tensor-core
+// convolution over the concatenated batch gets wrong: windows reaching into a neighbouring read, and the reference's
+// edge plan)
 int ffb_launch_conv(const float *x, float *y, void *yhi, void *ylo, const float *Wt, const float *bias,
                     const ffb::ReadGeom *geom, const ffb::ConvTail *tails, int n_reads, int64_t total_out_cols,
-                    int max_T_out, int nf, int nfilter, int winlen, int stride, int act, cudaStream_t st);
+                    int max_T_out, int nf, int nfilter, int winlen, int stride, int act, int fix_cols, cudaStream_t st);
 
 // gemm.cu: C[M][N] = A[M][K] * Wt[K][N] + bias[N]   (fp32 CUDA cores)
 int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,

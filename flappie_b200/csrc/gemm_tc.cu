@@ -130,6 +130,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                const float *__restrict__ bias, float *__restrict__ C, int64_t M, int N, int K, int n_out, float scale,
                __half *__restrict__ Chi, __half *__restrict__ Clo) {
     using Cfg = GemmTcCfg<BN>;
+    // ACT == 3 (convolution): accuracy over overlap.  The tensor core truncates on every accumulate, and 20 full-magnitude
+    // accumulations into one accumulator cost 1.2e-5 absolute on the pre-activation (2e-4 on `trans` five layers later).
+    // So every k-chunk of hi*hi gets its OWN accumulator (4 accumulations each), the cross terms one more, and the
+    // epilogue adds them in registers (round-to-nearest): (K/64 + 1) * BN columns, single-buffered.
+    constexpr bool PER_CHUNK = (ACT == 3);
+    constexpr int NBUF = PER_CHUNK ? 1 : Cfg::NBUF;
+    constexpr int TCOLS = PER_CHUNK ? 512 : Cfg::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES], acc_full[2], acc_empty[2];
@@ -143,13 +150,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < Cfg::NBUF; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < NBUF; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBhi); tma_prefetch_desc(&mapBlo);
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_alloc(&tmem_slot, TCOLS);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -182,8 +189,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
-                const uint32_t d = tmem + acc * 2 * BN, dx = d + BN;
+                const uint32_t d0 = tmem + acc * 2 * BN;
+                const uint32_t dx = PER_CHUNK ? tmem + nk * BN : d0 + BN;
                 for (int kc = 0; kc < nk; kc++) {
+                    const uint32_t d = PER_CHUNK ? tmem + kc * BN : d0;
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
@@ -196,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         const uint64_t dal = make_smem_desc(a_lo + ko, 16, 1024, LAYOUT_SW128);
                         const uint64_t dbh = make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128);
                         const uint64_t dbl = make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128);
-                        umma_f16(d, dah, dbh, idesc, (kc | k4) != 0);    // hi*hi
+                        umma_f16(d, dah, dbh, idesc, PER_CHUNK ? (k4 != 0) : ((kc | k4) != 0));    // hi*hi
                         umma_f16(dx, dah, dbl, idesc, (kc | k4) != 0);   // cross terms
                         umma_f16(dx, dal, dbh, idesc, 1);
                     }
@@ -204,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     if (kc == nk - 1) umma_commit(&acc_full[acc]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == Cfg::NBUF) { acc = 0; acc_phase ^= 1; }
+                if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -223,9 +232,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             for (int c = 0; c < BN; c += 16) {
                 if ((ACT == 1 || ACT == 2) && c >= n_out) break;          // warp-uniform: the padded columns are never read
                 float v[16], vx[16];
-                tmem_ld16(taddr + c, v);
-                tmem_ld16(taddr + BN + c, vx);
-                tmem_ld_wait();
+                if constexpr (PER_CHUNK) {
+                    tmem_ld16(taddr + c, v);                       // chunk 0
+                    tmem_ld16(taddr + nk * BN + c, vx);            // cross terms
+                    tmem_ld_wait();
+                    for (int kc = 1; kc < nk; kc++) {
+                        float w[16];
+                        tmem_ld16(taddr + kc * BN + c, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] += w[j];
+                    }
+                } else {
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld16(taddr + BN + c, vx);
+                    tmem_ld_wait();
+                }
 #pragma unroll
                 for (int j = 0; j < 16; j++) v[j] += vx[j];
                 if (row < M) {
@@ -266,12 +288,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
-            if (++acc == Cfg::NBUF) { acc = 0; acc_phase ^= 1; }
+            if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
 
@@ -716,13 +738,13 @@ int ffb_launch_ff_tanh_tc(const void *Ahi, const void *Alo, const void *Whi, con
 
 // Convolution as a GEMM over the im2col VIEW of the input planes: row r of A is the window of K = winlen * nf (padded to
 // a multiple of 64 with zero weights) elements starting at element r * hop of the planes.  Output: swish(A * W^T + b) as
-// fp16 hi/lo planes [M][N] (and fp32 C if non-NULL).  N % 128 == 0.
-int ffb_conv_tc_supported(int N, int K) { return N % 128 == 0 && K % 64 == 0 && K >= 64; }
+// fp16 hi/lo planes [M][N] (and fp32 C if non-NULL).  N % 64 == 0, K <= 448 (one 64-column accumulator per k-chunk).
+int ffb_conv_tc_supported(int N, int K) { return N % 64 == 0 && K % 64 == 0 && K >= 64 && (K / 64 + 1) * 64 <= 512; }
 int ffb_launch_conv_gemm_tc(const void *Xhi, const void *Xlo, int64_t hop, const void *Whi, const void *Wlo, const float *bias,
                             float *C, void *Chi, void *Clo, int64_t M, int N, int K, cudaStream_t st) {
     if (M <= 0) return 0;
     if (!ffb_conv_tc_supported(N, K) || hop <= 0 || (hop * 2) % 16 != 0 || !Chi || !Clo) return -1;
-    return launch_gemm_tc<128, 3>(Xhi, Xlo, Whi, Wlo, bias, C, M, N, K, st, 0, 1.0f, hop, Chi, Clo);
+    return launch_gemm_tc<64, 3>(Xhi, Xlo, Whi, Wlo, bias, C, M, N, K, st, 0, 1.0f, hop, Chi, Clo);
 }
 
 int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, int a_in_tmem, cudaStream_t st) {

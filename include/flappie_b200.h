@@ -149,6 +149,10 @@ void ffb_destroy(ffb_ctx *c);
 #define FFB_FLAG_WANT_TRANS 4u     /* copy trans (and tpost) back to the host */
 #define FFB_FLAG_KEEP_LAYERS 8u    /* keep every layer's output on the device for ffb_debug_fetch() */
 #define FFB_FLAG_FP32_SIMT 16u     /* force the fp32 CUDA-core GEMM / recurrence kernels */
+#define FFB_FLAG_FP32_CONV 32u     /* keep every convolution on the fp32 CUDA-core kernels: the tensor-core last convolution
+                                    * of the LSTM topology carries 22-bit operands, fine for med-MAD normalised signal
+                                    * (activations O(1)) but 1.6e-4 on trans for --delta input (activations O(100));
+                                    * ffb_upload_raw sets it by itself when delta != 0 */
 
 /* One batch of whole reads.  All pointers are HOST memory owned by the caller.
  * signal      : concatenated normalised samples of all reads

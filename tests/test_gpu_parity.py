@@ -137,7 +137,9 @@ def test_network_layers_small(gpu_lib, oracle, name, kind, size, nbase, fp32_sim
             continue
         trans_o, conv_o, layers_o = o
         assert b1 - b0 == trans_o.shape[0] == fm.nblock(len(sig))
-        assert np.max(np.abs(conv_g[b0:b1] - conv_o)) < 1e-5, f"conv read {i}"
+        # CUDA-core convolutions accumulate like the oracle (1e-5); the tensor-core last convolution of the LSTM topology
+        # (fp16 hi/lo operands, K = 320 in 20 truncating fp32 accumulations) stays within 2e-5 -- north-star tolerance 1e-4
+        assert np.max(np.abs(conv_g[b0:b1] - conv_o)) < (1e-5 if (fp32_simt or kind == KIND_GRU) else 2e-5), f"conv read {i}"
         for l in range(5):
             d = np.max(np.abs(layers_g[l][b0:b1] - layers_o[l]))
             assert d < TOL_LAYER, f"layer {l} read {i}: {d}"
