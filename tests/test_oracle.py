@@ -238,3 +238,25 @@ def test_runlength_head_oracle_vs_reference_object_code(oracle, ref):
     # quantised scores: ties resolved in the reference's visit order
     q = rng.integers(-2, 3, size=(300, 40)).astype(np.float32)
     assert np.array_equal(oracle.rle_viterbi(q)[1], ref.rle_viterbi(q)[1])
+
+
+def test_runlength_and_signal_golden(oracle):
+    """tests/golden/rle_golden.npz (generated from the reference's object code by make_golden_rle.py): pins the
+    run-length head of the oracle and the host signal prep where oracle/_ref itself is absent."""
+    from flappie_b200 import signal as hs
+    g = gold("rle_golden.npz")
+    for temp in (1.0, 0.7):
+        p, _ = oracle.globalnorm_runlength(g["h"], g["W"], g["b"], temp)
+        assert np.max(np.abs(p - g[f"param_t{temp}"])) < 2e-5
+    p = g["param_t1.0"]
+    s, path = oracle.rle_viterbi(p)
+    assert np.array_equal(path, g["vit_path"]) and s == g["vit_score"]
+    post = oracle.rle_transpost(p)
+    assert np.array_equal(post, g["post"])
+    s2, path2 = oracle.rle_viterbi(post)
+    assert np.array_equal(path2, g["post_path"]) and s2 == g["post_score"]
+    assert np.array_equal(oracle.rle_viterbi(g["tie_param"])[1], g["tie_path"])
+    x = g["sig"]
+    for p_, want in zip((0.0, 0.05, 0.3, 0.5, 0.77, 1.0), g["sig_q"]):
+        assert hs.quantilef(x, p_) == want
+    assert hs.madf(x) == g["sig_mad"] and np.array_equal(hs.medmad_normalise_array(x), g["sig_norm"])
