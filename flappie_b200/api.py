@@ -46,7 +46,7 @@ EXPORTS = [
     "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_emit_bases",
     "ffb_upload_raw", "ffb_basecall_raw_batch", "ffb_submit_batch", "ffb_submit_raw_batch", "ffb_collect",
     "ffb_alloc_pinned", "ffb_free_pinned",
-    "decode_crf_runlength", "transpost_crf_runlength", "ffb_emit_runs",
+    "decode_crf_runlength", "transpost_crf_runlength", "ffb_emit_runs", "ffb_plan_schedule",
 ]
 
 

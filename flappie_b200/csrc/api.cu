@@ -467,6 +467,79 @@ extern "C" int ffb_sync(ffb_ctx *c) {
         }                                                                    \
         c->launches += n_;                                                   \
     } while (0)
+// ---- schedule of the tensor recurrent kernel (host) ---------------------------------------------------------------
+// GROUPS of 16 length-sorted reads; a cluster has G slots, each slot walks a LIST of groups one after the other.
+// As few slots per cluster as still fit the batch into one wave of co-resident clusters (the layer is latency-bound:
+// more clusters = shorter chains per SM); when the batch has more groups than slots, or the reads differ in length, the
+// groups are dealt longest-first to the least-loaded slot (LPT) so every slot runs about the same number of steps.
+// blk_off: n_reads + 1 block offsets; sorted: read indices by descending length.
+static void plan_groups(const int64_t *blk_off, const int32_t *sorted, int64_t N, int maxc, int gmax, bool can_stream,
+                        int *G_out, int *ncl_out, std::vector<int32_t> &order, std::vector<int32_t> &slot_off,
+                        std::vector<int32_t> &slot_list, std::vector<int64_t> &group_start) {
+    const int64_t groups = (N + 15) / 16;
+    int G, ncl;
+    if (groups <= (int64_t)maxc * gmax) {
+        const int64_t gpc = (groups + maxc - 1) / maxc;
+        G = (int)std::min<int64_t>(std::max<int64_t>(gpc, 1), gmax);
+        ncl = (int)((groups + G - 1) / G);
+    } else {
+        G = gmax;
+        ncl = std::max(1, maxc - (can_stream ? 2 : 0));     // a few SMs stay free for the streamed input GEMM, where that exists
+    }
+    if (getenv("FFB_TC_SLOTS")) {             // experiments: slots per cluster
+        G = std::max(1, std::min(atoi(getenv("FFB_TC_SLOTS")), gmax));
+        ncl = (int)std::min<int64_t>((groups + G - 1) / G, maxc);
+    }
+    if (getenv("FFB_TC_CLUSTERS")) ncl = std::max(1, std::min(atoi(getenv("FFB_TC_CLUSTERS")), maxc));
+    if (groups == 0) ncl = 0;
+    order.assign((size_t)(groups * 16), -1);
+    std::copy(sorted, sorted + N, order.begin());
+    const int nslot = ncl * G;
+    std::vector<std::vector<int32_t>> lists((size_t)nslot);
+    std::vector<int64_t> load((size_t)nslot, 0);
+    group_start.assign((size_t)groups, 0);
+    for (int64_t g = 0; g < groups; g++) {          // groups are already in descending order of their longest read
+        const int32_t rd0 = order[(size_t)g * 16];
+        const int64_t Tg = blk_off[rd0 + 1] - blk_off[rd0];
+        int best = 0;
+        if (getenv("FFB_TC_ROUND_ROBIN")) {         // A/B: groups dealt in sorted order, as successive waves would run them
+            best = (int)(g % nslot);
+        } else {
+            for (int sl = 1; sl < nslot; sl++)
+                if (load[(size_t)sl] < load[(size_t)best]) best = sl;
+        }
+        group_start[(size_t)g] = load[(size_t)best];
+        lists[(size_t)best].push_back((int32_t)g);
+        load[(size_t)best] += Tg;
+    }
+    slot_off.assign((size_t)nslot + 1, 0);
+    slot_list.clear();
+    for (int sl = 0; sl < nslot; sl++) {
+        slot_off[(size_t)sl + 1] = slot_off[(size_t)sl] + (int32_t)lists[(size_t)sl].size();
+        slot_list.insert(slot_list.end(), lists[(size_t)sl].begin(), lists[(size_t)sl].end());
+    }
+    *G_out = G; *ncl_out = ncl;
+}
+
+// The same planner for callers / tests without a device: T[n] = blocks of read n.  Outputs: order (16 * groups entries,
+// -1 padded), slot_off (n_clusters * G + 1), slot_list (groups).  Returns the number of groups.
+extern "C" int64_t ffb_plan_schedule(const int64_t *T, int64_t n_reads, int max_clusters, int slots_max, int can_stream,
+                                     int32_t *order, int32_t *slot_off, int32_t *slot_list, int *n_clusters, int *slots) {
+    if (!T || n_reads < 0 || max_clusters < 1 || slots_max < 1 || !n_clusters || !slots) return -1;
+    std::vector<int64_t> off((size_t)n_reads + 1, 0);
+    for (int64_t n = 0; n < n_reads; n++) off[(size_t)n + 1] = off[(size_t)n] + std::max<int64_t>(T[n], 0);
+    std::vector<int32_t> idx((size_t)n_reads);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return (off[a + 1] - off[a]) > (off[b + 1] - off[b]); });
+    std::vector<int32_t> o, so, sl;
+    std::vector<int64_t> gs;
+    plan_groups(off.data(), idx.data(), n_reads, max_clusters, slots_max, can_stream != 0, slots, n_clusters, o, so, sl, gs);
+    if (order) std::copy(o.begin(), o.end(), order);
+    if (slot_off) std::copy(so.begin(), so.end(), slot_off);
+    if (slot_list) std::copy(sl.begin(), sl.end(), slot_list);
+    return (int64_t)sl.size();
+}
+
 // copy_signal = false: the normalised signal is produced on the device (ffb_upload_raw), only the plan is made here
 static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     if (!c || !b || (copy_signal && !b->signal) || !b->sig_off || b->n_reads < 0) { set_err("ffb_upload: bad arguments"); return FFB_ERR_ARG; }
@@ -557,59 +630,13 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     std::vector<int64_t> group_start;   // steps a group's slot has already run when the group begins
     c->slot_off.clear(); c->slot_list.clear(); c->tc_clusters = 0;
     if (c->use_tc_rnn) {
-        // GROUPS of 16 sorted reads; a cluster has G slots, each slot walks a LIST of groups one after the other.
-        // As few slots per cluster as still fit the batch into one wave of co-resident clusters (the layer is
-        // latency-bound: more clusters = shorter chains per SM); when the batch has more groups than slots, or the
-        // reads differ in length, the groups are dealt longest-first to the least-loaded slot (LPT) so every slot
-        // runs about the same number of steps -- short reads no longer idle behind the longest one.
-        const int rmax = ffb_rnn_tc_rmax(m->kind, m->S);
-        const int gmax = rmax / 16;
-        const int64_t groups = (N + 15) / 16;
-        const int maxc = std::max(m->tc_max_clusters, 1);
-        int G, ncl;
-        if (groups <= (int64_t)maxc * gmax) {
-            const int64_t gpc = (groups + maxc - 1) / maxc;
-            G = (int)std::min<int64_t>(std::max<int64_t>(gpc, 1), gmax);
-            ncl = (int)((groups + G - 1) / G);
-        } else {
-            G = gmax;
-            // a few SMs stay free for the streamed input GEMM -- where that exists (K <= 256)
-            const bool can_stream = ffb_gemm_tc_stream_supported(m->G * m->S, m->S) != 0;
-            ncl = std::max(1, maxc - (can_stream ? 2 : 0));
-        }
-        if (getenv("FFB_TC_SLOTS")) {             // experiments: slots per cluster
-            G = std::max(1, std::min(atoi(getenv("FFB_TC_SLOTS")), gmax));
-            ncl = (int)std::min<int64_t>((groups + G - 1) / G, maxc);
-        }
-        if (getenv("FFB_TC_CLUSTERS")) ncl = std::max(1, std::min(atoi(getenv("FFB_TC_CLUSTERS")), maxc));
+        const bool can_stream = ffb_gemm_tc_stream_supported(m->G * m->S, m->S) != 0;
+        int G = 1, ncl = 0;
+        plan_groups(c->blk_off.data(), idx.data(), N, std::max(m->tc_max_clusters, 1), ffb_rnn_tc_rmax(m->kind, m->S) / 16, can_stream,
+                    &G, &ncl, c->order, c->slot_off, c->slot_list, group_start);
         c->R_tc = G * 16;
-        c->tc_clusters = groups > 0 ? ncl : 0;
-        c->n_slots = (int)(groups * 16);
-        c->order.assign((size_t)c->n_slots, -1);
-        std::copy(idx.begin(), idx.end(), c->order.begin());
-        const int nslot = ncl * G;
-        std::vector<std::vector<int32_t>> lists((size_t)nslot);
-        std::vector<int64_t> load((size_t)nslot, 0);
-        group_start.assign((size_t)groups, 0);
-        for (int64_t g = 0; g < groups; g++) {          // groups are already in descending order of their longest read
-            const int32_t rd0 = c->order[(size_t)g * 16];
-            const int64_t Tg = c->blk_off[rd0 + 1] - c->blk_off[rd0];
-            int best = 0;
-            if (getenv("FFB_TC_ROUND_ROBIN")) {         // A/B: groups dealt in sorted order, as successive waves would run them
-                best = (int)(g % nslot);
-            } else {
-                for (int sl = 1; sl < nslot; sl++)
-                    if (load[(size_t)sl] < load[(size_t)best]) best = sl;
-            }
-            group_start[(size_t)g] = load[(size_t)best];
-            lists[(size_t)best].push_back((int32_t)g);
-            load[(size_t)best] += Tg;
-        }
-        c->slot_off.assign((size_t)nslot + 1, 0);
-        for (int sl = 0; sl < nslot; sl++) {
-            c->slot_off[(size_t)sl + 1] = c->slot_off[(size_t)sl] + (int32_t)lists[(size_t)sl].size();
-            c->slot_list.insert(c->slot_list.end(), lists[(size_t)sl].begin(), lists[(size_t)sl].end());
-        }
+        c->tc_clusters = ncl;
+        c->n_slots = (int)c->order.size();
     } else {
         c->n_slots = (int)(((N + R - 1) / R) * R);
         c->order.assign((size_t)c->n_slots, -1);

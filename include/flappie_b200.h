@@ -243,6 +243,13 @@ int ffb_forward_timed(ffb_ctx *c, float ms[8]);
  * `bytes` to host `dst`; returns bytes copied or negative error. */
 int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t bytes);
 
+/* The host-side schedule of the tensor recurrent kernel, callable without a device (tests, capacity planning): reads
+ * sorted by length form groups of 16; each of the n_clusters x slots slots gets a list of groups, longest first to the
+ * least-loaded slot.  T[n] = blocks of read n.  order: 16 * groups entries (-1 padded), slot_off: n_clusters * slots + 1,
+ * slot_list: groups entries; any of them may be NULL.  Returns the number of groups, or -1. */
+int64_t ffb_plan_schedule(const int64_t *T, int64_t n_reads, int max_clusters, int slots_max, int can_stream,
+                          int32_t *order, int32_t *slot_off, int32_t *slot_list, int *n_clusters, int *slots);
+
 /* Base / quality emission of calculate_post (reference src/flappie.c:284-297,
  * src/decode.c:66-79, src/util.h:285-305) on the host: returns the number of bases
  * written to basecall/quality (each needs nblock+1 chars, NUL-terminated). */

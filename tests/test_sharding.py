@@ -60,3 +60,52 @@ def test_two_rank_gloo_plumbing():
     assert sorted(res[0][1] + res[1][1]) == list(range(len(lens)))
     assert res[0][2] == res[1][2] == 11.0                        # MAX over ranks
     assert res[0][3] == res[1][3] == float(lens.sum())           # every sample counted once
+
+
+def _plan(lib, T, max_clusters, slots_max, can_stream=1):
+    import ctypes
+    from ctypes import POINTER, c_int, c_int32, c_int64
+    L = lib.lib
+    L.ffb_plan_schedule.restype = c_int64
+    L.ffb_plan_schedule.argtypes = [POINTER(c_int64), c_int64, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32),
+                                    POINTER(c_int32), POINTER(c_int), POINTER(c_int)]
+    T = np.ascontiguousarray(T, np.int64)
+    n = T.shape[0]
+    groups = (n + 15) // 16
+    order = np.full(max(groups * 16, 1), -2, np.int32)
+    slot_off = np.zeros(max_clusters * slots_max + 1, np.int32)
+    slot_list = np.full(max(groups, 1), -2, np.int32)
+    ncl, G = c_int(0), c_int(0)
+    r = L.ffb_plan_schedule(T.ctypes.data_as(POINTER(c_int64)), n, max_clusters, slots_max, can_stream,
+                            order.ctypes.data_as(POINTER(c_int32)), slot_off.ctypes.data_as(POINTER(c_int32)),
+                            slot_list.ctypes.data_as(POINTER(c_int32)), ctypes.byref(ncl), ctypes.byref(G))
+    assert r == groups
+    return order[:groups * 16], slot_off[:ncl.value * G.value + 1], slot_list[:groups], ncl.value, G.value
+
+
+def test_recurrent_group_schedule(lib):
+    """The host schedule of the tensor recurrent kernel (csrc/api.cu:plan_groups, no device needed): every group runs
+    exactly once, slots are balanced (LPT bound), a batch that fits one wave gets one group per slot."""
+    # configs[1]: 1024 equal reads, 15 co-resident clusters of 5 slots -> 13 clusters x 5 slots, one group each
+    order, so, sl, ncl, G = _plan(lib, np.full(1024, 1895), 15, 5)
+    assert (ncl, G) == (13, 5) and sorted(sl.tolist()) == list(range(64))
+    assert np.all(np.diff(so) <= 1) and sorted(order.tolist()) == list(range(1024))
+    # configs[2]: 4096 reads -> more groups than slots: all 13 x 5 slots busy, 3-4 groups each
+    order, so, sl, ncl, G = _plan(lib, np.full(4096, 1895), 15, 5)
+    assert (ncl, G) == (13, 5) and sorted(sl.tolist()) == list(range(256))
+    assert set(np.diff(so).tolist()) <= {3, 4}
+    # no streamed GEMM (K > 256): no SMs held back
+    assert _plan(lib, np.full(4096, 758), 12, 4, can_stream=0)[3] == 12
+    # ragged batch (configs[3] lengths): a partition, groups sorted by length, loads within one longest group of each other
+    rng = np.random.default_rng(2)
+    T = np.exp(rng.uniform(np.log(200), np.log(5000), size=4000)).astype(np.int64)
+    order, so, sl, ncl, G = _plan(lib, T, 15, 5)
+    assert sorted(order[order >= 0].tolist()) == list(range(4000)) and np.all(order[4000:] == -1)
+    Tg = T[order[::16]]                                       # longest read of every group
+    assert np.all(np.diff(Tg) <= 0) and sorted(sl.tolist()) == list(range(250))
+    loads = np.array([Tg[sl[so[k]:so[k + 1]]].sum() for k in range(ncl * G)])
+    assert loads.max() - loads.min() <= Tg.max()
+    # empty batch and a batch smaller than one group
+    assert _plan(lib, np.zeros(0, np.int64), 15, 5)[3] == 0
+    order, so, sl, ncl, G = _plan(lib, np.array([700, 10, 0]), 15, 5)
+    assert (ncl, G) == (1, 1) and order[:3].tolist() == [0, 1, 2] and np.all(order[3:] == -1)
