@@ -337,9 +337,9 @@ def main():
     rnn_ms_per_launch = groups["rnn"] / 5.0
     achieved_tf = rnn_flops / (rnn_ms_per_launch * 1e-3) / 1e12
     tensor_path = not a.fp32_simt and fm.size in (256, 384)
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_rnn_tc_v5_ncu_summary.txt,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_final_rnn_tc_ncu_summary.txt: 5.99 + 1.94 GB,
     # ncu --set full of this command); algorithmic = Xin read 4*G*S + planes written 4*S bytes per block
-    traffic = 7.94e9 if (tensor_path and a.model == "r941_native_gru" and a.reads == 1024) else None
+    traffic = 7.93e9 if (tensor_path and a.model == "r941_native_gru" and a.reads == 1024) else None
     roofline = {"kernel": "rnn_tc_kernel (recurrent layer: h*sW on tcgen05 + gates, 5 launches/step)" if tensor_path
                           else "rnn_layer_kernel (fp32 CUDA-core cluster kernel, 5 launches/step)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
