@@ -219,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     } else {
         // ===== epilogue warps 2..5 -> TMEM lane quadrants (warp % 4) =====
         const int quad = warp & 3;
+        uint8_t *ep_hi = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES, *ep_lo = ep_hi + 128 * BN * 2;   // ACT == 3 staging
         int acc = 0; uint32_t acc_phase = 0;
         for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
             const int64_t m0 = (tile / n_tiles) * Cfg::BM;
@@ -250,7 +251,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 }
 #pragma unroll
                 for (int j = 0; j < 16; j++) v[j] += vx[j];
-                if (row < M) {
+                float o3[16];                      // ACT == 3 only
+                if (row < M || ACT == 3) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(bias + n0 + c + j);
@@ -258,17 +260,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                             __stcs(reinterpret_cast<float4 *>(crow + c + j),
                                    make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w));
                         } else if constexpr (ACT == 3) {
-                            // convolution as a GEMM over the im2col view: swish(x + b) (src/layers.c:24-31), written as
-                            // the fp16 hi/lo planes the next GEMM reads
-                            const float o[4] = {fast_activate(v[j] + b4.x, FFB_ACT_SWISH), fast_activate(v[j + 1] + b4.y, FFB_ACT_SWISH),
-                                                fast_activate(v[j + 2] + b4.z, FFB_ACT_SWISH), fast_activate(v[j + 3] + b4.w, FFB_ACT_SWISH)};
-                            __half h[4], l[4];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) split_f16(o[q], h[q], l[q]);
-                            const int64_t idx = row * (int64_t)N + n0 + c + j;
-                            *reinterpret_cast<uint2 *>(Chi + idx) = *reinterpret_cast<uint2 *>(h);
-                            *reinterpret_cast<uint2 *>(Clo + idx) = *reinterpret_cast<uint2 *>(l);
-                            if (C) *reinterpret_cast<float4 *>(crow + c + j) = make_float4(o[0], o[1], o[2], o[3]);
+                            // convolution as a GEMM over the im2col view: swish(x + b) (src/layers.c:24-31); the fp16 hi/lo
+                            // planes go through a swizzled shared-memory tile (below), the optional fp32 copy directly
+                            o3[j] = fast_activate(v[j] + b4.x, FFB_ACT_SWISH); o3[j + 1] = fast_activate(v[j + 1] + b4.y, FFB_ACT_SWISH);
+                            o3[j + 2] = fast_activate(v[j + 2] + b4.z, FFB_ACT_SWISH); o3[j + 3] = fast_activate(v[j + 3] + b4.w, FFB_ACT_SWISH);
+                            if (C && row < M) *reinterpret_cast<float4 *>(crow + c + j) = make_float4(o3[j], o3[j + 1], o3[j + 2], o3[j + 3]);
                         } else if (c + j < n_out) {        // n_out % 4 == 0
                             if constexpr (ACT == 1) {
                                 // shift_scale_matrix_inplace divides: (x - 0) / scale (src/flappie_matrix.c:625-633)
@@ -284,6 +280,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         }
                     }
                 }
+                if constexpr (ACT == 3) {
+                    // this row's 16 outputs -> two 16-byte chunks per plane of the staging tile [128 rows][64 halfs],
+                    // chunk index XOR (row & 7): the writes of a warp spread over all banks, and so do the reads below
+                    __half h[16], l[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) split_f16(o3[j], h[j], l[j]);
+                    const int r = quad * 32 + lane;
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int sw = ((c >> 3) + q) ^ (r & 7);
+                        *reinterpret_cast<uint4 *>(ep_hi + r * 128 + sw * 16) = *reinterpret_cast<const uint4 *>(h + 8 * q);
+                        *reinterpret_cast<uint4 *>(ep_lo + r * 128 + sw * 16) = *reinterpret_cast<const uint4 *>(l + 8 * q);
+                    }
+                }
+            }
+            if constexpr (ACT == 3) {
+                // the warp's own 32 rows back out of shared memory: one instruction stores four whole 128-byte row segments
+                // (thread = row stores scattered 8 bytes over 32 lines per instruction and made the epilogue LSU-bound)
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int rr = quad * 32 + it * 4 + (lane >> 3), chunk = lane & 7;
+                    const int64_t grow = m0 + rr;
+                    if (grow < M) {
+                        const int so = rr * 128 + ((chunk ^ (rr & 7)) * 16);
+                        const int64_t idx = grow * (int64_t)N + n0 + chunk * 8;
+                        *reinterpret_cast<uint4 *>(Chi + idx) = *reinterpret_cast<const uint4 *>(ep_hi + so);
+                        *reinterpret_cast<uint4 *>(Clo + idx) = *reinterpret_cast<const uint4 *>(ep_lo + so);
+                    }
+                }
+                __syncwarp();
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -638,7 +665,7 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
         return -1;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(ffb::gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(ffb::gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM + (ACT == 3 ? 2 * 128 * BN * 2 : 0)) != cudaSuccess) return -1;
         attr_done = true;
     }
     const int64_t ntile = ((M + 127) / 128) * (N / BN);
@@ -646,7 +673,7 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(ntile < sms ? ntile : sms);
-    ffb::gemm_tc_kernel<BN, ACT><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K, n_out, scale,
+    ffb::gemm_tc_kernel<BN, ACT><<<grid, Cfg::THREADS, Cfg::SMEM + (ACT == 3 ? 2 * 128 * BN * 2 : 0), st>>>(mAh, mAl, mBh, mBl, bias, C, M, N, K, n_out, scale,
                                                                          (__half *)Chi, (__half *)Clo);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
