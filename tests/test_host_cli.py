@@ -204,3 +204,37 @@ def test_runnie_cli_end_to_end(gpu_lib, tmp_path, extra):
             want += ["%s\t%f\t%f\t%d\n" % (c, float(sh), float(sc), int(d)) for c, sh, sc, d in zip(bases, shape, scale, dwell)]
     assert open(out).read() == "".join(want) and len(want) > 50
     ctx.close(); m.close()
+
+
+def test_weight_bundle_roundtrip(host, tmp_path):
+    """FlipflopModel.save_bundle -> ffb_bundle_load (C): the `_Mat` images arrive in the reference's struct order with
+    their padded columns (no device needed)."""
+    from flappie_b200.model import KIND_LSTM, Mat
+
+    class Bundle(ctypes.Structure):
+        _fields_ = [("kind", ctypes.c_int), ("nconv", ctypes.c_int), ("nmat", ctypes.c_int), ("stride", ctypes.c_int * 3),
+                    ("mats", ctypes.POINTER(Mat))]
+
+    host.ffb_bundle_load.restype = ctypes.c_int
+    host.ffb_bundle_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(Bundle)]
+    host.ffb_bundle_free.restype = None
+    host.ffb_bundle_free.argtypes = [ctypes.POINTER(Bundle)]
+    for kind, nmat, strides, head in ((KIND_GRU, 19, [2, 0, 0], "flipflop"), (KIND_LSTM, 23, [1, 1, 5], "flipflop"),
+                                      (KIND_LSTM, 23, [1, 1, 5], "runlength")):
+        fm = FlipflopModel.synthetic(kind, 64, 4, seed=9)
+        fm.head = head
+        path = str(tmp_path / f"m{kind}{head}.ffbw")
+        fm.save_bundle(path)
+        b = Bundle()
+        assert host.ffb_bundle_load(path.encode(), ctypes.byref(b)) == 0
+        assert b.kind == (2 if head == "runlength" else kind) and b.nmat == nmat and list(b.stride) == strides
+        mats, keep = fm.to_mat_bundle()
+        for i, m in enumerate(mats):
+            got = b.mats[i]
+            assert (got.nr, got.nc, got.stride) == (m.nr, m.nc, m.stride)
+            n = m.nc * m.stride
+            assert np.array_equal(np.ctypeslib.as_array(got.data, shape=(n,)), np.ctypeslib.as_array(m.data, shape=(n,)))
+        host.ffb_bundle_free(ctypes.byref(b))
+    bad = tmp_path / "bad.ffbw"
+    bad.write_bytes(b"not a bundle")
+    assert host.ffb_bundle_load(str(bad).encode(), ctypes.byref(Bundle())) != 0
