@@ -663,10 +663,13 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
         !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, 128, (uint64_t)a_row_stride) ||
         !make_map_f16(&mBh, Whi, (uint64_t)N, (uint64_t)K, BN) || !make_map_f16(&mBl, Wlo, (uint64_t)N, (uint64_t)K, BN))
         return -1;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
+    static bool attr_done[64] = {false};
+    int adev = 0;
+    cudaGetDevice(&adev);
+    if (adev < 0 || adev >= 64 || !attr_done[adev]) {
         if (cudaFuncSetAttribute(ffb::gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM + (ACT == 3 ? 2 * 128 * BN * 2 : 0)) != cudaSuccess) return -1;
-        attr_done = true;
+        if (adev >= 0 && adev < 64) attr_done[adev] = true;
     }
     const int64_t ntile = ((M + 127) / 128) * (N / BN);
     int dev = 0, sms = 148;
@@ -684,10 +687,12 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
                           const int *progress = nullptr, int *queue = nullptr) {
     CUtensorMap mAh, mAl;
     if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, Cfg::BB) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, Cfg::BB)) return -1;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};      // per device ordinal
+    int adev = 0;
+    cudaGetDevice(&adev);
+    if (adev < 0 || adev >= 64 || !attr_done[adev]) {
         if (cudaFuncSetAttribute(ffb::gemm_ws_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
-        attr_done = true;
+        if (adev >= 0 && adev < 64) attr_done[adev] = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -127,3 +127,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in src and "flappie_oracle" not in src and "libflappie_ref" not in src, f
+
+
+def test_emit_runs_matches_oracle(lib, oracle):
+    """ffb_emit_runs (host C++, runnie.c:279-310) against the oracle's loop on random state paths: no device needed."""
+    rng = np.random.default_rng(5)
+    for T in (0, 1, 2, 50, 3000):
+        path = rng.integers(0, 8, size=T).astype(np.int32)
+        if T > 10:
+            path[:7] = 5                      # leading stay states before the first base: counted into nothing
+        post = rng.uniform(0.5, 9.0, size=(max(T, 1), 40)).astype(np.float32)[:T]
+        rle = np.ascontiguousarray(post[:, :8])
+        b_g, sh_g, sc_g, dw_g = lib.emit_runs(path, rle) if T else ("", np.zeros(0), np.zeros(0), np.zeros(0))
+        b_o, sh_o, sc_o, dw_o = oracle.emit_runs(path, post) if T else ("", np.zeros(0), np.zeros(0), np.zeros(0))
+        assert b_g == b_o and np.array_equal(dw_g, dw_o) and np.array_equal(sh_g, sh_o) and np.array_equal(sc_g, sc_o)
+        assert len(b_g) == int(np.sum(path < 4))
