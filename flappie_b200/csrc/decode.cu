@@ -287,112 +287,7 @@ __global__ void sub_logz_kernel(float *__restrict__ trans, const int64_t *__rest
 }
 
 // ---------------------------------------------------------------------------------
-// Transition posteriors.  Forward scan -> fwd[(T+1)][nstate]; backward scan emits
-// fwd + bwd + trans; a third, block-parallel kernel does the per-block log-normalisation
-// (a 39/59-term sequential logsumexp fold in the reference's order).
-// Lane = state; logsumexp folds run in the reference's source order (decode.c:396-484).
-template <int NBASE>
-__global__ void __launch_bounds__(32)
-transpost_fwd_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads,
-                     float *__restrict__ fwd) {
-    constexpr int NSTATE = 2 * NBASE;
-    constexpr int NR = NSTATE * (NBASE + 1);
-    __shared__ __align__(16) float stage[2][DEC_CHUNK * NR];
-    const int rd = blockIdx.x;
-    if (rd >= n_reads) return;
-    const int lane = threadIdx.x;
-    const int64_t b0 = blk_off[rd];
-    const int T = (int)(blk_off[rd + 1] - b0);
-    if (T <= 0) return;
-    const float *tr = trans + b0 * NR;
-    float *rf = fwd + (b0 + rd) * NSTATE;   // (T+1) x NSTATE
-    float P = 0.0f;                          // fwd[.,0] = 0 (make_flappie_matrix memsets)
-    if (lane < NSTATE) rf[lane] = 0.0f;
-    const int nchunk = (T + DEC_CHUNK - 1) / DEC_CHUNK;
-    stage_chunk(stage[0], tr, min(DEC_CHUNK, T), NR, lane);
-    for (int ch = 0; ch < nchunk; ch++) {
-        const int c0 = ch * DEC_CHUNK;
-        const int cn = min(DEC_CHUNK, T - c0);
-        if (ch + 1 < nchunk) {
-            stage_chunk(stage[(ch + 1) & 1], tr + (int64_t)(c0 + DEC_CHUNK) * NR, min(DEC_CHUNK, T - c0 - DEC_CHUNK), NR, lane);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncwarp();
-        const float *sb = stage[ch & 1];
-        for (int i = 0; i < cn; i++) {
-            const float *col = sb + i * NR;
-            const float *flop = col + NSTATE * NBASE;
-            float cur;
-            // flop destinations: logsumexp(stay, move)  (decode.c:404-411)
-            const float Pm = __shfl_sync(FULL, P, (lane - NBASE) & 31);
-            const float fl = (lane >= NBASE && lane < NSTATE) ? logsumexpf_ref(P + flop[lane], Pm + flop[lane - NBASE]) : 0.0f;
-            // flip destinations: sequential fold over sources 0..nstate-1 (decode.c:414-422)
-            const int b1 = lane < NBASE ? lane : 0;
-            cur = col[b1 * NSTATE] + __shfl_sync(FULL, P, 0);
-#pragma unroll
-            for (int f = 1; f < NSTATE; f++) {
-                const float pf = __shfl_sync(FULL, P, f);
-                cur = logsumexpf_ref(cur, col[b1 * NSTATE + f] + pf);
-            }
-            P = (lane < NBASE) ? cur : fl;
-            if (lane < NSTATE) rf[(int64_t)(c0 + i + 1) * NSTATE + lane] = P;
-        }
-        __syncwarp();
-    }
-}
-
-template <int NBASE>
-__global__ void __launch_bounds__(32)
-transpost_bwd_kernel(const float *__restrict__ trans, const int64_t *__restrict__ blk_off, int n_reads,
-                     const float *__restrict__ fwd, float *__restrict__ tpost) {
-    constexpr int NSTATE = 2 * NBASE;
-    constexpr int NR = NSTATE * (NBASE + 1);
-    const int rd = blockIdx.x;
-    if (rd >= n_reads) return;
-    const int lane = threadIdx.x;
-    const int64_t b0 = blk_off[rd];
-    const int T = (int)(blk_off[rd + 1] - b0);
-    if (T <= 0) return;
-    const float *tr = trans + b0 * NR;
-    float *tp = tpost + b0 * NR;
-    const float *rf = fwd + (b0 + rd) * NSTATE;
-    float B = 0.0f;   // backward vector at block `blk` (lane = state); calloc -> 0 (decode.c:426-432)
-    __shared__ float Bs[32];
-    for (int blk = T; blk > 0; blk--) {
-        const float *col = tr + (int64_t)(blk - 1) * NR;
-        const float *f = rf + (int64_t)(blk - 1) * NSTATE;
-        float *pc = tp + (int64_t)(blk - 1) * NR;
-        Bs[lane] = B;
-        __syncwarp();
-        // ---- emit tpost = fwd[from] + bwd[to] + trans (decode.c:446-461) ----
-        for (int e = lane; e < NR; e += 32) {
-            int to, fr;
-            if (e < NBASE * NSTATE) { to = e / NSTATE; fr = e % NSTATE; }
-            else { fr = e - NBASE * NSTATE; to = fr < NBASE ? fr + NBASE : fr; }
-            pc[e] = f[fr] + Bs[to] + col[e];
-        }
-        __syncwarp();
-        // ---- update backward vector (decode.c:465-482) ----
-        float cur = 0.0f;
-        const float Bup = __shfl_sync(FULL, B, (lane + NBASE) & 31);   // prev[from + nbase]
-        if (lane < NSTATE) {
-            const float flopv = col[NBASE * NSTATE + lane];
-            cur = (lane >= NBASE) ? (B + flopv) : (Bup + flopv);
-        }
-#pragma unroll
-        for (int b1 = 0; b1 < NBASE; b1++) {
-            const float pb = __shfl_sync(FULL, B, b1);
-            if (lane < NSTATE) cur = logsumexpf_ref(cur, col[b1 * NSTATE + lane] + pb);
-        }
-        B = cur;
-    }
-}
-
-
-// ---------------------------------------------------------------------------------
-// Transition posteriors, fused and shift-invariant ("fb" kernels): the production path.
+// Transition posteriors, shift-invariant ("fb" kernels).
 //
 // tpost[blk][e] = fwd[from, blk] + bwd[to, blk+1] + trans[blk][e], log-normalised per block
 // (decode.c:377-497, flappie_matrix.c:450-467).  Any constant added to a forward row, a
@@ -775,16 +670,6 @@ fb_combine_kernel(const float *__restrict__ trans, const int64_t *__restrict__ b
     }
 }
 
-// per-block log normalisation, sequential fold in row order (flappie_matrix.c:450-467)
-__global__ void lognorm_rows_kernel(float *__restrict__ tpost, int64_t nblk, int nr) {
-    const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (blk >= nblk) return;
-    float *p = tpost + blk * nr;
-    float lse = p[0];
-    for (int r = 1; r < nr; r++) lse = logsumexpf_ref(lse, p[r]);
-    for (int r = 0; r < nr; r++) p[r] -= lse;
-}
-
 // trace (decode.c:499-543) from LOG posteriors: one thread per (read-local) trace row.
 template <int NBASE, bool IS_LOG>
 __global__ void trace_kernel(const float *__restrict__ tpost, const int64_t *__restrict__ blk_off, int n_reads,
@@ -896,15 +781,6 @@ int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads
         ffb::fb_combine_kernel<5><<<grid, 256, 0, st>>>(trans, blk_off, n_reads, fwd_scratch, bwd_scratch, tpost, total_blocks);
     }
     return FFB_OKL(2);
-}
-
-// (the fused fb_bwd_kernel already log-normalises every block; this stays for callers that hold
-// un-normalised posteriors)
-int ffb_launch_lognorm(float *tpost, int64_t total_blocks, int nr, cudaStream_t st) {
-    if (total_blocks <= 0) return 0;
-    const int64_t grid = (total_blocks + 127) / 128;
-    ffb::lognorm_rows_kernel<<<(unsigned)grid, 128, 0, st>>>(tpost, total_blocks, nr);
-    return FFB_OKL(1);
 }
 
 int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, uint8_t *trace,

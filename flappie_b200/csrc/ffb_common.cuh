@@ -202,7 +202,6 @@ int ffb_launch_viterbi(const float *trans, const int64_t *blk_off, int n_reads, 
 // fwd_scratch: 2 * (total_blocks + n_reads) * nstate floats
 int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads, int nr, float *fwd_scratch,
                          float *tpost, int64_t total_blocks, cudaStream_t st);
-int ffb_launch_lognorm(float *tpost, int64_t total_blocks, int nr, cudaStream_t st);
 int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, uint8_t *trace, int is_log,
                      cudaStream_t st);
 int ffb_launch_exp_inplace(float *x, int64_t n, cudaStream_t st);
