@@ -142,3 +142,18 @@ def test_emit_runs_matches_oracle(lib, oracle):
         b_o, sh_o, sc_o, dw_o = oracle.emit_runs(path, post) if T else ("", np.zeros(0), np.zeros(0), np.zeros(0))
         assert b_g == b_o and np.array_equal(dw_g, dw_o) and np.array_equal(sh_g, sh_o) and np.array_equal(sc_g, sc_o)
         assert len(b_g) == int(np.sum(path < 4))
+
+
+def test_device_only_entry_points_fail_loudly_without_gpu(lib):
+    """New entry points of this round keep the rule: no device -> NULL / negative status, never a CPU path."""
+    import ctypes
+    if lib.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    L = lib.lib
+    L.ffb_alloc_pinned.restype = ctypes.c_void_p; L.ffb_alloc_pinned.argtypes = [ctypes.c_size_t]
+    assert not L.ffb_alloc_pinned(1 << 20)
+    p = np.zeros((5, 40), np.float32)
+    with pytest.raises(Exception):
+        lib.decode_crf_runlength(p)
+    with pytest.raises(Exception):
+        lib.transpost_crf_runlength(p)
