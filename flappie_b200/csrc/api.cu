@@ -95,13 +95,15 @@ struct ffb_model {
     bool tc_gemm = false;
     void *d_sW_img[FFB_NLAYER] = {nullptr};   // per-CTA shared-memory images of sW (fp16 hi/lo) for rnn_tc
     bool tc_rnn = false;
+    bool fuse_z = false;      // GRU: recurrent layer l also computes the z-gate third of layer l+1's input projection (rnn_tc.cu)
     int tc_max_clusters = 0;
     int layer_in[FFB_NLAYER] = {0};
     // conv edge plans, cached per (conv layer, T_in)
     std::mutex mu;
-    std::map<std::pair<int, int>, ffb::ConvTail> tail_cache;
+    std::map<std::pair<int, int>, ffb::ConvTail> tail_cache;   // at most FFB_TAIL_CACHE_MAX entries (~0.8 KB each)
 };
 
+static constexpr size_t FFB_TAIL_CACHE_MAX = 8192;
 static inline float mat_at(const _Mat *m, size_t r, size_t c) { return m->data.f[c * m->stride + r]; }
 
 static float *upload(const std::vector<float> &h) {
@@ -188,6 +190,8 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             ok = false;
         }
         m->simt_rnn = ffb_rnn_supported(kind, S) != 0;    // S = 512 has the tensor kernel only
+        const bool fuse_z = ffb_rnn_tc_can_fuse_z(kind, S) && ffb_gemm_tc_stream_supported(G * S, S) && getenv("FFB_NO_FUSE_Z") == nullptr;
+        m->fuse_z = fuse_z;
         int in = nf;
         for (int l = 0; ok && l < FFB_NLAYER; l++) {
             const _Mat *iW = L[3 * l], *sW = L[3 * l + 1], *b = L[3 * l + 2];
@@ -206,8 +210,18 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             m->d_iWt[l] = upload(iWt); m->d_b[l] = upload(bb); m->d_sWp[l] = upload(packed);
             ok = ok && m->d_iWt[l] && m->d_b[l] && m->d_sWp[l];
             if (ok && ffb_rnn_tc_supported(kind, S)) {
+                // the free quarter of a GRU layer's M=128 tiles carries the z-gate rows of the NEXT layer's projection
+                std::vector<float> zrows;
+                if (fuse_z && l + 1 < FFB_NLAYER) {
+                    const _Mat *iWn = L[3 * (l + 1)];
+                    if ((int)iWn->nr == S && (int)iWn->nc == G * S) {
+                        zrows.resize((size_t)S * S);
+                        for (int n = 0; n < S; n++)
+                            for (int k = 0; k < S; k++) zrows[(size_t)n * S + k] = mat_at(iWn, k, n);
+                    }
+                }
                 std::vector<uint16_t> img(ffb_rnn_tc_image_halfs(kind, S));
-                ffb_rnn_tc_pack(kind, S, sWd.data(), img.data());
+                ffb_rnn_tc_pack(kind, S, sWd.data(), img.data(), zrows.empty() ? nullptr : zrows.data());
                 ok = cudaMalloc(&m->d_sW_img[l], img.size() * 2) == cudaSuccess &&
                      cudaMemcpy(m->d_sW_img[l], img.data(), img.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
             }
@@ -546,6 +560,10 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     ffb_model *m = c->m;
     CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
     const int64_t N = b->n_reads;
+    if (N > 0x7fffffff) { set_err("ffb_upload: too many reads"); return FFB_ERR_ARG; }
+    for (int64_t n = 0; n < N; n++)
+        if (b->sig_off[n + 1] < b->sig_off[n]) { set_err("ffb_upload: sig_off must be non-decreasing (read %lld)", (long long)n); return FFB_ERR_ARG; }
+    if (b->sig_off[N] - b->sig_off[0] > ((int64_t)1 << 40)) { set_err("ffb_upload: batch too large"); return FFB_ERR_ARG; }
     c->n_reads = N; c->temperature = b->temperature; c->flags = b->flags;
     c->total_samples = b->sig_off[N] - b->sig_off[0];
 
@@ -582,6 +600,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
                             return FFB_ERR_UNSUPPORTED;
                         }
                         std::lock_guard<std::mutex> lk(m->mu);
+                        if (m->tail_cache.size() >= FFB_TAIL_CACHE_MAX) m->tail_cache.clear();   // bounded: a plan is cheap to rebuild
                         m->tail_cache[{i, (int)T}] = tl;
                     }
                     const int id = (int)tails[i].size();
@@ -598,6 +617,11 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     }
     c->blk_off = c->col_off[m->nconv];
     c->total_blocks = c->blk_off[N];
+    // kernels index blocks (and blocks * nparam / 16) with 32 bits
+    if (c->total_blocks > 0x7fffffff || c->col_off[0][N] > ((int64_t)1 << 40)) {
+        set_err("ffb_upload: %lld blocks in one batch exceed the 2^31 - 1 the kernels index", (long long)c->total_blocks);
+        return FFB_ERR_ARG;
+    }
     if (b->blk_off) memcpy(b->blk_off, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1));
     // tensor-core last convolution: its input planes use a SLOT layout -- read n's columns start at column
     // stride * blk_off[n], so that output block r (of the whole batch) is the window starting stride * r - padL columns
@@ -660,7 +684,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
         }
         const int64_t TR = ffb_gemm_tc_stream_tile_rows();
         const int64_t n_tiles = (Tt + TR - 1) / TR;
-        const int arrivals = 32;                       // gate warps per group and cluster: 8 CTAs x 4 quadrants
+        const int arrivals = 4 * ffb_rnn_tc_cluster_size(m->kind, m->S);   // gate warps per group and cluster: C CTAs x 4 quadrants
         for (int dir = 0; dir < 2; dir++) {
             work[dir].resize((size_t)n_tiles);
             std::vector<int32_t> ready((size_t)n_tiles, 0);
@@ -914,7 +938,10 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, m->device);
     const int free_sms = sm_count - c->tc_clusters * ffb_rnn_tc_cluster_size(m->kind, m->S);
-    const bool streamed = c->stream_gemm && tc_rnn && !timed && free_sms >= (G * S) / 128 && (G * S) / 128 <= 16;
+    // GRU: layer l's recurrence writes the first S columns (z gate) of layer l+1's Xin itself; the GEMM does the rest
+    const bool fuse_z = m->fuse_z && tc_rnn;
+    const int n0_next = fuse_z ? S : 0;
+    const bool streamed = c->stream_gemm && tc_rnn && !timed && free_sms >= (G * S - n0_next) / 128 && (G * S) / 128 <= 16;
     const size_t prog_stride = (size_t)c->n_groups + 1 + 16;   // per layer: group counters, finished-CTA counter, 16 ticket queues
     if (streamed) {
         if (cudaMemsetAsync(c->d_progress.p, 0, sizeof(int) * FFB_NLAYER * prog_stride, st) != cudaSuccess) return FFB_ERR_CUDA;
@@ -930,7 +957,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
                 // layer 0 gets its fp16 hi/lo planes from the convolution, later layers from the tensor recurrent kernel
                 if (l > 0 && !tc_rnn) LAUNCH(ffb_launch_split_f16(in, c->d_ahi.p, c->d_alo.p, Tt * m->layer_in[l], st));
                 LAUNCH(ffb_launch_gemm_tc(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l], m->d_iW_lo[l], m->d_b[l], xin, Tt,
-                                          G * S, m->layer_in[l], st));
+                                          G * S, m->layer_in[l], l > 0 ? n0_next : 0, st));
             }
         } else {
             LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], xin, Tt, G * S, m->layer_in[l], st));
@@ -942,13 +969,16 @@ static int forward_impl(ffb_ctx *c, bool timed) {
             float *out_f32 = (keep || (last && !tc_ff)) ? out : nullptr;
             int *prog = (streamed && !last) ? c->d_progress.as<int>() + (size_t)l * prog_stride : nullptr;
             RnnTcSched sched{c->d_slotoff.as<int32_t>(), c->d_slotlist.as<int32_t>(), c->tc_clusters, c->n_slots / 16};
+            // (unstreamed, xin_buf[0] == xin_buf[1]: in place -- the thread that writes column j of a row has read it already)
+            const bool fz = fuse_z && !last;
             LAUNCH(ffb_launch_rnn_tc(m->kind, S, xin, m->d_sW_img[l], out_f32, planes_out ? c->d_ahi.p : nullptr,
-                                     planes_out ? c->d_alo.p : nullptr, rb, sched, c->R_tc, (l % 2) == 0, c->d_ring.p, prog, st));
+                                     planes_out ? c->d_alo.p : nullptr, rb, sched, c->R_tc, (l % 2) == 0, c->d_ring.p, prog,
+                                     fz ? m->d_b[l + 1] : nullptr, fz ? xin_buf[(l + 1) & 1] : nullptr, st));
             if (streamed && !last) {
                 const int dir = (l % 2) == 0 ? 1 : 0;   // layer l runs backward for even l (networks.c:460-483)
                 LAUNCH(ffb_launch_gemm_tc_streamed(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l + 1], m->d_iW_lo[l + 1], m->d_b[l + 1],
                                                    xin_buf[(l + 1) & 1], Tt, G * S, S, c->d_work[dir].as<GemmWork>(), prog,
-                                                   prog + c->n_groups + 1, st));
+                                                   prog + c->n_groups + 1, n0_next, st));
             }
         } else {
             // the fp32 kernel ping-pongs between the two activation buffers
@@ -1010,7 +1040,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         LAUNCH(ffb_launch_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint64_t>(), c->d_path.as<int32_t>(),
                                   c->d_qpath.as<float>(), c->d_score.as<float>(), st));
         if (c->flags & FFB_FLAG_WANT_TRACE)
-            LAUNCH(ffb_launch_trace(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_trace.as<uint8_t>(), 1, st));
+            LAUNCH(ffb_launch_trace(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_trace.p, 1, 0, st));
     }
     if (timed) {
         cudaEventRecord(c->ev[4], st);
@@ -1278,16 +1308,24 @@ extern "C" const char *flappie_model_description(const enum model_type model) {
     exit(EXIT_FAILURE);
 }
 
-// model registry for calculate_transitions()
+// model registry for calculate_transitions().  The reference calls it from an OpenMP parallel-for (one read per call,
+// flappie.c:364-385), so the lock covers only the registry: every caller takes a context of its own out of a pool (one
+// stream + workspaces each), runs the read without the lock and puts the context back.
 static std::mutex g_reg_mu;
 static ffb_model *g_reg_model[RUNNIE_MODEL_INVALID + 1] = {nullptr};
-static ffb_ctx *g_reg_ctx[RUNNIE_MODEL_INVALID + 1] = {nullptr};
+static std::vector<ffb_ctx *> g_reg_pool[RUNNIE_MODEL_INVALID + 1];
+static uint64_t g_reg_gen[RUNNIE_MODEL_INVALID + 1] = {0};
 
 extern "C" int ffb_register_model(enum model_type which, ffb_model *m) {
     if ((int)which < 0 || (int)which >= RUNNIE_MODEL_INVALID || which == FLAPPIE_MODEL_INVALID) return FFB_ERR_ARG;
-    std::lock_guard<std::mutex> lk(g_reg_mu);
-    if (g_reg_ctx[which]) { ffb_destroy(g_reg_ctx[which]); g_reg_ctx[which] = nullptr; }
-    g_reg_model[which] = m;
+    std::vector<ffb_ctx *> old;
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        old.swap(g_reg_pool[which]);
+        g_reg_model[which] = m;
+        g_reg_gen[which]++;          // contexts still in use belong to the previous binding: destroyed when they come back
+    }
+    for (ffb_ctx *c : old) ffb_destroy(c);
     return FFB_OK;
 }
 
@@ -1297,12 +1335,30 @@ extern "C" flappie_matrix calculate_transitions(const raw_table signal, float te
         fprintf(stderr, "Invalid Flappie model  %s:%d\n", __FILE__, __LINE__);   // networks.c:98-104
         exit(EXIT_FAILURE);
     }
-    std::lock_guard<std::mutex> lk(g_reg_mu);
-    ffb_model *m = g_reg_model[model];
+    ffb_model *m = nullptr;
+    ffb_ctx *c = nullptr;
+    uint64_t gen = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        m = g_reg_model[model];
+        gen = g_reg_gen[model];
+        if (m && !g_reg_pool[model].empty()) { c = g_reg_pool[model].back(); g_reg_pool[model].pop_back(); }
+    }
     if (!m) { set_err("calculate_transitions: no weights registered for model %d (ffb_register_model)", (int)model); return nullptr; }
-    if (!g_reg_ctx[model]) g_reg_ctx[model] = ffb_create(m, nullptr);
-    ffb_ctx *c = g_reg_ctx[model];
+    if (!c) c = ffb_create(m, nullptr);
     if (!c) return nullptr;
+    // the context goes back to the pool on every path out of this function
+    struct Return {
+        ffb_ctx *c; int which; uint64_t gen;
+        ~Return() {
+            bool keep = false;
+            {
+                std::lock_guard<std::mutex> lk(g_reg_mu);
+                if (g_reg_gen[which] == gen) { g_reg_pool[which].push_back(c); keep = true; }
+            }
+            if (!keep) ffb_destroy(c);
+        }
+    } give_back{c, (int)model, gen};
     if (signal.end <= signal.start) return nullptr;
     const int64_t n = (int64_t)(signal.end - signal.start);
     const long T = ffb_model_nblock(m, n);
@@ -1321,23 +1377,30 @@ extern "C" flappie_matrix calculate_transitions(const raw_table signal, float te
     return out;
 }
 
-// standalone decode context (no model needed)
+// standalone decode contexts (no model needed): one per device, made on the device that is current at the first call
+// from it; each drop-in makes that device current again and holds the context's own lock while it uses the buffers
 struct DecodeCtx {
+    int device = 0;
     cudaStream_t st = nullptr;
+    std::mutex mu;
     DevBuf trans, tpost, fwd, tb, path, qpath, score, blkoff, trace;
 };
 static DecodeCtx *decode_ctx() {
-    static DecodeCtx *d = nullptr;
+    static std::map<int, DecodeCtx *> ctxs;
     static std::mutex mu;
+    if (ffb_device_count() < 1) { set_err("no CUDA device: the flappie_b200 decode entry points have no CPU fallback"); return nullptr; }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); set_err("cudaGetDevice failed"); return nullptr; }
     std::lock_guard<std::mutex> lk(mu);
-    if (!d) {
-        if (ffb_device_count() < 1) { set_err("no CUDA device: the flappie_b200 decode entry points have no CPU fallback"); return nullptr; }
-        d = new DecodeCtx();
-        if (cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking) != cudaSuccess) { delete d; d = nullptr; return nullptr; }
-    }
+    auto it = ctxs.find(dev);
+    if (it != ctxs.end()) return it->second;
+    DecodeCtx *d = new DecodeCtx();
+    d->device = dev;
+    if (cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete d; return nullptr; }
+    ctxs[dev] = d;
     return d;
 }
-static std::mutex g_dec_mu;
+#define DECODE_LOCK(d) std::lock_guard<std::mutex> lk((d)->mu); cudaSetDevice((d)->device)
 
 // _Mat [nr x nc] (padded columns) -> device dense [nc][nr]
 static int mat_to_device(const _Mat *mat, DevBuf &buf, cudaStream_t st) {
@@ -1354,7 +1417,7 @@ extern "C" float decode_crf_flipflop(const_flappie_matrix trans, bool combine_st
     if (nr != 40 && nr != 60) { set_err("decode_crf_flipflop: unsupported nr=%d", nr); return NAN; }
     DecodeCtx *d = decode_ctx();
     if (!d) return NAN;
-    std::lock_guard<std::mutex> lk(g_dec_mu);
+    DECODE_LOCK(d);
     int64_t off[2] = {0, T};
     bool ok = mat_to_device(trans, d->trans, d->st) == 0;
     ok = ok && d->tb.reserve(sizeof(uint64_t) * (size_t)T) == 0 && d->path.reserve(sizeof(int32_t) * (size_t)(T + 1)) == 0 &&
@@ -1384,7 +1447,7 @@ extern "C" flappie_matrix transpost_crf_flipflop(const_flappie_matrix trans, boo
     if (nr != 40 && nr != 60) { set_err("transpost_crf_flipflop: unsupported nr=%d", nr); return nullptr; }
     DecodeCtx *d = decode_ctx();
     if (!d) return nullptr;
-    std::lock_guard<std::mutex> lk(g_dec_mu);
+    DECODE_LOCK(d);
     const int nstate = 2 * (int)nbase_from_flipflop_nparam(nr);
     int64_t off[2] = {0, T};
     bool ok = mat_to_device(trans, d->trans, d->st) == 0;
@@ -1410,7 +1473,7 @@ extern "C" float decode_crf_runlength(const_flappie_matrix param, int *path) {
     if (nr != 40) { set_err("decode_crf_runlength: unsupported nr=%d", nr); return NAN; }
     DecodeCtx *d = decode_ctx();
     if (!d) return NAN;
-    std::lock_guard<std::mutex> lk(g_dec_mu);
+    DECODE_LOCK(d);
     int64_t off[2] = {0, T};
     bool ok = mat_to_device(param, d->trans, d->st) == 0;
     ok = ok && d->tb.reserve(sizeof(uint64_t) * (size_t)std::max<int64_t>(T, 1)) == 0 && d->path.reserve(sizeof(int32_t) * (size_t)(T + 1)) == 0 &&
@@ -1433,7 +1496,7 @@ extern "C" flappie_matrix transpost_crf_runlength(const_flappie_matrix param) {
     if (nr != 40) { set_err("transpost_crf_runlength: unsupported nr=%d", nr); return nullptr; }
     DecodeCtx *d = decode_ctx();
     if (!d) return nullptr;
-    std::lock_guard<std::mutex> lk(g_dec_mu);
+    DECODE_LOCK(d);
     int64_t off[2] = {0, T};
     bool ok = mat_to_device(param, d->trans, d->st) == 0;
     ok = ok && d->tpost.reserve(sizeof(float) * (size_t)(T * nr)) == 0 && d->fwd.reserve(2 * sizeof(float) * (size_t)((T + 1) * 8)) == 0 &&
@@ -1453,7 +1516,7 @@ extern "C" void exp_activation_inplace(flappie_matrix C) {
     if (!C) return;
     DecodeCtx *d = decode_ctx();
     if (!d) return;
-    std::lock_guard<std::mutex> lk(g_dec_mu);
+    DECODE_LOCK(d);
     const size_t n = C->stride * C->nc;   // the reference exponentiates the padding too (layers.c:58-63)
     if (d->trans.reserve(sizeof(float) * n) != 0) { set_err("exp_activation_inplace: device allocation failed"); return; }
     cudaMemcpyAsync(d->trans.p, C->data.f, sizeof(float) * n, cudaMemcpyHostToDevice, d->st);
@@ -1469,16 +1532,17 @@ extern "C" flappie_imatrix trace_from_posterior(flappie_matrix tpost) {
     if (nr != 40 && nr != 60) { set_err("trace_from_posterior: unsupported nr=%d", nr); return nullptr; }
     DecodeCtx *d = decode_ctx();
     if (!d) return nullptr;
-    std::lock_guard<std::mutex> lk(g_dec_mu);
+    DECODE_LOCK(d);
     const int nstate = 2 * (int)nbase_from_flipflop_nparam(nr);
     int64_t off[2] = {0, T};
-    bool ok = mat_to_device(tpost, d->trans, d->st) == 0 && d->trace.reserve((size_t)((T + 1) * nstate)) == 0 &&
+    bool ok = mat_to_device(tpost, d->trans, d->st) == 0 && d->trace.reserve(sizeof(int32_t) * (size_t)((T + 1) * nstate)) == 0 &&
               d->blkoff.reserve(sizeof(off)) == 0;
     if (!ok) { set_err("trace_from_posterior: device allocation / copy failed"); return nullptr; }
     cudaMemcpyAsync(d->blkoff.p, off, sizeof off, cudaMemcpyHostToDevice, d->st);
-    if (ffb_launch_trace(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->trace.as<uint8_t>(), 0, d->st) < 0) return nullptr;
-    std::vector<uint8_t> h((size_t)((T + 1) * nstate));
-    cudaMemcpyAsync(h.data(), d->trace.p, h.size(), cudaMemcpyDeviceToHost, d->st);
+    // int32 entries: the reference keeps round(255 * sum) as an int (decode.c:520-540), 256 included
+    if (ffb_launch_trace(d->trans.as<float>(), d->blkoff.as<int64_t>(), 1, nr, d->trace.p, 0, 1, d->st) < 0) return nullptr;
+    std::vector<int32_t> h((size_t)((T + 1) * nstate));
+    cudaMemcpyAsync(h.data(), d->trace.p, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost, d->st);
     if (cudaStreamSynchronize(d->st) != cudaSuccess) { set_err("trace_from_posterior: %s", cudaGetErrorString(cudaGetLastError())); return nullptr; }
     flappie_imatrix out = make_flappie_imatrix(nstate, (size_t)(T + 1));
     if (!out) return nullptr;

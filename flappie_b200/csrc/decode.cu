@@ -671,9 +671,11 @@ fb_combine_kernel(const float *__restrict__ trans, const int64_t *__restrict__ b
 }
 
 // trace (decode.c:499-543) from LOG posteriors: one thread per (read-local) trace row.
-template <int NBASE, bool IS_LOG>
+// OutT = uint8_t: the batched path (what fast5_interface.c:126-143 writes), saturating at 255; OutT = int32_t: the
+// trace_from_posterior drop-in, which keeps the reference's int (a posterior sum a shade above 1 rounds to 256 there).
+template <int NBASE, bool IS_LOG, typename OutT>
 __global__ void trace_kernel(const float *__restrict__ tpost, const int64_t *__restrict__ blk_off, int n_reads,
-                             uint8_t *__restrict__ trace) {
+                             OutT *__restrict__ trace) {
     constexpr int NSTATE = 2 * NBASE;
     constexpr int NR = NSTATE * (NBASE + 1);
     const int rd = blockIdx.y;
@@ -681,29 +683,34 @@ __global__ void trace_kernel(const float *__restrict__ tpost, const int64_t *__r
     const int T = (int)(blk_off[rd + 1] - b0);
     if (T <= 0) return;
     const float *tp = tpost + b0 * NR;
-    uint8_t *tr = trace + (b0 + rd) * NSTATE;
+    OutT *tr = trace + (b0 + rd) * NSTATE;
     auto ex = [](float v) { return IS_LOG ? expf(v) : v; };
+    auto quant = [](float sum) -> OutT {
+        const int v = (int)roundf(255.0f * sum);
+        if (sizeof(OutT) == 1) return (OutT)min(255, max(0, v));
+        return (OutT)v;
+    };
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row <= T; row += gridDim.x * blockDim.x) {
-        uint8_t *o = tr + (int64_t)row * NSTATE;
+        OutT *o = tr + (int64_t)row * NSTATE;
         if (row == 0) {
             // mass LEAVING each state in block 0 (decode.c:511-518)
             for (int from = 0; from < NSTATE; from++) {
                 float sum = 0.0f;
                 for (int to = 0; to < NBASE; to++) sum += ex(tp[to * NSTATE + from]);
                 sum += ex(tp[NBASE * NSTATE + from]);
-                o[from] = (uint8_t)(int)roundf(255.0f * sum);
+                o[from] = quant(sum);
             }
         } else {
             const float *pc = tp + (int64_t)(row - 1) * NR;
             for (int to = 0; to < NBASE; to++) {
                 float sum = ex(pc[to * NSTATE]);
                 for (int from = 1; from < NSTATE; from++) sum += ex(pc[to * NSTATE + from]);
-                o[to] = (uint8_t)(int)roundf(255.0f * sum);
+                o[to] = quant(sum);
             }
             const float *pf = pc + NBASE * NSTATE;
             for (int to = NBASE; to < NSTATE; to++) {
                 const float sum = ex(pf[to - NBASE]) + ex(pf[to]);
-                o[to] = (uint8_t)(int)roundf(255.0f * sum);
+                o[to] = quant(sum);
             }
         }
     }
@@ -783,9 +790,8 @@ int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads
     return FFB_OKL(2);
 }
 
-int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, uint8_t *trace,
-                     int is_log, cudaStream_t st) {
-    if (n_reads <= 0) return 0;
+template <typename OutT>
+static int launch_trace_t(const float *tpost, const int64_t *blk_off, int n_reads, int nr, OutT *trace, int is_log, cudaStream_t st) {
     int launches = 0;
     for (int r0 = 0; r0 < n_reads; r0 += 65535) {
         const int nrd = (n_reads - r0) < 65535 ? (n_reads - r0) : 65535;
@@ -793,15 +799,23 @@ int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, in
         // blk_off is absolute, so shifting the pointer keeps per-read addressing intact except
         // for the "+ rd" row padding of the trace, handled by passing the shifted trace base.
         const int nb = nbase_of(nr);
-        uint8_t *tb = trace + (int64_t)r0 * 2 * nb;
-        if (nb == 4 && is_log) ffb::trace_kernel<4, true><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
-        else if (nb == 4) ffb::trace_kernel<4, false><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
-        else if (nb == 5 && is_log) ffb::trace_kernel<5, true><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
-        else if (nb == 5) ffb::trace_kernel<5, false><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        OutT *tb = trace + (int64_t)r0 * 2 * nb;
+        if (nb == 4 && is_log) ffb::trace_kernel<4, true, OutT><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        else if (nb == 4) ffb::trace_kernel<4, false, OutT><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        else if (nb == 5 && is_log) ffb::trace_kernel<5, true, OutT><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
+        else if (nb == 5) ffb::trace_kernel<5, false, OutT><<<grid, 128, 0, st>>>(tpost, blk_off + r0, nrd, tb);
         else return -1;
         launches++;
     }
     return FFB_OKL(launches);
+}
+
+// wide = 0: one saturating byte per entry (batched path); wide = 1: int32 per entry, the reference's own values
+int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, void *trace, int is_log, int wide,
+                     cudaStream_t st) {
+    if (n_reads <= 0) return 0;
+    return wide ? launch_trace_t(tpost, blk_off, n_reads, nr, (int32_t *)trace, is_log, st)
+                : launch_trace_t(tpost, blk_off, n_reads, nr, (uint8_t *)trace, is_log, st);
 }
 
 int ffb_launch_exp_inplace(float *x, int64_t n, cudaStream_t st) {

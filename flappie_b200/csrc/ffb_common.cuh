@@ -113,8 +113,9 @@ struct GemmWork {
 // gemm_tc.cu: tcgen05 path.  Planes are fp16 [rows][K]; W planes keep the reference's [out][in] order.
 int ffb_gemm_tc_supported(int N, int K);
 int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st);
+// n0: first column computed (0 = all of C[M][N]); n0 > 0 needs the W-stationary kernels (N % 128 == n0 % 128 == 0, K <= 384)
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                       int64_t M, int N, int K, cudaStream_t st);
+                       int64_t M, int N, int K, int n0, cudaStream_t st);
 // Output layer on the same kernel family: trans[M][n_out] = tanh(A*W^T + b) / scale; W planes [FFB_FF_TC_ROWS][K] and
 // bias [FFB_FF_TC_ROWS] are zero-padded beyond n_out (n_out = 40 / 60)
 #define FFB_FF_TC_ROWS 64
@@ -133,7 +134,7 @@ int ffb_gemm_tc_stream_supported(int N, int K);
 int ffb_gemm_tc_stream_tile_rows(void);   // rows (blocks) per streamed tile
 // progress: counters published by the recurrent kernel; queue: N/128 zeroed ticket counters (one per weight panel)
 int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                                int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue,
+                                int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue, int n0,
                                 cudaStream_t st);
 
 // rnn.cu: one recurrent layer over a ragged batch.
@@ -155,7 +156,10 @@ int ffb_rnn_prepare(int kind, int S);   // one-time function attribute setup; re
 // rnn_tc.cu: tcgen05 recurrent layer (GRU / LSTM, S=256 at present); R = reads per cluster, multiple of 16
 int ffb_rnn_tc_supported(int kind, int S);
 size_t ffb_rnn_tc_image_halfs(int kind, int S);
-void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img);
+// fused_z: NULL, or [S][S] rows of the NEXT layer's input projection (GRU: its z gate) that ride in the free quarter of the
+// M=128 tile; the kernel then also writes that layer's Xin[.][0..S) (ffb_launch_rnn_tc: bnext / xnext)
+void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img, const float *fused_z);
+int ffb_rnn_tc_can_fuse_z(int kind, int S);
 int ffb_rnn_tc_prepare(int kind, int S);
 int ffb_rnn_tc_max_clusters(int kind, int S, int R);
 int ffb_rnn_tc_rmax(int kind, int S);
@@ -174,7 +178,7 @@ struct RnnTcSched {
 // progress[n_groups] counts CTAs that have finished the layer
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
                       const RnnBatch &rb, const RnnTcSched &sched, int R, int backward, void *ring, int *progress,
-                      cudaStream_t st);
+                      const float *bnext, float *xnext, cudaStream_t st);
 
 // signal.cu: trimming + normalisation of raw reads on the device (reference src/flappie.c:251-259)
 #define FFB_MAX_VARSEG_CHUNK 1024
@@ -202,6 +206,6 @@ int ffb_launch_viterbi(const float *trans, const int64_t *blk_off, int n_reads, 
 // fwd_scratch: 2 * (total_blocks + n_reads) * nstate floats
 int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads, int nr, float *fwd_scratch,
                          float *tpost, int64_t total_blocks, cudaStream_t st);
-int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, uint8_t *trace, int is_log,
+int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, void *trace, int is_log, int wide,
                      cudaStream_t st);
 int ffb_launch_exp_inplace(float *x, int64_t n, cudaStream_t st);

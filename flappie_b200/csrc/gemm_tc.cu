@@ -383,7 +383,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __half *__restrict__ Whi, const __half *__restrict__ Wlo, const float *__restrict__ bias,
                float *__restrict__ C, int64_t M, int N, int K, const GemmWork *__restrict__ work,
-               const int *progress, int *queue) {
+               const int *progress, int *queue, int n0, int ldc) {
+    // N = columns computed by this launch: features [n0, n0 + N) of a C whose rows are ldc floats long (the GRU recurrence
+    // computes the first S columns of the next layer's projection itself, rnn_tc.cu)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
     __shared__ uint64_t full_hi[Cfg::HI_SLOTS], empty_hi[Cfg::HI_SLOTS], full_lo[Cfg::LO_SLOTS], empty_lo[Cfg::LO_SLOTS];
@@ -415,7 +417,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     if (warp >= 2 && warp < 6) {
         // panel -> tensor memory: this thread owns lane 32*quad + lane = feature row of the panel
         const int quad = warp & 3;
-        const size_t row = (size_t)panel * Cfg::BF + quad * 32 + lane;
+        const size_t row = (size_t)n0 + (size_t)panel * Cfg::BF + quad * 32 + lane;
 #pragma unroll 1
         for (int plane = 0; plane < 2; plane++) {
             const uint4 *src = reinterpret_cast<const uint4 *>((plane ? Wlo : Whi) + row * K);
@@ -560,7 +562,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4; thread = feature =====
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int f = quad * 32 + lane;                     // feature within the panel
-        const float b = bias[panel * Cfg::BF + f];
+        const float b = bias[n0 + panel * Cfg::BF + f];
         int acc = 0; uint32_t acc_phase = 0;
         for (int tc = 0;; tc++) {
             mbar_wait(&tile_bar[tc & 15], (uint32_t)(tc >> 4) & 1u);
@@ -577,7 +579,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             const int c0 = half * (Cfg::BB / 2);
             const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + Cfg::ACC_COL0 + acc * Cfg::BB + c0;
             const int64_t m0 = tile * Cfg::BB + c0;
-            float *crow = C + m0 * (int64_t)N + panel * Cfg::BF + f;
+            float *crow = C + m0 * (int64_t)ldc + n0 + panel * Cfg::BF + f;
             const int nrow = (int)((M - m0 < Cfg::BB / 2) ? (M - m0) : Cfg::BB / 2);   // rows of this half inside the matrix (may be <= 0)
 #pragma unroll
             for (int c = 0; c < Cfg::BB / 2; c += 32) {
@@ -587,14 +589,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 tmem_ld_wait();
                 if (c + 32 <= nrow) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + j) * N, v[j] + b);
+                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + j) * ldc, v[j] + b);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + 16 + j) * N, w[j] + b);
+                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + 16 + j) * ldc, w[j] + b);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) if (c + j < nrow) __stcs(crow + (int64_t)(c + j) * N, v[j] + b);
+                    for (int j = 0; j < 16; j++) if (c + j < nrow) __stcs(crow + (int64_t)(c + j) * ldc, v[j] + b);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) if (c + 16 + j < nrow) __stcs(crow + (int64_t)(c + 16 + j) * N, w[j] + b);
+                    for (int j = 0; j < 16; j++) if (c + 16 + j < nrow) __stcs(crow + (int64_t)(c + 16 + j) * ldc, w[j] + b);
                 }
             }
             tcgen05_fence_before();
@@ -684,7 +686,9 @@ static int launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, con
 template <class Cfg = ffb::GemmWsCfg>
 static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                           int64_t M, int N, int K, cudaStream_t st, const GemmWork *work = nullptr,
-                          const int *progress = nullptr, int *queue = nullptr) {
+                          const int *progress = nullptr, int *queue = nullptr, int n0 = 0, int ldc = 0) {
+    if (ldc == 0) ldc = N;
+    if (n0 % Cfg::BF || n0 + N > ldc) return -1;
     CUtensorMap mAh, mAl;
     if (!make_map_f16(&mAh, Ahi, (uint64_t)M, (uint64_t)K, Cfg::BB) || !make_map_f16(&mAl, Alo, (uint64_t)M, (uint64_t)K, Cfg::BB)) return -1;
     static bool attr_done[64] = {false};      // per device ordinal
@@ -717,7 +721,7 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
     cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::gemm_ws_kernel<Cfg>, mAh, mAl, (const __half *)Whi, (const __half *)Wlo, bias, C, M, N,
-                                       K, work, progress, queue);
+                                       K, work, progress, queue, n0, ldc);
     return e == cudaSuccess ? 1 : -1;
 }
 
@@ -736,22 +740,24 @@ int ffb_gemm_tc_stream_tile_rows(void) { return ffb::GemmWsCfg::BB; }
 int ffb_gemm_tc_stream_supported(int N, int K) { return ffb_gemm_tc_supported(N, K) && N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX; }
 
 int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                                int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue,
+                                int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue, int n0,
                                 cudaStream_t st) {
     if (M <= 0) return 0;
-    if (!ffb_gemm_tc_stream_supported(N, K) || !work || !progress || !queue) return -1;
-    return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st, work, progress, queue);
+    if (!ffb_gemm_tc_stream_supported(N, K) || !work || !progress || !queue || n0 < 0 || n0 >= N) return -1;
+    return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N - n0, K, st, work, progress, queue, n0, N);
 }
 
 // A planes [M][K] fp16, W planes [N][K] fp16 (the reference's own [out][in] orientation)
+// n0 > 0: only columns [n0, N) are computed (W-stationary kernels only: N % 128 == 0, n0 % 128 == 0, K <= 384)
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                       int64_t M, int N, int K, cudaStream_t st) {
+                       int64_t M, int N, int K, int n0, cudaStream_t st) {
     if (M <= 0) return 0;
-    if (!ffb_gemm_tc_supported(N, K)) return -1;
-    if (N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX && getenv("FFB_GEMM_V1") == nullptr)
-        return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
-    if (N % 128 == 0 && K <= ffb::GemmWsCfg384::KMAX && getenv("FFB_GEMM_V1") == nullptr)
-        return launch_gemm_ws<ffb::GemmWsCfg384>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
+    if (!ffb_gemm_tc_supported(N, K) || n0 < 0 || n0 >= N) return -1;
+    if (N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX && (n0 > 0 || getenv("FFB_GEMM_V1") == nullptr))
+        return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N - n0, K, st, nullptr, nullptr, nullptr, n0, N);
+    if (N % 128 == 0 && K <= ffb::GemmWsCfg384::KMAX && (n0 > 0 || getenv("FFB_GEMM_V1") == nullptr))
+        return launch_gemm_ws<ffb::GemmWsCfg384>(Ahi, Alo, Whi, Wlo, bias, C, M, N - n0, K, st, nullptr, nullptr, nullptr, n0, N);
+    if (n0 > 0) return -1;
     if (N % 256 == 0) return launch_gemm_tc<256>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 128 == 0) return launch_gemm_tc<128>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     return launch_gemm_tc<64>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);

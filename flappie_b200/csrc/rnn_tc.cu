@@ -149,8 +149,13 @@ __global__ void __launch_bounds__(Cfg::MAX_THREADS, 1)
 rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, float *__restrict__ Hout,
               __half *__restrict__ Hhi, __half *__restrict__ Hlo, const int32_t *__restrict__ order,
               const int64_t *__restrict__ blk_off, const int32_t *__restrict__ slot_off, const int32_t *__restrict__ slot_list,
-              uint8_t *__restrict__ ring, int *__restrict__ progress, int G, int n_groups, int backward) {
+              uint8_t *__restrict__ ring, int *__restrict__ progress, int G, int n_groups, int backward,
+              const float *__restrict__ bnext, float *__restrict__ xnext) {
     constexpr int S = Cfg::S, C = Cfg::C, NGATE = Cfg::NGATE, NG = Cfg::NG, GMAX = Cfg::GMAX;
+    // GRU only: the fourth gate slot of the weight image (rows 24..31 of every TMEM quadrant, zero otherwise) carries the
+    // z-gate rows of the NEXT layer's input projection.  They ride in the same M=128 MMAs for free: at step s the slot
+    // holds iW_z * h_{s-1}, i.e. the next layer's Xin[.][0..S) of the previous time index (see the header comment).
+    const bool fuse = (NGATE == 3) && xnext != nullptr;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
     __shared__ uint32_t tmem_slot;
@@ -239,20 +244,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             uint8_t *ring_g = ring + ((((size_t)cluster_id * 2) * G + g) * C + crank) * Cfg::SLICE;   // parity 0
             const size_t ring_par = (size_t)G * C * Cfg::SLICE;
             PROF_DECL;
-            for (int sl = sl0; sl < sl1; sl++) {
-            // slots are sorted by length (descending): the group's first read is its longest
-            const int rd0 = order[slot_list[sl] * NG];
-            const int Tmax = rd0 >= 0 ? (int)(blk_off[rd0 + 1] - blk_off[rd0]) : 0;
-            for (int s = 0; s < Tmax; s++, gs++) {
-                const uint32_t ph = gs & 1u;
-                if (s > 0) mbar_wait(&h_full[g], ph ^ 1u);           // h_{s-1} complete in B
-                PROF(0);
-                mbar_arrive_expect_tx(&h_full[g], C * Cfg::SLICE);    // arm phase s: peers push h_s only after my MMA(s)
-                if (s == 0) {
-                    // h_{-1} = 0: nothing to multiply (and B still holds the previous group's last state) -- the gate
-                    // warps take a = 0 for this step
-                    mbar_arrive(&acc_full[g]);
-                } else {
+            uint32_t ga = 0;        // acc_full completions so far (one per step, plus one per group when the z rows are fused)
+            auto issue_mmas = [&]() {
                 tcgen05_fence_after();
                 // 3*S/16 MMAs into THREE accumulators -- for accuracy, not speed: N=16 MMAs with uniform-register
                 // operands issue at ~9 clk whichever accumulator they target (profiles/r01_mma_indep_microbench.txt).
@@ -286,13 +279,29 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 }
                 }
                 umma_commit(&acc_full[g]);
+            };
+            for (int sl = sl0; sl < sl1; sl++) {
+            // slots are sorted by length (descending): the group's first read is its longest
+            const int rd0 = order[slot_list[sl] * NG];
+            const int Tmax = rd0 >= 0 ? (int)(blk_off[rd0 + 1] - blk_off[rd0]) : 0;
+            for (int s = 0; s < Tmax; s++, gs++, ga += (NGATE == 3)) {
+                const uint32_t ph = gs & 1u;
+                if (s > 0) mbar_wait(&h_full[g], ph ^ 1u);           // h_{s-1} complete in B
+                PROF(0);
+                mbar_arrive_expect_tx(&h_full[g], C * Cfg::SLICE);    // arm phase s: peers push h_s only after my MMA(s)
+                if (s == 0) {
+                    // h_{-1} = 0: nothing to multiply (and B still holds the previous group's last state) -- the gate
+                    // warps take a = 0 for this step
+                    mbar_arrive(&acc_full[g]);
+                } else {
+                    issue_mmas();
                 }
                 PROF(1);
-                mbar_wait(&acc_full[g], ph);
+                mbar_wait(&acc_full[g], (NGATE == 3 ? ga : gs) & 1u);
                 PROF(2);
                 // the MMAs have retired: this CTA no longer reads h_{s-1}
                 for (uint32_t d = 0; d < (uint32_t)C; d++) mbar_arrive_remote_cta(&h_empty[g], d);
-                mbar_wait(&staged[g], ph);                            // the gate warps staged my slice of h_s
+                mbar_wait(&staged[g], (NGATE == 3 ? ga : gs) & 1u);                       // the gate warps staged my slice of h_s
                 PROF(3);
                 uint8_t *rg = ring_g + (size_t)ph * ring_par;
                 bulk_store_global(rg, stg, Cfg::SLICE);
@@ -307,6 +316,16 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             // drain: the group's last copies still target this CTA; they must have landed before h_full is re-armed for
             // the next group and before anybody exits
             if (Tmax > 0) mbar_wait(&h_full[g], (gs - 1u) & 1u);
+            if (fuse && Tmax > 0) {
+                // one more round of MMAs on the group's LAST state: the next layer's z rows of the last time index.  It
+                // has retired (acc_full) before this thread tells any peer that the operand may be overwritten.
+                // `staged`: all four gate warps have read it out of tensor memory -- only then may acc_full move on (a warp
+                // still waiting for this phase would miss it once the next group's first step completes the following one).
+                issue_mmas();
+                mbar_wait(&acc_full[g], (NGATE == 3 ? ga : gs) & 1u);
+                mbar_wait(&staged[g], (NGATE == 3 ? ga : gs) & 1u);
+                ga++;
+            }
             }
             PROF_FLUSH(0, 7);
         }
@@ -336,6 +355,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #ifdef FFB_RNN_PROFILE
         unsigned long long pt_ = clock64(), pa_[12] = {0}; const bool prof_ = (blockIdx.x == 0 && warp == 0 && lane == 0);
 #endif
+        uint32_t ga = 0;            // acc_full phases seen so far (steps + fused drain rounds)
+        const float bz = fuse ? bnext[j] : 0.0f;
+        float *const xz = fuse ? xnext + j : nullptr;       // next layer's Xin: z-gate column of hidden unit j
         for (int sl = sl0; sl < sl1; sl++) {
         const int grp = slot_list[sl];                      // this round's group of 16 reads
         int cT[4];
@@ -368,8 +390,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             cl_T = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
             cl_row = (rd >= 0 ? (int32_t)blk_off[rd] : 0) + ((backward && cl_T > 0) ? cl_T - 1 : 0);
         }
-        for (int s = 0; s < Tmax; s++, gs++) {
-            const uint32_t ph = gs & 1u;
+        for (int s = 0; s < Tmax; s++, gs++, ga += (NGATE == 3)) {
             const bool all = s < Tmin;          // warp-uniform
             // ---- prefetch this step's input projection ----
             float x[4][NGATE];
@@ -385,7 +406,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (s < cT[i]) ? __ldcs(xp[i] + gt * S) : 0.0f;
             }
             PROF(8);
-            mbar_wait(&acc_full[g], ph);
+            mbar_wait(&acc_full[g], (NGATE == 3 ? ga : gs) & 1u);
             PROF(9);
             tcgen05_fence_after();
             // ---- TMEM -> registers: a[i][gate], three partial accumulators added round-to-nearest ----
@@ -470,10 +491,17 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             PROF(11);
             // ---- layer output (not on the step's critical path) ----
             if (cl_dst && s < cl_T) *reinterpret_cast<uint4 *>(cl_dst + (int64_t)cl_row * S) = *cl_src;
+            __syncwarp();       // the staging tile has been read (by other lanes than those that rewrite it next step)
             if (Hout) {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (all || s < cT[i]) __stcs(Hout + (int64_t)orow[i] * S + j, hprev[i]);
+            }
+            if (fuse && s > 0) {
+                // gate slot 3 = iW_z(next layer) * h_{s-1}: the next layer's z pre-activation of the PREVIOUS time index
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (all || s <= cT[i]) __stcs(xz + (int64_t)(orow[i] - rstep) * XROW, a[i][3] + bz);
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) { xp[i] += xstep; orow[i] += rstep; }
@@ -484,6 +512,30 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 __syncwarp();
                 if (lane == 0) atomicAdd(progress + grp, 1);
             }
+        }
+        if (fuse && Tmax > 0) {
+            // fused drain round: the z rows of the group's last time index (only reads that ran all Tmax steps still owe it)
+            mbar_wait(&acc_full[g], (NGATE == 3 ? ga : gs) & 1u);
+            ga++;
+            tcgen05_fence_after();
+            float v0[8], v1[8], a3[4];
+            tmem_ld_16x256b_x2(t_hi, v0);
+            tmem_ld_16x256b_x2(t_hi + NG, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; i++) a3[i] = v0[(i >> 1) * 4 + (i & 1) + 2] + v1[(i >> 1) * 4 + (i & 1) + 2];
+            if constexpr (Cfg::NACC == 3) {
+                tmem_ld_16x256b_x2(t_hi + 2 * NG, v0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; i++) a3[i] += v0[(i >> 1) * 4 + (i & 1) + 2];
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&staged[g]);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (cT[i] == Tmax) __stcs(xz + (int64_t)(orow[i] - rstep) * XROW, a3[i] + bz);
         }
         }
         PROF_FLUSH(8, 12);
@@ -544,20 +596,21 @@ size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R) {
 }
 
 // sW [G*S][S] (row per output) -> per-CTA tensor-memory images (fp16 bit patterns):
-// [cta][plane hi/lo][row = 32*quad + 8*gate + e][S halfs]; GRU rows with gate 3 are zero
+// [cta][plane hi/lo][row = 32*quad + 8*gate + e][S halfs]; GRU rows with gate 3 are zero, or -- fused_z [S][S] given --
+// row jj of the next layer's input projection (its z gate), computed for free by the same MMAs
 template <class Cfg>
-static void pack_image(const float *sW, uint16_t *img) {
+static void pack_image(const float *sW, uint16_t *img, const float *fused_z) {
     constexpr int S = Cfg::S;
     const size_t plane_halfs = Cfg::A_PLANE / 2;
     for (size_t i = 0; i < (size_t)Cfg::C * 2 * plane_halfs; i++) img[i] = 0;
     for (int c = 0; c < Cfg::C; c++) {
         uint16_t *hi = img + (size_t)c * 2 * plane_halfs, *lo = hi + plane_halfs;
         for (int q = 0; q < Cfg::NQ; q++)
-            for (int g = 0; g < Cfg::NGATE; g++)
+            for (int g = 0; g < (Cfg::NGATE == 3 && fused_z ? 4 : Cfg::NGATE); g++)
                 for (int e = 0; e < 8; e++) {
                     const int jj = c * Cfg::HS + q * 8 + e, row = 32 * q + 8 * g + e;
                     for (int k = 0; k < S; k++) {
-                        const float w = sW[(size_t)(g * S + jj) * S + k];
+                        const float w = g < Cfg::NGATE ? sW[(size_t)(g * S + jj) * S + k] : fused_z[(size_t)jj * S + k];
                         const __half h = __float2half_rn(w);
                         const __half l = __float2half_rn(w - __half2float(h));
                         hi[(size_t)row * S + k] = __half_as_ushort(h);
@@ -566,9 +619,11 @@ static void pack_image(const float *sW, uint16_t *img) {
                 }
     }
 }
-void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img) {
-    tc_dispatch(kind, S, [&](auto cfg) { pack_image<decltype(cfg)>(sW, img); return 0; });
+void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img, const float *fused_z) {
+    tc_dispatch(kind, S, [&](auto cfg) { pack_image<decltype(cfg)>(sW, img, fused_z); return 0; });
 }
+// GRU: a quarter of every CTA's M=128 rows is free -- room for S rows of the next layer's input projection
+int ffb_rnn_tc_can_fuse_z(int kind, int S) { return kind == 0 && ffb_rnn_tc_supported(kind, S); }
 
 template <class Cfg>
 static int prepare_one() {
@@ -609,7 +664,8 @@ int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
 
 template <class Cfg>
 static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo, const RnnBatch &rb,
-                      const RnnTcSched &sched, int R, int backward, void *ring, int *progress, cudaStream_t st) {
+                      const RnnTcSched &sched, int R, int backward, void *ring, int *progress, const float *bnext, float *xnext,
+                      cudaStream_t st) {
     const int G = R / Cfg::NG;
     if (G < 1 || G > Cfg::GMAX || R % Cfg::NG || !ring || !sched.slot_off || !sched.slot_list) return -1;
     const int n_clusters = sched.n_clusters;
@@ -618,12 +674,14 @@ static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi
     rnn_tc_config<Cfg>(cfg, attr, n_clusters, G, st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::rnn_tc_kernel<Cfg>, Xin, (const __half *)Wimg, Hout, (__half *)Hhi,
                                        (__half *)Hlo, rb.order, rb.blk_off, sched.slot_off, sched.slot_list, (uint8_t *)ring, progress,
-                                       G, sched.n_groups, backward);
+                                       G, sched.n_groups, backward, bnext, xnext);
     return e == cudaSuccess ? 1 : -1;
 }
 
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
-                      const RnnBatch &rb, const RnnTcSched &sched, int R, int backward, void *ring, int *progress, cudaStream_t st) {
+                      const RnnBatch &rb, const RnnTcSched &sched, int R, int backward, void *ring, int *progress,
+                      const float *bnext, float *xnext, cudaStream_t st) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, sched, R, backward, ring, progress, st); });
+    if (xnext && (!bnext || !ffb_rnn_tc_can_fuse_z(kind, S))) return -1;
+    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, sched, R, backward, ring, progress, bnext, xnext, st); });
 }

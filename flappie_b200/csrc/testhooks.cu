@@ -9,7 +9,7 @@
 int ffb_launch_umma_probe(const void *A, const void *B, float *D, int N, int K, int a_in_tmem, cudaStream_t st);
 int ffb_launch_split_f16(const float *x, void *hi, void *lo, int64_t n, cudaStream_t st);
 int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
-                       int64_t M, int N, int K, cudaStream_t st);
+                       int64_t M, int N, int K, int n0, cudaStream_t st);
 
 #define TRY(x) do { if ((x) != cudaSuccess) { fprintf(stderr, "testhook: %s failed: %s\n", #x, cudaGetErrorString(cudaGetLastError())); return -1; } } while (0)
 
@@ -52,7 +52,7 @@ extern "C" int ffb_test_gemm(const float *A, const float *W, const float *bias, 
         for (int rep = 0; rep < 2; rep++) {   // second pass is the timed one
             cudaEventRecord(e0, 0);
             if (ffb_launch_split_f16(dA, ah, al, M * K, 0) < 0) return -2;
-            rc = ffb_launch_gemm_tc(ah, al, wh, wl, db, dC, M, N, K, 0);
+            rc = ffb_launch_gemm_tc(ah, al, wh, wl, db, dC, M, N, K, 0, 0);
             cudaEventRecord(e1, 0);
             if (rc < 0) return -3;
         }
