@@ -30,6 +30,7 @@ FLAG_WANT_TRANS = 4
 FLAG_KEEP_LAYERS = 8
 FLAG_FP32_SIMT = 16
 FLAG_FP32_CONV = 32
+FLAG_REVERSE = 64
 
 # enum model_type, reference src/networks.h:18-26
 MODEL_ENUM = {"r941_native": 0, "r941_rna002": 1, "r941_5mC": 2, "r103_native": 3, "r10C_pcr": 0, "rle_r941_native": 5}
@@ -46,7 +47,8 @@ EXPORTS = [
     "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_emit_bases",
     "ffb_upload_raw", "ffb_basecall_raw_batch", "ffb_submit_batch", "ffb_submit_raw_batch", "ffb_collect",
     "ffb_alloc_pinned", "ffb_free_pinned",
-    "decode_crf_runlength", "transpost_crf_runlength", "ffb_emit_runs", "ffb_plan_schedule",
+    "decode_crf_runlength", "transpost_crf_runlength", "ffb_emit_runs", "ffb_plan_schedule", "ffb_phred_table",
+    "change_positions", "nbase_from_crf_runlength_nparam", "array_from_flappie_imatrix", "ffb_model_load",
 ]
 
 
@@ -72,6 +74,7 @@ class Batch(ctypes.Structure):
         ("blk_off", POINTER(c_int64)), ("path", POINTER(c_int32)), ("qpath", POINTER(c_float)),
         ("score", POINTER(c_float)), ("trans", POINTER(c_float)), ("tpost", POINTER(c_float)),
         ("trace", POINTER(c_uint8)), ("rle_params", POINTER(c_float)),
+        ("bases", POINTER(ctypes.c_char)), ("quals", POINTER(ctypes.c_char)), ("nbases", POINTER(c_int32)),
     ]
 
 
@@ -142,6 +145,8 @@ class Library:
         L.ffb_launch_count.restype = c_int64; L.ffb_launch_count.argtypes = [c_void_p]
         L.ffb_forward_timed.restype = c_int; L.ffb_forward_timed.argtypes = [c_void_p, POINTER(c_float)]
         L.ffb_debug_fetch.restype = c_int64; L.ffb_debug_fetch.argtypes = [c_void_p, c_int, c_void_p, c_int64]
+        L.ffb_phred_table.restype = c_int
+        L.ffb_phred_table.argtypes = [POINTER(c_float), c_int]
         L.ffb_emit_bases.restype = c_int
         L.ffb_emit_bases.argtypes = [POINTER(c_int32), POINTER(c_float), c_int64, c_int, c_bool, c_char_p, c_char_p]
 
@@ -270,6 +275,12 @@ class Library:
             raise FlappieB200Error("ffb_emit_runs: bad arguments")
         return bases.raw[:n].decode(), shape[:n], scale[:n], dwell[:n]
 
+    def phred_table(self) -> np.ndarray:
+        """qpath thresholds of the quality characters (ascending): char = 33 + #{thresholds <= qpath}"""
+        out = np.zeros(128, np.float32)
+        n = self.lib.ffb_phred_table(out.ctypes.data_as(POINTER(c_float)), 128)
+        return out[:n]
+
     def emit_bases(self, path: np.ndarray, qpath: np.ndarray, nbase: int, reverse: bool = False):
         path = np.ascontiguousarray(path, np.int32)
         qpath = np.ascontiguousarray(qpath, np.float32)
@@ -319,6 +330,13 @@ class BatchResult:
         self.n_reads, self.blk_off, self.path, self.qpath, self.score = n_reads, blk_off, path, qpath, score
         self.trans, self.tpost, self.trace, self.nstate, self.nparam = trans, tpost, trace, nstate, nparam
         self.rle_params = None
+        self.bases = self.quals = self.nbases = None
+
+    def read_bases(self, i: int):
+        """(basecall, quality) strings of read i as emitted on the device"""
+        s = int(self.blk_off[i]) + i
+        k = int(self.nbases[i])
+        return self.bases[s:s + k].tobytes().decode("ascii"), self.quals[s:s + k].tobytes().decode("ascii")
 
     def nblock(self, i: int) -> int:
         return int(self.blk_off[i + 1] - self.blk_off[i])
@@ -364,7 +382,7 @@ class Context:
             raise FlappieB200Error(f"{what} failed ({r}): {self.lib.last_error()}")
 
     def make_batch(self, signal: np.ndarray, sig_off: np.ndarray, temperature=1.0, flags=0,
-                   out: Optional[dict] = None):
+                   out: Optional[dict] = None, emit: bool = False):
         """Build the C `ffb_batch` over caller-owned numpy (or pinned torch->numpy) buffers."""
         fm = self.model.fm
         n = sig_off.shape[0] - 1
@@ -386,6 +404,11 @@ class Context:
             o.setdefault("trace", np.zeros((tot_blocks + n, fm.nstate), np.uint8))
         if getattr(fm, "head", "flipflop") == "runlength":
             o.setdefault("rle_params", np.zeros((tot_blocks, 8), np.float32))
+        if emit:
+            # device-side emission (emit.cu): chars per read at blk_off[n] + n, like path
+            o.setdefault("bases", np.zeros(tot_blocks + n, np.uint8))
+            o.setdefault("quals", np.zeros(tot_blocks + n, np.uint8))
+            o.setdefault("nbases", np.zeros(max(n, 1), np.int32))
 
         def p(name, ct):
             a = o.get(name)
@@ -393,13 +416,14 @@ class Context:
 
         b = Batch(signal.ctypes.data_as(POINTER(c_float)), sig_off.ctypes.data_as(POINTER(c_int64)), n,
                   temperature, flags, p("blk_off", c_int64), p("path", c_int32), p("qpath", c_float),
-                  p("score", c_float), p("trans", c_float), p("tpost", c_float), p("trace", c_uint8), p("rle_params", c_float))
+                  p("score", c_float), p("trans", c_float), p("tpost", c_float), p("trace", c_uint8), p("rle_params", c_float),
+                  p("bases", ctypes.c_char), p("quals", ctypes.c_char), p("nbases", c_int32))
         self._keep = (signal, sig_off, o)
         return b, o
 
     def basecall(self, reads: Sequence[np.ndarray], temperature: float = 1.0, viterbi_only: bool = False,
                  want_trace: bool = False, want_trans: bool = False, keep_layers: bool = False,
-                 fp32_simt: bool = False) -> BatchResult:
+                 fp32_simt: bool = False, emit: bool = False, reverse: bool = False) -> BatchResult:
         """Whole hot path for a list of already-normalised reads (host numpy arrays)."""
         fm = self.model.fm
         n = len(reads)
@@ -409,12 +433,13 @@ class Context:
         signal = np.concatenate([np.asarray(r, np.float32) for r in reads]) if n else np.zeros(1, np.float32)
         flags = (FLAG_VITERBI_ONLY if viterbi_only else 0) | (FLAG_WANT_TRACE if want_trace else 0) | \
                 (FLAG_WANT_TRANS if want_trans else 0) | (FLAG_KEEP_LAYERS if keep_layers else 0) | \
-                (FLAG_FP32_SIMT if fp32_simt else 0)
-        b, o = self.make_batch(signal, sig_off, temperature, flags)
+                (FLAG_FP32_SIMT if fp32_simt else 0) | (FLAG_REVERSE if reverse else 0)
+        b, o = self.make_batch(signal, sig_off, temperature, flags, emit=emit)
         self._check(self.lib.lib.ffb_basecall_batch(self.handle, ctypes.byref(b)), "ffb_basecall_batch")
         res = BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),
                           o.get("trace"), fm.nstate, fm.nparam)
         res.rle_params = o.get("rle_params")
+        res.bases, res.quals, res.nbases = o.get("bases"), o.get("quals"), o.get("nbases")
         return res
 
     def make_raw_batch(self, raw: np.ndarray, raw_off: np.ndarray, trim=(200, 10), segmentation=(100, 0.0),
@@ -432,7 +457,7 @@ class Context:
 
     def basecall_raw(self, raws: Sequence[np.ndarray], temperature: float = 1.0, viterbi_only: bool = False,
                      want_trace: bool = False, want_trans: bool = False, trim=(200, 10), segmentation=(100, 0.0),
-                     delta: float = 0.0) -> BatchResult:
+                     delta: float = 0.0, emit: bool = False, reverse: bool = False) -> BatchResult:
         """calculate_post from the raw signal on (reference src/flappie.c:245-316) for a list of raw reads
         (pA floats): trimming + normalisation on the device, then the whole hot path.  The result carries
         `start` / `end` (kept range per read)."""
@@ -443,15 +468,16 @@ class Context:
         np.cumsum(lens, out=raw_off[1:])
         raw = np.concatenate([np.asarray(r, np.float32) for r in raws]) if n else np.zeros(1, np.float32)
         flags = (FLAG_VITERBI_ONLY if viterbi_only else 0) | (FLAG_WANT_TRACE if want_trace else 0) | \
-                (FLAG_WANT_TRANS if want_trans else 0)
+                (FLAG_WANT_TRANS if want_trans else 0) | (FLAG_REVERSE if reverse else 0)
         # outputs sized for the untrimmed lengths (upper bound on the block count)
-        b, o = self.make_batch(raw, raw_off, temperature, flags)
+        b, o = self.make_batch(raw, raw_off, temperature, flags, emit=emit)
         rb, start, end = self.make_raw_batch(raw, raw_off, trim, segmentation, delta)
         self._check(self.lib.lib.ffb_basecall_raw_batch(self.handle, ctypes.byref(rb), ctypes.byref(b)), "ffb_basecall_raw_batch")
         res = BatchResult(n, o["blk_off"], o["path"], o["qpath"], o["score"], o.get("trans"), o.get("tpost"),
                           o.get("trace"), fm.nstate, fm.nparam)
         res.start, res.end = start[:n], end[:n]
         res.rle_params = o.get("rle_params")
+        res.bases, res.quals, res.nbases = o.get("bases"), o.get("quals"), o.get("nbases")
         return res
 
     def fetch_signal(self, n_samples: int) -> np.ndarray:

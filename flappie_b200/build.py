@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(CSRC, "libflappie_b200.so")
-SOURCES = ["conv.cu", "signal.cu", "gemm.cu", "gemm_tc.cu", "rnn.cu", "rnn_tc.cu", "decode.cu", "rle.cu", "api.cu", "testhooks.cu"]
+SOURCES = ["conv.cu", "signal.cu", "gemm.cu", "gemm_tc.cu", "rnn.cu", "rnn_tc.cu", "decode.cu", "emit.cu", "rle.cu", "api.cu", "testhooks.cu"]
 HEADERS = ["ffb_common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "flappie_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=default", "--expt-relaxed-constexpr"]
@@ -86,7 +86,7 @@ def build_host(force: bool = False) -> None:
     deps = srcs + [os.path.join(HOST, "ffb_host.h"), os.path.join(HOST, "flappie_main.c"), LIB,
                    os.path.join(HERE, "..", "include", "flappie_b200.h")]
     flags = ["-std=c99", "-O2", "-Wall", "-Wextra", "-D_POSIX_C_SOURCE=200809L", "-fPIC"]
-    link = ["-L" + CSRC, "-lflappie_b200", "-Wl,-rpath,$ORIGIN/../csrc", "-lm"]
+    link = ["-L" + CSRC, "-lflappie_b200", "-Wl,-rpath,$ORIGIN/../csrc", "-lm", "-lpthread"]
     if force or _stale(HOST_BIN, deps):
         r = subprocess.run([cc] + flags + ["-o", HOST_BIN, os.path.join(HOST, "flappie_main.c")] + srcs + link,
                            capture_output=True, text=True)

@@ -91,6 +91,8 @@ struct ffb_model {
     void *d_ff_hi = nullptr, *d_ff_lo = nullptr;   // fp16 planes of FF_W [FFB_FF_TC_ROWS][S], zero-padded (tensor output layer)
     float *d_ffb_pad = nullptr;
     bool tc_ff = false;
+    float *d_phred_thr = nullptr;   // emit.cu: qpath thresholds of the quality characters
+    int n_phred_thr = 0;
     void *d_iW_hi[FFB_NLAYER] = {nullptr}, *d_iW_lo[FFB_NLAYER] = {nullptr};   // fp16 planes [G*S][in] for the tensor path
     bool tc_gemm = false;
     void *d_sW_img[FFB_NLAYER] = {nullptr};   // per-CTA shared-memory images of sW (fp16 hi/lo) for rnn_tc
@@ -104,6 +106,7 @@ struct ffb_model {
 };
 
 static constexpr size_t FFB_TAIL_CACHE_MAX = 8192;
+static const std::vector<float> &phred_thresholds();   // quality-character steps for the device emission (below)
 static inline float mat_at(const _Mat *m, size_t r, size_t c) { return m->data.f[c * m->stride + r]; }
 
 static float *upload(const std::vector<float> &h) {
@@ -123,6 +126,7 @@ extern "C" void ffb_model_destroy(ffb_model *m) {
     cudaFree(m->d_ffWt); cudaFree(m->d_ffb);
     cudaFree(m->d_ff_hi); cudaFree(m->d_ff_lo); cudaFree(m->d_ffb_pad);
     cudaFree(m->d_c3_hi); cudaFree(m->d_c3_lo);
+    cudaFree(m->d_phred_thr);
     delete m;
 }
 
@@ -275,6 +279,9 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
     if (ok) {
         m->tc_gemm = true;
         for (int l = 0; l < FFB_NLAYER; l++) m->tc_gemm = m->tc_gemm && m->d_iW_hi[l] && m->d_iW_lo[l];
+        m->d_phred_thr = upload(phred_thresholds());
+        m->n_phred_thr = (int)phred_thresholds().size();
+        ok = m->d_phred_thr != nullptr;
     }
     if (ok && ffb_rnn_tc_supported(kind, m->S) && m->tc_gemm) {
         if (ffb_rnn_tc_prepare(kind, m->S) == 0) {
@@ -412,6 +419,8 @@ struct ffb_ctx {
     DevBuf d_geom[FFB_MAX_CONV], d_tails[FFB_MAX_CONV], d_blkoff, d_order, d_keep[FFB_NLAYER];
     DevBuf d_raw, d_rawoff, d_chunkoff, d_mad, d_bounds, d_sigoff;
     DevBuf d_slotoff, d_slotlist;
+    DevBuf d_bases, d_quals, d_nbases;   // device-side emission (emit.cu), read n at blk_off[n] + n
+    bool want_emit = false;
     DevBuf d_c2hi, d_c2lo;        // tensor-core convolution: fp16 planes of its input in the slot layout (see forward_impl)
     int conv3_fix = 0;            // columns at either end of a read the CUDA-core kernel recomputes
     bool use_tc_conv3 = false;
@@ -454,7 +463,8 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
                      &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress,
-                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff, &c->d_slotoff, &c->d_slotlist, &c->d_rle, &c->d_c2hi, &c->d_c2lo};
+                     &c->d_raw, &c->d_rawoff, &c->d_chunkoff, &c->d_mad, &c->d_bounds, &c->d_sigoff, &c->d_slotoff, &c->d_slotlist, &c->d_rle, &c->d_c2hi, &c->d_c2lo,
+                     &c->d_bases, &c->d_quals, &c->d_nbases};
     for (auto *b : all) b->release();
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
@@ -729,15 +739,18 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     ok &= c->d_sig.reserve(sizeof(float) * (size_t)std::max<int64_t>(c->total_samples, 1)) == 0;
     for (int i = 0; i + 1 < m->nconv; i++)
         ok &= c->d_c[i].reserve(sizeof(float) * (size_t)std::max<int64_t>(c->col_off[i + 1][N] * m->conv_nfilter[i], 1)) == 0;
-    ok &= c->d_act[0].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
-    ok &= c->d_act[1].reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
+    // fp32 activations [Tt][S] exist only off the tensor path (there the layers hand each other fp16 hi/lo planes) or when
+    // the caller wants to look at them
+    const bool tensor_path = m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT) && c->use_tc_rnn && m->tc_ff && getenv("FFB_NO_TC_FF") == nullptr;
+    const size_t act_bytes = (tensor_path && !(c->flags & FFB_FLAG_KEEP_LAYERS)) ? 256 : sizeof(float) * (size_t)std::max<int64_t>(Tt * S, 1);
+    ok &= c->d_act[0].reserve(act_bytes) == 0;
+    ok &= c->d_act[1].reserve(act_bytes) == 0;
     ok &= c->d_xin.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * G * S, 1)) == 0;
     if (m->tc_gemm && !(c->flags & FFB_FLAG_FP32_SIMT)) {
         ok &= c->d_ahi.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
         ok &= c->d_alo.reserve(2 * (size_t)std::max<int64_t>(Tt * S, 1)) == 0;
     }
     if (c->stream_gemm) {
-        ok &= c->d_xin2.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt * G * S, 1)) == 0;
         for (int dir = 0; dir < 2; dir++) ok &= c->d_work[dir].reserve(sizeof(GemmWork) * work[dir].size()) == 0;
         ok &= c->d_progress.reserve(sizeof(int) * (size_t)FFB_NLAYER * (c->n_groups + 1 + 16)) == 0;
     }
@@ -756,6 +769,12 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     ok &= c->d_path.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(Tt + N, 1)) == 0;
     ok &= c->d_qpath.reserve(sizeof(float) * (size_t)std::max<int64_t>(Tt + N, 1)) == 0;
     ok &= c->d_score.reserve(sizeof(float) * (size_t)std::max<int64_t>(N, 1)) == 0;
+    c->want_emit = b->bases && b->quals && b->nbases && !m->head;
+    if (c->want_emit) {
+        ok &= c->d_bases.reserve((size_t)std::max<int64_t>(Tt + N, 1)) == 0;
+        ok &= c->d_quals.reserve((size_t)std::max<int64_t>(Tt + N, 1)) == 0;
+        ok &= c->d_nbases.reserve(sizeof(int32_t) * (size_t)std::max<int64_t>(N, 1)) == 0;
+    }
     ok &= c->d_logz.reserve(sizeof(double) * (size_t)std::max<int64_t>(N, 1)) == 0;
     if (c->flags & FFB_FLAG_WANT_TRACE) ok &= c->d_trace.reserve((size_t)std::max<int64_t>((Tt + N) * m->nstate, 1)) == 0;
     if (c->flags & FFB_FLAG_KEEP_LAYERS)
@@ -946,7 +965,11 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     if (streamed) {
         if (cudaMemsetAsync(c->d_progress.p, 0, sizeof(int) * FFB_NLAYER * prog_stride, st) != cudaSuccess) return FFB_ERR_CUDA;
     }
-    float *xin_buf[2] = {c->d_xin.as<float>(), streamed ? c->d_xin2.as<float>() : c->d_xin.as<float>()};
+    // ONE Xin buffer, also when streamed: the input GEMM of layer l+1 overwrites the projection of layer l IN PLACE.  A tile is
+    // released to it only once layer l's recurrence has published the steps that produce the tile's rows -- by then it has
+    // also read Xin for those rows (row t is read at step t and at no other time), and its own fused z columns of a row are
+    // written by the very thread that read them.  Halves the largest workspace (3 KB per block): twice the reads per batch.
+    float *xin_buf[2] = {c->d_xin.as<float>(), c->d_xin.as<float>()};
     for (int l = 0; l < FFB_NLAYER; l++) {
         const bool last = (l == FFB_NLAYER - 1);
         float *out = keep ? c->d_keep[l].as<float>() : c->d_act[1].as<float>();
@@ -1039,6 +1062,10 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         }
         LAUNCH(ffb_launch_viterbi(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_tb.as<uint64_t>(), c->d_path.as<int32_t>(),
                                   c->d_qpath.as<float>(), c->d_score.as<float>(), st));
+        if (c->want_emit)    // change_positions + base / quality characters (flappie.c:284-297), --reverse included
+            LAUNCH(ffb_launch_emit(c->d_path.as<int32_t>(), c->d_qpath.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, m->nbase,
+                                   (c->flags & FFB_FLAG_REVERSE) ? 1 : 0, m->d_phred_thr, m->n_phred_thr, c->d_bases.as<char>(),
+                                   c->d_quals.as<char>(), c->d_nbases.as<int32_t>(), st));
         if (c->flags & FFB_FLAG_WANT_TRACE)
             LAUNCH(ffb_launch_trace(post, c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_trace.p, 1, 0, st));
     }
@@ -1083,6 +1110,11 @@ static int download_enqueue(ffb_ctx *c, const ffb_batch *b) {
         if (b->path) CUDA_TRY(cudaMemcpyAsync(b->path, c->d_path.p, sizeof(int32_t) * (size_t)(Tt + N), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
         if (b->qpath) CUDA_TRY(cudaMemcpyAsync(b->qpath, c->d_qpath.p, sizeof(float) * (size_t)(Tt + N), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
         if (b->score) CUDA_TRY(cudaMemcpyAsync(b->score, c->d_score.p, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        if (c->want_emit && b->bases && b->quals && b->nbases) {
+            CUDA_TRY(cudaMemcpyAsync(b->bases, c->d_bases.p, (size_t)(Tt + N), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+            CUDA_TRY(cudaMemcpyAsync(b->quals, c->d_quals.p, (size_t)(Tt + N), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+            CUDA_TRY(cudaMemcpyAsync(b->nbases, c->d_nbases.p, sizeof(int32_t) * (size_t)N, cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
+        }
         if (b->trans && (c->flags & FFB_FLAG_WANT_TRANS))
             CUDA_TRY(cudaMemcpyAsync(b->trans, c->d_trans.p, sizeof(float) * (size_t)(Tt * m->nparam), cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
         if (b->tpost && (c->flags & FFB_FLAG_WANT_TRANS) && !(c->flags & FFB_FLAG_VITERBI_ONLY))
@@ -1141,7 +1173,7 @@ extern "C" int ffb_basecall_batch(ffb_ctx *c, const ffb_batch *b) {
 // pinned host memory for callers without the CUDA runtime (the C command line): async copies need it
 extern "C" void *ffb_alloc_pinned(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     memset(p, 0, bytes);
     return p;
 }
@@ -1192,6 +1224,34 @@ static inline char phredf_host(float p) {
     const float q = -(10.0f * 0.43429448190325182765) * log1pf(-p_clip);
     char ph = roundf(33.0f + q);
     return (ph < 126) ? ph : 126;
+}
+static inline char phred_of_qpath(float x) { return phredf_host(expf(x)); }
+
+// The quality character as a step function of qpath: thr[k] = the smallest float x with phred_of_qpath(x) >= 34 + k,
+// found by bisection over the float ordering with THIS host's expf / log1pf.  The device emission kernel (emit.cu) only
+// compares against the table, so its characters equal ffb_emit_bases' bit for bit.
+static inline int32_t float_key(float f) { int32_t i; memcpy(&i, &f, 4); return i >= 0 ? i : (int32_t)(0x80000000u - (uint32_t)i); }
+static inline float key_float(int32_t k) { int32_t i = k >= 0 ? k : (int32_t)(0x80000000u - (uint32_t)k); float f; memcpy(&f, &i, 4); return f; }
+static const std::vector<float> &phred_thresholds() {
+    static std::vector<float> thr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const int top = phred_of_qpath(88.0f);                 // expf saturates well before: the clipped maximum (83)
+        for (int ch = 34; ch <= top; ch++) {
+            int64_t lo = float_key(-1000.0f), hi = float_key(88.0f);   // f(lo) = 33 < ch <= f(hi)
+            while (hi - lo > 1) {
+                const int64_t mid = lo + (hi - lo) / 2;
+                if (phred_of_qpath(key_float((int32_t)mid)) >= ch) hi = mid; else lo = mid;
+            }
+            thr.push_back(key_float((int32_t)hi));
+        }
+    });
+    return thr;
+}
+extern "C" int ffb_phred_table(float *out, int cap) {
+    const std::vector<float> &t = phred_thresholds();
+    if (out) for (int k = 0; k < (int)t.size() && k < cap; k++) out[k] = t[(size_t)k];
+    return (int)t.size();
 }
 
 extern "C" int ffb_emit_bases(const int32_t *path, const float *qpath, int64_t nblock, int nbase, bool reverse,
@@ -1247,6 +1307,19 @@ extern "C" size_t nbase_from_flipflop_nparam(size_t nparam) {
     return (size_t)roundf((-1.0f + sqrtf(1 + 2 * nparam)) / 2.0f);   // layers.c:1029-1032
 }
 
+extern "C" size_t nbase_from_crf_runlength_nparam(size_t nparam) { return nbase_from_flipflop_nparam(nparam); }   // layers.c:1235-1239
+
+// decode.c:66-79 -- the one other function of the replaced decode.c that the reference's callers use (flappie.c:284)
+extern "C" size_t change_positions(int const *path, size_t npos, int *chpos) {
+    if (!path || !chpos) return 0;
+    size_t nch = 0;
+    for (size_t pos = 1; pos < npos; pos++) {
+        if (path[pos] == path[pos - 1]) continue;
+        chpos[nch++] = (int)pos;
+    }
+    return nch;
+}
+
 extern "C" flappie_matrix make_flappie_matrix(size_t nr, size_t nc) {
     if (nr == 0 || nc == 0) return nullptr;
     const size_t nrq = (nr + 3) / 4;
@@ -1269,6 +1342,16 @@ extern "C" flappie_imatrix make_flappie_imatrix(size_t nr, size_t nc) {
 extern "C" flappie_imatrix free_flappie_imatrix(flappie_imatrix mat) {
     if (mat) { free(mat->data.v); free(mat); }
     return nullptr;
+}
+
+// flappie_matrix.c:342-358 (used by fast5_interface.c:write_trace): dense column-major copy, caller frees
+extern "C" int32_t *array_from_flappie_imatrix(const_flappie_imatrix mat) {
+    if (!mat) return nullptr;
+    int32_t *res = (int32_t *)calloc(mat->nr * mat->nc, sizeof(int32_t));
+    if (!res) return nullptr;
+    for (size_t c = 0; c < mat->nc; c++)
+        for (size_t r = 0; r < mat->nr; r++) res[c * mat->nr + r] = mat->data.f[c * mat->stride + r];
+    return res;
 }
 
 extern "C" enum model_type get_flappie_model_type(const char *modelstr) {
@@ -1316,6 +1399,39 @@ static ffb_model *g_reg_model[RUNNIE_MODEL_INVALID + 1] = {nullptr};
 static std::vector<ffb_ctx *> g_reg_pool[RUNNIE_MODEL_INVALID + 1];
 static uint64_t g_reg_gen[RUNNIE_MODEL_INVALID + 1] = {0};
 
+// Weight bundle file -> model (the format flappie_b200/host/ffb_host.h documents: "FFBW1", kind, nconv, strides, nmat,
+// then nmat x {nr, nc, padded column-major floats} in guppy_model / guppy_stride5_model order).  The reference compiles
+// its weights in (src/models/*.mdl, git-LFS); a process that only knows the reference API -- the reference's own main()
+// linked against this library -- gets them from $FLAPPIE_B200_MODELS/<model name>.ffbw on first use.
+extern "C" ffb_model *ffb_model_load(const char *path, int device) {
+    if (!path) { set_err("ffb_model_load: NULL path"); return nullptr; }
+    FILE *fp = fopen(path, "rb");
+    if (!fp) { set_err("ffb_model_load: cannot open %s", path); return nullptr; }
+    char magic[8];
+    int32_t head[6];
+    std::vector<_Mat> mats;
+    std::vector<std::vector<float>> data;
+    bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "FFBW1\0\0\0", 8) == 0 && fread(head, sizeof(int32_t), 6, fp) == 6 &&
+              head[5] >= 1 && head[5] <= 64 && head[1] >= 1 && head[1] <= 3;
+    for (int i = 0; ok && i < head[5]; i++) {
+        uint64_t dim[2];
+        ok = fread(dim, sizeof(uint64_t), 2, fp) == 2 && dim[0] > 0 && dim[1] > 0 && dim[0] <= (1u << 24) && dim[1] <= (1u << 24);
+        if (!ok) break;
+        _Mat m;
+        m.nr = (size_t)dim[0]; m.nc = (size_t)dim[1]; m.nrq = (m.nr + 3) / 4; m.stride = 4 * m.nrq;
+        data.emplace_back(m.stride * m.nc);
+        ok = fread(data.back().data(), sizeof(float), data.back().size(), fp) == data.back().size();
+        m.data.f = data.back().data();
+        mats.push_back(m);
+    }
+    fclose(fp);
+    if (!ok) { set_err("ffb_model_load: %s is not a weight bundle", path); return nullptr; }
+    std::vector<const _Mat *> ptr;
+    for (auto &m : mats) ptr.push_back(&m);
+    const int stride[3] = {head[2], head[3], head[4]};
+    return ffb_model_create(device, head[0], ptr.data(), (int)ptr.size(), stride, head[1]);
+}
+
 extern "C" int ffb_register_model(enum model_type which, ffb_model *m) {
     if ((int)which < 0 || (int)which >= RUNNIE_MODEL_INVALID || which == FLAPPIE_MODEL_INVALID) return FFB_ERR_ARG;
     std::vector<ffb_ctx *> old;
@@ -1344,7 +1460,23 @@ extern "C" flappie_matrix calculate_transitions(const raw_table signal, float te
         gen = g_reg_gen[model];
         if (m && !g_reg_pool[model].empty()) { c = g_reg_pool[model].back(); g_reg_pool[model].pop_back(); }
     }
-    if (!m) { set_err("calculate_transitions: no weights registered for model %d (ffb_register_model)", (int)model); return nullptr; }
+    if (!m) {
+        // nothing bound to this enum value yet: a caller that only knows the reference API
+        const char *dir = getenv("FLAPPIE_B200_MODELS");
+        if (dir) {
+            static std::mutex load_mu;
+            std::lock_guard<std::mutex> lk(load_mu);
+            { std::lock_guard<std::mutex> lk2(g_reg_mu); m = g_reg_model[model]; gen = g_reg_gen[model]; }
+            if (!m) {
+                const std::string path = std::string(dir) + "/" + flappie_model_string(model) + ".ffbw";
+                int dev = 0;
+                if (getenv("FLAPPIE_B200_DEVICE")) dev = atoi(getenv("FLAPPIE_B200_DEVICE"));
+                m = ffb_model_load(path.c_str(), dev);
+                if (m) { ffb_register_model(model, m); std::lock_guard<std::mutex> lk2(g_reg_mu); gen = g_reg_gen[model]; }
+            }
+        }
+    }
+    if (!m) { set_err("calculate_transitions: no weights registered for model %d (ffb_register_model, or $FLAPPIE_B200_MODELS/<name>.ffbw)", (int)model); return nullptr; }
     if (!c) c = ffb_create(m, nullptr);
     if (!c) return nullptr;
     // the context goes back to the pool on every path out of this function

@@ -209,3 +209,7 @@ int ffb_launch_transpost(const float *trans, const int64_t *blk_off, int n_reads
 int ffb_launch_trace(const float *tpost, const int64_t *blk_off, int n_reads, int nr, void *trace, int is_log, int wide,
                      cudaStream_t st);
 int ffb_launch_exp_inplace(float *x, int64_t n, cudaStream_t st);
+// emit.cu: bases + quality characters per read (segments at blk_off[n] + n, NUL-terminated) and their counts; thr = the
+// ascending table of qpath values at which the quality character steps up (built by the host with its own libm)
+int ffb_launch_emit(const int32_t *path, const float *qpath, const int64_t *blk_off, int n_reads, int nbase, int reverse,
+                    const float *thr, int nthr, char *bases, char *quals, int32_t *nbases, cudaStream_t st);

@@ -268,7 +268,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     else
                         umma_f16_ts(acc + 2 * NG, tA_lo + i * 8, dB_hi + ob2, idesc, i != 0);
                 }
-                } else {
+                } else if constexpr (Cfg::NACC == 2) {
                     // two accumulators: acc 0 = Whi*hhi over all of K, acc 1 = Whi*hlo + Wlo*hhi
 #pragma unroll
                 for (int i = 0; i < KS; i++) {
@@ -277,6 +277,19 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     umma_f16_ts(acc + NG, tA_lo + i * 8, dB_hi + ob, idesc, 1);
                     umma_f16_ts(acc, tA_hi + i * 8, dB_hi + ob, idesc, i != 0);
                 }
+                } else {
+                    // ONE accumulator (as the input GEMM, gemm_tc.cu): the 2^-11-sized cross terms go in first -- their
+                    // truncation is invisible -- and the S/16 full-magnitude Whi*hhi products on top: the same number of
+                    // full-magnitude truncating accumulations as a dedicated accumulator, half the tcgen05.ld traffic
+#pragma unroll
+                for (int i = 0; i < KS; i++) {
+                    const uint64_t ob = (uint64_t)((i * 2 * Cfg::LBO_B) >> 4);
+                    umma_f16_ts(acc, tA_hi + i * 8, dB_lo + ob, idesc, i != 0);
+                    umma_f16_ts(acc, tA_lo + i * 8, dB_hi + ob, idesc, 1);
+                }
+#pragma unroll
+                for (int i = 0; i < KS; i++)
+                    umma_f16_ts(acc, tA_hi + i * 8, dB_hi + (uint64_t)((i * 2 * Cfg::LBO_B) >> 4), idesc, 1);
                 }
                 umma_commit(&acc_full[g]);
             };
@@ -304,6 +317,11 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 mbar_wait(&staged[g], (NGATE == 3 ? ga : gs) & 1u);                       // the gate warps staged my slice of h_s
                 PROF(3);
                 uint8_t *rg = ring_g + (size_t)ph * ring_par;
+#ifdef FFB_RNN_FENCE1
+                // the gate warps' generic-proxy writes of the slice happen-before this point (syncwarp -> arrive.release ->
+                // wait.acquire); ONE cross-proxy fence by the thread that issues the copy orders them before it
+                fence_proxy_async_smem();
+#endif
                 bulk_store_global(rg, stg, Cfg::SLICE);
                 PROF(4);
                 mbar_wait(&h_empty[g], ph);                           // every peer has consumed h_{s-1}
@@ -442,6 +460,17 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                     a[i][0] += v0[r0]; a[i][1] += v0[r0 + 2];
                     a[i][2] += v1[r0]; a[i][3] += v1[r0 + 2];
                 }
+            } else if constexpr (Cfg::NACC == 1) {
+                float v0[8], v2[8];
+                tmem_ld_16x256b_x2(t_lo, v0);
+                tmem_ld_16x256b_x2(t_hi, v2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int r0 = (i >> 1) * 4 + (i & 1);
+                    a[i][0] = v0[r0]; a[i][1] = v0[r0 + 2];
+                    a[i][2] = v2[r0]; a[i][3] = v2[r0 + 2];
+                }
             } else {
                 float v0[8], v1[8], v2[8], v3[8];
                 tmem_ld_16x256b_x2(t_lo, v0);
@@ -485,7 +514,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 st_hi[col * 8] = shv;
                 st_lo[col * 8] = slv;
             }
+#ifndef FFB_RNN_FENCE1
             fence_proxy_async_smem();      // staged slice -> visible to the bulk-copy engine
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(&staged[g]);
             PROF(11);
@@ -520,10 +551,10 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             tcgen05_fence_after();
             float v0[8], v1[8], a3[4];
             tmem_ld_16x256b_x2(t_hi, v0);
-            tmem_ld_16x256b_x2(t_hi + NG, v1);
+            if constexpr (Cfg::NACC > 1) tmem_ld_16x256b_x2(t_hi + NG, v1);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 4; i++) a3[i] = v0[(i >> 1) * 4 + (i & 1) + 2] + v1[(i >> 1) * 4 + (i & 1) + 2];
+            for (int i = 0; i < 4; i++) a3[i] = v0[(i >> 1) * 4 + (i & 1) + 2] + (Cfg::NACC > 1 ? v1[(i >> 1) * 4 + (i & 1) + 2] : 0.0f);
             if constexpr (Cfg::NACC == 3) {
                 tmem_ld_16x256b_x2(t_hi + 2 * NG, v0);
                 tmem_ld_wait();
@@ -555,8 +586,11 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 
 // two accumulators everywhere TMEM holds both weight planes: four tcgen05.ld instead of six on the step's critical path
 // (S=256: -4.5 % per layer, trans deviation 4.8e-5 vs 4.6e-5 with three accumulators, tests/report_parity.py)
-using GruTc256 = RnnTcCfg<256, 8, 3, false, 2>;
-using LstmTc256 = RnnTcCfg<256, 8, 4, false, 2>;
+#ifndef FFB_RNN_NACC
+#define FFB_RNN_NACC 2
+#endif
+using GruTc256 = RnnTcCfg<256, 8, 3, false, FFB_RNN_NACC>;
+using LstmTc256 = RnnTcCfg<256, 8, 4, false, FFB_RNN_NACC>;
 using GruTc384 = RnnTcCfg<384, 12, 3, false, 2>;    // 12-CTA clusters (non-portable size): 32 hidden units per CTA again,
 using LstmTc384 = RnnTcCfg<384, 12, 4, false, 2>;   // 2 x 192 TMEM columns of weights + 4 groups of 2 accumulators
 using GruTc512 = RnnTcCfg<512, 16, 3, true>;    // r103_native: 16-CTA clusters, hi plane in tensor memory (256 columns),

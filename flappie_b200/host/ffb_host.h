@@ -31,6 +31,14 @@ typedef struct {
 void ffb_fprintf_read(enum ffb_outformat fmt, FILE *fp, const char *uuid, const char *readname, bool uuid_primary,
                       const char *prefix, const ffb_read_result *res);
 
+/* ---- state trace (--trace) -----------------------------------------------------------------
+ * The reference writes the trace of every read into an HDF5 file (src/fast5_interface.c:126-143, one u8 dataset
+ * [nblock + 1][nstate] per read).  Without libhdf5 the same bytes go into a flat file of records
+ *   char magic[4] = "FFBT"; uint32 name_len; char name[name_len]; uint64 nrow (= nblock + 1); uint32 nstate;
+ *   uint8 trace[nrow * nstate]          (row-major: row = block boundary, column = flip-flop state)
+ * in input order. */
+void ffb_write_trace(FILE *fp, const char *name, const uint8_t *trace, size_t nblock, size_t nstate);
+
 /* ---- weight bundles -----------------------------------------------------------------
  * The reference compiles its weights in from generated headers (src/models/ *.mdl, git-LFS); this driver loads the
  * same `_Mat` images from a binary bundle instead:

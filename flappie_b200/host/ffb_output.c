@@ -58,3 +58,15 @@ void ffb_fprintf_read(enum ffb_outformat fmt, FILE *fp, const char *uuid, const 
     }
     fflush(fp);
 }
+
+void ffb_write_trace(FILE *fp, const char *name, const uint8_t *trace, size_t nblock, size_t nstate) {
+    if (!fp || !name || !trace) return;
+    const uint32_t len = (uint32_t)strlen(name), ns = (uint32_t)nstate;
+    const uint64_t nrow = (uint64_t)nblock + 1;
+    fwrite("FFBT", 1, 4, fp);
+    fwrite(&len, sizeof len, 1, fp);
+    fwrite(name, 1, len, fp);
+    fwrite(&nrow, sizeof nrow, 1, fp);
+    fwrite(&ns, sizeof ns, 1, fp);
+    fwrite(trace, 1, (size_t)nrow * nstate, fp);
+}

@@ -1,12 +1,24 @@
 /* flappie_main.c -- the `flappie` command line on the B200 path (host code in C, reference src/flappie.c).
  *
- * Same options, defaults, model names and record formats as the reference binary; the per-file calculate_post
- * loop (src/flappie.c:364-385) is rewired to: read up to --batch raw reads -> ffb_basecall_raw_batch (trimming,
- * normalisation, network, decoding on the device) -> emit bases -> print in input order.
+ * Same options, defaults, model names and record formats as the reference binary.  The reference's parallelism is "run N
+ * processes" (README.md:80-83, an OpenMP loop over files in src/flappie.c:364-385); here ONE process drives any number of
+ * GPUs of the box (--devices 0-7).  The per-file calculate_post loop is rewired to:
  *
- * Differences forced by this image: no libhdf5, so reads come from <name>.f32 / <name>.crp files instead of
- * fast5 (ffb_host.h) and --trace is refused; weights come from a bundle file (--weights, or
- * $FLAPPIE_B200_MODELS/<model>.ffbw) because the reference's compiled-in .mdl headers are git-LFS objects.
+ *   window  = the next (devices x --batch) files, in input order
+ *   read    : every device thread reads its share of the window's files                      (parallel host I/O)
+ *   deal    : reads sorted by length, longest first to the least-loaded device (LPT)         (main thread)
+ *   submit  : each device thread packs its batch into pinned memory and enqueues upload + trimming + normalisation +
+ *             network + decoding + base/quality emission + the device-to-host copies, without waiting (two contexts
+ *             per device: window w+1 is read, dealt and uploaded while the GPUs work on window w)
+ *   collect : wait for the older window's batches
+ *   print   : the records of that window in INPUT ORDER, whatever device called them           (main thread)
+ *
+ * Reads never cross devices and there is no collective: basecalling shards embarrassingly.
+ *
+ * Differences forced by this image: no libhdf5, so reads come from <name>.f32 / <name>.crp files instead of fast5
+ * (ffb_host.h) and --trace writes a flat binary file instead of HDF5 (format in ffb_host.h); weights come from a bundle
+ * file (--weights, or $FLAPPIE_B200_MODELS/<model>.ffbw) because the reference's compiled-in .mdl headers are git-LFS
+ * objects.
  */
 #define _GNU_SOURCE
 #include <dirent.h>
@@ -14,9 +26,11 @@
 #include <glob.h>
 #include <libgen.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <time.h>
 
 #include "ffb_host.h"
 
@@ -31,6 +45,7 @@
 #define DEFAULT_MODEL_NAME "r941_native"
 #define PROGRAM "flappie"
 #endif
+#define MAX_DEVICES 64
 
 struct arguments {
     float delta;
@@ -51,7 +66,9 @@ struct arguments {
     /* additions */
     const char *weights;
     int batch;
-    int device;
+    int ndev;
+    int devices[MAX_DEVICES];
+    bool stats;
 };
 
 /* defaults of the reference, src/flappie.c:93-112 */
@@ -59,7 +76,7 @@ static struct arguments args = {
     .delta = 0.0f, .trace = NULL, .outformat = FFB_OUT_FASTQ, .limit = 0, .model = DEFAULT_MODEL,
     .model_name = DEFAULT_MODEL_NAME, .output = NULL, .prefix = "", .reverse = false, .temperature = 1.0f,
     .trim_start = 200, .trim_end = 10, .varseg_chunk = 100, .varseg_thresh = 0.0f, .viterbi_only = false,
-    .uuid = true, .weights = NULL, .batch = 1024, .device = 0};
+    .uuid = true, .weights = NULL, .batch = 1024, .ndev = 1, .devices = {0}, .stats = false};
 
 static void die(const char *fmt, const char *arg) {
     fprintf(stderr, PROGRAM ": ");
@@ -90,17 +107,19 @@ static void usage(FILE *fh) {
           "  -r, --reverse, --no-reverse  Reverse output base calls\n"
           "      --temperature=factor   Temperature for weights\n"
           "  -t, --trim=start:end       Number of samples to trim, as start:end\n"
-          "  -T, --trace=filename       Dump trace to HDF5 file (needs libhdf5: refused by this build)\n"
+          "  -T, --trace=filename       Dump trace to file (flat binary records, see ffb_host.h: this build has no libhdf5)\n"
           "      --segmentation=chunk:percentile  Chunk size and percentile for variance based segmentation\n"
           "  -v, --viterbi, --no-viterbi, --fb  Use viterbi decoding only / forward-backward followed by viterbi\n"
           "      --uuid, --no-uuid      Output UUID / read file name\n"
           "      --weights=file         Weight bundle (default $FLAPPIE_B200_MODELS/<model>.ffbw)\n"
           "      --batch=nreads         Reads per device batch (default 1024)\n"
-          "      --device=index         CUDA device (default 0)\n", fh);
+          "      --device=index         CUDA device (default 0)\n"
+          "      --devices=list         CUDA devices to shard the reads over: \"0-7\", \"0,2,3\" or \"all\"\n"
+          "      --stats                Print reads, samples and samples/s to stderr at the end\n", fh);
 }
 
 enum { OPT_SEG = 3, OPT_NOREV = 6, OPT_TEMP, OPT_NOVIT, OPT_FB, OPT_LIC, OPT_LIC2, OPT_H5C, OPT_H5K, OPT_UUID, OPT_NOUUID,
-       OPT_WEIGHTS = 1000, OPT_BATCH, OPT_DEVICE, OPT_HELP };
+       OPT_WEIGHTS = 1000, OPT_BATCH, OPT_DEVICE, OPT_DEVICES, OPT_STATS, OPT_HELP };
 
 static const struct option long_opts[] = {
     {"delta", required_argument, 0, 'd'}, {"format", required_argument, 0, 'f'}, {"limit", required_argument, 0, 'l'},
@@ -111,7 +130,32 @@ static const struct option long_opts[] = {
     {"no-viterbi", no_argument, 0, OPT_NOVIT}, {"fb", no_argument, 0, OPT_FB}, {"hdf5-compression", required_argument, 0, OPT_H5C},
     {"hdf5-chunk", required_argument, 0, OPT_H5K}, {"uuid", no_argument, 0, OPT_UUID}, {"no-uuid", no_argument, 0, OPT_NOUUID},
     {"weights", required_argument, 0, OPT_WEIGHTS}, {"batch", required_argument, 0, OPT_BATCH},
-    {"device", required_argument, 0, OPT_DEVICE}, {"help", no_argument, 0, OPT_HELP}, {0, 0, 0, 0}};
+    {"device", required_argument, 0, OPT_DEVICE}, {"devices", required_argument, 0, OPT_DEVICES}, {"stats", no_argument, 0, OPT_STATS},
+    {"help", no_argument, 0, OPT_HELP}, {0, 0, 0, 0}};
+
+/* "0-7", "0,2,3", "1-2,5" or "all" */
+static void parse_devices(const char *spec) {
+    args.ndev = 0;
+    if (0 == strcasecmp(spec, "all")) {
+        const int n = ffb_device_count();
+        for (int d = 0; d < n && d < MAX_DEVICES; d++) args.devices[args.ndev++] = d;
+        if (args.ndev == 0) die("--devices all: no CUDA device%s", "");
+        return;
+    }
+    char *copy = strdup(spec), *save = NULL;
+    for (char *tok = strtok_r(copy, ",", &save); tok; tok = strtok_r(NULL, ",", &save)) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1 || a < 0) die("--devices: cannot parse \"%s\"", spec);
+        if (k == 1) b = a;
+        for (int d = a; d <= b; d++) {
+            if (args.ndev >= MAX_DEVICES) die("--devices: too many devices%s", "");
+            args.devices[args.ndev++] = d;       /* naming a device twice gives it two independent pipelines */
+        }
+    }
+    free(copy);
+    if (args.ndev == 0) die("--devices: cannot parse \"%s\"", spec);
+}
 
 static void parse_args(int argc, char **argv) {
     int key;
@@ -167,12 +211,14 @@ static void parse_args(int argc, char **argv) {
         case OPT_LIC: case OPT_LIC2:
             fputs("flappie_b200: see the reference's LICENCE.txt for the Oxford Nanopore Technologies Public License\n", stdout);
             exit(EXIT_SUCCESS);
-        case OPT_H5C: case OPT_H5K: break;   /* only meaningful with --trace */
+        case OPT_H5C: case OPT_H5K: break;   /* HDF5 tuning of the reference's --trace: nothing to tune in the flat file */
         case OPT_UUID: args.uuid = true; break;
         case OPT_NOUUID: args.uuid = false; break;
         case OPT_WEIGHTS: args.weights = optarg; break;
         case OPT_BATCH: args.batch = atoi(optarg) > 0 ? atoi(optarg) : 1; break;
-        case OPT_DEVICE: args.device = atoi(optarg); break;
+        case OPT_DEVICE: args.ndev = 1; args.devices[0] = atoi(optarg); break;
+        case OPT_DEVICES: parse_devices(optarg); break;
+        case OPT_STATS: args.stats = true; break;
         case OPT_HELP: usage(stdout); exit(EXIT_SUCCESS);
         default: usage(stderr); exit(EXIT_FAILURE);
         }
@@ -180,164 +226,22 @@ static void parse_args(int argc, char **argv) {
     if (optind >= argc) { usage(stderr); exit(EXIT_FAILURE); }
 }
 
-/* ---- a batch of raw reads waiting for the device ---- */
-struct pending {
-    char **name;            /* basename of each file (printed as "filename", and as the id with --no-uuid) */
-    char **uuid;
-    float *raw;             /* concatenated samples */
-    int64_t *raw_off;
-    int n, cap;
-    size_t raw_cap;
-};
+/* ---- the work list: every signal file named on the command line, in the reference's order ------------------------- */
+struct filelist { char **path; size_t n, cap; };
 
-static void pending_add(struct pending *p, const char *path, float *sig, long n) {
-    if (p->n == p->cap) {
-        p->cap = p->cap ? 2 * p->cap : 256;
-        p->name = realloc(p->name, sizeof(char *) * (size_t)p->cap);
-        p->uuid = realloc(p->uuid, sizeof(char *) * (size_t)p->cap);
-        p->raw_off = realloc(p->raw_off, sizeof(int64_t) * ((size_t)p->cap + 1));
-        if (!p->name || !p->uuid || !p->raw_off) die("out of memory%s", "");
+static void filelist_add(struct filelist *fl, const char *p) {
+    if (fl->n == fl->cap) {
+        fl->cap = fl->cap ? 2 * fl->cap : 1024;
+        fl->path = realloc(fl->path, sizeof(char *) * fl->cap);
+        if (!fl->path) die("out of memory%s", "");
     }
-    if (p->n == 0) p->raw_off[0] = 0;
-    const size_t need = (size_t)p->raw_off[p->n] + (size_t)n;
-    if (need > p->raw_cap) {
-        p->raw_cap = need * 2 + 4096;
-        p->raw = realloc(p->raw, sizeof(float) * p->raw_cap);
-        if (!p->raw) die("out of memory%s", "");
-    }
-    memcpy(p->raw + p->raw_off[p->n], sig, sizeof(float) * (size_t)n);
-    char *tmp = strdup(path);
-    p->name[p->n] = strdup(basename(tmp));
-    free(tmp);
-    /* fast5 files carry a read uuid attribute; a bare signal file has none: its stem stands in */
-    p->uuid[p->n] = strdup(p->name[p->n]);
-    char *dot = strrchr(p->uuid[p->n], '.');
-    if (dot) *dot = 0;
-    p->raw_off[p->n + 1] = (int64_t)need;
-    p->n++;
+    fl->path[fl->n++] = strdup(p);
 }
 
-static void pending_clear(struct pending *p) {
-    for (int i = 0; i < p->n; i++) { free(p->name[i]); free(p->uuid[i]); }
-    p->n = 0;
-}
-
-/* One batch in flight on one context: calculate_post for every pending read at once (submitted without waiting),
- * then -- at collect time -- the reference's per-read printing in input order.  main() keeps two of these going, so
- * the files of batch i+1 are read while the device works on batch i. */
-struct inflight {
-    ffb_ctx *ctx;
-    struct pending pend;
-    bool busy;
-    int64_t *blk_off, *start, *end;
-    int32_t *path;
-    float *qpath, *score, *rle;
-    ffb_batch b;
-};
-
-static void submit_batch(struct inflight *f, ffb_model *model) {
-    struct pending *p = &f->pend;
-    if (p->n == 0) return;
-    const int n = p->n;
-    int64_t tot_blocks = 0;
-    for (int i = 0; i < n; i++) {
-        const long t = ffb_model_nblock(model, (long)(p->raw_off[i + 1] - p->raw_off[i]));
-        tot_blocks += t > 0 ? t : 0;                  /* upper bound: the kept range is shorter */
-    }
-    f->blk_off = calloc((size_t)n + 1, sizeof(int64_t));
-    f->start = calloc((size_t)n, sizeof(int64_t));
-    f->end = calloc((size_t)n, sizeof(int64_t));
-    /* page-locked, so that the device-to-host copies really are asynchronous */
-    f->path = ffb_alloc_pinned((size_t)(tot_blocks + n) * sizeof(int32_t));
-    f->qpath = ffb_alloc_pinned((size_t)(tot_blocks + n) * sizeof(float));
-    f->score = ffb_alloc_pinned((size_t)n * sizeof(float));
-#ifdef FFB_RUNNIE
-    f->rle = ffb_alloc_pinned((size_t)(tot_blocks + 1) * 8 * sizeof(float));
-    if (!f->rle) die("out of memory%s", "");
-#endif
-    if (!f->blk_off || !f->start || !f->end || !f->path || !f->qpath || !f->score) die("out of memory%s", "");
-    ffb_raw_batch rb = {.raw = p->raw, .raw_off = p->raw_off, .n_reads = n, .trim_start = args.trim_start, .trim_end = args.trim_end,
-                        .varseg_chunk = args.varseg_chunk, .varseg_thresh = args.varseg_thresh, .delta = args.delta,
-                        .start = f->start, .end = f->end};
-    memset(&f->b, 0, sizeof f->b);
-    f->b.n_reads = n; f->b.temperature = args.temperature;
-    f->b.flags = args.viterbi_only ? FFB_FLAG_VITERBI_ONLY : 0;
-    f->b.blk_off = f->blk_off; f->b.path = f->path; f->b.qpath = f->qpath; f->b.score = f->score;
-    f->b.rle_params = f->rle;
-    if (ffb_submit_raw_batch(f->ctx, &rb, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
-    f->busy = true;
-}
-
-static void collect_batch(struct inflight *f, ffb_model *model) {
-    if (!f->busy) return;
-    struct pending *p = &f->pend;
-    const int n = p->n;
-    if (ffb_collect(f->ctx, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
-    const int nbase = (int)nbase_from_flipflop_nparam((size_t)ffb_model_nparam(model));
-    for (int i = 0; i < n; i++) {
-        const int64_t nblock = f->blk_off[i + 1] - f->blk_off[i];
-        if (nblock <= 0) {
-            fprintf(stderr, PROGRAM ": No basecall returned for %s\n", p->name[i]);   /* src/flappie.c:370-373 */
-            continue;
-        }
-#ifdef FFB_RUNNIE
-        {
-            char *bases = calloc((size_t)nblock + 2, 1);
-            float *shape = calloc((size_t)nblock + 1, sizeof(float)), *scale = calloc((size_t)nblock + 1, sizeof(float));
-            int32_t *dwell = calloc((size_t)nblock + 1, sizeof(int32_t));
-            if (!bases || !shape || !scale || !dwell) die("out of memory%s", "");
-            const int64_t nrun = ffb_emit_runs(f->path + f->blk_off[i] + i, f->rle + f->blk_off[i] * 8, nblock, nbase, bases, shape, scale, dwell);
-            fprintf(args.output, "# %s\n", p->uuid[i]);                                  /* src/runnie.c:277 */
-            for (int64_t r = 0; r < nrun; r++) fprintf(args.output, "%c\t%f\t%f\t%d\n", bases[r], shape[r], scale[r], dwell[r]);
-            free(bases); free(shape); free(scale); free(dwell);
-            continue;
-        }
-#endif
-        char *basecall = calloc((size_t)nblock + 2, 1), *quality = calloc((size_t)nblock + 2, 1);
-        if (!basecall || !quality) die("out of memory%s", "");
-        const int nb = ffb_emit_bases(f->path + f->blk_off[i] + i, f->qpath + f->blk_off[i] + i, nblock, nbase, args.reverse, basecall, quality);
-        ffb_read_result res = {.score = f->score[i], .n = (size_t)(p->raw_off[i + 1] - p->raw_off[i]), .start = (size_t)f->start[i],
-                               .end = (size_t)f->end[i], .basecall = basecall, .quality = quality, .basecall_length = (size_t)(nb > 0 ? nb : 0),
-                               .nblock = (size_t)nblock};
-        ffb_fprintf_read(args.outformat, args.output, p->uuid[i], p->name[i], args.uuid, args.prefix, &res);
-        free(basecall); free(quality);
-    }
-    free(f->blk_off); free(f->start); free(f->end);
-    ffb_free_pinned(f->path); ffb_free_pinned(f->qpath); ffb_free_pinned(f->score); ffb_free_pinned(f->rle);
-    f->rle = NULL;
-    pending_clear(p);
-    f->busy = false;
-}
-
-int main(int argc, char **argv) {
-    parse_args(argc, argv);
-    if (!args.output) args.output = stdout;
-    if (args.trace) die("--trace %s: HDF5 output needs libhdf5, which this build does not have", args.trace);
-    if (ffb_device_count() <= args.device) die("no CUDA device: flappie_b200 has no CPU fallback%s", "");
-
-    char wpath[4096];
-    if (!args.weights) {
-        const char *dir = getenv("FLAPPIE_B200_MODELS");
-        if (!dir) die("no weights: give --weights <bundle> or set FLAPPIE_B200_MODELS (model %s)", args.model_name);
-        snprintf(wpath, sizeof wpath, "%s/%s.ffbw", dir, args.model_name);
-        args.weights = wpath;
-    }
-    ffb_bundle bundle;
-    if (ffb_bundle_load(args.weights, &bundle) != 0) die("cannot read weight bundle \"%s\"", args.weights);
-    ffb_model *model = ffb_bundle_to_model(&bundle, args.device);
-    if (!model) die("weight bundle rejected: %s", ffb_last_error());
-    ffb_bundle_free(&bundle);
-    struct inflight fl[2];
-    memset(fl, 0, sizeof fl);
-    for (int k = 0; k < 2; k++) {
-        fl[k].ctx = ffb_create(model, NULL);
-        if (!fl[k].ctx) die("ffb_create: %s", ffb_last_error());
-    }
-    int cur = 0;                                    /* the batch being filled; the other one may be on the device */
-    int reads_started = 0;
+/* files and directories, through the system glob as the reference does (src/flappie.c:338-362) */
+static void expand_arguments(int argc, char **argv, struct filelist *fl) {
     for (int fn = optind; fn < argc; fn++) {
-        if (args.limit > 0 && reads_started >= args.limit) continue;
-        /* files and directories, through the system glob as the reference does (src/flappie.c:338-362) */
+        if (args.limit > 0 && fl->n >= (size_t)args.limit) break;
         glob_t globbuf;
         char *pattern = calloc(strlen(argv[fn]) + 16, 1);
         strcpy(pattern, argv[fn]);
@@ -354,29 +258,342 @@ int main(int argc, char **argv) {
         for (size_t k = 0; k < globbuf.gl_pathc; k++) {
             const char *filename = globbuf.gl_pathv[k];
             if (is_dir && !ffb_is_signal_file(filename)) continue;
-            if (args.limit > 0 && reads_started >= args.limit) continue;
-            reads_started += 1;
-            float *sig = NULL;
-            const long n = ffb_read_raw_file(filename, &sig);
-            if (n == -2) { fprintf(stderr, PROGRAM ": %s: fast5 input needs libhdf5, which this build does not have\n", filename); continue; }
-            if (n <= 0) { fprintf(stderr, PROGRAM ": No basecall returned for %s\n", filename); free(sig); continue; }
-            pending_add(&fl[cur].pend, filename, sig, n);
-            free(sig);
-            if (fl[cur].pend.n >= args.batch) {
-                submit_batch(&fl[cur], model);
-                cur ^= 1;
-                collect_batch(&fl[cur], model);     /* the older batch: print it, then refill its slot */
-            }
+            if (args.limit > 0 && fl->n >= (size_t)args.limit) break;
+            filelist_add(fl, filename);
         }
         globfree(&globbuf);
     }
-    collect_batch(&fl[cur ^ 1], model);             /* older batch first: records stay in input order */
-    submit_batch(&fl[cur], model);
-    collect_batch(&fl[cur], model);
+}
 
-    ffb_destroy(fl[0].ctx);
-    ffb_destroy(fl[1].ctx);
-    ffb_model_destroy(model);
+/* ---- one read of a window ------------------------------------------------------------------------------------------ */
+struct read_slot {
+    char *name, *uuid;      /* basename (printed as "filename", and as the id with --no-uuid); stem as the uuid */
+    float *raw;             /* samples, malloc'ed by the reader, freed once packed */
+    long n;                 /* > 0: samples; <= 0: unreadable / empty; -2: fast5 */
+    int dev, pos;           /* device batch this read was dealt to, and its index there */
+};
+
+/* ---- one batch in flight on one context of one device; all result buffers are pinned and grow-only ------------------- */
+struct dev_batch {
+    ffb_ctx *ctx;
+    int n;                          /* reads in this batch */
+    int *member; int member_cap;    /* window-relative read index of each member, ascending */
+    float *raw; size_t raw_cap;
+    int64_t *raw_off, *blk_off, *start, *end; float *score; int32_t *nbases; size_t read_cap;
+    char *bases, *quals; int32_t *path; float *qpath; float *rle; uint8_t *trace; size_t blk_cap;
+    int64_t tot_blocks;
+    ffb_batch b;
+    ffb_raw_batch rb;
+    bool busy;
+};
+
+struct window { size_t first; int n; struct read_slot *rd; int cap; };
+
+struct device {
+    int id, rank;
+    ffb_model *model;
+    struct dev_batch bat[2];
+    pthread_t th;
+};
+
+static struct {
+    struct filelist files;
+    struct window win[3];       /* window w lives in slot w % 3: w-1 is being printed while w+1 is being read */
+    struct device dev[MAX_DEVICES];
+    int ndev, nwin, nstate, nbase;
+    size_t window_reads;
+    pthread_barrier_t bar;
+} G;
+
+static void *pinned_grow(void *old, size_t bytes) {
+    ffb_free_pinned(old);
+    void *p = ffb_alloc_pinned(bytes);
+    if (!p) die("out of pinned host memory%s", "");
+    return p;
+}
+
+static void read_one(struct read_slot *s, const char *path) {
+    char *tmp = strdup(path);
+    s->name = strdup(basename(tmp));
+    free(tmp);
+    /* fast5 files carry a read uuid attribute; a bare signal file has none: its stem stands in */
+    s->uuid = strdup(s->name);
+    char *dot = strrchr(s->uuid, '.');
+    if (dot) *dot = 0;
+    s->raw = NULL;
+    s->n = ffb_read_raw_file(path, &s->raw);
+    if (s->n <= 0) { free(s->raw); s->raw = NULL; }
+    s->dev = -1; s->pos = -1;
+}
+
+/* LPT: the longest read first, each to the device with the fewest samples so far (and room left) -- equal work per device
+ * whatever the length distribution (BASELINE configs[3]: 1 k - 50 k samples) */
+static int cmp_len_desc(const void *a, const void *b, void *ctx) {
+    const struct read_slot *rd = ctx;
+    const long la = rd[*(const int *)a].n, lb = rd[*(const int *)b].n;
+    if (la != lb) return la > lb ? -1 : 1;
+    return *(const int *)a - *(const int *)b;
+}
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+
+static void deal_window(struct window *w, int slot) {
+    int *idx = malloc(sizeof(int) * (size_t)(w->n > 0 ? w->n : 1));
+    int m = 0;
+    for (int i = 0; i < w->n; i++)
+        if (w->rd[i].n > 0) idx[m++] = i;
+    qsort_r(idx, (size_t)m, sizeof(int), cmp_len_desc, w->rd);
+    int64_t load[MAX_DEVICES] = {0};
+    for (int d = 0; d < G.ndev; d++) G.dev[d].bat[slot].n = 0;
+    for (int k = 0; k < m; k++) {
+        int best = -1;
+        for (int d = 0; d < G.ndev; d++) {
+            if (G.dev[d].bat[slot].n >= args.batch) continue;
+            if (best < 0 || load[d] < load[best]) best = d;
+        }
+        struct dev_batch *b = &G.dev[best].bat[slot];
+        if (b->n == b->member_cap) {
+            b->member_cap = b->member_cap ? 2 * b->member_cap : 1024;
+            b->member = realloc(b->member, sizeof(int) * (size_t)b->member_cap);
+            if (!b->member) die("out of memory%s", "");
+        }
+        b->member[b->n++] = idx[k];
+        load[best] += w->rd[idx[k]].n;
+    }
+    for (int d = 0; d < G.ndev; d++) {
+        struct dev_batch *b = &G.dev[d].bat[slot];
+        qsort(b->member, (size_t)b->n, sizeof(int), cmp_int);      /* input order within the batch */
+        for (int k = 0; k < b->n; k++) { w->rd[b->member[k]].dev = d; w->rd[b->member[k]].pos = k; }
+    }
+    free(idx);
+}
+
+static void submit_batch(struct device *dv, struct dev_batch *f, struct window *w) {
+    f->busy = false;
+    if (f->n == 0) return;
+    const int n = f->n;
+    size_t tot_raw = 0;
+    int64_t tot_blocks = 0;
+    for (int k = 0; k < n; k++) {
+        const long len = w->rd[f->member[k]].n;
+        tot_raw += (size_t)len;
+        const long t = ffb_model_nblock(dv->model, len);
+        tot_blocks += t > 0 ? t : 0;                  /* upper bound: the kept range is shorter */
+    }
+    if ((size_t)n > f->read_cap) {
+        f->read_cap = (size_t)n + (size_t)n / 4 + 16;
+        f->raw_off = pinned_grow(f->raw_off, (f->read_cap + 1) * sizeof(int64_t));
+        f->blk_off = pinned_grow(f->blk_off, (f->read_cap + 1) * sizeof(int64_t));
+        f->start = pinned_grow(f->start, f->read_cap * sizeof(int64_t));
+        f->end = pinned_grow(f->end, f->read_cap * sizeof(int64_t));
+        f->score = pinned_grow(f->score, f->read_cap * sizeof(float));
+        f->nbases = pinned_grow(f->nbases, f->read_cap * sizeof(int32_t));
+    }
+    if (tot_raw > f->raw_cap) {
+        f->raw_cap = tot_raw + tot_raw / 4 + 4096;
+        f->raw = pinned_grow(f->raw, f->raw_cap * sizeof(float));
+    }
+    const size_t need_blk = (size_t)tot_blocks + (size_t)n + 1;
+    if (need_blk > f->blk_cap) {
+        f->blk_cap = need_blk + need_blk / 4 + 4096;
+#ifdef FFB_RUNNIE
+        f->path = pinned_grow(f->path, f->blk_cap * sizeof(int32_t));
+        f->qpath = pinned_grow(f->qpath, f->blk_cap * sizeof(float));
+        f->rle = pinned_grow(f->rle, f->blk_cap * 8 * sizeof(float));
+#else
+        f->bases = pinned_grow(f->bases, f->blk_cap);
+        f->quals = pinned_grow(f->quals, f->blk_cap);
+        if (args.trace) f->trace = pinned_grow(f->trace, f->blk_cap * (size_t)G.nstate);
+#endif
+    }
+    f->raw_off[0] = 0;
+    for (int k = 0; k < n; k++) {
+        struct read_slot *s = &w->rd[f->member[k]];
+        memcpy(f->raw + f->raw_off[k], s->raw, sizeof(float) * (size_t)s->n);
+        f->raw_off[k + 1] = f->raw_off[k] + s->n;
+        free(s->raw);
+        s->raw = NULL;
+    }
+    f->tot_blocks = tot_blocks;
+    f->rb = (ffb_raw_batch){.raw = f->raw, .raw_off = f->raw_off, .n_reads = n, .trim_start = args.trim_start, .trim_end = args.trim_end,
+                            .varseg_chunk = args.varseg_chunk, .varseg_thresh = args.varseg_thresh, .delta = args.delta,
+                            .start = f->start, .end = f->end};
+    memset(&f->b, 0, sizeof f->b);
+    f->b.n_reads = n; f->b.temperature = args.temperature;
+    f->b.flags = (args.viterbi_only ? FFB_FLAG_VITERBI_ONLY : 0) | (args.reverse ? FFB_FLAG_REVERSE : 0) | (args.trace ? FFB_FLAG_WANT_TRACE : 0);
+    f->b.blk_off = f->blk_off; f->b.score = f->score;
+#ifdef FFB_RUNNIE
+    f->b.path = f->path; f->b.qpath = f->qpath; f->b.rle_params = f->rle;
+#else
+    /* bases and quality characters come off the device (emit.cu): path / qpath stay there */
+    f->b.bases = f->bases; f->b.quals = f->quals; f->b.nbases = f->nbases; f->b.trace = f->trace;
+#endif
+    if (ffb_submit_raw_batch(f->ctx, &f->rb, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
+    f->busy = true;
+}
+
+static void collect_batch(struct dev_batch *f) {
+    if (!f->busy) return;
+    if (ffb_collect(f->ctx, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
+    f->busy = false;
+}
+
+/* the reference's per-read printing (src/flappie.c:364-385), for one window, in input order */
+static FILE *trace_fp = NULL;
+static void print_window(struct window *w, int slot, int64_t *reads_called, int64_t *samples) {
+    for (int i = 0; i < w->n; i++) {
+        struct read_slot *s = &w->rd[i];
+        if (s->n == -2) fprintf(stderr, PROGRAM ": %s: fast5 input needs libhdf5, which this build does not have\n", s->name);
+        const struct dev_batch *f = s->dev >= 0 ? &G.dev[s->dev].bat[slot] : NULL;
+        const int k = s->pos;
+        const int64_t nblock = f ? f->blk_off[k + 1] - f->blk_off[k] : 0;
+        if (nblock <= 0) {
+            if (s->n != -2) fprintf(stderr, PROGRAM ": No basecall returned for %s\n", s->name);   /* src/flappie.c:370-373 */
+            free(s->name); free(s->uuid);
+            continue;
+        }
+        *reads_called += 1;
+        *samples += s->n;
+        const int64_t o0 = f->blk_off[k] + k;
+#ifdef FFB_RUNNIE
+        {
+            char *bases = calloc((size_t)nblock + 2, 1);
+            float *shape = calloc((size_t)nblock + 1, sizeof(float)), *scale = calloc((size_t)nblock + 1, sizeof(float));
+            int32_t *dwell = calloc((size_t)nblock + 1, sizeof(int32_t));
+            if (!bases || !shape || !scale || !dwell) die("out of memory%s", "");
+            const int64_t nrun = ffb_emit_runs(f->path + o0, f->rle + f->blk_off[k] * 8, nblock, G.nbase, bases, shape, scale, dwell);
+            fprintf(args.output, "# %s\n", s->uuid);                                  /* src/runnie.c:277 */
+            for (int64_t r = 0; r < nrun; r++) fprintf(args.output, "%c\t%f\t%f\t%d\n", bases[r], shape[r], scale[r], dwell[r]);
+            free(bases); free(shape); free(scale); free(dwell);
+        }
+#else
+        ffb_read_result res = {.score = f->score[k], .n = (size_t)s->n, .start = (size_t)f->start[k], .end = (size_t)f->end[k],
+                               .basecall = f->bases + o0, .quality = f->quals + o0, .basecall_length = (size_t)f->nbases[k],
+                               .nblock = (size_t)nblock};
+        ffb_fprintf_read(args.outformat, args.output, s->uuid, s->name, args.uuid, args.prefix, &res);
+        if (trace_fp) ffb_write_trace(trace_fp, args.uuid ? s->uuid : s->name, f->trace + (size_t)o0 * (size_t)G.nstate, (size_t)nblock, (size_t)G.nstate);
+#endif
+        free(s->name); free(s->uuid);
+    }
+}
+
+/* ---- device thread: read my share -> (deal) -> pack + submit window w, collect window w-1 ---------------------------- */
+static void *device_main(void *arg) {
+    struct device *dv = arg;
+    for (int w = 0; w <= G.nwin; w++) {
+        if (w < G.nwin) {
+            struct window *win = &G.win[w % 3];
+            for (int i = dv->rank; i < win->n; i += G.ndev) read_one(&win->rd[i], G.files.path[win->first + (size_t)i]);
+        }
+        pthread_barrier_wait(&G.bar);       /* B1: window w is in memory */
+        pthread_barrier_wait(&G.bar);       /* B2: the main thread has dealt it */
+        if (w < G.nwin) submit_batch(dv, &dv->bat[w & 1], &G.win[w % 3]);
+        if (w > 0) collect_batch(&dv->bat[(w - 1) & 1]);
+        pthread_barrier_wait(&G.bar);       /* B3: window w-1 is complete: the main thread prints it */
+    }
+    return NULL;
+}
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+int main(int argc, char **argv) {
+    parse_args(argc, argv);
+    if (!args.output) args.output = stdout;
+#ifdef FFB_RUNNIE
+    if (args.trace) die("--trace %s: runnie writes no trace", args.trace);
+#endif
+    const int have = ffb_device_count();
+    for (int d = 0; d < args.ndev; d++)
+        if (args.devices[d] < 0 || args.devices[d] >= have) die("no such CUDA device (flappie_b200 has no CPU fallback)%s", "");
+
+    char wpath[4096];
+    if (!args.weights) {
+        const char *dir = getenv("FLAPPIE_B200_MODELS");
+        if (!dir) die("no weights: give --weights <bundle> or set FLAPPIE_B200_MODELS (model %s)", args.model_name);
+        snprintf(wpath, sizeof wpath, "%s/%s.ffbw", dir, args.model_name);
+        args.weights = wpath;
+    }
+    ffb_bundle bundle;
+    if (ffb_bundle_load(args.weights, &bundle) != 0) die("cannot read weight bundle \"%s\"", args.weights);
+    G.ndev = args.ndev;
+    for (int d = 0; d < G.ndev; d++) {
+        struct device *dv = &G.dev[d];
+        dv->id = args.devices[d]; dv->rank = d;
+        dv->model = ffb_bundle_to_model(&bundle, dv->id);
+        if (!dv->model) die("weight bundle rejected: %s", ffb_last_error());
+        for (int k = 0; k < 2; k++) {
+            dv->bat[k].ctx = ffb_create(dv->model, NULL);
+            if (!dv->bat[k].ctx) die("ffb_create: %s", ffb_last_error());
+        }
+    }
+    ffb_bundle_free(&bundle);
+    G.nbase = (int)nbase_from_flipflop_nparam((size_t)ffb_model_nparam(G.dev[0].model));
+    G.nstate = 2 * G.nbase;
+    if (args.trace) {
+        trace_fp = fopen(args.trace, "wb");
+        if (!trace_fp) die("Failed to open \"%s\" for the trace.", args.trace);
+    }
+
+    const double t0 = now_s();
+    expand_arguments(argc, argv, &G.files);
+    G.window_reads = (size_t)G.ndev * (size_t)args.batch;
+    G.nwin = (int)((G.files.n + G.window_reads - 1) / G.window_reads);
+    for (int k = 0; k < 3; k++) {
+        G.win[k].cap = (int)G.window_reads;
+        G.win[k].rd = calloc(G.window_reads, sizeof(struct read_slot));
+        if (!G.win[k].rd) die("out of memory%s", "");
+    }
+    pthread_barrier_init(&G.bar, NULL, (unsigned)G.ndev + 1);
+    /* window geometry is a pure function of w; slot w % 3 is set by the main thread before any device thread reads it:
+     * window 0 here, window w+1 between B1 and B2 of iteration w (its slot held window w-2, printed an iteration ago) */
+    if (G.nwin > 0) {
+        G.win[0].first = 0;
+        G.win[0].n = (int)(G.files.n < G.window_reads ? G.files.n : G.window_reads);
+    }
+    for (int d = 0; d < G.ndev; d++)
+        if (pthread_create(&G.dev[d].th, NULL, device_main, &G.dev[d]) != 0) die("pthread_create failed%s", "");
+
+    int64_t reads_called = 0, samples = 0;
+    for (int w = 0; w <= G.nwin; w++) {
+        pthread_barrier_wait(&G.bar);       /* B1 */
+        if (w < G.nwin) deal_window(&G.win[w % 3], w & 1);
+        if (w + 1 < G.nwin) {
+            struct window *nx = &G.win[(w + 1) % 3];
+            nx->first = (size_t)(w + 1) * G.window_reads;
+            const size_t left = G.files.n - nx->first;
+            nx->n = (int)(left < G.window_reads ? left : G.window_reads);
+        }
+        pthread_barrier_wait(&G.bar);       /* B2 */
+        pthread_barrier_wait(&G.bar);       /* B3 */
+        /* the device threads are already reading window w+1 (another slot); its batches reuse the buffers printed here
+         * only after the next B2, which this thread reaches after printing */
+        if (w > 0) print_window(&G.win[(w - 1) % 3], (w - 1) & 1, &reads_called, &samples);
+    }
+    for (int d = 0; d < G.ndev; d++) pthread_join(G.dev[d].th, NULL);
+    const double t1 = now_s();
+    if (args.stats)
+        fprintf(stderr, PROGRAM ": stats { \"devices\": %d, \"files\": %zu, \"reads_called\": %lld, \"samples\": %lld, \"seconds\": %.3f, "
+                "\"samples_per_s\": %.0f }\n", G.ndev, G.files.n, (long long)reads_called, (long long)samples, t1 - t0,
+                (double)samples / (t1 - t0 > 0 ? t1 - t0 : 1));
+
+    for (int d = 0; d < G.ndev; d++) {
+        for (int k = 0; k < 2; k++) {
+            struct dev_batch *f = &G.dev[d].bat[k];
+            ffb_destroy(f->ctx);
+            ffb_free_pinned(f->raw); ffb_free_pinned(f->raw_off); ffb_free_pinned(f->blk_off); ffb_free_pinned(f->start);
+            ffb_free_pinned(f->end); ffb_free_pinned(f->score); ffb_free_pinned(f->nbases); ffb_free_pinned(f->bases);
+            ffb_free_pinned(f->quals); ffb_free_pinned(f->path); ffb_free_pinned(f->qpath); ffb_free_pinned(f->rle);
+            ffb_free_pinned(f->trace);
+            free(f->member);
+        }
+        ffb_model_destroy(G.dev[d].model);
+    }
+    for (size_t i = 0; i < G.files.n; i++) free(G.files.path[i]);
+    free(G.files.path); free(G.win[0].rd); free(G.win[1].rd); free(G.win[2].rd);
+    if (trace_fp) fclose(trace_fp);
     if (stdout != args.output) fclose(args.output);
     return EXIT_SUCCESS;
 }

@@ -94,6 +94,11 @@ float decode_crf_flipflop(const_flappie_matrix trans, bool combine_stays, int *p
 flappie_imatrix trace_from_posterior(flappie_matrix tpost);
 void exp_activation_inplace(flappie_matrix C);
 size_t nbase_from_flipflop_nparam(size_t nparam);
+/* the other symbols of the replaced files that the reference's remaining sources link against (flappie.c:284,
+ * runnie.c:262, fast5_interface.c:138): reference src/decode.h:21, src/layers.h:95, src/flappie_matrix.h:63 */
+size_t change_positions(int const *path, size_t npos, int *chpos);
+size_t nbase_from_crf_runlength_nparam(size_t nparam);
+int32_t *array_from_flappie_imatrix(const_flappie_imatrix mat);
 /* run-length ("runnie") decoding, reference src/decode.h:27,37 (src/decode.c:901-1159); path has nblock entries */
 float decode_crf_runlength(const_flappie_matrix param, int *path);
 flappie_matrix transpost_crf_runlength(const_flappie_matrix param);
@@ -127,6 +132,11 @@ const char *ffb_version(void);
  * (convolution filters: nr = nf4*winlen - nf4 + nf).  conv_stride has 1 or 3 entries. */
 ffb_model *ffb_model_create(int device, int kind, const _Mat *const *mats, int nmat,
                             const int *conv_stride, int nconv);
+/* The same from a weight bundle file ("FFBW1": kind, nconv, strides, nmat, then nmat x {uint64 nr, uint64 nc, padded
+ * column-major floats}; written by flappie_b200.model.FlipflopModel.save_bundle).  calculate_transitions() loads
+ * $FLAPPIE_B200_MODELS/<model name>.ffbw by itself (on device $FLAPPIE_B200_DEVICE, default 0) when nothing has been
+ * registered for a model -- which is all the reference's own main() needs to run on this library. */
+ffb_model *ffb_model_load(const char *path, int device);
 void ffb_model_destroy(ffb_model *m);
 int ffb_model_size(const ffb_model *m);      /* S */
 int ffb_model_nparam(const ffb_model *m);    /* rows of trans: nstate*(nbase+1) */
@@ -153,6 +163,7 @@ void ffb_destroy(ffb_ctx *c);
                                     * of the LSTM topology carries 22-bit operands, fine for med-MAD normalised signal
                                     * (activations O(1)) but 1.6e-4 on trans for --delta input (activations O(100));
                                     * ffb_upload_raw sets it by itself when delta != 0 */
+#define FFB_FLAG_REVERSE 64u       /* --reverse: bases / quals of every read come out reversed (reference src/flappie.c:293-297) */
 
 /* One batch of whole reads.  All pointers are HOST memory owned by the caller.
  * signal      : concatenated normalised samples of all reads
@@ -163,6 +174,10 @@ void ffb_destroy(ffb_ctx *c);
  * score       : n_reads   (NAN for a rejected read)
  * trans,tpost : sum(T_n) * nparam floats, [block][nparam] row-major (= reference columns)
  * trace       : sum(T_n + 1) * nstate bytes, read n starts at (blk_off[n] + n) * nstate
+ * bases, quals, nbases (all three or none): the called bases and their quality characters, emitted on the device
+ *               (reference src/decode.c:66-79, src/flappie.c:284-297, src/util.h:285-305).  bases / quals: sum(T_n + 1)
+ *               chars, read n's NUL-terminated string starts at blk_off[n] + n; nbases[n] = its length.  Identical to
+ *               ffb_emit_bases() on path / qpath, which then need not be copied back at all.
  * Returns FFB_OK or a negative error; a read shorter than a filter window gets T_n = 0. */
 typedef struct {
     const float *signal;
@@ -179,6 +194,9 @@ typedef struct {
     uint8_t *trace;
     float *rle_params;   /* FFB_KIND_RUNLENGTH models only (may be NULL): sum(T_n) * 8 floats, [block][shape ACGT, scale ACGT];
                           * for those models path[] holds the run-length states (T_n entries + one -1), qpath zeros */
+    char *bases;
+    char *quals;
+    int32_t *nbases;
 } ffb_batch;
 
 /* Upload, run the whole hot path, download, synchronise. */
@@ -255,6 +273,9 @@ int64_t ffb_plan_schedule(const int64_t *T, int64_t n_reads, int max_clusters, i
  * written to basecall/quality (each needs nblock+1 chars, NUL-terminated). */
 int ffb_emit_bases(const int32_t *path, const float *qpath, int64_t nblock, int nbase, bool reverse,
                    char *basecall, char *quality);
+/* The quality character is a step function of qpath: out[k] (ascending) = the smallest qpath value whose character is
+ * >= 34 + k under the host's libm; the device emission compares against this table.  Returns the table length. */
+int ffb_phred_table(float *out, int cap);
 /* The run loop of runnie's calculate_post (reference src/runnie.c:279-310): returns the number of runs written to
  * bases (NUL-terminated) / shape / scale / dwell (each needs nblock + 1 entries). */
 int64_t ffb_emit_runs(const int32_t *path, const float *rle_params, int64_t nblock, int nbase, char *bases,

@@ -82,6 +82,30 @@ def test_emit_bases_matches_oracle(lib, oracle):
     assert b == "C" and q == "S"
 
 
+def test_phred_table_reproduces_host_quality_chars(lib):
+    """The device emission (emit.cu) only compares qpath against ffb_phred_table(): that lookup must give the very
+    characters ffb_emit_bases computes with the host's expf / log1pf (reference src/util.h:285-305), everywhere --
+    random values, a dense sweep, and the floats next to every step."""
+    thr = lib.phred_table()
+    assert 40 <= len(thr) <= 60 and np.all(np.diff(thr) > 0)
+    rng = np.random.default_rng(9)
+    xs = [rng.uniform(-12, 0.5, 200000).astype(np.float32), np.linspace(-3e-5, 1e-6, 50001, dtype=np.float32),
+          np.array([-np.inf, -1000.0, -88.0, 0.0, 1.0, 80.0, np.inf, np.nan], np.float32)]
+    for t in thr:                                       # neighbours of every step, a few ulps either side
+        k = np.float32(t).view(np.int32)
+        xs.append((k + np.arange(-4, 5, dtype=np.int32)).astype(np.int32).view(np.float32))
+    x = np.concatenate(xs)
+    look = 33 + np.searchsorted(thr, x, side="right")
+    look[np.isnan(x)] = 33 + len(thr)
+    path = (np.arange(len(x) + 2) % 2).astype(np.int32)              # nblock = len(x) + 1: a base at every pos in [1, nblock)
+    qpath = np.concatenate([[0.0], x, [0.0]]).astype(np.float32)
+    b, q = lib.emit_bases(path, qpath, 4)
+    assert len(q) == len(x)
+    got = np.frombuffer(q.encode("ascii"), np.uint8)
+    assert np.array_equal(got, look.astype(np.uint8)), np.flatnonzero(got != look)[:10]
+    assert got.max() == 83 and got.min() == 33                       # clipped at Q50 = 'S'
+
+
 def test_mat_bundle_layout():
     # the `_Mat` images are exactly what the generated model headers define
     # (misc/taiyaki_flipflop5_guppy.py:38-99)

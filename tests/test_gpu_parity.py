@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from flappie_b200.api import Context, Model
-from flappie_b200.model import KIND_GRU, KIND_LSTM, FlipflopModel
+from flappie_b200.model import KIND_GRU, KIND_LSTM, FlipflopModel, synthetic_reads
 from ffb_testutil import norm_reads
 
 pytestmark = pytest.mark.gpu
@@ -200,4 +200,31 @@ def test_empty_batch(gpu_lib):
     assert res.n_reads == 0
     res = ctx.basecall([np.zeros(5, np.float32)], viterbi_only=True)
     assert res.nblock(0) == 0 and np.isnan(res.score[0])
+    ctx.close(); m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,reverse", [("r941_native_gru", False), ("r941_5mC", True), ("r941_rna002", True)])
+def test_device_emission_identical_to_host_emission(gpu_lib, name, reverse):
+    """Bases and quality characters emitted on the device (emit.cu) against ffb_emit_bases on the downloaded
+    path / qpath (reference src/decode.c:66-79, src/flappie.c:284-297, src/util.h:285-305) -- every read identical,
+    >= 1000 reads over the three parametrisations, ragged lengths, --reverse and the 5-base alphabet included."""
+    fm = FlipflopModel.for_name(name, seed=5)
+    m = Model(fm); ctx = Context(m)
+    rng = np.random.default_rng(17)
+    raws = [r[: int(rng.integers(300, 1400))] for r in synthetic_reads(400, 1400, seed=23)]
+    raws[7] = raws[7][:12]                                            # rejected read: no bases, empty strings
+    for vit in (False, True):
+        res = ctx.basecall_raw(raws, viterbi_only=vit, emit=True, reverse=reverse)
+        nb_total = 0
+        for i in range(len(raws)):
+            T = res.nblock(i)
+            if T <= 0:
+                assert res.nbases[i] == 0
+                continue
+            p, q = res.read_path(i)
+            want = gpu_lib.emit_bases(p, q, fm.nbase, reverse=reverse)
+            assert res.read_bases(i) == want, (name, i)
+            nb_total += len(want[0])
+        assert nb_total > 10000
     ctx.close(); m.close()

@@ -238,3 +238,70 @@ def test_weight_bundle_roundtrip(host, tmp_path):
     bad = tmp_path / "bad.ffbw"
     bad.write_bytes(b"not a bundle")
     assert host.ffb_bundle_load(str(bad).encode(), ctypes.byref(Bundle())) != 0
+
+
+def _write_reads(tmp_path, lens, seed):
+    raws = synthetic_reads(len(lens), lens, seed=seed)
+    rdir = tmp_path / "reads"; rdir.mkdir()
+    names = [f"read_{i:03d}.f32" for i in range(len(lens))]
+    for nm, r in zip(names, raws):
+        r.tofile(rdir / nm)
+    return rdir, names, raws
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "all", "0,0,0"])
+def test_cli_sharded_over_devices_prints_the_single_device_bytes(gpu_lib, tmp_path, devices):
+    """--devices: reads of a window are dealt longest-first to the least-loaded device, every device runs its own batch,
+    records come out in INPUT order -- byte for byte what one device prints (reference semantics: one record per file in
+    the order of the command line, src/flappie.c:364-385).  "0,0" = two independent pipelines on one GPU, so the path runs
+    on a 1-GPU box too; "all" uses every GPU of the box."""
+    fm = FlipflopModel.synthetic(KIND_GRU, 96, 4, seed=3, name="r941_native")
+    fm.save_bundle(str(tmp_path / "r941_native.ffbw"))
+    rng = np.random.default_rng(8)
+    lens = [int(x) for x in np.exp(rng.uniform(np.log(600), np.log(9000), 61))] + [150, 90]   # ragged, two rejects
+    rng.shuffle(lens)
+    rdir, names, raws = _write_reads(tmp_path, lens, 37)
+    env = dict(os.environ, FLAPPIE_B200_MODELS=str(tmp_path))
+    outs = {}
+    for tag, opts in (("one", ["--device", "0", "--batch", "64"]), ("many", ["--devices", devices, "--batch", "9"])):
+        out = tmp_path / f"{tag}.fastq"
+        r = subprocess.run([os.path.join(HOST, "flappie"), "--output", str(out), "--stats"] + opts + [str(rdir)],
+                           capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.stderr.count("No basecall returned") == 2 and "samples_per_s" in r.stderr
+        outs[tag] = open(out, "rb").read()
+    assert outs["one"] == outs["many"]
+    heads = [ln.split()[0][1:] for ln in outs["one"].decode().splitlines() if ln.startswith("@read_")]
+    assert heads == [n[:-4] for n, ln in zip(names, lens) if ln > 400]          # input order, rejects dropped
+
+
+@pytest.mark.gpu
+def test_cli_trace_sink(gpu_lib, tmp_path):
+    """--trace: the u8 trace of every read (reference src/flappie.c:299-300, written to HDF5 by fast5_interface.c:126-143)
+    in the flat record file of ffb_host.h; equals trace_from_posterior over the same C ABI."""
+    from flappie_b200.api import Context, Model
+    fm = FlipflopModel.synthetic(KIND_GRU, 96, 4, seed=3, name="r941_native")
+    fm.save_bundle(str(tmp_path / "r941_native.ffbw"))
+    lens = [3000, 1500, 4200]
+    rdir, names, raws = _write_reads(tmp_path, lens, 41)
+    env = dict(os.environ, FLAPPIE_B200_MODELS=str(tmp_path))
+    tr = tmp_path / "trace.bin"
+    r = subprocess.run([os.path.join(HOST, "flappie"), "--trace", str(tr), "--output", str(tmp_path / "o.fastq"), str(rdir)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    m = Model(fm); ctx = Context(m)
+    res = ctx.basecall_raw(raws, want_trace=True)
+    blob = open(tr, "rb").read()
+    off = 0
+    for i, nm in enumerate(names):
+        assert blob[off:off + 4] == b"FFBT"
+        ln = int(np.frombuffer(blob, np.uint32, 1, off + 4)[0]); off += 8
+        assert blob[off:off + ln].decode() == nm[:-4]; off += ln
+        nrow = int(np.frombuffer(blob[off:off + 8], np.uint64)[0]); ns = int(np.frombuffer(blob[off + 8:off + 12], np.uint32)[0]); off += 12
+        assert nrow == res.nblock(i) + 1 and ns == 8
+        got = np.frombuffer(blob, np.uint8, nrow * ns, off).reshape(nrow, ns); off += nrow * ns
+        assert np.array_equal(got, res.read_trace(i))
+        assert abs(int(got[1:].sum(axis=1).mean()) - 255) <= 3           # posterior mass per block ~ 1
+    assert off == len(blob)
+    ctx.close(); m.close()
