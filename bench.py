@@ -9,9 +9,14 @@ path): "scaling": "weak".
 
   value : whole-job samples/s with the normalised signals already resident in HBM
           (CUDA events on the library's stream around exactly K x ffb_forward()).
-  e2e   : same metric through the reference-facing C-ABI call ffb_basecall_batch() with
-          HOST buffers: H2D of the signals from pinned memory and D2H of path/qpath/score
-          inside the timed region.
+  e2e   : same metric through the reference-facing C-ABI calls ffb_submit_raw_batch() /
+          ffb_collect() with HOST buffers: H2D of the RAW samples from pinned memory, trimming +
+          normalisation + network + decoding + base/quality emission on the device, D2H of the
+          called bases, quality characters and scores -- all inside the timed region.
+  extra : the other BASELINE configs (r941_native LSTM-384 x1024, r941_5mC x4096, r10C_pcr mixed
+          1 k-50 k, r941_rna002 --delta --reverse) with value / e2e / roofline.frac each, and the
+          STRONG-scaling set: a fixed 8192-read configs[3] workload dealt over the N ranks by
+          flappie_b200.shard.shard_reads.
   roofline     : the recurrent-layer kernel (dominant), algorithmic flops / CUDA-event time.
   cpu_baseline : the reference's own code (oracle/_ref, OpenBLAS, 1 thread per process,
                  one process per core as its README recommends) on a bounded sample.
@@ -180,12 +185,126 @@ def run_reference_arm(a):
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * nread * RAW_SAMPLES / val, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{a.reads} synthetic {RAW_SAMPLES}-sample reads, {a.model}; each step = bounded sample of {nread} reads on {cores} host cores"},
+        # the SAME config as the b200 arm measures; the CPU arm times a bounded sample of it and extrapolates the rate
+        # (a rate metric): which sample is in cpu_baseline.sample
+        "config": build_config(a, a.gpus, (RAW_SAMPLES - 210 + 1) // 2 * a.reads if "gru" in a.model or a.model in ("r941_5mC", "r10C_pcr") else None),
+        "reference_sample": f"each step = {nread} of the {a.reads} reads ({per_core} per core on {cores} host cores), rate extrapolated",
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def mixed_lengths(n, lo, hi, seed):
+    """configs[3]: lengths log-uniform in [lo, hi] samples"""
+    rng = np.random.default_rng(seed)
+    return [int(x) for x in np.exp(rng.uniform(np.log(lo), np.log(hi), n))]
+
+
+def run_extras(a, api, lib, peaks, world, rank, local, barrier, max_over_ranks):
+    """The other BASELINE configs, one short measurement each (1 warm-up + 2 timed steps): `value` = K x ffb_forward with the
+    batch resident after ONE ffb_upload_raw (CUDA events), `e2e` = the blocking C-ABI call ffb_basecall_raw_batch from pinned
+    host memory with device-side emission (wall clock), roofline.frac of the recurrent kernel from ffb_forward_timed."""
+    import ctypes
+    import torch
+    from flappie_b200.model import FlipflopModel, synthetic_reads
+    from flappie_b200.shard import shard_reads
+    out = []
+    cases = [
+        ("configs[1b] r941_native @4de542f (LSTM-384, stride 5), 1024 x 4000", "r941_native", [RAW_SAMPLES] * 1024, {}),
+        ("configs[2] r941_5mC (GRU-256, 5 bases), 4096 x 4000", "r941_5mC", [RAW_SAMPLES] * 4096, {}),
+        ("configs[3] r10C_pcr (GRU-256), 3072 reads log-uniform 1 k-50 k samples per GPU", "r10C_pcr", mixed_lengths(3072, 1000, 50000, 100 + rank), {}),
+        ("configs[4] r941_rna002 (LSTM-256) --delta 1.0 --reverse, 1024 x 4000", "r941_rna002", [RAW_SAMPLES] * 1024, {"delta": 1.0, "reverse": True}),
+    ]
+    # the strong-scaling set: ONE fixed configs[3] workload, dealt over the ranks by shard_reads (LPT on length), every
+    # rank runs its shard in batches of at most 3072 reads
+    strong_lens = mixed_lengths(a.strong_reads, 1000, 50000, 4242)
+    mine = shard_reads(strong_lens, world)[rank]
+    cases.append((f"configs[3] STRONG scaling: fixed {a.strong_reads}-read set (log-uniform 1 k-50 k) sharded over {world} GPU(s) by shard_reads",
+                  "r10C_pcr", [strong_lens[i] for i in mine], {"strong": True}))
+    for title, name, lens, opt in cases:
+        fm = FlipflopModel.for_name(name, seed=1)
+        model = api.Model(fm, device=local)
+        stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+        ctx = api.Context(model, stream=stream.cuda_stream)
+        flags = api.FLAG_REVERSE if opt.get("reverse") else 0
+        chunks = [lens[i::(len(lens) + 3071) // 3072] for i in range((len(lens) + 3071) // 3072)] if len(lens) > 4096 else [lens]
+        work = []
+        for ci, cl in enumerate(chunks):
+            raws = synthetic_reads(len(cl), cl, seed=1000 * ci + 11 + rank)
+            off = np.zeros(len(cl) + 1, np.int64); np.cumsum([len(r) for r in raws], out=off[1:])
+            raw = torch.empty(int(off[-1]), dtype=torch.float32).pin_memory().numpy(); raw[:] = np.concatenate(raws)
+            blocks = sum(max(fm.nblock(int(x)), 0) for x in cl)
+            o = {"blk_off": np.zeros(len(cl) + 1, np.int64), "score": np.zeros(len(cl), np.float32),
+                 "bases": torch.empty(blocks + len(cl), dtype=torch.uint8).pin_memory().numpy(),
+                 "quals": torch.empty(blocks + len(cl), dtype=torch.uint8).pin_memory().numpy(), "nbases": np.zeros(len(cl), np.int32)}
+            b_, o = ctx.make_batch(raw, off, 1.0, flags, o, emit=True, want_path=False)
+            rb_, _, _ = ctx.make_raw_batch(raw, off, delta=opt.get("delta", 0.0))
+            work.append((rb_, b_, o, raw, off))
+            del raws
+        samples = int(sum(lens))
+        K = 2
+        # e2e: blocking raw call per chunk, host buffers in, bases out
+        for rb_, b_, o, _, _ in work[:1]:
+            ctx._check(lib.lib.ffb_basecall_raw_batch(ctx.handle, ctypes.byref(rb_), ctypes.byref(b_)), "warm-up")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            for rb_, b_, o, _, _ in work:
+                ctx._check(lib.lib.ffb_basecall_raw_batch(ctx.handle, ctypes.byref(rb_), ctypes.byref(b_)), "ffb_basecall_raw_batch")
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
+        entry = {"config": title, "model": name, "reads_this_rank": len(lens), "samples_this_rank": samples}
+        if opt.get("strong"):
+            total = int(sum(strong_lens))
+            entry.update({"scaling": "strong", "n_gpus": world, "value": total / (e2e_ms * 1e-3), "unit": "samples/s",
+                          "ms_per_pass": e2e_ms, "what": "whole fixed set / max-over-ranks wall time of the blocking C-ABI calls (host buffers in, bases out)",
+                          "shard_imbalance": float(max_over_ranks(float(samples)) * world / total)})
+        else:
+            # device-resident value + roofline of the recurrent kernel (single chunk by construction)
+            rb_, b_, o, _, _ = work[0]
+            ctx._check(lib.lib.ffb_upload_raw(ctx.handle, ctypes.byref(rb_), ctypes.byref(b_)), "ffb_upload_raw")
+            ctx.forward(); barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sampler = ClockSampler(local); sampler.start()
+            tw0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(K):
+                ctx.forward()
+            e1.record(stream)
+            barrier()
+            clocks = sampler.stop(tw0, time.perf_counter())
+            dev_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+            groups = ctx.forward_timed()
+            T = ctx.total_blocks()
+            S, G = fm.size, fm.ngate
+            ach = 2.0 * T * S * G * S / (groups["rnn"] / 5.0 * 1e-3) / 1e12
+            entry.update({"scaling": "weak", "n_gpus": world, "value": samples * world / (dev_ms * 1e-3), "unit": "samples/s", "ms_per_step": dev_ms,
+                          "e2e": {"value": samples * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
+                                  "what": "blocking ffb_basecall_raw_batch, one context (no overlap of host and device)"},
+                          "blocks_this_rank": int(T), "roofline_frac": ach / peaks["tf_sustained"], "rnn_ms_per_launch": groups["rnn"] / 5.0,
+                          "step_breakdown_ms": groups, "clocks": clocks})
+        out.append(entry)
+        ctx.close(); model.close()
+        del work, ctx, model
+        torch.cuda.empty_cache()
+    return out
+
+
+def build_config(a, world, tot_blocks):
+    return {"workload": f"{a.reads} synthetic {RAW_SAMPLES}-sample reads per GPU ({RAW_SAMPLES - 210} after the default trim), "
+                        f"{a.model}: {MODEL_CHOICES[a.model][1]}; random-init weights; "
+                        f"{'--viterbi' if a.viterbi_only else 'forward-backward + Viterbi (CLI default)'}",
+            "blocks_per_gpu": int(tot_blocks) if tot_blocks is not None else None, "reads_per_gpu": a.reads,
+            "l2": "working set per step (Xin + activations, ~10 GB) far exceeds the 126 MB L2; no flush needed",
+            "schedule": "layer l+1's input GEMM streamed behind layer l's recurrence (PDL); GRU: its z-gate third computed by the recurrence itself"
+                        if os.environ.get("FFB_NO_STREAM_GEMM") is None else "sequential kernels",
+            "signal_prep": "value: normalised signal resident in HBM (prepared once, outside the timed region); "
+                           "e2e: RAW signal from pinned host memory, trimming + med-MAD normalisation on the device inside the timed "
+                           "region, two batches in flight (ffb_submit_raw_batch / ffb_collect on two contexts), bases + quality "
+                           "characters emitted on the device and copied back, wall clock",
+            "parallelism": f"read-shard x{world}, no collective"}
 
 
 def main():
@@ -201,6 +320,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-reads-per-core", type=int, default=6)
     ap.add_argument("--ref-reads-total", type=int, default=256)
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` configs (A/B runs)")
+    ap.add_argument("--strong-reads", type=int, default=8192, help="reads of the fixed configs[3] strong-scaling set")
     a = ap.parse_args()
 
     if a.impl == "reference":
@@ -278,6 +399,7 @@ def main():
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     samples_per_step = n * RAW_SAMPLES * world
     value = samples_per_step * a.steps / (dev_ms * 1e-3)
+    ctx.download(batch)                    # path / qpath of this arm: the e2e arm's device-emitted bases are checked against them
 
     # ---- end-to-end arm: RAW host buffers through the C ABI (ffb_basecall_raw_batch): H2D of the raw samples,
     #      trimming + normalisation + network + decode on the device, D2H of path/qpath/score, all inside the timed region ----
@@ -288,29 +410,34 @@ def main():
     raw_pinned.numpy()[:] = np.concatenate(raws)
     raw_np = raw_pinned.numpy()
     raw_blocks = sum(max(fm.nblock(int(x)), 0) for x in raw_lens)       # outputs sized for the untrimmed lengths
-    out_raw = {
-        "blk_off": np.zeros(n + 1, np.int64),
-        "path": torch.empty(raw_blocks + n, dtype=torch.int32).pin_memory().numpy(),
-        "qpath": torch.empty(raw_blocks + n, dtype=torch.float32).pin_memory().numpy(),
-        "score": torch.empty(n, dtype=torch.float32).pin_memory().numpy(),
-    }
     # two contexts on two streams: while the device works on batch i the host trims / plans / uploads batch i+1
-    # (ffb_submit_raw_batch / ffb_collect); every step still pays its own H2D, device prep and D2H
+    # (ffb_submit_raw_batch / ffb_collect); every step still pays its own H2D, device prep and D2H.  The step ends with the
+    # called bases and quality characters in host memory (emitted on the device): path / qpath stay in HBM.
     stream2 = torch.cuda.Stream()
     ctx2 = api.Context(model, stream=stream2.cuda_stream)
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
     pipe = []
     for cx in (ctx, ctx2):
-        o = {k: (torch.empty(v.shape, dtype=torch.from_numpy(v).dtype).pin_memory().numpy() if k != "blk_off" else np.zeros_like(v))
-             for k, v in out_raw.items()}
-        b_, o = cx.make_batch(raw_np, raw_off_np, 1.0, flags, o)
+        o = {"blk_off": np.zeros(n + 1, np.int64), "score": pinned(n, torch.float32), "bases": pinned(raw_blocks + n, torch.uint8),
+             "quals": pinned(raw_blocks + n, torch.uint8), "nbases": pinned(n, torch.int32)}
+        b_, o = cx.make_batch(raw_np, raw_off_np, 1.0, flags, o, emit=True, want_path=False)
         rb_, rstart, rend = cx.make_raw_batch(raw_np, raw_off_np)
         pipe.append((cx, rb_, b_, o))
     for cx, rb_, b_, o in pipe:                       # warm-up: workspaces of both contexts
         for _ in range(min(a.warmup, 2)):
             cx.submit_raw(rb_, b_); cx.collect(b_)
-    # the device-prepared path must reproduce the host-prepared one bit for bit
+    # the device-prepared, device-emitted path must reproduce the host-prepared one: same blocks, and the bases that
+    # ffb_emit_bases makes of the device-resident arm's path
     assert np.array_equal(pipe[0][3]["blk_off"], out["blk_off"]) and np.array_equal(pipe[1][3]["blk_off"], out["blk_off"])
-    assert np.array_equal(pipe[0][3]["path"][:tot_blocks + n], pipe[1][3]["path"][:tot_blocks + n])
+    for i in (0, n // 2, n - 1):
+        s0 = int(out["blk_off"][i]) + i
+        nb_i = int(pipe[0][3]["nbases"][i])
+        want_b, want_q = lib.emit_bases(out["path"][s0:s0 + int(out["blk_off"][i + 1] - out["blk_off"][i]) + 1],
+                                        out["qpath"][s0:s0 + int(out["blk_off"][i + 1] - out["blk_off"][i]) + 1], fm.nbase)
+        assert pipe[0][3]["bases"][s0:s0 + nb_i].tobytes().decode() == want_b and pipe[1][3]["quals"][s0:s0 + nb_i].tobytes().decode() == want_q
     barrier()
     t0 = time.perf_counter()
     for i in range(a.steps):
@@ -326,7 +453,7 @@ def main():
     e2e_value = samples_per_step * a.steps / (e2e_ms * 1e-3)
     out_raw = pipe[0][3]
     h2d = int(raw_np.nbytes + 3 * raw_off_np.nbytes + 4 * n)
-    d2h = int(out_raw["blk_off"][-1] + n) * 8 + 4 * n + 16 * n     # path + qpath of the blocks produced, score, trim bounds
+    d2h = int(out_raw["blk_off"][-1] + n) * 2 + 8 * n + 16 * n     # bases + quality chars of the blocks produced, counts, scores, trim bounds
 
     # ---- per-kernel-group timing for the roofline (up to three extra passes of the same step, sequential schedule,
     #      CUDA events on the library's stream around each kernel group, averaged; not part of `value`) ----
@@ -337,41 +464,46 @@ def main():
     rnn_ms_per_launch = groups["rnn"] / 5.0
     achieved_tf = rnn_flops / (rnn_ms_per_launch * 1e-3) / 1e12
     tensor_path = not a.fp32_simt and fm.size in (256, 384)
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_final_rnn_tc_ncu_summary.txt: 5.99 + 1.94 GB,
-    # ncu --set full of this command); algorithmic = Xin read 4*G*S + planes written 4*S bytes per block
-    traffic = 7.93e9 if (tensor_path and a.model == "r941_native_gru" and a.reads == 1024) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel, from the committed `ncu --set full` capture of
+    # this very command (a number taken under the profiler cannot be re-measured inside a timed run): read from the file
+    # tools/ncu_summary.py wrote, never a constant in this script
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "r02_rnn_tc_traffic.json")
+    if tensor_path and a.model == "r941_native_gru" and a.reads == 1024 and os.path.exists(tj):
+        tdoc = json.load(open(tj))
+        traffic, traffic_src = float(tdoc["dram_bytes_per_launch"]), f"profiles/r02_rnn_tc_traffic.json ({tdoc.get('source', 'ncu --set full')})"
+    fused = tensor_path and fm.kind == 0
     roofline = {"kernel": "rnn_tc_kernel (recurrent layer: h*sW on tcgen05 + gates, 5 launches/step)" if tensor_path
                           else "rnn_layer_kernel (fp32 CUDA-core cluster kernel, 5 launches/step)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic,
+                "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "timed": "CUDA events around each launch in the SEQUENTIAL schedule (ffb_forward_timed, extra passes after the timed "
+                         "region); `value` runs the streamed schedule, where the same launches overlap the next layer's input GEMM",
                 "peak_source": f"{peaks['src']} bf16 dense sustained (kernel timed inside a long step)",
-                "algorithmic_bytes_per_launch": float(T) * (4 * G * S + 4 * S),
-                "note": "algorithmic flops = 2*blocks*S*G*S per launch; the fp32-faithful fp16 hi/lo split issues 3 MMAs per "
-                        "product and pads 96 gate rows to M=128, so raw tensor-pipe work is 4x algorithmic (GRU-256); the layer is "
-                        "T dependent steps of ~1.9 us each, i.e. bound by the latency of the step chain, not by the pipe "
-                        "(DESIGN.md 4.2)",
+                "algorithmic_bytes_per_launch": float(T) * (4 * G * S + 4 * S + (4 * S if fused else 0)),
+                "note": "algorithmic flops = 2*blocks*S*G*S per launch (h*sW only); the fp32-faithful fp16 hi/lo split issues 3 MMAs per "
+                        "product; GRU: the fourth quarter of each M=128 tile carries the z-gate rows of the next layer's input "
+                        "projection (another 2*blocks*S*S useful flops per launch, not counted here); the layer is T dependent steps "
+                        "of ~2.5 us each, i.e. bound by the latency of the step chain, not by the pipe (DESIGN.md 4.2)",
                 "step_breakdown_ms": groups}
 
     line = {
         "metric": "raw-signal samples/sec basecalled", "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dev_ms / a.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{a.reads} synthetic {RAW_SAMPLES}-sample reads per GPU ({RAW_SAMPLES - 210} after the default trim), "
-                               f"{a.model}: {MODEL_CHOICES[a.model][1]}; random-init weights; "
-                               f"{'--viterbi' if a.viterbi_only else 'forward-backward + Viterbi (CLI default)'}",
-                   "blocks_per_gpu": int(tot_blocks), "reads_per_gpu": n,
-                   "l2": "working set per step (Xin + activations, ~16 GB) far exceeds the 126 MB L2; no flush needed",
-                   "schedule": "layer l+1's input GEMM streamed behind layer l's recurrence (PDL)" if os.environ.get("FFB_NO_STREAM_GEMM") is None else "sequential kernels",
-                   "signal_prep": "value: normalised signal resident in HBM (prepared once, outside the timed region); "
-                                  "e2e: RAW signal from pinned host memory, trimming + med-MAD normalisation on the device inside the timed "
-                                  "region, two batches in flight (ffb_submit_raw_batch / ffb_collect on two contexts), wall clock",
-                   "parallelism": f"read-shard x{world}, no collective"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (GEMM operands split into fp16 hi + lo, 3 tcgen05 MMAs per product, fp32 accumulate; gates ex2/rcp.approx)",
+        "data": "synthetic",
+        "config": build_config(a, world, tot_blocks),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / a.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    ctx2.close(); ctx.close(); model.close()
+    del ctx2, ctx, model
+    if not a.no_extra:
+        line["extra"] = run_extras(a, api, lib, peaks, world, rank, local, barrier, max_over_ranks)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             cores = len(os.sched_getaffinity(0))
@@ -380,7 +512,6 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    ctx2.close(); ctx.close(); model.close()
     if world > 1:
         dist.destroy_process_group()
 

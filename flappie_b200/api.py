@@ -382,7 +382,7 @@ class Context:
             raise FlappieB200Error(f"{what} failed ({r}): {self.lib.last_error()}")
 
     def make_batch(self, signal: np.ndarray, sig_off: np.ndarray, temperature=1.0, flags=0,
-                   out: Optional[dict] = None, emit: bool = False):
+                   out: Optional[dict] = None, emit: bool = False, want_path: bool = True):
         """Build the C `ffb_batch` over caller-owned numpy (or pinned torch->numpy) buffers."""
         fm = self.model.fm
         n = sig_off.shape[0] - 1
@@ -393,8 +393,9 @@ class Context:
             tot_blocks += max(t, 0)
         o = out if out is not None else {}
         o.setdefault("blk_off", np.zeros(n + 1, np.int64))
-        o.setdefault("path", np.zeros(tot_blocks + n, np.int32))
-        o.setdefault("qpath", np.zeros(tot_blocks + n, np.float32))
+        if want_path:       # with device-side emission the path / qpath need not come back at all
+            o.setdefault("path", np.zeros(tot_blocks + n, np.int32))
+            o.setdefault("qpath", np.zeros(tot_blocks + n, np.float32))
         o.setdefault("score", np.zeros(max(n, 1), np.float32))
         if flags & FLAG_WANT_TRANS:
             o.setdefault("trans", np.zeros((tot_blocks, fm.nparam), np.float32))

@@ -98,6 +98,8 @@ struct ffb_model {
     void *d_sW_img[FFB_NLAYER] = {nullptr};   // per-CTA shared-memory images of sW (fp16 hi/lo) for rnn_tc
     bool tc_rnn = false;
     bool fuse_z = false;      // GRU: recurrent layer l also computes the z-gate third of layer l+1's input projection (rnn_tc.cu)
+    bool fuse_ff = false;     // ... and the top layer the flip-flop output layer (FF_W rows in the same free quarter)
+    float *d_ffb_s = nullptr; // FF bias zero-padded to S entries
     int tc_max_clusters = 0;
     int layer_in[FFB_NLAYER] = {0};
     // conv edge plans, cached per (conv layer, T_in)
@@ -126,7 +128,7 @@ extern "C" void ffb_model_destroy(ffb_model *m) {
     cudaFree(m->d_ffWt); cudaFree(m->d_ffb);
     cudaFree(m->d_ff_hi); cudaFree(m->d_ff_lo); cudaFree(m->d_ffb_pad);
     cudaFree(m->d_c3_hi); cudaFree(m->d_c3_lo);
-    cudaFree(m->d_phred_thr);
+    cudaFree(m->d_phred_thr); cudaFree(m->d_ffb_s);
     delete m;
 }
 
@@ -216,6 +218,16 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             if (ok && ffb_rnn_tc_supported(kind, S)) {
                 // the free quarter of a GRU layer's M=128 tiles carries the z-gate rows of the NEXT layer's projection
                 std::vector<float> zrows;
+                if (fuse_z && l + 1 == FFB_NLAYER && !head && getenv("FFB_NO_FUSE_FF") == nullptr) {
+                    // top layer: the flip-flop output layer's rows (FF_W is [S x nparam], nparam <= S), zero beyond
+                    const _Mat *FW = L[15];
+                    if ((int)FW->nr == S && (int)FW->nc <= S) {
+                        zrows.assign((size_t)S * S, 0.0f);
+                        for (int n = 0; n < (int)FW->nc; n++)
+                            for (int k = 0; k < S; k++) zrows[(size_t)n * S + k] = mat_at(FW, k, n);
+                        m->fuse_ff = true;
+                    }
+                }
                 if (fuse_z && l + 1 < FFB_NLAYER) {
                     const _Mat *iWn = L[3 * (l + 1)];
                     if ((int)iWn->nr == S && (int)iWn->nc == G * S) {
@@ -259,6 +271,12 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             }
             m->d_ffWt = upload(Wt); m->d_ffb = upload(bb);
             ok = m->d_ffWt && m->d_ffb;
+            if (ok && m->fuse_ff) {
+                std::vector<float> bs((size_t)m->S, 0.0f);
+                std::copy(bb.begin(), bb.end(), bs.begin());
+                m->d_ffb_s = upload(bs);
+                ok = m->d_ffb_s != nullptr;
+            }
             if (ok && ffb_ff_tc_supported(m->nparam, m->S)) {
                 // [out][in] planes like iW, zero rows beyond nparam
                 std::vector<float> Wd((size_t)FFB_FF_TC_ROWS * m->S, 0.0f), bp(FFB_FF_TC_ROWS, 0.0f);
@@ -421,6 +439,7 @@ struct ffb_ctx {
     DevBuf d_slotoff, d_slotlist;
     DevBuf d_bases, d_quals, d_nbases;   // device-side emission (emit.cu), read n at blk_off[n] + n
     bool want_emit = false;
+    bool ff_done = false;         // this forward: the top recurrent layer produced trans
     DevBuf d_c2hi, d_c2lo;        // tensor-core convolution: fp16 planes of its input in the slot layout (see forward_impl)
     int conv3_fix = 0;            // columns at either end of a read the CUDA-core kernel recomputes
     bool use_tc_conv3 = false;
@@ -950,6 +969,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     // ---- five recurrent layers, directions B,F,B,F,B (networks.c:460-483 / :557-580) ----
     RnnBatch rb{c->d_order.as<int32_t>(), c->d_blkoff.as<int64_t>(), c->n_slots, (int)N};
     float gemm_ms = 0.f, rnn_ms = 0.f;
+    c->ff_done = false;
     const bool tc_rnn = c->use_tc_rnn && tc_gemm;
     const bool tc_ff = tc_rnn && m->tc_ff && getenv("FFB_NO_TC_FF") == nullptr;
     const float *in = c->d_act[0].as<float>();   // fp32 input of the current layer (NULL when only planes exist)
@@ -988,15 +1008,20 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         if (timed) cudaEventRecord(c->ev[6], st);
         if (tc_rnn) {
             // the top layer feeds the output layer: fp16 planes for the tensor version, fp32 otherwise
-            const bool planes_out = !last || tc_ff;
+            const bool ff_here = last && fuse_z && m->fuse_ff && tc_ff;     // the top layer writes trans itself
+            const bool planes_out = !last || (tc_ff && !ff_here);
             float *out_f32 = (keep || (last && !tc_ff)) ? out : nullptr;
             int *prog = (streamed && !last) ? c->d_progress.as<int>() + (size_t)l * prog_stride : nullptr;
             RnnTcSched sched{c->d_slotoff.as<int32_t>(), c->d_slotlist.as<int32_t>(), c->tc_clusters, c->n_slots / 16};
             // (unstreamed, xin_buf[0] == xin_buf[1]: in place -- the thread that writes column j of a row has read it already)
             const bool fz = fuse_z && !last;
+            const float ffs = m->head ? c->temperature : c->temperature / 5.0f;
             LAUNCH(ffb_launch_rnn_tc(m->kind, S, xin, m->d_sW_img[l], out_f32, planes_out ? c->d_ahi.p : nullptr,
                                      planes_out ? c->d_alo.p : nullptr, rb, sched, c->R_tc, (l % 2) == 0, c->d_ring.p, prog,
-                                     fz ? m->d_b[l + 1] : nullptr, fz ? xin_buf[(l + 1) & 1] : nullptr, st));
+                                     fz ? m->d_b[l + 1] : (ff_here ? m->d_ffb_s : nullptr),
+                                     fz ? xin_buf[(l + 1) & 1] : (ff_here ? c->d_trans.as<float>() : nullptr),
+                                     ff_here ? nr : 0, ffs, st));
+            c->ff_done = ff_here;
             if (streamed && !last) {
                 const int dir = (l % 2) == 0 ? 1 : 0;   // layer l runs backward for even l (networks.c:460-483)
                 LAUNCH(ffb_launch_gemm_tc_streamed(c->d_ahi.p, c->d_alo.p, m->d_iW_hi[l + 1], m->d_iW_lo[l + 1], m->d_b[l + 1],
@@ -1023,7 +1048,9 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     // ---- globalnorm_flipflop (layers.c:1082-1106) ----
     // scale: flip-flop divides tanh by temperature / 5 (layers.c:1087); the run-length head computes 5 tanhf / temperature
     const float ff_scale = m->head ? c->temperature : c->temperature / 5.0f;
-    if (tc_ff)
+    if (c->ff_done) {
+        // trans was written by the top recurrent layer (its free MMA rows carry FF_W)
+    } else if (tc_ff)
         LAUNCH(ffb_launch_ff_tanh_tc(c->d_ahi.p, c->d_alo.p, m->d_ff_hi, m->d_ff_lo, m->d_ffb_pad, c->d_trans.as<float>(), Tt, nr, S,
                                      ff_scale, m->head, st));
     else

@@ -33,6 +33,23 @@ __device__ __forceinline__ float fast_logistic(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return r;
 }
+// A/B of the recurrent gates' accuracy (tools/gpu_call5.sh): the same two MUFU ops with the argument scaling and the
+// reciprocal repaired in fp32 -- x * log2(e) carried as product + rounding error (folded in as 2^t * (1 + err ln 2)) and one
+// Newton step on the reciprocal.  ~7 extra ALU ops per logistic, no extra MUFU.
+__device__ __forceinline__ float mid_logistic(float x) {
+    const float t = x * -1.4426950408889634f;
+    const float err = fmaf(x, -1.4426950408889634f, -t) + x * -1.925963033500097e-8f;     // log2(e) = hi + lo
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    e = fmaf(e, err * 0.6931471805599453f, e);
+    const float d = 1.0f + e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+__device__ __forceinline__ float mid_tanh(float x) {
+    const float y = mid_logistic(x + x);
+    return (y + y) - 1.0f;
+}
 __device__ __forceinline__ float fast_tanh(float x) {
     const float y = fast_logistic(x + x);
     return (y + y) - 1.0f;
@@ -157,7 +174,9 @@ int ffb_rnn_prepare(int kind, int S);   // one-time function attribute setup; re
 int ffb_rnn_tc_supported(int kind, int S);
 size_t ffb_rnn_tc_image_halfs(int kind, int S);
 // fused_z: NULL, or [S][S] rows of the NEXT layer's input projection (GRU: its z gate) that ride in the free quarter of the
-// M=128 tile; the kernel then also writes that layer's Xin[.][0..S) (ffb_launch_rnn_tc: bnext / xnext)
+// M=128 tile; the kernel then also writes that layer's Xin[.][0..S) (ffb_launch_rnn_tc: bnext / xnext, next_rows = 0).  For the
+// top layer the rows are the flip-flop output layer's (FF_W, zero beyond nparam): next_rows = nparam, xnext = trans
+// [blocks][nparam] = tanh(. + bnext) / ff_scale
 void ffb_rnn_tc_pack(int kind, int S, const float *sW, uint16_t *img, const float *fused_z);
 int ffb_rnn_tc_can_fuse_z(int kind, int S);
 int ffb_rnn_tc_prepare(int kind, int S);
@@ -178,7 +197,7 @@ struct RnnTcSched {
 // progress[n_groups] counts CTAs that have finished the layer
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
                       const RnnBatch &rb, const RnnTcSched &sched, int R, int backward, void *ring, int *progress,
-                      const float *bnext, float *xnext, cudaStream_t st);
+                      const float *bnext, float *xnext, int next_rows, float ff_scale, cudaStream_t st);
 
 // signal.cu: trimming + normalisation of raw reads on the device (reference src/flappie.c:251-259)
 #define FFB_MAX_VARSEG_CHUNK 1024

@@ -144,18 +144,45 @@ __device__ unsigned long long ffb_rnn_prof_dev[16];
 #define PROF_FLUSH(lo, hi)
 #endif
 
+// gate arithmetic of the cells: 0 = MUFU ex2 / rcp as they come, 1 = expf + IEEE division, 2 = MUFU with repaired argument
+// scaling and one Newton step (ffb_common.cuh)
+#ifndef FFB_RNN_GATES
+#define FFB_RNN_GATES 0
+#endif
+__device__ __forceinline__ float gate_logistic(float x) {
+#if FFB_RNN_GATES == 1
+    return logisticf(x);
+#elif FFB_RNN_GATES == 2
+    return mid_logistic(x);
+#else
+    return fast_logistic(x);
+#endif
+}
+__device__ __forceinline__ float gate_tanh(float x) {
+#if FFB_RNN_GATES == 1
+    return tanh_ref(x);
+#elif FFB_RNN_GATES == 2
+    return mid_tanh(x);
+#else
+    return fast_tanh(x);
+#endif
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::MAX_THREADS, 1)
 rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, float *__restrict__ Hout,
               __half *__restrict__ Hhi, __half *__restrict__ Hlo, const int32_t *__restrict__ order,
               const int64_t *__restrict__ blk_off, const int32_t *__restrict__ slot_off, const int32_t *__restrict__ slot_list,
               uint8_t *__restrict__ ring, int *__restrict__ progress, int G, int n_groups, int backward,
-              const float *__restrict__ bnext, float *__restrict__ xnext) {
+              const float *__restrict__ bnext, float *__restrict__ xnext, int next_ld, int next_rows, float ff_scale) {
     constexpr int S = Cfg::S, C = Cfg::C, NGATE = Cfg::NGATE, NG = Cfg::NG, GMAX = Cfg::GMAX;
     // GRU only: the fourth gate slot of the weight image (rows 24..31 of every TMEM quadrant, zero otherwise) carries the
     // z-gate rows of the NEXT layer's input projection.  They ride in the same M=128 MMAs for free: at step s the slot
     // holds iW_z * h_{s-1}, i.e. the next layer's Xin[.][0..S) of the previous time index (see the header comment).
+    // The TOP layer carries the flip-flop output layer there instead (next_rows = 40 / 60 rows of FF_W, the rest zero):
+    // xnext = trans [blocks][next_ld], written as tanh(. + b) / ff_scale (globalnorm_manystay, src/layers.c:1082-1087).
     const bool fuse = (NGATE == 3) && xnext != nullptr;
+    const bool fuse_ff = next_rows > 0;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
     __shared__ uint32_t tmem_slot;
@@ -492,17 +519,17 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             for (int i = 0; i < 4; i++) {
                 float hn, cn = 0.0f;
                 if constexpr (NGATE == 3) {
-                    const float z = fast_logistic(x[i][0] + a[i][0]);                   // layers.c:697-699
-                    const float r = fast_logistic(x[i][1] + a[i][1]);
-                    const float hbar = fast_tanh(r * a[i][2] + x[i][2]);               // layers.c:704-709
+                    const float z = gate_logistic(x[i][0] + a[i][0]);                   // layers.c:697-699
+                    const float r = gate_logistic(x[i][1] + a[i][1]);
+                    const float hbar = gate_tanh(r * a[i][2] + x[i][2]);               // layers.c:704-709
                     hn = z * hprev[i] + (1.0f - z) * hbar;                             // layers.c:712-714
                 } else {
-                    const float ig = fast_logistic(x[i][0] + a[i][0]);                  // layers.c:1013-1024
-                    const float fg = fast_logistic(x[i][1] + a[i][1]);
-                    const float gg = fast_tanh(x[i][2] + a[i][2]);
-                    const float og = fast_logistic(x[i][3] + a[i][3]);
+                    const float ig = gate_logistic(x[i][0] + a[i][0]);                  // layers.c:1013-1024
+                    const float fg = gate_logistic(x[i][1] + a[i][1]);
+                    const float gg = gate_tanh(x[i][2] + a[i][2]);
+                    const float og = gate_logistic(x[i][3] + a[i][3]);
                     cn = fg * cstate[i] + ig * gg;
-                    hn = og * fast_tanh(cn);
+                    hn = og * gate_tanh(cn);
                 }
                 if (all || s < cT[i]) {             // finished reads keep (and keep pushing) their frozen state
                     hprev[i] = hn;
@@ -530,9 +557,15 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             }
             if (fuse && s > 0) {
                 // gate slot 3 = iW_z(next layer) * h_{s-1}: the next layer's z pre-activation of the PREVIOUS time index
+                if (!fuse_ff) {
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    if (all || s <= cT[i]) __stcs(xz + (int64_t)(orow[i] - rstep) * XROW, a[i][3] + bz);
+                    for (int i = 0; i < 4; i++)
+                        if (all || s <= cT[i]) __stcs(xz + (int64_t)(orow[i] - rstep) * next_ld, a[i][3] + bz);
+                } else if (j < next_rows) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (all || s <= cT[i]) xz[(int64_t)(orow[i] - rstep) * next_ld] = tanh_ref(a[i][3] + bz) / ff_scale;
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) { xp[i] += xstep; orow[i] += rstep; }
@@ -564,9 +597,15 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&staged[g]);
+            if (!fuse_ff) {
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                if (cT[i] == Tmax) __stcs(xz + (int64_t)(orow[i] - rstep) * XROW, a3[i] + bz);
+                for (int i = 0; i < 4; i++)
+                    if (cT[i] == Tmax) __stcs(xz + (int64_t)(orow[i] - rstep) * next_ld, a3[i] + bz);
+            } else if (j < next_rows) {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (cT[i] == Tmax) xz[(int64_t)(orow[i] - rstep) * next_ld] = tanh_ref(a3[i] + bz) / ff_scale;
+            }
         }
         }
         PROF_FLUSH(8, 12);
@@ -699,7 +738,7 @@ int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
 template <class Cfg>
 static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo, const RnnBatch &rb,
                       const RnnTcSched &sched, int R, int backward, void *ring, int *progress, const float *bnext, float *xnext,
-                      cudaStream_t st) {
+                      int next_rows, float ff_scale, cudaStream_t st) {
     const int G = R / Cfg::NG;
     if (G < 1 || G > Cfg::GMAX || R % Cfg::NG || !ring || !sched.slot_off || !sched.slot_list) return -1;
     const int n_clusters = sched.n_clusters;
@@ -708,14 +747,15 @@ static int launch_one(const float *Xin, const void *Wimg, float *Hout, void *Hhi
     rnn_tc_config<Cfg>(cfg, attr, n_clusters, G, st);
     cudaError_t e = cudaLaunchKernelEx(&cfg, ffb::rnn_tc_kernel<Cfg>, Xin, (const __half *)Wimg, Hout, (__half *)Hhi,
                                        (__half *)Hlo, rb.order, rb.blk_off, sched.slot_off, sched.slot_list, (uint8_t *)ring, progress,
-                                       G, sched.n_groups, backward, bnext, xnext);
+                                       G, sched.n_groups, backward, bnext, xnext, next_rows > 0 ? next_rows : Cfg::NGATE * Cfg::S,
+                                       next_rows, ff_scale);
     return e == cudaSuccess ? 1 : -1;
 }
 
 int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float *Hout, void *Hhi, void *Hlo,
                       const RnnBatch &rb, const RnnTcSched &sched, int R, int backward, void *ring, int *progress,
-                      const float *bnext, float *xnext, cudaStream_t st) {
+                      const float *bnext, float *xnext, int next_rows, float ff_scale, cudaStream_t st) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
-    if (xnext && (!bnext || !ffb_rnn_tc_can_fuse_z(kind, S))) return -1;
-    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, sched, R, backward, ring, progress, bnext, xnext, st); });
+    if (xnext && (!bnext || !ffb_rnn_tc_can_fuse_z(kind, S) || next_rows < 0 || next_rows > S)) return -1;
+    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, sched, R, backward, ring, progress, bnext, xnext, next_rows, ff_scale, st); });
 }

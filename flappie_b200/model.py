@@ -140,10 +140,10 @@ class FlipflopModel:
                   winlen: int = 19, saturate: bool = False) -> "FlipflopModel":
         """Seeded weights at a reference model's shape.
         Scales keep the gates out of saturation and the recurrence contractive, as for
-        trained models.  saturate=True: three times the input gain and +-1.5 biases -- gate
-        pre-activations of +-10 and more, so that sigmoid / tanh spend much of a read pinned at
-        0 / 1 / +-1 (the wide-dynamic-range regime of trained gates; the recurrent gain stays
-        contractive)."""
+        trained models.  saturate=True: gate biases drawn from U(-4, 4) instead of U(-0.1, 0.1),
+        so that a good part of the sigmoids / tanhs sit pinned at 0 / 1 / +-1 for whole reads (the
+        wide-dynamic-range regime of trained gates) while the gains -- and with them the
+        layer-to-layer amplification of rounding noise -- stay what they are."""
         rng = np.random.default_rng(seed)
         G = 3 if kind == KIND_GRU else 4
 
@@ -166,11 +166,9 @@ class FlipflopModel:
         # gains chosen (tests/golden/README.md) so that the output follows the signal
         # (hundreds of base transitions per read) while a 1e-6 input perturbation grows
         # by < 10x through the five layers, like a trained, contractive model
-        if saturate:
-            g_i *= 3.0
         iW = [u((G * size, size), g_i / np.sqrt(size)) for _ in range(5)]
         sW = [u((G * size, size), g_s / np.sqrt(size)) for _ in range(5)]
-        b = [u((G * size,), 1.5 if saturate else 0.1) for _ in range(5)]
+        b = [u((G * size,), 4.0 if saturate else 0.1) for _ in range(5)]
         nstate = 2 * nbase
         nparam = nstate * (nbase + 1)
         ff_W = u((nparam, size), g_f / np.sqrt(size))

@@ -105,13 +105,15 @@ def test_reference_main_on_this_library_equals_the_b200_cli(gpu_lib, tmp_path, e
     lens = [4000, 2500, 6000, 150, 3000]
     raws = synthetic_reads(len(lens), lens, seed=31) + [pa]
     rdir = tmp_path / "reads"; rdir.mkdir()
+    files = []
     for i, r in enumerate(raws):
         np.asarray(r, np.float32).tofile(rdir / f"read_{i:02d}.f32")
+        files.append(str(rdir / f"read_{i:02d}.f32"))       # named one by one: the reference globs "<dir>/*.fast5" only
     env = dict(os.environ, FLAPPIE_B200_MODELS=str(tmp_path))
     outs = []
     for exe, more in ((EXE, []), (os.path.join(HOST, "flappie"), ["--batch", "4"])):
         out = tmp_path / (os.path.basename(exe) + ".out")
-        r = subprocess.run([exe, "--model", "r941_native", "--output", str(out)] + more + extra + [str(rdir)],
+        r = subprocess.run([exe, "--model", "r941_native", "--output", str(out)] + more + extra + files,
                            capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(open(out, "rb").read())
