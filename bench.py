@@ -240,8 +240,8 @@ def run_extras(a, api, lib, peaks, world, rank, local, barrier, max_over_ranks):
                  "bases": torch.empty(blocks + len(cl), dtype=torch.uint8).pin_memory().numpy(),
                  "quals": torch.empty(blocks + len(cl), dtype=torch.uint8).pin_memory().numpy(), "nbases": np.zeros(len(cl), np.int32)}
             b_, o = ctx.make_batch(raw, off, 1.0, flags, o, emit=True, want_path=False)
-            rb_, _, _ = ctx.make_raw_batch(raw, off, delta=opt.get("delta", 0.0))
-            work.append((rb_, b_, o, raw, off))
+            rb_, st_, en_ = ctx.make_raw_batch(raw, off, delta=opt.get("delta", 0.0))
+            work.append((rb_, b_, o, raw, (off, st_, en_)))      # everything the C structs point at stays referenced here
             del raws
         samples = int(sum(lens))
         K = 2

@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 HOST = os.path.join(HERE, "host")
-HOST_SOURCES = ["ffb_output.c", "ffb_weights.c", "ffb_rawio.c"]
+HOST_SOURCES = ["ffb_output.c", "ffb_weights.c", "ffb_rawio.c", "ffb_shard.c"]
 HOST_BIN = os.path.join(HOST, "flappie")
 HOST_LIB = os.path.join(HOST, "libffb_host.so")
 

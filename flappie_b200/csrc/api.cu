@@ -516,18 +516,53 @@ extern "C" int ffb_sync(ffb_ctx *c) {
 // more clusters = shorter chains per SM); when the batch has more groups than slots, or the reads differ in length, the
 // groups are dealt longest-first to the least-loaded slot (LPT) so every slot runs about the same number of steps.
 // blk_off: n_reads + 1 block offsets; sorted: read indices by descending length.
-static void plan_groups(const int64_t *blk_off, const int32_t *sorted, int64_t N, int maxc, int gmax, bool can_stream,
+static void plan_groups(const int64_t *blk_off, const int32_t *sorted, int64_t N, int maxc, int gmax, bool can_stream, int csize,
                         int *G_out, int *ncl_out, std::vector<int32_t> &order, std::vector<int32_t> &slot_off,
                         std::vector<int32_t> &slot_list, std::vector<int64_t> &group_start) {
     const int64_t groups = (N + 15) / 16;
-    int G, ncl;
-    if (groups <= (int64_t)maxc * gmax) {
-        const int64_t gpc = (groups + maxc - 1) / maxc;
-        G = (int)std::min<int64_t>(std::max<int64_t>(gpc, 1), gmax);
-        ncl = (int)((groups + G - 1) / G);
-    } else {
-        G = gmax;
-        ncl = std::max(1, maxc - (can_stream ? 2 : 0));     // a few SMs stay free for the streamed input GEMM, where that exists
+    int G = 1, ncl = 0;
+    // Which (slots per cluster, clusters)?  The layer lasts makespan(groups dealt longest-first over G * ncl slots) steps,
+    // a step costs chain(G) (more slots per CTA = more contention for the tensor pipe: +8 % from five to six, measured,
+    // profiles/r02_slots_ab.txt), and the streamed input GEMM of the next layer hides behind it only as far as the SMs the
+    // clusters leave free can carry it (its full-chip time: 0.24 steps per 1000 blocks at S = 256).  Candidates are few;
+    // each is simulated.  One wave of 16-read groups (BASELINE configs[1]: 64 groups) lands on five slots x 13 clusters
+    // as before; 4096 equal reads on six slots x 15 clusters (three rounds instead of four).
+    {
+        std::vector<int64_t> Tg((size_t)groups);
+        int64_t blocks = 0;
+        for (int64_t g = 0; g < groups; g++) {
+            const int32_t rd0 = sorted[g * 16];
+            Tg[(size_t)g] = blk_off[rd0 + 1] - blk_off[rd0];
+        }
+        for (int64_t n = 0; n < N; n++) blocks += blk_off[n + 1] - blk_off[n];
+        const double gemm_steps = can_stream ? 0.243e-3 * (double)blocks : 0.0;
+        const int sms = 148;
+        double best = -1.0;
+        for (int g = 1; g <= gmax; g++) {
+            int tried[4] = {(int)std::min<int64_t>((groups + g - 1) / g, maxc), maxc - 2, maxc - 1, maxc};   // ties: fewer clusters
+            for (int k = 0; k < 4; k++) {
+                const int c = tried[k];
+                if (c < 1) continue;
+                bool dup = false;
+                for (int q = 0; q < k; q++) dup = dup || tried[q] == c;
+                if (dup) continue;
+                const int nslot = g * c;
+                std::vector<int64_t> load((size_t)nslot, 0);
+                for (int64_t i = 0; i < groups; i++) {       // LPT on the (already descending) group lengths
+                    size_t b = 0;
+                    for (size_t sl = 1; sl < load.size(); sl++)
+                        if (load[sl] < load[b]) b = sl;
+                    load[b] += Tg[(size_t)i];
+                }
+                const double makespan = (double)*std::max_element(load.begin(), load.end());
+                const double chain = g <= 5 ? 1.0 : 1.0 + 0.08 * (g - 5);
+                const double t_rnn = makespan * chain;
+                const double hidden = t_rnn * std::max(0, sms - csize * c) / sms;
+                const double cost = t_rnn + std::max(0.05 * gemm_steps, gemm_steps - hidden);
+                if (best < 0.0 || cost < best * 0.995) { best = cost; G = g; ncl = c; }      // ties: fewer slots, fewer clusters
+            }
+        }
+        if (groups == 0) { G = 1; ncl = 0; }
     }
     if (getenv("FFB_TC_SLOTS")) {             // experiments: slots per cluster
         G = std::max(1, std::min(atoi(getenv("FFB_TC_SLOTS")), gmax));
@@ -576,7 +611,7 @@ extern "C" int64_t ffb_plan_schedule(const int64_t *T, int64_t n_reads, int max_
     std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return (off[a + 1] - off[a]) > (off[b + 1] - off[b]); });
     std::vector<int32_t> o, so, sl;
     std::vector<int64_t> gs;
-    plan_groups(off.data(), idx.data(), n_reads, max_clusters, slots_max, can_stream != 0, slots, n_clusters, o, so, sl, gs);
+    plan_groups(off.data(), idx.data(), n_reads, max_clusters, slots_max, can_stream != 0, 8, slots, n_clusters, o, so, sl, gs);
     if (order) std::copy(o.begin(), o.end(), order);
     if (slot_off) std::copy(so.begin(), so.end(), slot_off);
     if (slot_list) std::copy(sl.begin(), sl.end(), slot_list);
@@ -686,7 +721,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
         const bool can_stream = ffb_gemm_tc_stream_supported(m->G * m->S, m->S) != 0;
         int G = 1, ncl = 0;
         plan_groups(c->blk_off.data(), idx.data(), N, std::max(m->tc_max_clusters, 1), ffb_rnn_tc_rmax(m->kind, m->S) / 16, can_stream,
-                    &G, &ncl, c->order, c->slot_off, c->slot_list, group_start);
+                    ffb_rnn_tc_cluster_size(m->kind, m->S), &G, &ncl, c->order, c->slot_off, c->slot_list, group_start);
         c->R_tc = G * 16;
         c->tc_clusters = ncl;
         c->n_slots = (int)c->order.size();

@@ -62,7 +62,7 @@ using namespace tc;
 // NACC: accumulators per group.  3 (default): Whi*hhi split over the two K-halves + one for the cross terms.  2: all of
 // Whi*hhi in one accumulator (S/16 truncating full-magnitude accumulations instead of S/32) + the cross terms -- used
 // where the third accumulator would cost a whole slot of the cluster (S = 384: 4 slots instead of 2).
-template <int S_, int C_, int NGATE_, bool LO_SMEM_ = false, int NACC_ = 3>
+template <int S_, int C_, int NGATE_, bool LO_SMEM_ = false, int NACC_ = 3, int GCAP_ = 5>
 struct RnnTcCfg {
     static constexpr int S = S_, C = C_, NGATE = NGATE_, NACC = NACC_;
     static constexpr bool LO_SMEM = LO_SMEM_;
@@ -79,7 +79,7 @@ struct RnnTcCfg {
     // fits next to it there
     // 5 slots x 5 warps = 800 threads leave 72 registers per thread; 6 slots (960 threads, 64 registers, spills in the
     // gate warps) measured slower: 34.9 vs 34.2 ms per step at S=256 although 16 more SMs went to the streamed GEMM
-    static constexpr int GCAP = 5;
+    static constexpr int GCAP = GCAP_;
     static constexpr int GMAX_T = (TMEM_COLS - ACC_COL0_) / (NACC * 16) < GCAP ? (TMEM_COLS - ACC_COL0_) / (NACC * 16) : GCAP;
     static constexpr int GMAX = LO_SMEM ? (GMAX_T < 2 ? GMAX_T : 2) : GMAX_T;
     static constexpr int LBO_B = 2 * NG * 16;         // bytes between k-groups of B (hi and lo planes interleaved)
@@ -383,7 +383,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         constexpr int XROW = NGATE * S;
         // this thread's four cells: reads col(i) = (i>>1)*8 + 2*cp + (i&1) of the group.  Per cell a
         // running pointer into Xin and a running output row, stepped by +-1 block per step.
-        const int xstep = backward ? -XROW : XROW, rstep = backward ? -1 : 1;
+        const int rstep = backward ? -1 : 1;
+        const float *const xj = Xin + j;                    // this thread's column of the input projection; row = orow[i]
         // second role of the lane: after the slice is staged, copy one 16-byte chunk (8 hidden units of one
         // read, one plane) from the staging tile to the fp16 layer output -- off the critical path
         const int cl_read = lane & 15, cl_plane = lane >> 4;
@@ -406,7 +407,6 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         for (int sl = sl0; sl < sl1; sl++) {
         const int grp = slot_list[sl];                      // this round's group of 16 reads
         int cT[4];
-        const float *xp[4];
         int32_t orow[4];            // the host guarantees total blocks < 2^31
         float hprev[4], cstate[4];
         int Tmin = 0x7fffffff;
@@ -417,7 +417,6 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             cT[i] = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
             const int32_t base = rd >= 0 ? (int32_t)blk_off[rd] : 0;
             orow[i] = base + ((backward && cT[i] > 0) ? cT[i] - 1 : 0);
-            xp[i] = Xin + (int64_t)orow[i] * XROW + j;
             hprev[i] = 0.0f; cstate[i] = 0.0f;
             Tmin = min(Tmin, cT[i]);
         }
@@ -443,12 +442,12 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xp[i] + gt * S);
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xj + (int64_t)orow[i] * XROW + gt * S);
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (s < cT[i]) ? __ldcs(xp[i] + gt * S) : 0.0f;
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (s < cT[i]) ? __ldcs(xj + (int64_t)orow[i] * XROW + gt * S) : 0.0f;
             }
             PROF(8);
             mbar_wait(&acc_full[g], (NGATE == 3 ? ga : gs) & 1u);
@@ -568,7 +567,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) { xp[i] += xstep; orow[i] += rstep; }
+            for (int i = 0; i < 4; i++) orow[i] += rstep;
             cl_row += rstep;
             // ---- publish progress for the consumer of the output planes ----
             if (progress && (((s + 1) % FFB_RNN_PUBLISH_PERIOD) == 0 || s == Tmax - 1)) {
@@ -630,6 +629,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #endif
 using GruTc256 = RnnTcCfg<256, 8, 3, false, FFB_RNN_NACC>;
 using LstmTc256 = RnnTcCfg<256, 8, 4, false, FFB_RNN_NACC>;
+// six slots per cluster (960 threads, 64 registers): more groups in flight per SM for batches that do not fit one wave
+using GruTc256x6 = RnnTcCfg<256, 8, 3, false, FFB_RNN_NACC, 6>;
+using LstmTc256x6 = RnnTcCfg<256, 8, 4, false, FFB_RNN_NACC, 6>;
 using GruTc384 = RnnTcCfg<384, 12, 3, false, 2>;    // 12-CTA clusters (non-portable size): 32 hidden units per CTA again,
 using LstmTc384 = RnnTcCfg<384, 12, 4, false, 2>;   // 2 x 192 TMEM columns of weights + 4 groups of 2 accumulators
 using GruTc512 = RnnTcCfg<512, 16, 3, true>;    // r103_native: 16-CTA clusters, hi plane in tensor memory (256 columns),
@@ -639,10 +641,13 @@ using LstmTc512 = RnnTcCfg<512, 16, 4, true>;   // lo plane in shared memory (12
 
 // ---------------------------------------------------------------------------------------
 // shape dispatch: f is a generic lambda called with a value-initialised config object
+// wide = true: the instance with the most slots per cluster (S = 256: six, 960 threads at 64 registers); launches with
+// G <= 5 use the five-slot instance (72 registers)
 template <class F>
-static auto tc_dispatch(int kind, int S, F &&f) {
+static auto tc_dispatch(int kind, int S, F &&f, bool wide = false) {
     if (S == 384) return kind == 0 ? f(ffb::GruTc384{}) : f(ffb::LstmTc384{});
     if (S == 512) return kind == 0 ? f(ffb::GruTc512{}) : f(ffb::LstmTc512{});
+    if (wide) return kind == 0 ? f(ffb::GruTc256x6{}) : f(ffb::LstmTc256x6{});
     return kind == 0 ? f(ffb::GruTc256{}) : f(ffb::LstmTc256{});
 }
 
@@ -658,14 +663,14 @@ int ffb_rnn_tc_prof(unsigned long long *out, int reset) {
 }
 int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && (S == 256 || S == 384 || S == 512); }
 int ffb_rnn_tc_cluster_size(int kind, int S) { return tc_dispatch(kind, S, [](auto cfg) { return (int)decltype(cfg)::C; }); }
-int ffb_rnn_tc_rmax(int kind, int S) { return tc_dispatch(kind, S, [](auto cfg) { return (int)(decltype(cfg)::GMAX * decltype(cfg)::NG); }); }
+int ffb_rnn_tc_rmax(int kind, int S) { return tc_dispatch(kind, S, [](auto cfg) { return (int)(decltype(cfg)::GMAX * decltype(cfg)::NG); }, true); }
 
 size_t ffb_rnn_tc_image_halfs(int kind, int S) {
     return tc_dispatch(kind, S, [](auto cfg) { using Cfg = decltype(cfg); return (size_t)Cfg::C * 2 * Cfg::A_PLANE / 2; });
 }
 
 size_t ffb_rnn_tc_ring_bytes(int kind, int S, int n_clusters, int R) {
-    return tc_dispatch(kind, S, [&](auto cfg) { return decltype(cfg)::ring_bytes(n_clusters, R / 16); });
+    return tc_dispatch(kind, S, [&](auto cfg) { return decltype(cfg)::ring_bytes(n_clusters, R / 16); }, true);
 }
 
 // sW [G*S][S] (row per output) -> per-CTA tensor-memory images (fp16 bit patterns):
@@ -706,6 +711,7 @@ static int prepare_one() {
 }
 int ffb_rnn_tc_prepare(int kind, int S) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
+    if (tc_dispatch(kind, S, [](auto cfg) { return prepare_one<decltype(cfg)>(); }, true) != 0) return -1;
     return tc_dispatch(kind, S, [](auto cfg) { return prepare_one<decltype(cfg)>(); });
 }
 
@@ -732,7 +738,7 @@ static int max_clusters_one(int G) {
 }
 int ffb_rnn_tc_max_clusters(int kind, int S, int R) {
     if (!ffb_rnn_tc_supported(kind, S)) return 0;
-    return tc_dispatch(kind, S, [&](auto cfg) { return max_clusters_one<decltype(cfg)>(std::min(R / 16, (int)decltype(cfg)::GMAX)); });
+    return tc_dispatch(kind, S, [&](auto cfg) { return max_clusters_one<decltype(cfg)>(std::min(R / 16, (int)decltype(cfg)::GMAX)); }, true);
 }
 
 template <class Cfg>
@@ -757,5 +763,6 @@ int ffb_launch_rnn_tc(int kind, int S, const float *Xin, const void *Wimg, float
                       const float *bnext, float *xnext, int next_rows, float ff_scale, cudaStream_t st) {
     if (!ffb_rnn_tc_supported(kind, S)) return -1;
     if (xnext && (!bnext || !ffb_rnn_tc_can_fuse_z(kind, S) || next_rows < 0 || next_rows > S)) return -1;
-    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, sched, R, backward, ring, progress, bnext, xnext, next_rows, ff_scale, st); });
+    return tc_dispatch(kind, S, [&](auto cfg) { return launch_one<decltype(cfg)>(Xin, Wimg, Hout, Hhi, Hlo, rb, sched, R, backward, ring, progress, bnext, xnext, next_rows, ff_scale, st); },
+                       R / 16 > 5);
 }

@@ -54,6 +54,11 @@ int ffb_bundle_load(const char *path, ffb_bundle *out);   /* 0 on success */
 void ffb_bundle_free(ffb_bundle *b);
 ffb_model *ffb_bundle_to_model(const ffb_bundle *b, int device);
 
+/* ---- read sharding over the GPUs of the box ----------------------------------------------
+ * len[i] = samples of read i (<= 0: unreadable, dealt to nobody); dev_of[i] = device rank in [0, ndev) or -1.  Longest
+ * first to the least-loaded device with fewer than `cap` reads.  Returns the number of reads dealt, -1 on bad arguments. */
+int ffb_deal_lpt(const long *len, int n, int ndev, int cap, int *dev_of);
+
 /* ---- raw signal input -----------------------------------------------------------------
  * <name>.f32 : little-endian float32 samples in pA, as read_raw(..., scale=true) returns them
  *              (src/fast5_interface.c:231-300)

@@ -326,45 +326,32 @@ static void read_one(struct read_slot *s, const char *path) {
     s->dev = -1; s->pos = -1;
 }
 
-/* LPT: the longest read first, each to the device with the fewest samples so far (and room left) -- equal work per device
- * whatever the length distribution (BASELINE configs[3]: 1 k - 50 k samples) */
-static int cmp_len_desc(const void *a, const void *b, void *ctx) {
-    const struct read_slot *rd = ctx;
-    const long la = rd[*(const int *)a].n, lb = rd[*(const int *)b].n;
-    if (la != lb) return la > lb ? -1 : 1;
-    return *(const int *)a - *(const int *)b;
-}
+/* LPT deal of the window (ffb_shard.c), then every device's members in input order */
 static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
 
 static void deal_window(struct window *w, int slot) {
-    int *idx = malloc(sizeof(int) * (size_t)(w->n > 0 ? w->n : 1));
-    int m = 0;
-    for (int i = 0; i < w->n; i++)
-        if (w->rd[i].n > 0) idx[m++] = i;
-    qsort_r(idx, (size_t)m, sizeof(int), cmp_len_desc, w->rd);
-    int64_t load[MAX_DEVICES] = {0};
+    long *len = malloc(sizeof(long) * (size_t)(w->n > 0 ? w->n : 1));
+    int *dev_of = malloc(sizeof(int) * (size_t)(w->n > 0 ? w->n : 1));
+    if (!len || !dev_of) die("out of memory%s", "");
+    for (int i = 0; i < w->n; i++) len[i] = w->rd[i].n;
+    if (ffb_deal_lpt(len, w->n, G.ndev, args.batch, dev_of) < 0) die("internal: read sharding failed%s", "");
     for (int d = 0; d < G.ndev; d++) G.dev[d].bat[slot].n = 0;
-    for (int k = 0; k < m; k++) {
-        int best = -1;
-        for (int d = 0; d < G.ndev; d++) {
-            if (G.dev[d].bat[slot].n >= args.batch) continue;
-            if (best < 0 || load[d] < load[best]) best = d;
-        }
-        struct dev_batch *b = &G.dev[best].bat[slot];
+    for (int i = 0; i < w->n; i++) {
+        if (dev_of[i] < 0) continue;
+        struct dev_batch *b = &G.dev[dev_of[i]].bat[slot];
         if (b->n == b->member_cap) {
             b->member_cap = b->member_cap ? 2 * b->member_cap : 1024;
             b->member = realloc(b->member, sizeof(int) * (size_t)b->member_cap);
             if (!b->member) die("out of memory%s", "");
         }
-        b->member[b->n++] = idx[k];
-        load[best] += w->rd[idx[k]].n;
+        b->member[b->n++] = i;
     }
     for (int d = 0; d < G.ndev; d++) {
         struct dev_batch *b = &G.dev[d].bat[slot];
         qsort(b->member, (size_t)b->n, sizeof(int), cmp_int);      /* input order within the batch */
         for (int k = 0; k < b->n; k++) { w->rd[b->member[k]].dev = d; w->rd[b->member[k]].pos = k; }
     }
-    free(idx);
+    free(len); free(dev_of);
 }
 
 static void submit_batch(struct device *dv, struct dev_batch *f, struct window *w) {

@@ -36,6 +36,9 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
     if ref and os.path.isdir("/root/reference/src"):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+        # the link proof: the reference's own main() against libflappie_b200.so (needs the product library to exist)
+        if os.path.exists(os.path.join(HERE, "..", "flappie_b200", "csrc", "libflappie_b200.so")):
+            subprocess.run(["make", "-C", HERE, "linkproof"], check=True, capture_output=True)
 
 
 class ConvTerm(ctypes.Structure):

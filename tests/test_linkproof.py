@@ -109,7 +109,10 @@ def test_reference_main_on_this_library_equals_the_b200_cli(gpu_lib, tmp_path, e
     for i, r in enumerate(raws):
         np.asarray(r, np.float32).tofile(rdir / f"read_{i:02d}.f32")
         files.append(str(rdir / f"read_{i:02d}.f32"))       # named one by one: the reference globs "<dir>/*.fast5" only
-    env = dict(os.environ, FLAPPIE_B200_MODELS=str(tmp_path))
+    # default mode: the batched path skips the -logZ/T shift of trans (the posteriors are invariant under it, api.cu) -- which
+    # moves their last bits and with them the sixth decimal of the printed score.  FFB_ALWAYS_LOGZ=1 keeps the shift, as the
+    # per-read calls of the reference main do: then the two outputs agree byte for byte in every mode.
+    env = dict(os.environ, FLAPPIE_B200_MODELS=str(tmp_path), FFB_ALWAYS_LOGZ="1")
     outs = []
     for exe, more in ((EXE, []), (os.path.join(HOST, "flappie"), ["--batch", "4"])):
         out = tmp_path / (os.path.basename(exe) + ".out")

@@ -94,6 +94,12 @@ def test_recurrent_group_schedule(lib):
     order, so, sl, ncl, G = _plan(lib, np.full(4096, 1895), 15, 5)
     assert (ncl, G) == (13, 5) and sorted(sl.tolist()) == list(range(256))
     assert set(np.diff(so).tolist()) <= {3, 4}
+    # ... and with SIX slots per cluster available (S = 256): six slots x all 15 clusters = 90 slots finish the 256 groups in
+    # three rounds instead of four, which outweighs the slower step and the SMs taken from the streamed GEMM; the one-wave
+    # batch stays on five slots
+    order, so, sl, ncl, G = _plan(lib, np.full(4096, 1895), 15, 6)
+    assert (ncl, G) == (15, 6) and sorted(sl.tolist()) == list(range(256)) and set(np.diff(so).tolist()) <= {2, 3}
+    assert _plan(lib, np.full(1024, 1895), 15, 6)[3:] == (13, 5)
     # no streamed GEMM (K > 256): no SMs held back
     assert _plan(lib, np.full(4096, 758), 12, 4, can_stream=0)[3] == 12
     # ragged batch (configs[3] lengths): a partition, groups sorted by length, loads within one longest group of each other
@@ -109,3 +115,37 @@ def test_recurrent_group_schedule(lib):
     assert _plan(lib, np.zeros(0, np.int64), 15, 5)[3] == 0
     order, so, sl, ncl, G = _plan(lib, np.array([700, 10, 0]), 15, 5)
     assert (ncl, G) == (1, 1) and order[:3].tolist() == [0, 1, 2] and np.all(order[3:] == -1)
+
+
+def test_c_lpt_deal_matches_the_python_rule():
+    """ffb_deal_lpt (flappie_b200/host/ffb_shard.c, what `flappie --devices` uses per window) against shard_reads: same
+    loads per device, capacity respected, unreadable reads dealt to nobody, deterministic."""
+    import ctypes
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = ctypes.CDLL(os.path.join(here, "flappie_b200", "host", "libffb_host.so"))
+    host.ffb_deal_lpt.restype = ctypes.c_int
+    host.ffb_deal_lpt.argtypes = [ctypes.POINTER(ctypes.c_long), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    rng = np.random.default_rng(3)
+    for ndev, n in ((8, 8 * 1024), (2, 301), (3, 7), (4, 0)):
+        lens = np.exp(rng.uniform(np.log(1000), np.log(50000), n)).astype(np.int64)
+        if n > 10:
+            lens[[3, 9]] = [0, -2]                        # unreadable / fast5 without libhdf5
+        cl = (ctypes.c_long * max(n, 1))(*lens.tolist())
+        dev = (ctypes.c_int * max(n, 1))()
+        cap = (n + ndev - 1) // ndev + 2
+        dealt = host.ffb_deal_lpt(cl, n, ndev, cap, dev)
+        d = np.array(dev[:n])
+        assert dealt == int(np.sum(lens > 0)) and np.all(d[lens <= 0] == -1) and np.all(d[lens > 0] >= 0)
+        loads = np.array([lens[d == k].sum() for k in range(ndev)])
+        counts = np.array([np.sum(d == k) for k in range(ndev)])
+        assert counts.max(initial=0) <= cap
+        if n > 10:
+            assert loads.max() - loads.min() <= lens.max()           # LPT: within one (longest) read of each other
+            ref = shard_reads(np.where(lens > 0, lens, 0), ndev)
+            ref_loads = sorted(int(lens[s][lens[s] > 0].sum()) for s in ref)
+            assert abs(max(ref_loads) - loads.max()) <= lens.max()
+        dev2 = (ctypes.c_int * max(n, 1))()
+        host.ffb_deal_lpt(cl, n, ndev, cap, dev2)
+        assert list(dev2[:n]) == list(dev[:n])
+    assert host.ffb_deal_lpt(None, 1, 1, 1, None) == -1
