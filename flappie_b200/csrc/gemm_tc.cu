@@ -113,7 +113,7 @@ struct GemmTcCfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;   // + alignment slack
-    // two accumulators per tile: the tensor core truncates on every accumulate (tests/probe_acc.py), so the
+    // two accumulators per tile: the tensor core truncates on every accumulate (tools/probe_acc.py), so the
     // 2^-11-sized cross terms get their own accumulator and are added in registers (round-to-nearest)
     static constexpr int NBUF = (BN == 256) ? 1 : 2;
     static constexpr int TMEM_COLS = 2 * BN * NBUF;
@@ -505,7 +505,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         }
     } else if (warp == 1) {
         // ===== MMA issuer: D[feature][block] (+)= W_panel (TMEM) * act_tile^T (smem) =====
-        // ONE accumulator per tile: the tensor core truncates on every accumulate (tests/probe_acc.py), so the
+        // ONE accumulator per tile: the tensor core truncates on every accumulate (tools/probe_acc.py), so the
         // 2^-11-sized cross terms go in FIRST (their truncation is invisible) and the 16 full-size hi*hi products
         // on top -- the same number of full-magnitude truncations as a dedicated hi*hi accumulator, at half the
         // TMEM columns and half the tcgen05.ld traffic in the epilogue

@@ -21,7 +21,7 @@
 //       gate arithmetic needs no shuffles.
 //   B = the previous state of the group's 16 reads, [k-group][plane hi/lo][read][8 halfs],
 //   D = fp32 in tensor memory.  fp32-faithful product: hi*hi + hi*lo + lo*hi (tc_common.cuh).
-//       The tensor core truncates on every accumulate (tests/probe_acc.py), so the hi*hi
+//       The tensor core truncates on every accumulate (tools/probe_acc.py), so the hi*hi
 //       product is split over two K-halves into separate accumulators and the cross terms
 //       into a third; the three are added in registers with round-to-nearest.
 //
@@ -623,7 +623,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 }
 
 // two accumulators everywhere TMEM holds both weight planes: four tcgen05.ld instead of six on the step's critical path
-// (S=256: -4.5 % per layer, trans deviation 4.8e-5 vs 4.6e-5 with three accumulators, tests/report_parity.py)
+// (S=256: -4.5 % per layer, trans deviation 4.8e-5 vs 4.6e-5 with three accumulators, tools/report_parity.py)
 #ifndef FFB_RNN_NACC
 #define FFB_RNN_NACC 2
 #endif

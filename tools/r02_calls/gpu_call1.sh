@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 call 1: where are we on today's box?
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/c1_smi.txt 2>&1
 tools/microbench/cluster_probe > gpurun_out/c1_cluster_probe.txt 2>&1

@@ -1,8 +1,8 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/c2_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/c2_pytest.txt
-timeout 300 python tests/report_parity.py gru > gpurun_out/c2_parity_gru.txt 2>&1
+timeout 300 python tools/report_parity.py gru > gpurun_out/c2_parity_gru.txt 2>&1
 for rep in 1 2; do
   timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/c2_bench_fuse_$rep.txt 2>&1
   FFB_NO_FUSE_Z=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/c2_bench_nofuse_$rep.txt 2>&1

@@ -1,12 +1,12 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/c3_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/c3_pytest.txt
 tail -3 gpurun_out/c3_pytest.txt
 for v in A B C D; do
   cp flappie_b200/csrc/lib$v.so flappie_b200/csrc/libflappie_b200.so
-  timeout 300 python tests/report_parity.py gru > gpurun_out/c3_parity_gru_$v.txt 2>&1
-  timeout 300 python tests/report_parity.py lstm > gpurun_out/c3_parity_lstm_$v.txt 2>&1
+  timeout 300 python tools/report_parity.py gru > gpurun_out/c3_parity_gru_$v.txt 2>&1
+  timeout 300 python tools/report_parity.py lstm > gpurun_out/c3_parity_lstm_$v.txt 2>&1
   echo "== $v"; grep tensor gpurun_out/c3_parity_gru_$v.txt gpurun_out/c3_parity_lstm_$v.txt
 done
 for rep in 1 2; do

@@ -1,11 +1,11 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 cp flappie_b200/csrc/libflappie_b200.so flappie_b200/csrc/libKEEP.so
 for v in G0 G1 G2; do
   cp flappie_b200/csrc/lib$v.so flappie_b200/csrc/libflappie_b200.so
-  timeout 300 python tests/report_parity.py gru > gpurun_out/c5_parity_gru_$v.txt 2>&1
-  timeout 300 python tests/report_parity.py lstm > gpurun_out/c5_parity_lstm_$v.txt 2>&1
+  timeout 300 python tools/report_parity.py gru > gpurun_out/c5_parity_gru_$v.txt 2>&1
+  timeout 300 python tools/report_parity.py lstm > gpurun_out/c5_parity_lstm_$v.txt 2>&1
   echo "== $v"; grep tensor gpurun_out/c5_parity_gru_$v.txt gpurun_out/c5_parity_lstm_$v.txt
   timeout 600 python tools/parity_report.py 32 > gpurun_out/c5_report_$v.txt 2>&1; grep -v "^#" gpurun_out/c5_report_$v.txt
 done

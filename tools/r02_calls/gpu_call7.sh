@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/c7_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/c7_pytest.txt
 grep -E "\[parity\]|passed|failed|^FAILED|^ERROR" gpurun_out/c7_pytest.txt | tail -30

@@ -1,9 +1,9 @@
 """Print (not assert) the deviation of every stage of the GPU path from the oracle for the
 tcgen05 shapes -- used on the GPU box when tuning the recurrent kernel's numerics.
-    python tests/report_parity.py [gru|lstm]"""
+    python tools/report_parity.py [gru|lstm]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from flappie_b200.api import Context, Model
 from flappie_b200.model import KIND_GRU, KIND_LSTM, FlipflopModel
