@@ -109,18 +109,19 @@ class ClockSampler:
         if not rows:
             rows = [r for t, r in self.rows]
             window = "warm-up + timed region (no sample fell inside the timed region)"
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
+                power.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for k, nm in enumerate(names):
                 if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "window": window}
+                "power_w": float(np.median(power)) if power else None, "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -279,7 +280,8 @@ def run_extras(a, api, lib, peaks, world, rank, local, barrier, max_over_ranks):
             groups = ctx.forward_timed()
             T = ctx.total_blocks()
             S, G = fm.size, fm.ngate
-            ach = 2.0 * T * S * G * S / (groups["rnn"] / 5.0 * 1e-3) / 1e12
+            fl = 2.0 * T * S * G * S + ((4 * 2.0 * T * S * S + 2.0 * T * S * fm.nparam) / 5.0 if (fm.kind == 0 and S in (256, 384)) else 0.0)
+            ach = fl / (groups["rnn"] / 5.0 * 1e-3) / 1e12
             entry.update({"scaling": "weak", "n_gpus": world, "value": samples * world / (dev_ms * 1e-3), "unit": "samples/s", "ms_per_step": dev_ms,
                           "e2e": {"value": samples * world / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
                                   "what": "blocking ffb_basecall_raw_batch, one context (no overlap of host and device)"},
@@ -460,10 +462,15 @@ def main():
     passes = [ctx.forward_timed() for _ in range(max(1, min(a.steps, 3)))]
     groups = {k: float(np.mean([p_[k] for p_ in passes])) for k in passes[0]}
     S, G, T = fm.size, fm.ngate, tot_blocks
-    rnn_flops = 2.0 * T * S * G * S                      # one layer's h_{t-1} * sW, all reads (algorithmic)
+    tensor_path = not a.fp32_simt and fm.size in (256, 384)
+    fused = tensor_path and fm.kind == 0
+    rnn_flops_sw = 2.0 * T * S * G * S                   # one layer's h_{t-1} * sW, all reads (algorithmic)
+    # GRU: four of the five launches also compute the z-gate third of the next layer's input projection (2*T*S*S each) and the
+    # fifth the output layer (2*T*S*nparam) in the same MMAs -- useful flops of the path that the input / output GEMMs no
+    # longer do; average per launch
+    rnn_flops = rnn_flops_sw + ((4 * 2.0 * T * S * S + 2.0 * T * S * fm.nparam) / 5.0 if fused else 0.0)
     rnn_ms_per_launch = groups["rnn"] / 5.0
     achieved_tf = rnn_flops / (rnn_ms_per_launch * 1e-3) / 1e12
-    tensor_path = not a.fp32_simt and fm.size in (256, 384)
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel, from the committed `ncu --set full` capture of
     # this very command (a number taken under the profiler cannot be re-measured inside a timed run): read from the file
     # tools/ncu_summary.py wrote, never a constant in this script
@@ -472,19 +479,21 @@ def main():
     if tensor_path and a.model == "r941_native_gru" and a.reads == 1024 and os.path.exists(tj):
         tdoc = json.load(open(tj))
         traffic, traffic_src = float(tdoc["dram_bytes_per_launch"]), f"profiles/r02_rnn_tc_traffic.json ({tdoc.get('source', 'ncu --set full')})"
-    fused = tensor_path and fm.kind == 0
     roofline = {"kernel": "rnn_tc_kernel (recurrent layer: h*sW on tcgen05 + gates, 5 launches/step)" if tensor_path
                           else "rnn_layer_kernel (fp32 CUDA-core cluster kernel, 5 launches/step)",
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "achieved_sW_only": rnn_flops_sw / (rnn_ms_per_launch * 1e-3) / 1e12,
+                "frac_sW_only": rnn_flops_sw / (rnn_ms_per_launch * 1e-3) / 1e12 / peaks["tf_sustained"],
                 "timed": "CUDA events around each launch in the SEQUENTIAL schedule (ffb_forward_timed, extra passes after the timed "
                          "region); `value` runs the streamed schedule, where the same launches overlap the next layer's input GEMM",
                 "peak_source": f"{peaks['src']} bf16 dense sustained (kernel timed inside a long step)",
                 "algorithmic_bytes_per_launch": float(T) * (4 * G * S + 4 * S + (4 * S if fused else 0)),
-                "note": "algorithmic flops = 2*blocks*S*G*S per launch (h*sW only); the fp32-faithful fp16 hi/lo split issues 3 MMAs per "
-                        "product; GRU: the fourth quarter of each M=128 tile carries the z-gate rows of the next layer's input "
-                        "projection (another 2*blocks*S*S useful flops per launch, not counted here); the layer is T dependent steps "
-                        "of ~2.5 us each, i.e. bound by the latency of the step chain, not by the pipe (DESIGN.md 4.2)",
+                "note": "algorithmic flops per launch = 2*blocks*S*G*S (h*sW) + for the GRU the rows that ride in the fourth quarter of "
+                        "each M=128 tile: the z-gate third of the next layer's input projection (2*blocks*S*S, four launches) or the "
+                        "output layer (fifth launch) -- work the input / output GEMMs no longer do; `*_sW_only` leaves them out (the "
+                        "round-1 definition).  The fp32-faithful fp16 hi/lo split issues 3 MMAs per product; the layer is T dependent "
+                        "steps of ~2.5 us each, i.e. bound by the latency of the step chain, not by the pipe (DESIGN.md 4.2)",
                 "step_breakdown_ms": groups}
 
     line = {

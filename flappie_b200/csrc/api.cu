@@ -521,12 +521,16 @@ static void plan_groups(const int64_t *blk_off, const int32_t *sorted, int64_t N
                         std::vector<int32_t> &slot_list, std::vector<int64_t> &group_start) {
     const int64_t groups = (N + 15) / 16;
     int G = 1, ncl = 0;
-    // Which (slots per cluster, clusters)?  The layer lasts makespan(groups dealt longest-first over G * ncl slots) steps,
-    // a step costs chain(G) (more slots per CTA = more contention for the tensor pipe: +8 % from five to six, measured,
-    // profiles/r02_slots_ab.txt), and the streamed input GEMM of the next layer hides behind it only as far as the SMs the
-    // clusters leave free can carry it (its full-chip time: 0.24 steps per 1000 blocks at S = 256).  Candidates are few;
-    // each is simulated.  One wave of 16-read groups (BASELINE configs[1]: 64 groups) lands on five slots x 13 clusters
-    // as before; 4096 equal reads on six slots x 15 clusters (three rounds instead of four).
+    // Which (slots per cluster, clusters)?  The layer lasts makespan(groups dealt longest-first over G * ncl slots) steps and
+    // a step costs chain(G): the groups of a CTA share its tensor pipe, MUFU and issue slots, so the step chain grows with
+    // the slots in use -- measured 1.72 / 2.0 / 2.26 / 2.7 us per step at 3 / 4 / 5 / 6 slots (profiles/r02_slots_ab.txt), i.e.
+    // ~ (3.5 + G) / 8.5 of the five-slot chain, and another 15 % when six slots run on all 15 clusters (the board is power
+    // capped: more work in flight lowers the clock).  How much of the streamed input GEMM hides behind the layer did NOT
+    // follow the SMs left free in that measurement (six slots x 15 clusters exposed less of it than five x 13), so the
+    // model leaves it out.  Candidates are few; each is simulated.  One wave of 16-read groups (BASELINE configs[1]: 64 groups) lands on
+    // five slots x 13 clusters as before; 4096 equal reads on six slots x 15 clusters (three rounds instead of four); a
+    // ragged batch whose longest read outlasts the average slot on FEWER slots per cluster (its makespan is that read
+    // whatever the slot count, so the shorter chain wins: configs[3] runs 24 % faster on three slots than on five).
     {
         std::vector<int64_t> Tg((size_t)groups);
         int64_t blocks = 0;
@@ -535,8 +539,7 @@ static void plan_groups(const int64_t *blk_off, const int32_t *sorted, int64_t N
             Tg[(size_t)g] = blk_off[rd0 + 1] - blk_off[rd0];
         }
         for (int64_t n = 0; n < N; n++) blocks += blk_off[n + 1] - blk_off[n];
-        const double gemm_steps = can_stream ? 0.243e-3 * (double)blocks : 0.0;
-        const int sms = 148;
+        (void)blocks; (void)can_stream; (void)csize;
         double best = -1.0;
         for (int g = 1; g <= gmax; g++) {
             int tried[4] = {(int)std::min<int64_t>((groups + g - 1) / g, maxc), maxc - 2, maxc - 1, maxc};   // ties: fewer clusters
@@ -555,10 +558,8 @@ static void plan_groups(const int64_t *blk_off, const int32_t *sorted, int64_t N
                     load[b] += Tg[(size_t)i];
                 }
                 const double makespan = (double)*std::max_element(load.begin(), load.end());
-                const double chain = g <= 5 ? 1.0 : 1.0 + 0.08 * (g - 5);
-                const double t_rnn = makespan * chain;
-                const double hidden = t_rnn * std::max(0, sms - csize * c) / sms;
-                const double cost = t_rnn + std::max(0.05 * gemm_steps, gemm_steps - hidden);
+                const double chain = (3.5 + std::max(g, 3)) / 8.5 * ((g >= 6 && g * c > 80) ? 1.15 : 1.0);   // not measured below 3
+                const double cost = makespan * chain;
                 if (best < 0.0 || cost < best * 0.995) { best = cost; G = g; ncl = c; }      // ties: fewer slots, fewer clusters
             }
         }

@@ -90,13 +90,13 @@ def test_recurrent_group_schedule(lib):
     order, so, sl, ncl, G = _plan(lib, np.full(1024, 1895), 15, 5)
     assert (ncl, G) == (13, 5) and sorted(sl.tolist()) == list(range(64))
     assert np.all(np.diff(so) <= 1) and sorted(order.tolist()) == list(range(1024))
-    # configs[2]: 4096 reads -> more groups than slots: all 13 x 5 slots busy, 3-4 groups each
+    # configs[2]: 4096 reads -> more groups than slots: every slot of all 15 clusters busy, 3-4 groups each
     order, so, sl, ncl, G = _plan(lib, np.full(4096, 1895), 15, 5)
-    assert (ncl, G) == (13, 5) and sorted(sl.tolist()) == list(range(256))
+    assert (ncl, G) == (15, 5) and sorted(sl.tolist()) == list(range(256))
     assert set(np.diff(so).tolist()) <= {3, 4}
     # ... and with SIX slots per cluster available (S = 256): six slots x all 15 clusters = 90 slots finish the 256 groups in
-    # three rounds instead of four, which outweighs the slower step and the SMs taken from the streamed GEMM; the one-wave
-    # batch stays on five slots
+    # three rounds instead of four, which outweighs the slower step (profiles/r02_slots_ab.txt); the one-wave batch stays
+    # on five slots
     order, so, sl, ncl, G = _plan(lib, np.full(4096, 1895), 15, 6)
     assert (ncl, G) == (15, 6) and sorted(sl.tolist()) == list(range(256)) and set(np.diff(so).tolist()) <= {2, 3}
     assert _plan(lib, np.full(1024, 1895), 15, 6)[3:] == (13, 5)
@@ -111,6 +111,13 @@ def test_recurrent_group_schedule(lib):
     assert np.all(np.diff(Tg) <= 0) and sorted(sl.tolist()) == list(range(250))
     loads = np.array([Tg[sl[so[k]:so[k + 1]]].sum() for k in range(ncl * G)])
     assert loads.max() - loads.min() <= Tg.max()
+    # a batch whose longest read outlasts the average slot (configs[3]: 1 k - 50 k): the makespan is that read whatever the
+    # slot count, so the planner takes FEWER slots per cluster -- a shorter step chain -- as long as the makespan stays there
+    T = np.exp(rng.uniform(np.log(395), np.log(24895), size=1024)).astype(np.int64)
+    order, so, sl, ncl, G = _plan(lib, T, 15, 6)
+    Tg = T[order[::16]]
+    loads = np.array([Tg[sl[so[k]:so[k + 1]]].sum() for k in range(ncl * G)])
+    assert G < 5 and loads.max() == Tg.max()
     # empty batch and a batch smaller than one group
     assert _plan(lib, np.zeros(0, np.int64), 15, 5)[3] == 0
     order, so, sl, ncl, G = _plan(lib, np.array([700, 10, 0]), 15, 5)

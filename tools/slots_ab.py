@@ -29,7 +29,8 @@ for title, name, lens in shapes:
     samples = int(lensa.sum())
     for tag, env in (("auto", {}), ("G=5 x13", {"FFB_TC_SLOTS": "5", "FFB_TC_CLUSTERS": "13"}), ("G=5 x15", {"FFB_TC_SLOTS": "5", "FFB_TC_CLUSTERS": "15"}),
                      ("G=6 x13", {"FFB_TC_SLOTS": "6", "FFB_TC_CLUSTERS": "13"}), ("G=6 x15", {"FFB_TC_SLOTS": "6", "FFB_TC_CLUSTERS": "15"}),
-                     ("G=4 x15", {"FFB_TC_SLOTS": "4", "FFB_TC_CLUSTERS": "15"})):
+                     ("G=4 x15", {"FFB_TC_SLOTS": "4", "FFB_TC_CLUSTERS": "15"}), ("G=3 x15", {"FFB_TC_SLOTS": "3", "FFB_TC_CLUSTERS": "15"}),
+                     ("G=2 x15", {"FFB_TC_SLOTS": "2", "FFB_TC_CLUSTERS": "15"}), ("G=1 x15", {"FFB_TC_SLOTS": "1", "FFB_TC_CLUSTERS": "15"})):
         for k in ("FFB_TC_SLOTS", "FFB_TC_CLUSTERS"):
             os.environ.pop(k, None)
         os.environ.update(env)
