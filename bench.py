@@ -170,7 +170,9 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fm, reads, _ = make_workload(MODEL_CHOICES[a.model][0], a.ref_reads_total, RAW_SAMPLES, seed=7)
+    # the very workload of the b200 arm (rank 0's reads): the config printed below is computed from it, not asserted
+    fm, reads, _ = make_workload(MODEL_CHOICES[a.model][0], a.reads, RAW_SAMPLES, seed=7)
+    tot_blocks = sum(max(fm.nblock(len(r)), 0) for r in reads)
     cores = len(os.sched_getaffinity(0))
     per_core = max(1, a.ref_reads_per_core)
     rates = []
@@ -185,10 +187,10 @@ def run_reference_arm(a):
         "impl": "reference", "metric": "raw-signal samples/sec basecalled", "value": val, "unit": "samples/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * nread * RAW_SAMPLES / val, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32 (the reference's own fp32 / OpenBLAS code)", "data": "synthetic",
         # the SAME config as the b200 arm measures; the CPU arm times a bounded sample of it and extrapolates the rate
         # (a rate metric): which sample is in cpu_baseline.sample
-        "config": build_config(a, a.gpus, (RAW_SAMPLES - 210 + 1) // 2 * a.reads if "gru" in a.model or a.model in ("r941_5mC", "r10C_pcr") else None),
+        "config": build_config(a, a.gpus, tot_blocks),
         "reference_sample": f"each step = {nread} of the {a.reads} reads ({per_core} per core on {cores} host cores), rate extrapolated",
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -25,6 +25,15 @@ __device__ __forceinline__ float activate(float x, int act) {
     if (act == FFB_ACT_SWISH) return x * logisticf(x);
     return x;
 }
+// The tensor core TRUNCATES on every accumulate into TMEM (tools/probe_acc.py: -0.6e-7 relative per MMA on a growing sum).
+// Unlike round-to-nearest noise this is a bias: it has one sign, so an integrating LSTM cell (forget gate ~ 1) adds it up
+// step after step.  An accumulator that took n full-magnitude accumulations is scaled back by (1 + FFB_ACC_COMP) when it is
+// read out; calibrated in profiles/r02_acc_comp.txt.
+#ifndef FFB_ACC_COMP
+#define FFB_ACC_COMP 0.0f
+#endif
+__device__ __forceinline__ float acc_comp(float v) { return FFB_ACC_COMP != 0.0f ? fmaf(v, FFB_ACC_COMP, v) : v; }
+
 // MUFU versions for the throughput kernels: ex2.approx (2 ulp) + rcp.approx (1 ulp); same formulas as the
 // reference (src/util.h:331-339), errors of a few 1e-7, far below the parity tolerances (1e-5 .. 1e-4)
 __device__ __forceinline__ float fast_logistic(float x) {

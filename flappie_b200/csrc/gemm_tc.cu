@@ -250,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     tmem_ld_wait();
                 }
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] += vx[j];
+                for (int j = 0; j < 16; j++) v[j] = acc_comp(v[j]) + vx[j];
                 float o3[16];                      // ACT == 3 only
                 if (row < M || ACT == 3) {
 #pragma unroll
@@ -589,14 +589,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 tmem_ld_wait();
                 if (c + 32 <= nrow) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + j) * ldc, v[j] + b);
+                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + j) * ldc, acc_comp(v[j]) + b);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + 16 + j) * ldc, w[j] + b);
+                    for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + 16 + j) * ldc, acc_comp(w[j]) + b);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) if (c + j < nrow) __stcs(crow + (int64_t)(c + j) * ldc, v[j] + b);
+                    for (int j = 0; j < 16; j++) if (c + j < nrow) __stcs(crow + (int64_t)(c + j) * ldc, acc_comp(v[j]) + b);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) if (c + 16 + j < nrow) __stcs(crow + (int64_t)(c + 16 + j) * ldc, w[j] + b);
+                    for (int j = 0; j < 16; j++) if (c + 16 + j < nrow) __stcs(crow + (int64_t)(c + 16 + j) * ldc, acc_comp(w[j]) + b);
                 }
             }
             tcgen05_fence_before();

@@ -483,8 +483,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int r0 = (i >> 1) * 4 + (i & 1);
-                    a[i][0] += v0[r0]; a[i][1] += v0[r0 + 2];
-                    a[i][2] += v1[r0]; a[i][3] += v1[r0 + 2];
+                    a[i][0] = acc_comp(a[i][0]) + v0[r0]; a[i][1] = acc_comp(a[i][1]) + v0[r0 + 2];
+                    a[i][2] = acc_comp(a[i][2]) + v1[r0]; a[i][3] = acc_comp(a[i][3]) + v1[r0 + 2];
                 }
             } else if constexpr (Cfg::NACC == 1) {
                 float v0[8], v2[8];
@@ -494,8 +494,8 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int r0 = (i >> 1) * 4 + (i & 1);
-                    a[i][0] = v0[r0]; a[i][1] = v0[r0 + 2];
-                    a[i][2] = v2[r0]; a[i][3] = v2[r0 + 2];
+                    a[i][0] = acc_comp(v0[r0]); a[i][1] = acc_comp(v0[r0 + 2]);
+                    a[i][2] = acc_comp(v2[r0]); a[i][3] = acc_comp(v2[r0 + 2]);
                 }
             } else {
                 float v0[8], v1[8], v2[8], v3[8];
@@ -507,8 +507,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int r0 = (i >> 1) * 4 + (i & 1);
-                    a[i][0] = v0[r0] + v1[r0]; a[i][1] = v0[r0 + 2] + v1[r0 + 2];
-                    a[i][2] = v2[r0] + v3[r0]; a[i][3] = v2[r0 + 2] + v3[r0 + 2];
+                    // accumulator 0 (Whi*hhi) took the full-magnitude truncating accumulations, accumulator 1 the small cross terms
+                    a[i][0] = acc_comp(v0[r0]) + v1[r0]; a[i][1] = acc_comp(v0[r0 + 2]) + v1[r0 + 2];
+                    a[i][2] = acc_comp(v2[r0]) + v3[r0]; a[i][3] = acc_comp(v2[r0 + 2]) + v3[r0 + 2];
                 }
             }
             tcgen05_fence_before();
@@ -586,7 +587,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             if constexpr (Cfg::NACC > 1) tmem_ld_16x256b_x2(t_hi + NG, v1);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 4; i++) a3[i] = v0[(i >> 1) * 4 + (i & 1) + 2] + (Cfg::NACC > 1 ? v1[(i >> 1) * 4 + (i & 1) + 2] : 0.0f);
+            for (int i = 0; i < 4; i++) a3[i] = acc_comp(v0[(i >> 1) * 4 + (i & 1) + 2]) + (Cfg::NACC > 1 ? v1[(i >> 1) * 4 + (i & 1) + 2] : 0.0f);
             if constexpr (Cfg::NACC == 3) {
                 tmem_ld_16x256b_x2(t_hi + 2 * NG, v0);
                 tmem_ld_wait();

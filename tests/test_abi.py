@@ -181,3 +181,48 @@ def test_device_only_entry_points_fail_loudly_without_gpu(lib):
         lib.decode_crf_runlength(p)
     with pytest.raises(Exception):
         lib.transpost_crf_runlength(p)
+
+
+def test_round2_entry_points_without_gpu(lib, tmp_path):
+    """ffb_model_load / lazy registration / the host-only helpers added in round 2: the host parts work without a device, the
+    device parts refuse loudly (NULL + message), nothing computes on the CPU."""
+    import ctypes
+    L = lib.lib
+    # host-only: change_positions (decode.c:66-79), nbase_from_crf_runlength_nparam (layers.c:1235), array_from_flappie_imatrix
+    L.change_positions.restype = ctypes.c_size_t
+    L.change_positions.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]
+    path = np.array([3, 3, 1, 1, 1, 5, 2, 2], np.int32)
+    ch = np.zeros(8, np.int32)
+    n = L.change_positions(path.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), 8, ch.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert n == 3 and ch[:3].tolist() == [2, 5, 6]
+    assert L.change_positions(None, 8, ch.ctypes.data_as(ctypes.POINTER(ctypes.c_int))) == 0          # RETURN_NULL_IF
+    L.nbase_from_crf_runlength_nparam.restype = ctypes.c_size_t
+    L.nbase_from_crf_runlength_nparam.argtypes = [ctypes.c_size_t]
+    assert L.nbase_from_crf_runlength_nparam(40) == 4
+    L.array_from_flappie_imatrix.restype = ctypes.POINTER(ctypes.c_int32)
+    L.array_from_flappie_imatrix.argtypes = [ctypes.POINTER(api.IMat)]
+    assert not L.array_from_flappie_imatrix(None)
+    im = L.make_flappie_imatrix(3, 2)
+    np.ctypeslib.as_array(im.contents.data, shape=(2, 4))[:] = [[1, 2, 3, 0], [4, 5, 6, 0]]
+    dense = L.array_from_flappie_imatrix(im)
+    assert np.ctypeslib.as_array(dense, shape=(6,)).tolist() == [1, 2, 3, 4, 5, 6]
+    ctypes.CDLL(None).free(dense)
+    L.free_flappie_imatrix(im)
+    # bundle loader: rejects junk on any box; on a box without a GPU a good bundle is refused with a message, not computed
+    L.ffb_model_load.restype = ctypes.c_void_p
+    L.ffb_model_load.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    bad = tmp_path / "bad.ffbw"; bad.write_bytes(b"FFBW1\0\0\0" + b"\0" * 8)
+    assert not L.ffb_model_load(str(bad).encode(), 0) and b"not a weight bundle" in L.ffb_last_error()
+    assert not L.ffb_model_load(b"/nonexistent.ffbw", 0)
+    if lib.device_count() == 0:
+        fm = FlipflopModel.synthetic(KIND_GRU, 64, 4, seed=1)
+        good = tmp_path / "r941_native.ffbw"
+        fm.save_bundle(str(good))
+        assert not L.ffb_model_load(str(good).encode(), 0) and b"not available" in L.ffb_last_error()
+        os.environ["FLAPPIE_B200_MODELS"] = str(tmp_path)
+        try:
+            sig = np.zeros(500, np.float32)
+            rt = api.RawTable(None, 500, 0, 500, sig.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+            assert not L.calculate_transitions(rt, 1.0, 0)            # lazy load attempted, refused: NULL, no fallback
+        finally:
+            del os.environ["FLAPPIE_B200_MODELS"]

@@ -27,11 +27,11 @@ for title, name, lens in shapes:
     del raws
     import ctypes, torch
     samples = int(lensa.sum())
-    for tag, env in (("auto", {}), ("G=5 x13", {"FFB_TC_SLOTS": "5", "FFB_TC_CLUSTERS": "13"}), ("G=5 x15", {"FFB_TC_SLOTS": "5", "FFB_TC_CLUSTERS": "15"}),
+    for tag, env in (("auto", {}), ("auto, GEMM not streamed", {"FFB_NO_STREAM_GEMM": "1"}), ("G=5 x13", {"FFB_TC_SLOTS": "5", "FFB_TC_CLUSTERS": "13"}), ("G=5 x15", {"FFB_TC_SLOTS": "5", "FFB_TC_CLUSTERS": "15"}),
                      ("G=6 x13", {"FFB_TC_SLOTS": "6", "FFB_TC_CLUSTERS": "13"}), ("G=6 x15", {"FFB_TC_SLOTS": "6", "FFB_TC_CLUSTERS": "15"}),
                      ("G=4 x15", {"FFB_TC_SLOTS": "4", "FFB_TC_CLUSTERS": "15"}), ("G=3 x15", {"FFB_TC_SLOTS": "3", "FFB_TC_CLUSTERS": "15"}),
                      ("G=2 x15", {"FFB_TC_SLOTS": "2", "FFB_TC_CLUSTERS": "15"}), ("G=1 x15", {"FFB_TC_SLOTS": "1", "FFB_TC_CLUSTERS": "15"})):
-        for k in ("FFB_TC_SLOTS", "FFB_TC_CLUSTERS"):
+        for k in ("FFB_TC_SLOTS", "FFB_TC_CLUSTERS", "FFB_NO_STREAM_GEMM"):
             os.environ.pop(k, None)
         os.environ.update(env)
         b, o = ctx.make_batch(raw, off, 1.0, 0, want_path=True)
@@ -42,5 +42,5 @@ for title, name, lens in shapes:
         for _ in range(3):
             torch.cuda.synchronize(); t0 = time.perf_counter(); ctx.forward(); ctx.sync(); ts.append((time.perf_counter() - t0) * 1e3)
         g = ctx.forward_timed()
-        print(f"{title:45s} {tag:8s} {np.median(ts):8.2f} ms  {samples / np.median(ts) / 1e3:7.1f} M samples/s   sequential: rnn {g['rnn']:.1f} gemm {g['gemm']:.1f} ms", flush=True)
+        print(f"{title:45s} {tag:24s} {np.median(ts):8.2f} ms  {samples / np.median(ts) / 1e3:7.1f} M samples/s   sequential: rnn {g['rnn']:.1f} gemm {g['gemm']:.1f} ms", flush=True)
     ctx.close(); m.close()
