@@ -15,7 +15,7 @@ path): "scaling": "weak".
           called bases, quality characters and scores -- all inside the timed region.
   extra : the other BASELINE configs (r941_native LSTM-384 x1024, r941_5mC x4096, r10C_pcr mixed
           1 k-50 k, r941_rna002 --delta --reverse) with value / e2e / roofline.frac each, and the
-          STRONG-scaling set: a fixed 8192-read configs[3] workload dealt over the N ranks by
+          STRONG-scaling set: a fixed 24576-read configs[3] workload dealt over the N ranks by
           flappie_b200.shard.shard_reads.
   roofline     : the recurrent-layer kernel (dominant), algorithmic flops / CUDA-event time.
   cpu_baseline : the reference's own code (oracle/_ref, OpenBLAS, 1 thread per process,
@@ -325,7 +325,9 @@ def main():
     ap.add_argument("--ref-reads-per-core", type=int, default=6)
     ap.add_argument("--ref-reads-total", type=int, default=256)
     ap.add_argument("--no-extra", action="store_true", help="skip the `extra` configs (A/B runs)")
-    ap.add_argument("--strong-reads", type=int, default=8192, help="reads of the fixed configs[3] strong-scaling set")
+    ap.add_argument("--strong-reads", type=int, default=24576,
+                    help="reads of the fixed configs[3] strong-scaling set (3072 per GPU at N=8: a batch large enough that its "
+                         "longest read -- 24 895 dependent steps per layer -- does not dominate)")
     a = ap.parse_args()
 
     if a.impl == "reference":

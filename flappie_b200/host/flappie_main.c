@@ -285,6 +285,10 @@ struct dev_batch {
     ffb_batch b;
     ffb_raw_batch rb;
     bool busy;
+    /* the batch's records as text, formatted by the device thread right after the batch is collected; the main thread only
+     * copies read k's bytes [rec_off[k], rec_off[k+1]) out in input order */
+    char *text; size_t text_len;
+    size_t *rec_off; size_t rec_cap;
 };
 
 struct window { size_t first; int n; struct read_slot *rd; int cap; };
@@ -424,7 +428,46 @@ static void collect_batch(struct dev_batch *f) {
     f->busy = false;
 }
 
-/* the reference's per-read printing (src/flappie.c:364-385), for one window, in input order */
+/* the reference's per-read printing (src/flappie.c:364-385 -> fprintf_format), into memory: one device thread per batch */
+static void format_batch(struct dev_batch *f, const struct window *w) {
+    free(f->text); f->text = NULL; f->text_len = 0;
+    if (f->n == 0) return;
+    if ((size_t)f->n + 1 > f->rec_cap) {
+        f->rec_cap = (size_t)f->n + 1 + 256;
+        f->rec_off = realloc(f->rec_off, sizeof(size_t) * f->rec_cap);
+        if (!f->rec_off) die("out of memory%s", "");
+    }
+    FILE *ms = open_memstream(&f->text, &f->text_len);
+    if (!ms) die("out of memory%s", "");
+    f->rec_off[0] = 0;
+    for (int k = 0; k < f->n; k++) {
+        const struct read_slot *s = &w->rd[f->member[k]];
+        const int64_t nblock = f->blk_off[k + 1] - f->blk_off[k];
+        if (nblock > 0) {
+            const int64_t o0 = f->blk_off[k] + k;
+#ifdef FFB_RUNNIE
+            char *bases = calloc((size_t)nblock + 2, 1);
+            float *shape = calloc((size_t)nblock + 1, sizeof(float)), *scale = calloc((size_t)nblock + 1, sizeof(float));
+            int32_t *dwell = calloc((size_t)nblock + 1, sizeof(int32_t));
+            if (!bases || !shape || !scale || !dwell) die("out of memory%s", "");
+            const int64_t nrun = ffb_emit_runs(f->path + o0, f->rle + f->blk_off[k] * 8, nblock, G.nbase, bases, shape, scale, dwell);
+            fprintf(ms, "# %s\n", s->uuid);                                  /* src/runnie.c:277 */
+            for (int64_t r = 0; r < nrun; r++) fprintf(ms, "%c\t%f\t%f\t%d\n", bases[r], shape[r], scale[r], dwell[r]);
+            free(bases); free(shape); free(scale); free(dwell);
+#else
+            ffb_read_result res = {.score = f->score[k], .n = (size_t)s->n, .start = (size_t)f->start[k], .end = (size_t)f->end[k],
+                                   .basecall = f->bases + o0, .quality = f->quals + o0, .basecall_length = (size_t)f->nbases[k],
+                                   .nblock = (size_t)nblock};
+            ffb_fprintf_read(args.outformat, ms, s->uuid, s->name, args.uuid, args.prefix, &res);
+#endif
+        }
+        fflush(ms);
+        f->rec_off[k + 1] = f->text_len;
+    }
+    fclose(ms);
+}
+
+/* one window, in input order: the records the device threads formatted, the reference's messages for the reads without one */
 static FILE *trace_fp = NULL;
 static void print_window(struct window *w, int slot, int64_t *reads_called, int64_t *samples) {
     for (int i = 0; i < w->n; i++) {
@@ -440,27 +483,13 @@ static void print_window(struct window *w, int slot, int64_t *reads_called, int6
         }
         *reads_called += 1;
         *samples += s->n;
-        const int64_t o0 = f->blk_off[k] + k;
-#ifdef FFB_RUNNIE
-        {
-            char *bases = calloc((size_t)nblock + 2, 1);
-            float *shape = calloc((size_t)nblock + 1, sizeof(float)), *scale = calloc((size_t)nblock + 1, sizeof(float));
-            int32_t *dwell = calloc((size_t)nblock + 1, sizeof(int32_t));
-            if (!bases || !shape || !scale || !dwell) die("out of memory%s", "");
-            const int64_t nrun = ffb_emit_runs(f->path + o0, f->rle + f->blk_off[k] * 8, nblock, G.nbase, bases, shape, scale, dwell);
-            fprintf(args.output, "# %s\n", s->uuid);                                  /* src/runnie.c:277 */
-            for (int64_t r = 0; r < nrun; r++) fprintf(args.output, "%c\t%f\t%f\t%d\n", bases[r], shape[r], scale[r], dwell[r]);
-            free(bases); free(shape); free(scale); free(dwell);
-        }
-#else
-        ffb_read_result res = {.score = f->score[k], .n = (size_t)s->n, .start = (size_t)f->start[k], .end = (size_t)f->end[k],
-                               .basecall = f->bases + o0, .quality = f->quals + o0, .basecall_length = (size_t)f->nbases[k],
-                               .nblock = (size_t)nblock};
-        ffb_fprintf_read(args.outformat, args.output, s->uuid, s->name, args.uuid, args.prefix, &res);
-        if (trace_fp) ffb_write_trace(trace_fp, args.uuid ? s->uuid : s->name, f->trace + (size_t)o0 * (size_t)G.nstate, (size_t)nblock, (size_t)G.nstate);
+        fwrite(f->text + f->rec_off[k], 1, f->rec_off[k + 1] - f->rec_off[k], args.output);
+#ifndef FFB_RUNNIE
+        if (trace_fp) ffb_write_trace(trace_fp, args.uuid ? s->uuid : s->name, f->trace + (size_t)(f->blk_off[k] + k) * (size_t)G.nstate, (size_t)nblock, (size_t)G.nstate);
 #endif
         free(s->name); free(s->uuid);
     }
+    fflush(args.output);
 }
 
 /* ---- device thread: read my share -> (deal) -> pack + submit window w, collect window w-1 ---------------------------- */
@@ -474,7 +503,10 @@ static void *device_main(void *arg) {
         pthread_barrier_wait(&G.bar);       /* B1: window w is in memory */
         pthread_barrier_wait(&G.bar);       /* B2: the main thread has dealt it */
         if (w < G.nwin) submit_batch(dv, &dv->bat[w & 1], &G.win[w % 3]);
-        if (w > 0) collect_batch(&dv->bat[(w - 1) & 1]);
+        if (w > 0) {
+            collect_batch(&dv->bat[(w - 1) & 1]);
+            format_batch(&dv->bat[(w - 1) & 1], &G.win[(w - 1) % 3]);
+        }
         pthread_barrier_wait(&G.bar);       /* B3: window w-1 is complete: the main thread prints it */
     }
     return NULL;
@@ -489,6 +521,7 @@ static double now_s(void) {
 int main(int argc, char **argv) {
     parse_args(argc, argv);
     if (!args.output) args.output = stdout;
+    setvbuf(args.output, NULL, _IOFBF, 1 << 22);
 #ifdef FFB_RUNNIE
     if (args.trace) die("--trace %s: runnie writes no trace", args.trace);
 #endif
@@ -574,7 +607,7 @@ int main(int argc, char **argv) {
             ffb_free_pinned(f->end); ffb_free_pinned(f->score); ffb_free_pinned(f->nbases); ffb_free_pinned(f->bases);
             ffb_free_pinned(f->quals); ffb_free_pinned(f->path); ffb_free_pinned(f->qpath); ffb_free_pinned(f->rle);
             ffb_free_pinned(f->trace);
-            free(f->member);
+            free(f->member); free(f->text); free(f->rec_off);
         }
         ffb_model_destroy(G.dev[d].model);
     }

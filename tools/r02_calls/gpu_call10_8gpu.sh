@@ -15,5 +15,5 @@ for l in open('gpurun_out/r02_scale8.txt'):
         for e in d.get('extra', []):
             print(' ', e['config'][:80], '| value', round(e['value']/1e6,1), 'M/s | e2e', round(e.get('e2e',{}).get('value',0)/1e6,1), '| ms', round(e.get('ms_per_step', e.get('ms_per_pass',0)),1), e.get('shard_imbalance'))
 P
-timeout 900 python tools/cli_bench.py 16384 > gpurun_out/r02_cli_bench.txt 2>&1; cat gpurun_out/r02_cli_bench.txt
+timeout 1200 python tools/cli_bench.py 131072 > gpurun_out/r02_cli_bench.txt 2>&1; cat gpurun_out/r02_cli_bench.txt
 timeout 600 python -m pytest tests/test_host_cli.py -m gpu -q -k "devices or trace" > gpurun_out/r02_8gpu_pytest.txt 2>&1; tail -3 gpurun_out/r02_8gpu_pytest.txt
