@@ -747,7 +747,7 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
             group_of[(size_t)rd] = sl / R16;
             if (sl % R16 == 0) group_T[(size_t)(sl / R16)] = (int32_t)(c->blk_off[rd + 1] - c->blk_off[rd]);
         }
-        const int64_t TR = ffb_gemm_tc_stream_tile_rows();
+        const int64_t TR = ffb_gemm_tc_stream_tile_rows((int)S);
         const int64_t n_tiles = (Tt + TR - 1) / TR;
         const int arrivals = 4 * ffb_rnn_tc_cluster_size(m->kind, m->S);   // gate warps per group and cluster: C CTAs x 4 quadrants
         for (int dir = 0; dir < 2; dir++) {

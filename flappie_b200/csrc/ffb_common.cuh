@@ -125,7 +125,7 @@ int ffb_launch_sgemm_bias(const float *A, const float *Wt, const float *bias, fl
 int ffb_launch_ff_tanh(const float *A, const float *Wt, const float *bias, float *C, int64_t M, int N, int K,
                        float scale, int head, cudaStream_t st);
 
-// One work item of the streamed input GEMM: a tile (ffb_gemm_tc_stream_tile_rows() blocks) and what it waits
+// One work item of the streamed input GEMM: a tile (ffb_gemm_tc_stream_tile_rows(K) blocks) and what it waits
 // for -- the tile may be loaded once progress[idx[d]] >= cnt[d] for every d with idx[d] >= 0.  Items are
 // sorted by the step at which the producing recurrent layer completes them.
 struct GemmWork {
@@ -157,7 +157,7 @@ int ffb_launch_conv_gemm_tc(const void *Xhi, const void *Xlo, int64_t hop, const
 // writing the A planes; work items are taken from per-panel ticket queues in `work` order and each waits for its dependencies;
 // CTAs that find no free SM while the recurrence runs start when it ends and drain what is left.  Returns 0 (nothing launched) when the shape is unsupported.
 int ffb_gemm_tc_stream_supported(int N, int K);
-int ffb_gemm_tc_stream_tile_rows(void);   // rows (blocks) per streamed tile
+int ffb_gemm_tc_stream_tile_rows(int K);   // rows (blocks) per streamed tile of a projection with inner dimension K
 // progress: counters published by the recurrent kernel; queue: N/128 zeroed ticket counters (one per weight panel)
 int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                                 int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue, int n0,

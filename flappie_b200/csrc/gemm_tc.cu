@@ -736,14 +736,17 @@ int ffb_gemm_tc_prof(unsigned long long *out, int reset) {
 #endif
 }
 
-int ffb_gemm_tc_stream_tile_rows(void) { return ffb::GemmWsCfg::BB; }
-int ffb_gemm_tc_stream_supported(int N, int K) { return ffb_gemm_tc_supported(N, K) && N % 128 == 0 && K <= ffb::GemmWsCfg::KMAX; }
+// the streamed schedule runs on the W-stationary kernels: 128-block tiles up to K = 256, 64-block tiles up to K = 384
+int ffb_gemm_tc_stream_tile_rows(int K) { return K <= ffb::GemmWsCfg::KMAX ? ffb::GemmWsCfg::BB : ffb::GemmWsCfg384::BB; }
+int ffb_gemm_tc_stream_supported(int N, int K) { return ffb_gemm_tc_supported(N, K) && N % 128 == 0 && K <= ffb::GemmWsCfg384::KMAX; }
 
 int ffb_launch_gemm_tc_streamed(const void *Ahi, const void *Alo, const void *Whi, const void *Wlo, const float *bias, float *C,
                                 int64_t M, int N, int K, const GemmWork *work, const int *progress, int *queue, int n0,
                                 cudaStream_t st) {
     if (M <= 0) return 0;
     if (!ffb_gemm_tc_stream_supported(N, K) || !work || !progress || !queue || n0 < 0 || n0 >= N) return -1;
+    if (K > ffb::GemmWsCfg::KMAX)
+        return launch_gemm_ws<ffb::GemmWsCfg384>(Ahi, Alo, Whi, Wlo, bias, C, M, N - n0, K, st, work, progress, queue, n0, N);
     return launch_gemm_ws(Ahi, Alo, Whi, Wlo, bias, C, M, N - n0, K, st, work, progress, queue, n0, N);
 }
 

@@ -165,3 +165,24 @@ def test_repeat_bitwise_stress_cfg1(gpu_lib):
     for c in ctxs:
         c.close()
     m.close()
+
+
+@pytest.mark.parametrize("name,n,nsamp", [("gru256", 300, 3000), ("lstm384", 300, 3000), ("lstm256", 200, 2500), ("gru256_5", 2100, 1500)])
+def test_streamed_schedule_is_bit_identical_to_the_sequential_one(gpu_lib, name, n, nsamp):
+    """The input GEMM of layer l+1 streamed behind layer l's recurrence (programmatic dependent launch, per-tile progress
+    counters, Xin overwritten IN PLACE) against the plain kernel-after-kernel schedule (FFB_FLAG_KEEP_LAYERS switches the
+    streaming off): same arithmetic, so every bit of trans / path / qpath / score must agree -- for the 128-block tiles of
+    K = 256, the 64-block tiles of K = 384 (LSTM-384), ragged lengths, and a batch of several rounds per slot."""
+    fm = _model(name, 4)
+    rng = np.random.default_rng(5)
+    raws = [r[: int(rng.integers(nsamp // 3, nsamp + 1))] for r in synthetic_reads(n, nsamp, seed=29)]
+    sigs = [s for s in (hs.prepare_read(r) for r in raws) if s is not None]
+    m = Model(fm); ctx = Context(m)
+    a = ctx.basecall(sigs, want_trans=True)                        # streamed
+    b = ctx.basecall(sigs, want_trans=True, keep_layers=True)      # sequential
+    c = ctx.basecall(sigs, want_trans=True)                        # streamed again (workspaces reused)
+    nb = int(a.blk_off[-1]) + a.n_reads
+    for x in (b, c):
+        assert np.array_equal(a.trans, x.trans) and np.array_equal(a.path[:nb], x.path[:nb])
+        assert np.array_equal(a.qpath[:nb], x.qpath[:nb]) and np.array_equal(a.score, x.score)
+    ctx.close(); m.close()

@@ -173,8 +173,9 @@ def test_basecall_forward_backward_small(gpu_lib, oracle, name, kind, size, nbas
         full = oracle.basecall(fm, sig, 1.0, False)
         bases_g, qual_g = gpu_lib.emit_bases(p_g, q_g, fm.nbase)
         nb_same += int(bases_g == full["basecall"])
-        assert abs(len(bases_g) - len(full["basecall"])) <= 2
-    assert nb_same >= len(reads) - 1
+    # base for base on every read of this set (measured over 64 reads x 4000 samples per model: 0 reads with a differing
+    # base, profiles/r02_parity_report.txt; the rate over 256 reads is asserted in test_gpu_hardening.py)
+    assert nb_same == len(reads), f"{len(reads) - nb_same} of {len(reads)} reads differ from the oracle in a called base"
     ctx.close(); m.close()
 
 
