@@ -184,5 +184,5 @@ def test_streamed_schedule_is_bit_identical_to_the_sequential_one(gpu_lib, name,
     nb = int(a.blk_off[-1]) + a.n_reads
     for x in (b, c):
         assert np.array_equal(a.trans, x.trans) and np.array_equal(a.path[:nb], x.path[:nb])
-        assert np.array_equal(a.qpath[:nb], x.qpath[:nb]) and np.array_equal(a.score, x.score)
+        assert a.qpath[:nb].tobytes() == x.qpath[:nb].tobytes() and a.score.tobytes() == x.score.tobytes()   # qpath[0] is NAN
     ctx.close(); m.close()
