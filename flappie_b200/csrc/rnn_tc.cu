@@ -633,8 +633,15 @@ using LstmTc256 = RnnTcCfg<256, 8, 4, false, FFB_RNN_NACC>;
 // six slots per cluster (960 threads, 64 registers): more groups in flight per SM for batches that do not fit one wave
 using GruTc256x6 = RnnTcCfg<256, 8, 3, false, FFB_RNN_NACC, 6>;
 using LstmTc256x6 = RnnTcCfg<256, 8, 4, false, FFB_RNN_NACC, 6>;
-using GruTc384 = RnnTcCfg<384, 12, 3, false, 2>;    // 12-CTA clusters (non-portable size): 32 hidden units per CTA again,
-using LstmTc384 = RnnTcCfg<384, 12, 4, false, 2>;   // 2 x 192 TMEM columns of weights + 4 groups of 2 accumulators
+// S = 384: 12-CTA clusters (non-portable size), 32 hidden units per CTA again; 2 x 192 TMEM columns of weights leave 128 for
+// the accumulators.  ONE accumulator per group (cross terms first, then the full-magnitude Whi*hhi products: the same number
+// of full-magnitude truncating accumulations as a dedicated accumulator, profiles/r02_ab_notes.txt) makes room for FIVE slots
+// instead of four: 7 clusters x 5 = 35 slots take the 64 groups of a 1024-read batch in two rounds instead of three.
+#ifndef FFB_RNN_NACC384
+#define FFB_RNN_NACC384 1
+#endif
+using GruTc384 = RnnTcCfg<384, 12, 3, false, FFB_RNN_NACC384>;
+using LstmTc384 = RnnTcCfg<384, 12, 4, false, FFB_RNN_NACC384>;
 using GruTc512 = RnnTcCfg<512, 16, 3, true>;    // r103_native: 16-CTA clusters, hi plane in tensor memory (256 columns),
 using LstmTc512 = RnnTcCfg<512, 16, 4, true>;   // lo plane in shared memory (128 KB), 2 groups
 
