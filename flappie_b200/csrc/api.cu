@@ -74,6 +74,36 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Grow-only PINNED host staging area for the small per-batch plan arrays (offsets, geometry, schedules): copies out of
+// pageable memory make cudaMemcpyAsync wait for the stream first, copies out of this do not, and its contents live until
+// the context's next batch -- so nothing has to be synchronised just to keep a std::vector alive.
+struct PinArena {
+    uint8_t *p = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes) {            // invalidates earlier contents: callers reserve once per batch phase, up front
+        used = 0;
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaHostAlloc((void **)&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+        cap = want;
+        return 0;
+    }
+    void *take(size_t bytes) {             // 16-byte aligned slice; the caller has reserved enough
+        const size_t at = (used + 15) & ~(size_t)15;
+        if (at + bytes > cap) return nullptr;
+        used = at + bytes;
+        return p + at;
+    }
+    void *put(const void *src, size_t bytes) {
+        void *d = take(bytes);
+        if (d && bytes) memcpy(d, src, bytes);
+        return d;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = used = 0; }
+};
+
 // ------------------------------------------------------------------------------------
 struct ffb_model {
     int device = 0, kind = 0, S = 0, G = 0, nparam = 0, nbase = 0, nstate = 0, nconv = 0;
@@ -440,6 +470,15 @@ struct ffb_ctx {
     DevBuf d_bases, d_quals, d_nbases;   // device-side emission (emit.cu), read n at blk_off[n] + n
     bool want_emit = false;
     bool ff_done = false;         // this forward: the top recurrent layer produced trans
+    // pinned staging of the plan arrays (upload_impl) and of the raw phase (offsets out, trim bounds back)
+    PinArena h_plan, h_raw;
+    cudaEvent_t ev_plan = nullptr;    // recorded behind the last copy out of the arenas: the next batch waits for it first
+    bool plan_pending = false;
+    // ffb_submit_raw_begin .. ffb_submit_raw_finish
+    bool raw_begun = false;
+    ffb_raw_batch raw_rb;
+    ffb_batch raw_b;
+    int64_t *h_bounds = nullptr;      // in h_raw
     DevBuf d_c2hi, d_c2lo;        // tensor-core convolution: fp16 planes of its input in the slot layout (see forward_impl)
     int conv3_fix = 0;            // columns at either end of a read the CUDA-core kernel recomputes
     bool use_tc_conv3 = false;
@@ -472,6 +511,7 @@ extern "C" ffb_ctx *ffb_create(ffb_model *m, void *stream) {
         c->own_stream = true;
     }
     for (auto &e : c->ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming);
     return c;
 }
 
@@ -488,6 +528,8 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     for (int i = 0; i < FFB_MAX_CONV; i++) { c->d_geom[i].release(); c->d_tails[i].release(); }
     for (int i = 0; i < FFB_NLAYER; i++) c->d_keep[i].release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->ev_plan) cudaEventDestroy(c->ev_plan);
+    c->h_plan.release(); c->h_raw.release();
     if (c->own_stream) cudaStreamDestroy(c->st);
     delete c;
 }
@@ -851,27 +893,37 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
     if (!ok) { set_err("ffb_upload: out of device memory for %lld reads / %lld blocks", (long long)N, (long long)Tt); return FFB_ERR_NOMEM; }
 
     // ---- H2D (signal is the only bulk input: 4 bytes per raw sample) ----
+    // the plan arrays go through the pinned arena: no copy waits for the stream, nothing to synchronise afterwards
+    if (c->plan_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_plan), FFB_ERR_CUDA); c->plan_pending = false; }   // an earlier batch still reading it
+    {
+        size_t need = 256 + sizeof(int64_t) * (size_t)(N + 1) + sizeof(int32_t) * ((size_t)c->n_slots + c->slot_off.size() + c->slot_list.size());
+        for (int i = 0; i < m->nconv; i++) need += 64 + sizeof(ffb::ReadGeom) * (size_t)N + sizeof(ffb::ConvTail) * tails[i].size();
+        for (int dir = 0; dir < 2; dir++) need += 64 + sizeof(GemmWork) * work[dir].size();
+        if (c->h_plan.reserve(need + 1024) != 0) { set_err("ffb_upload: out of pinned host memory"); return FFB_ERR_NOMEM; }
+    }
+    auto h2d = [&](void *dst, const void *src, size_t bytes) -> bool {
+        if (bytes == 0) return true;
+        void *stage = c->h_plan.put(src, bytes);
+        return stage && cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, c->st) == cudaSuccess;
+    };
     if (c->total_samples > 0 && copy_signal)
         CUDA_TRY(cudaMemcpyAsync(c->d_sig.p, b->signal + b->sig_off[0], sizeof(float) * (size_t)c->total_samples,
                                  cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
-    CUDA_TRY(cudaMemcpyAsync(c->d_blkoff.p, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
-    if (c->n_slots > 0)
-        CUDA_TRY(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int32_t) * (size_t)c->n_slots, cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+    bool up = h2d(c->d_blkoff.p, c->blk_off.data(), sizeof(int64_t) * (size_t)(N + 1));
+    if (c->n_slots > 0) up = up && h2d(c->d_order.p, c->order.data(), sizeof(int32_t) * (size_t)c->n_slots);
     if (!c->slot_off.empty()) {
-        CUDA_TRY(cudaMemcpyAsync(c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * c->slot_off.size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
-        if (!c->slot_list.empty())
-            CUDA_TRY(cudaMemcpyAsync(c->d_slotlist.p, c->slot_list.data(), sizeof(int32_t) * c->slot_list.size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+        up = up && h2d(c->d_slotoff.p, c->slot_off.data(), sizeof(int32_t) * c->slot_off.size());
+        up = up && h2d(c->d_slotlist.p, c->slot_list.data(), sizeof(int32_t) * c->slot_list.size());
     }
     for (int i = 0; i < m->nconv; i++) {
-        if (N > 0) CUDA_TRY(cudaMemcpyAsync(c->d_geom[i].p, geom[i].data(), sizeof(ffb::ReadGeom) * (size_t)N, cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
-        if (!tails[i].empty())
-            CUDA_TRY(cudaMemcpyAsync(c->d_tails[i].p, tails[i].data(), sizeof(ffb::ConvTail) * tails[i].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
+        if (N > 0) up = up && h2d(c->d_geom[i].p, geom[i].data(), sizeof(ffb::ReadGeom) * (size_t)N);
+        up = up && h2d(c->d_tails[i].p, tails[i].data(), sizeof(ffb::ConvTail) * tails[i].size());
     }
     if (c->stream_gemm)
-        for (int dir = 0; dir < 2; dir++)
-            CUDA_TRY(cudaMemcpyAsync(c->d_work[dir].p, work[dir].data(), sizeof(GemmWork) * work[dir].size(), cudaMemcpyHostToDevice, c->st), FFB_ERR_CUDA);
-    // the staging vectors above are pageable: make sure the copies have consumed them
-    CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
+        for (int dir = 0; dir < 2; dir++) up = up && h2d(c->d_work[dir].p, work[dir].data(), sizeof(GemmWork) * work[dir].size());
+    if (!up) { set_err("ffb_upload: plan upload failed: %s", cudaGetErrorString(cudaGetLastError())); return FFB_ERR_CUDA; }
+    CUDA_TRY(cudaEventRecord(c->ev_plan, c->st), FFB_ERR_CUDA);
+    c->plan_pending = true;
     return FFB_OK;
 }
 
@@ -879,7 +931,10 @@ extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) { return upload_impl(c
 
 // ---- raw reads: trimming + normalisation on the device, then the same plan -----------------------
 // (reference src/flappie.c:251-259; kernels in signal.cu)
-extern "C" int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
+// Two halves, because the plan needs the trimmed lengths back from the device: `begin` enqueues the raw upload, the chunk
+// MADs, the trim bounds and their copy back, and returns; `finish` waits for the bounds, plans and enqueues the rest.  A host
+// thread can do something useful in between (the command line reads the next window's files).
+static int upload_raw_begin(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
     if (!c || !rb || !b || !rb->raw || !rb->raw_off || rb->n_reads < 0 || rb->n_reads != b->n_reads) {
         set_err("ffb_upload_raw: bad arguments");
         return FFB_ERR_ARG;
@@ -909,38 +964,66 @@ extern "C" int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_bat
               c->d_sigoff.reserve(sizeof(int64_t) * (size_t)(N + 1)) == 0;
     if (!ok) { set_err("ffb_upload_raw: out of device memory"); return FFB_ERR_NOMEM; }
     cudaStream_t st = c->st;
-    std::vector<int64_t> bounds(2 * (size_t)N, 0), soff((size_t)N + 1, 0);
+    if (c->plan_pending) { CUDA_TRY(cudaEventSynchronize(c->ev_plan), FFB_ERR_CUDA); c->plan_pending = false; }
+    if (c->h_raw.reserve(sizeof(int64_t) * (5 * (size_t)N + 8) + 256) != 0) { set_err("ffb_upload_raw: out of pinned host memory"); return FFB_ERR_NOMEM; }
+    const int64_t *h_roff = (const int64_t *)c->h_raw.put(roff.data(), sizeof(int64_t) * (size_t)(N + 1));
+    const int64_t *h_coff = (const int64_t *)c->h_raw.put(coff.data(), sizeof(int64_t) * (size_t)(N + 1));
+    c->h_bounds = (int64_t *)c->h_raw.take(sizeof(int64_t) * 2 * (size_t)std::max<int64_t>(N, 1));
+    if (!h_roff || !h_coff || !c->h_bounds) return FFB_ERR_NOMEM;
     if (N > 0) {
         if (total_raw > 0)
             CUDA_TRY(cudaMemcpyAsync(c->d_raw.p, rb->raw + rb->raw_off[0], sizeof(float) * (size_t)total_raw, cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
-        CUDA_TRY(cudaMemcpyAsync(c->d_rawoff.p, roff.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
-        CUDA_TRY(cudaMemcpyAsync(c->d_chunkoff.p, coff.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        CUDA_TRY(cudaMemcpyAsync(c->d_rawoff.p, h_roff, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        CUDA_TRY(cudaMemcpyAsync(c->d_chunkoff.p, h_coff, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
         LAUNCH_RAW(ffb_launch_chunk_mad(c->d_raw.as<float>(), c->d_rawoff.as<int64_t>(), c->d_chunkoff.as<int64_t>(), (int)N, chunk,
                                         total_chunks, c->d_mad.as<float>(), st));
         LAUNCH_RAW(ffb_launch_trim_bounds(c->d_mad.as<float>(), c->d_rawoff.as<int64_t>(), c->d_chunkoff.as<int64_t>(), (int)N, chunk,
                                           rb->varseg_thresh, rb->trim_start, rb->trim_end, c->d_bounds.as<int64_t>(), st));
-        CUDA_TRY(cudaMemcpyAsync(bounds.data(), c->d_bounds.p, sizeof(int64_t) * 2 * (size_t)N, cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
-        CUDA_TRY(cudaStreamSynchronize(st), FFB_ERR_CUDA);     // the plan below needs the trimmed lengths
+        CUDA_TRY(cudaMemcpyAsync(c->h_bounds, c->d_bounds.p, sizeof(int64_t) * 2 * (size_t)N, cudaMemcpyDeviceToHost, st), FFB_ERR_CUDA);
     }
+    c->raw_rb = *rb; c->raw_b = *b;
+    c->raw_begun = true;
+    return FFB_OK;
+}
+
+static int upload_raw_finish(ffb_ctx *c) {
+    if (!c || !c->raw_begun) { set_err("ffb_submit_raw_finish: no batch was begun on this context"); return FFB_ERR_ARG; }
+    c->raw_begun = false;
+    ffb_model *m = c->m;
+    CUDA_TRY(cudaSetDevice(m->device), FFB_ERR_CUDA);
+    const ffb_raw_batch *rb = &c->raw_rb;
+    const int64_t N = rb->n_reads;
+    cudaStream_t st = c->st;
+    if (N > 0) CUDA_TRY(cudaStreamSynchronize(st), FFB_ERR_CUDA);     // the plan below needs the trimmed lengths
+    std::vector<int64_t> soff((size_t)N + 1, 0);
     for (int64_t n = 0; n < N; n++) {
-        const int64_t s = bounds[2 * (size_t)n], e = bounds[2 * (size_t)n + 1];
+        const int64_t s = c->h_bounds[2 * (size_t)n], e = c->h_bounds[2 * (size_t)n + 1];
         soff[(size_t)n + 1] = soff[(size_t)n] + (s < e ? e - s : 0);    // start >= end: the reference drops the read (flappie_common.c:22-25)
         if (rb->start) rb->start[n] = s;
         if (rb->end) rb->end[n] = e;
     }
-    ffb_batch plan = *b;
+    ffb_batch plan = c->raw_b;
     plan.signal = nullptr;
     plan.sig_off = soff.data();
     if (rb->delta != 0.0f) plan.flags |= FFB_FLAG_FP32_CONV;      // unnormalised delta samples: see flappie_b200.h
     const int r = upload_impl(c, &plan, false);
     if (r != FFB_OK) return r;
     if (N > 0) {
-        CUDA_TRY(cudaMemcpyAsync(c->d_sigoff.p, soff.data(), sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        // soff rides in what is left of the raw arena (its first copies were consumed before the synchronisation above)
+        const int64_t *h_soff = (const int64_t *)c->h_raw.put(soff.data(), sizeof(int64_t) * (size_t)(N + 1));
+        if (!h_soff) return FFB_ERR_NOMEM;
+        CUDA_TRY(cudaMemcpyAsync(c->d_sigoff.p, h_soff, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
         LAUNCH_RAW(ffb_launch_normalise(c->d_raw.as<float>(), c->d_rawoff.as<int64_t>(), c->d_bounds.as<int64_t>(), c->d_sigoff.as<int64_t>(),
                                         (int)N, rb->delta, c->d_sig.as<float>(), st));
-        CUDA_TRY(cudaStreamSynchronize(st), FFB_ERR_CUDA);     // soff is a stack-lifetime staging vector
+        CUDA_TRY(cudaEventRecord(c->ev_plan, st), FFB_ERR_CUDA);     // behind the last copy out of either arena
+        c->plan_pending = true;
     }
     return FFB_OK;
+}
+
+extern "C" int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
+    const int r = upload_raw_begin(c, rb, b);
+    return r != FFB_OK ? r : upload_raw_finish(c);
 }
 
 // ---- all kernels of the path ------------------------------------------------------------
@@ -1223,6 +1306,17 @@ extern "C" int ffb_submit_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const f
     r = ffb_forward(c);
     if (r != FFB_OK) return r;
     return download_enqueue(c, b);
+}
+
+// the same in two halves (see upload_raw_begin): nothing is waited for in `begin`; `finish` blocks only until the trim bounds
+// of THIS batch are back (a few hundred microseconds of device work, queued behind whatever else the device is doing)
+extern "C" int ffb_submit_raw_begin(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) { return upload_raw_begin(c, rb, b); }
+extern "C" int ffb_submit_raw_finish(ffb_ctx *c) {
+    int r = upload_raw_finish(c);
+    if (r != FFB_OK) return r;
+    r = ffb_forward(c);
+    if (r != FFB_OK) return r;
+    return download_enqueue(c, &c->raw_b);
 }
 
 extern "C" int ffb_basecall_batch(ffb_ctx *c, const ffb_batch *b) {

@@ -1,7 +1,10 @@
 /* ffb_rawio.c -- raw signal readers for the command line (stand-ins for read_raw, src/fast5_interface.c:231-300,
  * which needs libhdf5). */
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "ffb_host.h"
 
@@ -14,21 +17,26 @@ bool ffb_is_signal_file(const char *path) {
     return path && (has_suffix(path, ".f32") || has_suffix(path, ".crp") || has_suffix(path, ".fast5"));
 }
 
+/* one open / fstat / read / close per file: the command line reads thousands of single-read files per second per thread */
 static long read_f32(const char *path, float **out) {
-    FILE *fp = fopen(path, "rb");
-    if (!fp) return -1;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return -1;
+    struct stat sb;
     long n = -1;
-    if (fseek(fp, 0, SEEK_END) == 0) {
-        const long bytes = ftell(fp);
-        rewind(fp);
-        if (bytes >= 0 && bytes % (long)sizeof(float) == 0) {
-            n = bytes / (long)sizeof(float);
-            float *buf = malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
-            if (!buf || fread(buf, sizeof(float), (size_t)n, fp) != (size_t)n) { free(buf); n = -1; }
-            else *out = buf;
+    if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size % (off_t)sizeof(float) == 0) {
+        n = (long)(sb.st_size / (off_t)sizeof(float));
+        float *buf = malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+        size_t got = 0;
+        const size_t want = (size_t)n * sizeof(float);
+        while (buf && got < want) {
+            const ssize_t r = read(fd, (char *)buf + got, want - got);
+            if (r <= 0) break;
+            got += (size_t)r;
         }
+        if (!buf || got != want) { free(buf); n = -1; }
+        else *out = buf;
     }
-    fclose(fp);
+    close(fd);
     return n;
 }
 

@@ -7,11 +7,13 @@
  *   window  = the next (devices x --batch) files, in input order
  *   read    : every device thread reads its share of the window's files                      (parallel host I/O)
  *   deal    : reads sorted by length, longest first to the least-loaded device (LPT)         (main thread)
- *   submit  : each device thread packs its batch into pinned memory and enqueues upload + trimming + normalisation +
- *             network + decoding + base/quality emission + the device-to-host copies, without waiting (two contexts
- *             per device: window w+1 is read, dealt and uploaded while the GPUs work on window w)
- *   collect : wait for the older window's batches
- *   print   : the records of that window in INPUT ORDER, whatever device called them           (main thread)
+ *   submit  : each device thread packs its batch into pinned memory and enqueues the raw upload + trimming
+ *             (ffb_submit_raw_begin), reads its share of the NEXT window while the device trims, then plans and enqueues
+ *             normalisation + network + decoding + base/quality emission + the device-to-host copies
+ *             (ffb_submit_raw_finish) -- two contexts per device, so the GPUs work on window w-1 meanwhile
+ *   collect : wait for the older window's batch and format its records into memory           (device threads)
+ *   print   : the records of a window in INPUT ORDER, whatever device called them             (main thread, one window
+ *             behind the formatting, concurrent with the device threads)
  *
  * Reads never cross devices and there is no collective: basecalling shards embarrassingly.
  *
@@ -285,13 +287,12 @@ struct dev_batch {
     ffb_batch b;
     ffb_raw_batch rb;
     bool busy;
-    /* the batch's records as text, formatted by the device thread right after the batch is collected; the main thread only
-     * copies read k's bytes [rec_off[k], rec_off[k+1]) out in input order */
-    char *text; size_t text_len;
-    size_t *rec_off; size_t rec_cap;
 };
 
-struct window { size_t first; int n; struct read_slot *rd; int cap; };
+/* what a device thread leaves behind for the printer once it has collected its batch of a window: the records as text
+ * (read k of the batch = bytes [rec_off[k], rec_off[k+1])), the block counts, and -- with --trace -- a copy of the trace rows */
+struct win_out { char *text; size_t text_len; size_t *rec_off; int64_t *nblock; uint8_t *trace; size_t *trace_off; int n; };
+struct window { size_t first; int n; struct read_slot *rd; int cap; struct win_out out[MAX_DEVICES]; };
 
 struct device {
     int id, rank;
@@ -302,7 +303,8 @@ struct device {
 
 static struct {
     struct filelist files;
-    struct window win[3];       /* window w lives in slot w % 3: w-1 is being printed while w+1 is being read */
+    struct window win[4];       /* window w lives in slot w % 4: while w is on the devices, w+1 is being read, w-1 collected
+                                 * and formatted, w-2 printed */
     struct device dev[MAX_DEVICES];
     int ndev, nwin, nstate, nbase;
     size_t window_reads;
@@ -358,7 +360,8 @@ static void deal_window(struct window *w, int slot) {
     free(len); free(dev_of);
 }
 
-static void submit_batch(struct device *dv, struct dev_batch *f, struct window *w) {
+/* pack the batch into pinned memory and enqueue its raw upload + trimming (ffb_submit_raw_begin: returns at once) */
+static void submit_begin(struct device *dv, struct dev_batch *f, struct window *w) {
     f->busy = false;
     if (f->n == 0) return;
     const int n = f->n;
@@ -418,8 +421,14 @@ static void submit_batch(struct device *dv, struct dev_batch *f, struct window *
     /* bases and quality characters come off the device (emit.cu): path / qpath stay there */
     f->b.bases = f->bases; f->b.quals = f->quals; f->b.nbases = f->nbases; f->b.trace = f->trace;
 #endif
-    if (ffb_submit_raw_batch(f->ctx, &f->rb, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
+    if (ffb_submit_raw_begin(f->ctx, &f->rb, &f->b) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
     f->busy = true;
+}
+
+/* ... and, once the trim bounds are back, the plan and every other kernel (ffb_submit_raw_finish) */
+static void submit_finish(struct dev_batch *f) {
+    if (!f->busy) return;
+    if (ffb_submit_raw_finish(f->ctx) != FFB_OK) die("device basecall failed: %s", ffb_last_error());
 }
 
 static void collect_batch(struct dev_batch *f) {
@@ -429,22 +438,25 @@ static void collect_batch(struct dev_batch *f) {
 }
 
 /* the reference's per-read printing (src/flappie.c:364-385 -> fprintf_format), into memory: one device thread per batch */
-static void format_batch(struct dev_batch *f, const struct window *w) {
-    free(f->text); f->text = NULL; f->text_len = 0;
+static void format_batch(const struct dev_batch *f, struct window *w, int d) {
+    struct win_out *o = &w->out[d];
+    memset(o, 0, sizeof *o);
+    o->n = f->n;
     if (f->n == 0) return;
-    if ((size_t)f->n + 1 > f->rec_cap) {
-        f->rec_cap = (size_t)f->n + 1 + 256;
-        f->rec_off = realloc(f->rec_off, sizeof(size_t) * f->rec_cap);
-        if (!f->rec_off) die("out of memory%s", "");
-    }
-    FILE *ms = open_memstream(&f->text, &f->text_len);
+    o->rec_off = malloc(sizeof(size_t) * ((size_t)f->n + 1));
+    o->nblock = malloc(sizeof(int64_t) * (size_t)f->n);
+    if (!o->rec_off || !o->nblock) die("out of memory%s", "");
+    FILE *ms = open_memstream(&o->text, &o->text_len);
     if (!ms) die("out of memory%s", "");
-    f->rec_off[0] = 0;
+    o->rec_off[0] = 0;
+    size_t trace_bytes = 0;
     for (int k = 0; k < f->n; k++) {
         const struct read_slot *s = &w->rd[f->member[k]];
         const int64_t nblock = f->blk_off[k + 1] - f->blk_off[k];
+        o->nblock[k] = nblock;
         if (nblock > 0) {
             const int64_t o0 = f->blk_off[k] + k;
+            trace_bytes += (size_t)(nblock + 1) * (size_t)G.nstate;
 #ifdef FFB_RUNNIE
             char *bases = calloc((size_t)nblock + 2, 1);
             float *shape = calloc((size_t)nblock + 1, sizeof(float)), *scale = calloc((size_t)nblock + 1, sizeof(float));
@@ -462,20 +474,37 @@ static void format_batch(struct dev_batch *f, const struct window *w) {
 #endif
         }
         fflush(ms);
-        f->rec_off[k + 1] = f->text_len;
+        o->rec_off[k + 1] = o->text_len;
     }
     fclose(ms);
+#ifndef FFB_RUNNIE
+    if (args.trace && trace_bytes > 0) {          /* the pinned trace buffer is reused two windows later: keep the rows */
+        o->trace = malloc(trace_bytes);
+        o->trace_off = malloc(sizeof(size_t) * ((size_t)f->n + 1));
+        if (!o->trace || !o->trace_off) die("out of memory%s", "");
+        size_t at = 0;
+        for (int k = 0; k < f->n; k++) {
+            o->trace_off[k] = at;
+            if (o->nblock[k] > 0) {
+                const size_t nb = (size_t)(o->nblock[k] + 1) * (size_t)G.nstate;
+                memcpy(o->trace + at, f->trace + (size_t)(f->blk_off[k] + k) * (size_t)G.nstate, nb);
+                at += nb;
+            }
+        }
+        o->trace_off[f->n] = at;
+    }
+#endif
 }
 
 /* one window, in input order: the records the device threads formatted, the reference's messages for the reads without one */
 static FILE *trace_fp = NULL;
-static void print_window(struct window *w, int slot, int64_t *reads_called, int64_t *samples) {
+static void print_window(struct window *w, int64_t *reads_called, int64_t *samples) {
     for (int i = 0; i < w->n; i++) {
         struct read_slot *s = &w->rd[i];
         if (s->n == -2) fprintf(stderr, PROGRAM ": %s: fast5 input needs libhdf5, which this build does not have\n", s->name);
-        const struct dev_batch *f = s->dev >= 0 ? &G.dev[s->dev].bat[slot] : NULL;
+        const struct win_out *o = s->dev >= 0 ? &w->out[s->dev] : NULL;
         const int k = s->pos;
-        const int64_t nblock = f ? f->blk_off[k + 1] - f->blk_off[k] : 0;
+        const int64_t nblock = o ? o->nblock[k] : 0;
         if (nblock <= 0) {
             if (s->n != -2) fprintf(stderr, PROGRAM ": No basecall returned for %s\n", s->name);   /* src/flappie.c:370-373 */
             free(s->name); free(s->uuid);
@@ -483,31 +512,38 @@ static void print_window(struct window *w, int slot, int64_t *reads_called, int6
         }
         *reads_called += 1;
         *samples += s->n;
-        fwrite(f->text + f->rec_off[k], 1, f->rec_off[k + 1] - f->rec_off[k], args.output);
-#ifndef FFB_RUNNIE
-        if (trace_fp) ffb_write_trace(trace_fp, args.uuid ? s->uuid : s->name, f->trace + (size_t)(f->blk_off[k] + k) * (size_t)G.nstate, (size_t)nblock, (size_t)G.nstate);
-#endif
+        fwrite(o->text + o->rec_off[k], 1, o->rec_off[k + 1] - o->rec_off[k], args.output);
+        if (trace_fp && o->trace) ffb_write_trace(trace_fp, args.uuid ? s->uuid : s->name, o->trace + o->trace_off[k], (size_t)nblock, (size_t)G.nstate);
         free(s->name); free(s->uuid);
     }
     fflush(args.output);
+    for (int d = 0; d < G.ndev; d++) {
+        struct win_out *o = &w->out[d];
+        free(o->text); free(o->rec_off); free(o->nblock); free(o->trace); free(o->trace_off);
+        memset(o, 0, sizeof *o);
+    }
 }
 
-/* ---- device thread: read my share -> (deal) -> pack + submit window w, collect window w-1 ---------------------------- */
+/* ---- device thread.  Iteration w: enqueue the raw upload + trimming of window w, read the files of window w+1 while the
+ * device trims (and still computes window w-1), plan and enqueue the rest of w, then collect and format window w-1 ------ */
+static void read_window(const struct device *dv, struct window *win) {
+    for (int i = dv->rank; i < win->n; i += G.ndev) read_one(&win->rd[i], G.files.path[win->first + (size_t)i]);
+}
+
 static void *device_main(void *arg) {
     struct device *dv = arg;
+    if (G.nwin > 0) read_window(dv, &G.win[0]);
     for (int w = 0; w <= G.nwin; w++) {
-        if (w < G.nwin) {
-            struct window *win = &G.win[w % 3];
-            for (int i = dv->rank; i < win->n; i += G.ndev) read_one(&win->rd[i], G.files.path[win->first + (size_t)i]);
-        }
         pthread_barrier_wait(&G.bar);       /* B1: window w is in memory */
-        pthread_barrier_wait(&G.bar);       /* B2: the main thread has dealt it */
-        if (w < G.nwin) submit_batch(dv, &dv->bat[w & 1], &G.win[w % 3]);
+        pthread_barrier_wait(&G.bar);       /* B2: the main thread has dealt it (and set the geometry of window w+1) */
+        if (w < G.nwin) submit_begin(dv, &dv->bat[w & 1], &G.win[w % 4]);
+        if (w + 1 < G.nwin) read_window(dv, &G.win[(w + 1) % 4]);
+        if (w < G.nwin) submit_finish(&dv->bat[w & 1]);
         if (w > 0) {
             collect_batch(&dv->bat[(w - 1) & 1]);
-            format_batch(&dv->bat[(w - 1) & 1], &G.win[(w - 1) % 3]);
+            format_batch(&dv->bat[(w - 1) & 1], &G.win[(w - 1) % 4], dv->rank);
         }
-        pthread_barrier_wait(&G.bar);       /* B3: window w-1 is complete: the main thread prints it */
+        pthread_barrier_wait(&G.bar);       /* B3: window w-1 is formatted; the main thread prints it during iteration w+1 */
     }
     return NULL;
 }
@@ -561,14 +597,14 @@ int main(int argc, char **argv) {
     expand_arguments(argc, argv, &G.files);
     G.window_reads = (size_t)G.ndev * (size_t)args.batch;
     G.nwin = (int)((G.files.n + G.window_reads - 1) / G.window_reads);
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 4; k++) {
         G.win[k].cap = (int)G.window_reads;
         G.win[k].rd = calloc(G.window_reads, sizeof(struct read_slot));
         if (!G.win[k].rd) die("out of memory%s", "");
     }
     pthread_barrier_init(&G.bar, NULL, (unsigned)G.ndev + 1);
-    /* window geometry is a pure function of w; slot w % 3 is set by the main thread before any device thread reads it:
-     * window 0 here, window w+1 between B1 and B2 of iteration w (its slot held window w-2, printed an iteration ago) */
+    /* window geometry is a pure function of w; slot w % 4 is set by the main thread before any device thread reads it:
+     * window 0 here, window w+1 between B1 and B2 of iteration w (its slot held window w-3, printed two iterations ago) */
     if (G.nwin > 0) {
         G.win[0].first = 0;
         G.win[0].n = (int)(G.files.n < G.window_reads ? G.files.n : G.window_reads);
@@ -579,19 +615,19 @@ int main(int argc, char **argv) {
     int64_t reads_called = 0, samples = 0;
     for (int w = 0; w <= G.nwin; w++) {
         pthread_barrier_wait(&G.bar);       /* B1 */
-        if (w < G.nwin) deal_window(&G.win[w % 3], w & 1);
+        if (w < G.nwin) deal_window(&G.win[w % 4], w & 1);
         if (w + 1 < G.nwin) {
-            struct window *nx = &G.win[(w + 1) % 3];
+            struct window *nx = &G.win[(w + 1) % 4];
             nx->first = (size_t)(w + 1) * G.window_reads;
             const size_t left = G.files.n - nx->first;
             nx->n = (int)(left < G.window_reads ? left : G.window_reads);
         }
         pthread_barrier_wait(&G.bar);       /* B2 */
+        /* while the device threads work on iteration w: print window w-2 (formatted before B3 of iteration w-1) */
+        if (w >= 2) print_window(&G.win[(w - 2) % 4], &reads_called, &samples);
         pthread_barrier_wait(&G.bar);       /* B3 */
-        /* the device threads are already reading window w+1 (another slot); its batches reuse the buffers printed here
-         * only after the next B2, which this thread reaches after printing */
-        if (w > 0) print_window(&G.win[(w - 1) % 3], (w - 1) & 1, &reads_called, &samples);
     }
+    if (G.nwin >= 1) print_window(&G.win[(G.nwin - 1) % 4], &reads_called, &samples);     /* formatted in the last iteration */
     for (int d = 0; d < G.ndev; d++) pthread_join(G.dev[d].th, NULL);
     const double t1 = now_s();
     if (args.stats)
@@ -607,12 +643,12 @@ int main(int argc, char **argv) {
             ffb_free_pinned(f->end); ffb_free_pinned(f->score); ffb_free_pinned(f->nbases); ffb_free_pinned(f->bases);
             ffb_free_pinned(f->quals); ffb_free_pinned(f->path); ffb_free_pinned(f->qpath); ffb_free_pinned(f->rle);
             ffb_free_pinned(f->trace);
-            free(f->member); free(f->text); free(f->rec_off);
+            free(f->member);
         }
         ffb_model_destroy(G.dev[d].model);
     }
     for (size_t i = 0; i < G.files.n; i++) free(G.files.path[i]);
-    free(G.files.path); free(G.win[0].rd); free(G.win[1].rd); free(G.win[2].rd);
+    free(G.files.path); free(G.win[0].rd); free(G.win[1].rd); free(G.win[2].rd); free(G.win[3].rd);
     if (trace_fp) fclose(trace_fp);
     if (stdout != args.output) fclose(args.output);
     return EXIT_SUCCESS;

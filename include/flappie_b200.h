@@ -244,6 +244,12 @@ int ffb_basecall_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch 
  * ffb_collect returns. */
 int ffb_submit_batch(ffb_ctx *c, const ffb_batch *b);
 int ffb_submit_raw_batch(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
+/* ffb_submit_raw_batch in two halves.  The plan of a raw batch needs the trimmed lengths back from the device: `begin`
+ * enqueues the raw upload, the trimming kernels and the copy back of their bounds and returns at once; `finish` waits for
+ * those bounds, plans, and enqueues everything else (it is what blocks in ffb_submit_raw_batch).  A host thread can read the
+ * next batch's files in between.  `rb`, `b` and what they point to belong to the library until ffb_collect returns. */
+int ffb_submit_raw_begin(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b);
+int ffb_submit_raw_finish(ffb_ctx *c);
 int ffb_collect(ffb_ctx *c, const ffb_batch *b);
 /* zero-filled page-locked host memory (NULL on failure), for callers that do not link the CUDA runtime */
 void *ffb_alloc_pinned(size_t bytes);
