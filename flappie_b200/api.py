@@ -49,7 +49,7 @@ EXPORTS = [
     "ffb_alloc_pinned", "ffb_free_pinned",
     "decode_crf_runlength", "transpost_crf_runlength", "ffb_emit_runs", "ffb_plan_schedule", "ffb_phred_table",
     "change_positions", "nbase_from_crf_runlength_nparam", "array_from_flappie_imatrix", "ffb_model_load",
-    "ffb_submit_raw_begin", "ffb_submit_raw_finish",
+    "ffb_submit_raw_begin", "ffb_submit_raw_finish", "ffb_reserve",
 ]
 
 

@@ -929,6 +929,28 @@ static int upload_impl(ffb_ctx *c, const ffb_batch *b, bool copy_signal) {
 
 extern "C" int ffb_upload(ffb_ctx *c, const ffb_batch *b) { return upload_impl(c, b, true); }
 
+// Size the context's grow-only workspaces for batches of n_reads reads of samples_per_read samples before the first real
+// batch arrives (cudaMalloc of gigabytes is slow and serialises across the threads of a process): plans a dummy uniform
+// batch, which reserves everything, and uploads nothing but its plan.
+extern "C" int ffb_reserve(ffb_ctx *c, int64_t n_reads, int64_t samples_per_read, uint32_t flags) {
+    if (!c || n_reads < 0 || samples_per_read < 0) return FFB_ERR_ARG;
+    std::vector<int64_t> off((size_t)n_reads + 1);
+    for (int64_t n = 0; n <= n_reads; n++) off[(size_t)n] = n * samples_per_read;
+    ffb_batch plan;
+    memset(&plan, 0, sizeof plan);
+    plan.sig_off = off.data(); plan.n_reads = n_reads; plan.temperature = 1.0f; plan.flags = flags;
+    char dummy = 0;
+    plan.bases = &dummy; plan.quals = &dummy; int32_t nb = 0; plan.nbases = &nb;      // the emission buffers too
+    int r = upload_impl(c, &plan, false);
+    if (r != FFB_OK) return r;
+    const int64_t total = n_reads * samples_per_read;
+    const bool ok = c->d_raw.reserve(sizeof(float) * (size_t)std::max<int64_t>(total, 1)) == 0 &&
+                    c->d_mad.reserve(sizeof(float) * (size_t)std::max<int64_t>(total / 2 + n_reads, 1)) == 0;
+    CUDA_TRY(cudaStreamSynchronize(c->st), FFB_ERR_CUDA);
+    c->n_reads = 0; c->total_blocks = 0; c->total_samples = 0; c->want_emit = false;     // nothing to run or download
+    return ok ? FFB_OK : FFB_ERR_NOMEM;
+}
+
 // ---- raw reads: trimming + normalisation on the device, then the same plan -----------------------
 // (reference src/flappie.c:251-259; kernels in signal.cu)
 // Two halves, because the plan needs the trimmed lengths back from the device: `begin` enqueues the raw upload, the chunk

@@ -299,6 +299,7 @@ struct device {
     ffb_model *model;
     struct dev_batch bat[2];
     pthread_t th;
+    double t_read, t_begin, t_finish, t_collect, t_format, t_wait;     /* --stats: seconds this thread spent where */
 };
 
 static struct {
@@ -360,6 +361,35 @@ static void deal_window(struct window *w, int slot) {
     free(len); free(dev_of);
 }
 
+/* grow-only pinned buffers of one batch slot: reads, raw samples, blocks (+ one entry per read) */
+static void reserve_batch(struct dev_batch *f, size_t n, size_t tot_raw, size_t need_blk) {
+    if (n > f->read_cap) {
+        f->read_cap = n + n / 4 + 16;
+        f->raw_off = pinned_grow(f->raw_off, (f->read_cap + 1) * sizeof(int64_t));
+        f->blk_off = pinned_grow(f->blk_off, (f->read_cap + 1) * sizeof(int64_t));
+        f->start = pinned_grow(f->start, f->read_cap * sizeof(int64_t));
+        f->end = pinned_grow(f->end, f->read_cap * sizeof(int64_t));
+        f->score = pinned_grow(f->score, f->read_cap * sizeof(float));
+        f->nbases = pinned_grow(f->nbases, f->read_cap * sizeof(int32_t));
+    }
+    if (tot_raw > f->raw_cap) {
+        f->raw_cap = tot_raw + tot_raw / 4 + 4096;
+        f->raw = pinned_grow(f->raw, f->raw_cap * sizeof(float));
+    }
+    if (need_blk > f->blk_cap) {
+        f->blk_cap = need_blk + need_blk / 4 + 4096;
+#ifdef FFB_RUNNIE
+        f->path = pinned_grow(f->path, f->blk_cap * sizeof(int32_t));
+        f->qpath = pinned_grow(f->qpath, f->blk_cap * sizeof(float));
+        f->rle = pinned_grow(f->rle, f->blk_cap * 8 * sizeof(float));
+#else
+        f->bases = pinned_grow(f->bases, f->blk_cap);
+        f->quals = pinned_grow(f->quals, f->blk_cap);
+        if (args.trace) f->trace = pinned_grow(f->trace, f->blk_cap * (size_t)G.nstate);
+#endif
+    }
+}
+
 /* pack the batch into pinned memory and enqueue its raw upload + trimming (ffb_submit_raw_begin: returns at once) */
 static void submit_begin(struct device *dv, struct dev_batch *f, struct window *w) {
     f->busy = false;
@@ -373,32 +403,7 @@ static void submit_begin(struct device *dv, struct dev_batch *f, struct window *
         const long t = ffb_model_nblock(dv->model, len);
         tot_blocks += t > 0 ? t : 0;                  /* upper bound: the kept range is shorter */
     }
-    if ((size_t)n > f->read_cap) {
-        f->read_cap = (size_t)n + (size_t)n / 4 + 16;
-        f->raw_off = pinned_grow(f->raw_off, (f->read_cap + 1) * sizeof(int64_t));
-        f->blk_off = pinned_grow(f->blk_off, (f->read_cap + 1) * sizeof(int64_t));
-        f->start = pinned_grow(f->start, f->read_cap * sizeof(int64_t));
-        f->end = pinned_grow(f->end, f->read_cap * sizeof(int64_t));
-        f->score = pinned_grow(f->score, f->read_cap * sizeof(float));
-        f->nbases = pinned_grow(f->nbases, f->read_cap * sizeof(int32_t));
-    }
-    if (tot_raw > f->raw_cap) {
-        f->raw_cap = tot_raw + tot_raw / 4 + 4096;
-        f->raw = pinned_grow(f->raw, f->raw_cap * sizeof(float));
-    }
-    const size_t need_blk = (size_t)tot_blocks + (size_t)n + 1;
-    if (need_blk > f->blk_cap) {
-        f->blk_cap = need_blk + need_blk / 4 + 4096;
-#ifdef FFB_RUNNIE
-        f->path = pinned_grow(f->path, f->blk_cap * sizeof(int32_t));
-        f->qpath = pinned_grow(f->qpath, f->blk_cap * sizeof(float));
-        f->rle = pinned_grow(f->rle, f->blk_cap * 8 * sizeof(float));
-#else
-        f->bases = pinned_grow(f->bases, f->blk_cap);
-        f->quals = pinned_grow(f->quals, f->blk_cap);
-        if (args.trace) f->trace = pinned_grow(f->trace, f->blk_cap * (size_t)G.nstate);
-#endif
-    }
+    reserve_batch(f, (size_t)n, tot_raw, (size_t)tot_blocks + (size_t)n + 1);
     f->raw_off[0] = 0;
     for (int k = 0; k < n; k++) {
         struct read_slot *s = &w->rd[f->member[k]];
@@ -530,20 +535,23 @@ static void read_window(const struct device *dv, struct window *win) {
     for (int i = dv->rank; i < win->n; i += G.ndev) read_one(&win->rd[i], G.files.path[win->first + (size_t)i]);
 }
 
+static double now_s(void);
+#define TIMED(acc, stmt) do { const double t_ = now_s(); stmt; (acc) += now_s() - t_; } while (0)
+
 static void *device_main(void *arg) {
     struct device *dv = arg;
-    if (G.nwin > 0) read_window(dv, &G.win[0]);
+    if (G.nwin > 0) TIMED(dv->t_read, read_window(dv, &G.win[0]));
     for (int w = 0; w <= G.nwin; w++) {
-        pthread_barrier_wait(&G.bar);       /* B1: window w is in memory */
-        pthread_barrier_wait(&G.bar);       /* B2: the main thread has dealt it (and set the geometry of window w+1) */
-        if (w < G.nwin) submit_begin(dv, &dv->bat[w & 1], &G.win[w % 4]);
-        if (w + 1 < G.nwin) read_window(dv, &G.win[(w + 1) % 4]);
-        if (w < G.nwin) submit_finish(&dv->bat[w & 1]);
+        TIMED(dv->t_wait, pthread_barrier_wait(&G.bar));       /* B1: window w is in memory */
+        TIMED(dv->t_wait, pthread_barrier_wait(&G.bar));       /* B2: the main thread has dealt it (and set the geometry of window w+1) */
+        if (w < G.nwin) TIMED(dv->t_begin, submit_begin(dv, &dv->bat[w & 1], &G.win[w % 4]));
+        if (w + 1 < G.nwin) TIMED(dv->t_read, read_window(dv, &G.win[(w + 1) % 4]));
+        if (w < G.nwin) TIMED(dv->t_finish, submit_finish(&dv->bat[w & 1]));
         if (w > 0) {
-            collect_batch(&dv->bat[(w - 1) & 1]);
-            format_batch(&dv->bat[(w - 1) & 1], &G.win[(w - 1) % 4], dv->rank);
+            TIMED(dv->t_collect, collect_batch(&dv->bat[(w - 1) & 1]));
+            TIMED(dv->t_format, format_batch(&dv->bat[(w - 1) & 1], &G.win[(w - 1) % 4], dv->rank));
         }
-        pthread_barrier_wait(&G.bar);       /* B3: window w-1 is formatted; the main thread prints it during iteration w+1 */
+        TIMED(dv->t_wait, pthread_barrier_wait(&G.bar));       /* B3: window w-1 is formatted; the main thread prints it during iteration w+1 */
     }
     return NULL;
 }
@@ -588,6 +596,16 @@ int main(int argc, char **argv) {
     ffb_bundle_free(&bundle);
     G.nbase = (int)nbase_from_flipflop_nparam((size_t)ffb_model_nparam(G.dev[0].model));
     G.nstate = 2 * G.nbase;
+    /* start-up, like the weight upload: page-locked buffers for batches of --batch reads of up to 8192 samples each (they
+     * still grow when the reads turn out longer); cudaHostAlloc is slow and serialises across threads, so not in the loop */
+    for (int d = 0; d < G.ndev; d++)
+        for (int k = 0; k < 2; k++) {
+            const long nb = ffb_model_nblock(G.dev[d].model, 8192);
+            reserve_batch(&G.dev[d].bat[k], (size_t)args.batch, (size_t)args.batch * 8192, (size_t)args.batch * (size_t)((nb > 0 ? nb : 4096) + 1) + 1);
+            /* ... and the context's device workspaces for batches of 4096-sample reads (grow-only as well) */
+            if (ffb_reserve(G.dev[d].bat[k].ctx, args.batch, 4096, (args.viterbi_only ? FFB_FLAG_VITERBI_ONLY : 0) | (args.trace ? FFB_FLAG_WANT_TRACE : 0)) != FFB_OK)
+                die("ffb_reserve: %s", ffb_last_error());
+        }
     if (args.trace) {
         trace_fp = fopen(args.trace, "wb");
         if (!trace_fp) die("Failed to open \"%s\" for the trace.", args.trace);
@@ -613,27 +631,35 @@ int main(int argc, char **argv) {
         if (pthread_create(&G.dev[d].th, NULL, device_main, &G.dev[d]) != 0) die("pthread_create failed%s", "");
 
     int64_t reads_called = 0, samples = 0;
+    double m_deal = 0, m_print = 0, m_wait = 0;
+    const double t_list = now_s() - t0;
     for (int w = 0; w <= G.nwin; w++) {
-        pthread_barrier_wait(&G.bar);       /* B1 */
-        if (w < G.nwin) deal_window(&G.win[w % 4], w & 1);
+        TIMED(m_wait, pthread_barrier_wait(&G.bar));       /* B1 */
+        if (w < G.nwin) TIMED(m_deal, deal_window(&G.win[w % 4], w & 1));
         if (w + 1 < G.nwin) {
             struct window *nx = &G.win[(w + 1) % 4];
             nx->first = (size_t)(w + 1) * G.window_reads;
             const size_t left = G.files.n - nx->first;
             nx->n = (int)(left < G.window_reads ? left : G.window_reads);
         }
-        pthread_barrier_wait(&G.bar);       /* B2 */
+        TIMED(m_wait, pthread_barrier_wait(&G.bar));       /* B2 */
         /* while the device threads work on iteration w: print window w-2 (formatted before B3 of iteration w-1) */
-        if (w >= 2) print_window(&G.win[(w - 2) % 4], &reads_called, &samples);
-        pthread_barrier_wait(&G.bar);       /* B3 */
+        if (w >= 2) TIMED(m_print, print_window(&G.win[(w - 2) % 4], &reads_called, &samples));
+        TIMED(m_wait, pthread_barrier_wait(&G.bar));       /* B3 */
     }
-    if (G.nwin >= 1) print_window(&G.win[(G.nwin - 1) % 4], &reads_called, &samples);     /* formatted in the last iteration */
+    if (G.nwin >= 1) TIMED(m_print, print_window(&G.win[(G.nwin - 1) % 4], &reads_called, &samples));     /* formatted in the last iteration */
     for (int d = 0; d < G.ndev; d++) pthread_join(G.dev[d].th, NULL);
     const double t1 = now_s();
     if (args.stats)
         fprintf(stderr, PROGRAM ": stats { \"devices\": %d, \"files\": %zu, \"reads_called\": %lld, \"samples\": %lld, \"seconds\": %.3f, "
                 "\"samples_per_s\": %.0f }\n", G.ndev, G.files.n, (long long)reads_called, (long long)samples, t1 - t0,
                 (double)samples / (t1 - t0 > 0 ? t1 - t0 : 1));
+    if (args.stats) {
+        fprintf(stderr, PROGRAM ": where the host time went (s): file list %.3f; main thread: deal %.3f print %.3f waiting %.3f\n", t_list, m_deal, m_print, m_wait);
+        for (int d = 0; d < G.ndev; d++)
+            fprintf(stderr, PROGRAM ":   device thread %d (GPU %d): read files %.3f  pack+begin %.3f  plan+enqueue %.3f  wait for GPU %.3f  format %.3f  barriers %.3f\n",
+                    d, G.dev[d].id, G.dev[d].t_read, G.dev[d].t_begin, G.dev[d].t_finish, G.dev[d].t_collect, G.dev[d].t_format, G.dev[d].t_wait);
+    }
 
     for (int d = 0; d < G.ndev; d++) {
         for (int k = 0; k < 2; k++) {

@@ -211,6 +211,10 @@ int ffb_forward(ffb_ctx *c);
 int ffb_download(ffb_ctx *c, const ffb_batch *b);
 int ffb_sync(ffb_ctx *c);
 
+/* Optional: size the context's (grow-only) device workspaces for batches of n_reads reads of samples_per_read samples
+ * ahead of the first batch, e.g. at start-up next to the weight upload.  `flags` as in ffb_batch.flags. */
+int ffb_reserve(ffb_ctx *c, int64_t n_reads, int64_t samples_per_read, uint32_t flags);
+
 /* Raw reads: the signal preparation of calculate_post (reference src/flappie.c:251-259) on the device --
  * trim_and_segment_raw (src/flappie_common.c:13-81, chunk MADs + threshold quantile), then
  * medmad_normalise_array (src/util.c:198-212), or difference_array + shift_scale_array when delta != 0

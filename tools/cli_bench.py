@@ -34,6 +34,10 @@ try:
             wall = time.time() - t0
             m = re.search(r"stats (\{.*\})", r.stderr)
             print(f"--devices {devs:4s} run {rep}: rc={r.returncode} wall {wall:.2f} s (incl. process start, model upload)  {m.group(1) if m else r.stderr[-300:]}", flush=True)
+            if rep == 1:
+                for ln in r.stderr.splitlines():
+                    if "where the host time went" in ln or "device thread" in ln:
+                        print("      " + ln.split(": ", 1)[1], flush=True)
             outs[devs] = open(out, "rb").read() if os.path.exists(out) else b""
     ref = outs["0"]
     for k, v in outs.items():
