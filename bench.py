@@ -46,7 +46,7 @@ MODEL_CHOICES = {
     "r941_5mC": ("r941_5mC", "conv + 5 grumod S=256, 5 bases"),
     "r941_rna002": ("r941_rna002", "3 conv + 5 LSTM S=256"),
     "r10C_pcr": ("r10C_pcr", "alias: conv + 5 grumod S=256, 4 bases"),
-    "r103_native": ("r103_native", "3 conv + 5 LSTM S=512 (fp32 CUDA-core recurrence: no tensor variant yet)"),
+    "r103_native": ("r103_native", "3 conv + 5 LSTM S=512 (16-CTA clusters, lo weight plane in shared memory)"),
     "rle_r941_native": ("rle_r941_native", "runnie: 3 conv + 5 LSTM S=256 + run-length head"),
 }
 

@@ -494,6 +494,18 @@ class Context:
         """enqueue upload + kernels + D2H for one raw batch; results are valid after collect(b)"""
         self._check(self.lib.lib.ffb_submit_raw_batch(self.handle, ctypes.byref(rb), ctypes.byref(b)), "ffb_submit_raw_batch")
 
+    def submit_raw_begin(self, rb: RawBatch, b: Batch):
+        """first half of submit_raw: raw H2D + trimming / normalisation kernels enqueued, returns at once"""
+        self._check(self.lib.lib.ffb_submit_raw_begin(self.handle, ctypes.byref(rb), ctypes.byref(b)), "ffb_submit_raw_begin")
+
+    def submit_raw_finish(self, b: Batch):
+        """second half: waits for the kept ranges, plans the batch and enqueues the network, decode and D2H"""
+        self._check(self.lib.lib.ffb_submit_raw_finish(self.handle, ctypes.byref(b)), "ffb_submit_raw_finish")
+
+    def reserve(self, n_reads: int, samples_per_read: int, flags: int = 0):
+        """size every device workspace and the pinned plan arena for batches up to this shape before the first one"""
+        self._check(self.lib.lib.ffb_reserve(self.handle, c_int64(n_reads), c_int64(samples_per_read), c_uint32(flags)), "ffb_reserve")
+
     def submit(self, b: Batch):
         self._check(self.lib.lib.ffb_submit_batch(self.handle, ctypes.byref(b)), "ffb_submit_batch")
 

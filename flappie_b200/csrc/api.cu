@@ -225,7 +225,7 @@ extern "C" ffb_model *ffb_model_create(int device, int kind, const _Mat *const *
             set_err("ffb_model_create: no recurrent kernel for kind %d size %d", kind, S);
             ok = false;
         }
-        m->simt_rnn = ffb_rnn_supported(kind, S) != 0;    // S = 512 has the tensor kernel only
+        m->simt_rnn = ffb_rnn_supported(kind, S) != 0;    // every shipped size (S = 512: weights half-resident, cross-check speed)
         const bool fuse_z = ffb_rnn_tc_can_fuse_z(kind, S) && ffb_gemm_tc_stream_supported(G * S, S) && getenv("FFB_NO_FUSE_Z") == nullptr;
         m->fuse_z = fuse_z;
         int in = nf;

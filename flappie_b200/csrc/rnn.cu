@@ -24,21 +24,25 @@
 // Gate order: GRU (z, r, n) -- layers.c:697-714; LSTM (i, f, g, o) -- layers.c:1013-1024.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "ffb_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace ffb {
 
-template <int G_, int S_, int C_, int R_>
+// KRES_: rows k of the weight slice held in shared memory; rows [KRES, S) are read from the packed image in global
+// memory (L2-resident) every step -- only S = 512, whose 256 KB slice does not fit next to H.  Same k order, same bits.
+template <int G_, int S_, int C_, int R_, int KRES_ = S_>
 struct RnnCfg {
-    static constexpr int G = G_, S = S_, C = C_, R = R_;
+    static constexpr int G = G_, S = S_, C = C_, R = R_, KRES = KRES_;
     static constexpr int HS = S / C;          // hidden units per CTA
     static constexpr int NC = G * HS;         // weight columns per CTA
     static constexpr int NHP = HS / 2;        // hidden pairs
     static constexpr int WARPS = (R / 32) * (NHP / 4);
     static constexpr int THREADS = WARPS * 32;
-    static constexpr size_t SMEM_W = (size_t)S * NC * sizeof(float);
+    static constexpr size_t SMEM_W = (size_t)KRES * NC * sizeof(float);
     static constexpr size_t SMEM_H = (size_t)S * R * sizeof(float);
     static constexpr size_t SMEM = SMEM_W + SMEM_H;
     static_assert(S % C == 0 && HS % 8 == 0 && R % 32 == 0, "bad recurrent tiling");
@@ -54,8 +58,9 @@ rnn_layer_kernel(const float *__restrict__ Xin, const float *__restrict__ Wp, fl
                  const int32_t *__restrict__ order, const int64_t *__restrict__ blk_off, int backward) {
     constexpr int G = Cfg::G, S = Cfg::S, C = Cfg::C, R = Cfg::R, HS = Cfg::HS, NC = Cfg::NC;
     extern __shared__ __align__(16) float smem[];
-    float *Ws = smem;                 // [S][NC]
-    float *Hs = smem + (size_t)S * NC; // [S][R]
+    constexpr int KRES = Cfg::KRES;
+    float *Ws = smem;                    // [KRES][NC]
+    float *Hs = smem + (size_t)KRES * NC; // [S][R]
 
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -69,7 +74,7 @@ rnn_layer_kernel(const float *__restrict__ Xin, const float *__restrict__ Wp, fl
     {
         const float4 *src = reinterpret_cast<const float4 *>(Wp + (size_t)crank * S * NC);
         float4 *dst = reinterpret_cast<float4 *>(Ws);
-        for (int i = tid; i < S * NC / 4; i += Cfg::THREADS) dst[i] = src[i];
+        for (int i = tid; i < KRES * NC / 4; i += Cfg::THREADS) dst[i] = src[i];
         float4 *hz = reinterpret_cast<float4 *>(Hs);
         for (int i = tid; i < S * R / 4; i += Cfg::THREADS) hz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -135,19 +140,24 @@ rnn_layer_kernel(const float *__restrict__ Xin, const float *__restrict__ Wp, fl
             for (int q = 0; q < 2 * G; q++) acc[i][q] = 0.0f;
         const float *hptr = Hs + 4 * rq;
         const float *wptr = Ws + hp * 2 * G;
-#pragma unroll 8
-        for (int k = 0; k < S; k++) {
+        auto kstep = [&](int k, const float *wk, auto from_global) {
             const float4 hv = *reinterpret_cast<const float4 *>(hptr + k * R);
             float w[2 * G];
             if constexpr (G == 4) {
-                const float4 w0 = *reinterpret_cast<const float4 *>(wptr + k * NC);
-                const float4 w1 = *reinterpret_cast<const float4 *>(wptr + k * NC + 4);
+                float4 w0, w1;
+                if constexpr (decltype(from_global)::value) {
+                    w0 = __ldg(reinterpret_cast<const float4 *>(wk));
+                    w1 = __ldg(reinterpret_cast<const float4 *>(wk + 4));
+                } else {
+                    w0 = *reinterpret_cast<const float4 *>(wk);
+                    w1 = *reinterpret_cast<const float4 *>(wk + 4);
+                }
                 w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w;
                 w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
             } else {
 #pragma unroll
                 for (int g = 0; g < G; g++) {
-                    const float2 wg = *reinterpret_cast<const float2 *>(wptr + k * NC + 2 * g);
+                    const float2 wg = *reinterpret_cast<const float2 *>(wk + 2 * g);
                     w[2 * g] = wg.x; w[2 * g + 1] = wg.y;
                 }
             }
@@ -156,6 +166,14 @@ rnn_layer_kernel(const float *__restrict__ Xin, const float *__restrict__ Wp, fl
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int q = 0; q < 2 * G; q++) acc[i][q] = fmaf(h4[i], w[q], acc[i][q]);
+        };
+#pragma unroll 8
+        for (int k = 0; k < KRES; k++) kstep(k, wptr + k * NC, std::false_type{});
+        if constexpr (KRES < S) {
+            static_assert(KRES == S || G == 4, "the L2-streamed tail exists for the LSTM only");
+            const float *wglob = Wp + (size_t)crank * S * NC + hp * 2 * G;
+#pragma unroll 8
+            for (int k = KRES; k < S; k++) kstep(k, wglob + (size_t)k * NC, std::true_type{});
         }
 
         // previous state of this thread's own (read, hidden) cells, before anyone overwrites H
@@ -239,6 +257,8 @@ using GruCfg96 = RnnCfg<3, 96, 2, 64>;      // small shapes for tests
 using GruCfg64 = RnnCfg<3, 64, 2, 64>;
 using LstmCfg256 = RnnCfg<4, 256, 8, 64>;   // r941_rna002: 128 KB W + 64 KB H
 using LstmCfg384 = RnnCfg<4, 384, 16, 32>;  // r941_native @4de542f: 144 KB W + 48 KB H, 16-CTA cluster
+using LstmCfg512 = RnnCfg<4, 512, 16, 32, 256>;  // r103_native: cross-check path only -- half of the 256 KB slice in shared
+                                                 // memory (128 KB W + 64 KB H), the other half re-read from L2 every step
 using LstmCfg128 = RnnCfg<4, 128, 4, 64>;
 using LstmCfg96 = RnnCfg<4, 96, 2, 32>;
 
@@ -290,26 +310,27 @@ static void pack_cfg(const float *sW, float *packed) {
 
 }  // namespace ffb
 
-#define FFB_RNN_DISPATCH(kind, S, EXPR_GRU256, EXPR_GRU96, EXPR_GRU64, EXPR_L256, EXPR_L384, EXPR_L128, EXPR_L96, DEFAULT) \
+#define FFB_RNN_DISPATCH(kind, S, EXPR_GRU256, EXPR_GRU96, EXPR_GRU64, EXPR_L256, EXPR_L384, EXPR_L512, EXPR_L128, EXPR_L96, DEFAULT) \
     do {                                                                                                                \
         if ((kind) == 0 && (S) == 256) { EXPR_GRU256; }                                                                 \
         else if ((kind) == 0 && (S) == 96) { EXPR_GRU96; }                                                              \
         else if ((kind) == 0 && (S) == 64) { EXPR_GRU64; }                                                              \
         else if ((kind) == 1 && (S) == 256) { EXPR_L256; }                                                              \
         else if ((kind) == 1 && (S) == 384) { EXPR_L384; }                                                              \
+        else if ((kind) == 1 && (S) == 512) { EXPR_L512; }                                                              \
         else if ((kind) == 1 && (S) == 128) { EXPR_L128; }                                                              \
         else if ((kind) == 1 && (S) == 96) { EXPR_L96; }                                                                \
         else { DEFAULT; }                                                                                               \
     } while (0)
 
 int ffb_rnn_supported(int kind, int S) {
-    FFB_RNN_DISPATCH(kind, S, return 1, return 1, return 1, return 1, return 1, return 1, return 1, return 0);
+    FFB_RNN_DISPATCH(kind, S, return 1, return 1, return 1, return 1, return 1, return 1, return 1, return 1, return 0);
 }
 
 int ffb_rnn_reads_per_cluster(int kind, int S) {
     using namespace ffb;
     FFB_RNN_DISPATCH(kind, S, return GruCfg256::R, return GruCfg96::R, return GruCfg64::R, return LstmCfg256::R,
-                     return LstmCfg384::R, return LstmCfg128::R, return LstmCfg96::R, return 0);
+                     return LstmCfg384::R, return LstmCfg512::R, return LstmCfg128::R, return LstmCfg96::R, return 0);
 }
 
 size_t ffb_rnn_packed_floats(int kind, int S) { return (size_t)(kind == 0 ? 3 : 4) * S * S; }
@@ -318,7 +339,7 @@ void ffb_rnn_pack_weights(int kind, int S, const float *sW, float *packed) {
     using namespace ffb;
     FFB_RNN_DISPATCH(kind, S, pack_cfg<GruCfg256>(sW, packed), pack_cfg<GruCfg96>(sW, packed),
                      pack_cfg<GruCfg64>(sW, packed), pack_cfg<LstmCfg256>(sW, packed),
-                     pack_cfg<LstmCfg384>(sW, packed), pack_cfg<LstmCfg128>(sW, packed),
+                     pack_cfg<LstmCfg384>(sW, packed), pack_cfg<LstmCfg512>(sW, packed), pack_cfg<LstmCfg128>(sW, packed),
                      pack_cfg<LstmCfg96>(sW, packed), (void)0);
 }
 
@@ -326,7 +347,7 @@ int ffb_rnn_prepare(int kind, int S) {
     using namespace ffb;
     FFB_RNN_DISPATCH(kind, S, return prepare_cfg<GruCfg256>(), return prepare_cfg<GruCfg96>(),
                      return prepare_cfg<GruCfg64>(), return prepare_cfg<LstmCfg256>(),
-                     return prepare_cfg<LstmCfg384>(), return prepare_cfg<LstmCfg128>(),
+                     return prepare_cfg<LstmCfg384>(), return prepare_cfg<LstmCfg512>(), return prepare_cfg<LstmCfg128>(),
                      return prepare_cfg<LstmCfg96>(), return -1);
 }
 
@@ -338,6 +359,7 @@ int ffb_launch_rnn(int kind, int S, const float *Xin, const float *sW_packed, fl
                      return launch_cfg<GruCfg64>(Xin, sW_packed, Hout, rb, backward, st),
                      return launch_cfg<LstmCfg256>(Xin, sW_packed, Hout, rb, backward, st),
                      return launch_cfg<LstmCfg384>(Xin, sW_packed, Hout, rb, backward, st),
+                     return launch_cfg<LstmCfg512>(Xin, sW_packed, Hout, rb, backward, st),
                      return launch_cfg<LstmCfg128>(Xin, sW_packed, Hout, rb, backward, st),
                      return launch_cfg<LstmCfg96>(Xin, sW_packed, Hout, rb, backward, st), return -1);
 }

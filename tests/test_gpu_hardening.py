@@ -100,6 +100,33 @@ def test_measured_base_mismatch_rate(gpu_lib, name, n, nsamp):
     ctx.close(); m.close()
 
 
+def test_s512_tensor_path_against_the_fp32_kernels(gpu_lib):
+    """r103_native's size (S = 512, 16-CTA clusters, lo weight plane in shared memory) has two independent implementations
+    on the device: the tcgen05 recurrence + W-stationary / A-tile GEMMs, and the fp32 CUDA-core kernels (FFB_FLAG_FP32_SIMT:
+    plain FMA chains in k order, exact expf -- the same code that is oracle-checked at every other size).  64 reads, both
+    against each other and against the oracle on a sample of reads."""
+    fm = FlipflopModel.synthetic(KIND_LSTM, 512, 4, seed=4)
+    sigs = [hs.prepare_read(r) for r in synthetic_reads(64, 3000, seed=31)]
+    m = Model(fm); ctx = Context(m)
+    simt = ctx.basecall(sigs, viterbi_only=True, want_trans=True, fp32_simt=True)
+    res = ctx.basecall(sigs, viterbi_only=True, want_trans=True)
+    assert np.array_equal(simt.blk_off, res.blk_off)
+    nb = int(res.blk_off[-1])
+    d = float(np.max(np.abs(res.trans[:nb] - simt.trans[:nb])))
+    same = sum(int(np.array_equal(res.read_path(i)[0], simt.read_path(i)[0])) for i in range(len(sigs)))
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    do = ds = 0.0
+    for i in (0, 17, 63):
+        t = orc.transitions(fm, sigs[i], 1.0)
+        do = max(do, float(np.max(np.abs(res.read_trans(i) - t))))
+        ds = max(ds, float(np.max(np.abs(simt.read_trans(i) - t))))
+    print(f"\n[parity] lstm512: 64 reads x 3000 samples: max|d trans| tensor vs fp32 kernels {d:.2e}; identical Viterbi paths "
+          f"{same}/64; vs oracle (3 reads): tensor {do:.2e}, fp32 kernels {ds:.2e}")
+    assert d < TOL_TRANS and do < TOL_TRANS and ds < TOL_TRANS and same >= 62
+    ctx.close(); m.close()
+
+
 @pytest.mark.parametrize("name", ["gru256", "lstm256"])
 def test_saturated_gates(gpu_lib, name):
     """A weight seed with gate biases in U(-4, 4) (trained gates saturate; the U(-0.1, 0.1) biases of the other tests keep

@@ -101,3 +101,45 @@ def test_device_matches_reference_object_code(gpu_lib, ref):
     got = ctx.fetch_signal(want.shape[0])
     assert np.max(np.abs(got - want)) < 1e-6
     ctx.close(); m.close()
+
+
+def test_begin_finish_and_reserve_do_not_change_results(gpu_lib):
+    """ffb_reserve (workspaces sized up front) and the ffb_submit_raw_begin / ffb_submit_raw_finish split (what the
+    `flappie --devices` pipeline calls) give the bytes of the one-call path."""
+    from flappie_b200.api import FLAG_WANT_TRANS
+    fm = FlipflopModel.synthetic(KIND_GRU, 96, 4, seed=5)
+    m = Model(fm)
+    raws = synthetic_reads(40, [4000, 2500, 7000, 1500, 300, 4000, 9000, 123] * 5, seed=21)
+    ctx = Context(m)
+    want = ctx.basecall_raw(raws, want_trans=True, emit=True)
+    ctx.close()
+
+    ctx = Context(m)
+    ctx.reserve(64, 8192, FLAG_WANT_TRANS)
+    assert ctx.total_blocks() == 0                                # a reservation leaves no batch behind
+    lens = np.array([len(r) for r in raws], np.int64)
+    raw_off = np.zeros(len(raws) + 1, np.int64)
+    np.cumsum(lens, out=raw_off[1:])
+    raw = np.concatenate(raws).astype(np.float32)
+    for _ in range(2):                                            # twice: the second batch reuses every buffer
+        b, o = ctx.make_batch(raw, raw_off, 1.0, FLAG_WANT_TRANS, emit=True)
+        rb, start, end = ctx.make_raw_batch(raw, raw_off)
+        ctx.submit_raw_begin(rb, b)
+        ctx.submit_raw_finish(b)
+        ctx.collect(b)
+        assert np.array_equal(start[:len(raws)], want.start) and np.array_equal(end[:len(raws)], want.end)
+        assert np.array_equal(o["blk_off"], want.blk_off)
+        nb = int(want.blk_off[-1])
+        assert o["trans"][:nb].tobytes() == want.trans[:nb].tobytes()
+        assert np.array_equal(o["path"][:nb + len(raws)], want.path[:nb + len(raws)])
+        assert o["score"].tobytes() == want.score.tobytes()
+        assert np.array_equal(o["nbases"], want.nbases)
+        for i in range(len(raws)):
+            s, k = int(want.blk_off[i]) + i, int(want.nbases[i])
+            assert o["bases"][s:s + k].tobytes() == want.bases[s:s + k].tobytes()
+            assert o["quals"][s:s + k].tobytes() == want.quals[s:s + k].tobytes()
+    # finish without begin is an error, not a crash
+    b, o = ctx.make_batch(raw, raw_off, 1.0, 0)
+    with pytest.raises(Exception):
+        ctx.submit_raw_finish(b)
+    ctx.close(); m.close()
