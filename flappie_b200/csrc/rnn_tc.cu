@@ -149,8 +149,16 @@ __device__ unsigned long long ffb_rnn_prof_dev[16];
 #ifndef FFB_RNN_GATES
 #define FFB_RNN_GATES 0
 #endif
+// Timing-only ablations (results are garbage): which part of the step bounds the recurrence?  Bit mask, see
+// tools/ablate_timing.py: 1 = cells without MUFU, 2 = a quarter of the MMAs, 4 = no Xin loads / no output stores,
+// 8 = no cross-proxy fence after staging, 16 = no bulk store to the ring, 32 = no tcgen05.ld
+#ifndef FFB_RNN_ABLATE
+#define FFB_RNN_ABLATE 0
+#endif
 __device__ __forceinline__ float gate_logistic(float x) {
-#if FFB_RNN_GATES == 1
+#if FFB_RNN_ABLATE & 1
+    return fminf(fmaxf(fmaf(x, 0.25f, 0.5f), 0.0f), 1.0f);
+#elif FFB_RNN_GATES == 1
     return logisticf(x);
 #elif FFB_RNN_GATES == 2
     return mid_logistic(x);
@@ -159,7 +167,9 @@ __device__ __forceinline__ float gate_logistic(float x) {
 #endif
 }
 __device__ __forceinline__ float gate_tanh(float x) {
-#if FFB_RNN_GATES == 1
+#if FFB_RNN_ABLATE & 1
+    return fminf(fmaxf(x, -1.0f), 1.0f);
+#elif FFB_RNN_GATES == 1
     return tanh_ref(x);
 #elif FFB_RNN_GATES == 2
     return mid_tanh(x);
@@ -280,7 +290,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 // full-magnitude (truncating) accumulations.
                 //   chain 0: Whi*hlo then Whi*hhi over K-half 0     chain 1: the same over K-half 1
                 //   chain 2: Wlo*hhi over all of K
-                constexpr int KS = S / 16, KH = S / 32;
+                constexpr int KS = (FFB_RNN_ABLATE & 2) ? S / 64 : S / 16, KH = KS / 2;
                 if constexpr (Cfg::NACC == 3) {
 #pragma unroll
                 for (int i = 0; i < KS; i++) {
@@ -349,7 +359,7 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 // wait.acquire); ONE cross-proxy fence by the thread that issues the copy orders them before it
                 fence_proxy_async_smem();
 #endif
-                bulk_store_global(rg, stg, Cfg::SLICE);
+                if (!(FFB_RNN_ABLATE & 16)) bulk_store_global(rg, stg, Cfg::SLICE);
                 PROF(4);
                 mbar_wait(&h_empty[g], ph);                           // every peer has consumed h_{s-1}
                 PROF(5);
@@ -434,28 +444,44 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             cl_T = rd >= 0 ? (int)(blk_off[rd + 1] - blk_off[rd]) : 0;
             cl_row = (rd >= 0 ? (int32_t)blk_off[rd] : 0) + ((backward && cl_T > 0) ? cl_T - 1 : 0);
         }
-        for (int s = 0; s < Tmax; s++, gs++, ga += (NGATE == 3)) {
-            const bool all = s < Tmin;          // warp-uniform
-            // ---- prefetch this step's input projection ----
-            float x[4][NGATE];
-            if (all) {
+        // the input projection of step sn, rows orow[i] + dr: issued a whole step ahead (right after this warp has staged
+        // step sn - 1), because with a lead of only the other phases of the step (~1200 clk) the loads of the slowest of the
+        // cluster's 32 gate warps were still in flight when its accumulators arrived -- ~300 clk per step and warp of
+        // long-scoreboard stall at the first use of x, on the step's critical path (profiles/r02_rnn_tc_ncu_summary.txt)
+        float x[4][NGATE];
+        auto fetch_x = [&](int sn, int dr) {
+            if (FFB_RNN_ABLATE & 4) {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xj + (int64_t)orow[i] * XROW + gt * S);
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = 0.01f * (float)(i + gt);
+            } else if (sn < Tmin) {                    // warp-uniform
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xj + (int64_t)(orow[i] + dr) * XROW + gt * S);
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (s < cT[i]) ? __ldcs(xj + (int64_t)orow[i] * XROW + gt * S) : 0.0f;
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (sn < cT[i]) ? __ldcs(xj + (int64_t)(orow[i] + dr) * XROW + gt * S) : 0.0f;
             }
+        };
+#ifndef FFB_RNN_LATE_PREFETCH
+        fetch_x(0, 0);
+#endif
+        for (int s = 0; s < Tmax; s++, gs++, ga += (NGATE == 3)) {
+            const bool all = s < Tmin;          // warp-uniform
+#ifdef FFB_RNN_LATE_PREFETCH
+            fetch_x(s, 0);                      // A/B: the round-1 placement, at the top of the step
+#endif
             PROF(8);
             mbar_wait(&acc_full[g], (NGATE == 3 ? ga : gs) & 1u);
             PROF(9);
             tcgen05_fence_after();
             // ---- TMEM -> registers: a[i][gate], three partial accumulators added round-to-nearest ----
             float a[4][4];
-            if (s == 0) {
+            if (s == 0 || (FFB_RNN_ABLATE & 32)) {
                 // h_{-1} = 0 (layers.c:586 / :892 zero the initial state): no MMAs were issued for this step
 #pragma unroll
                 for (int i = 0; i < 4; i++) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.0f;
@@ -541,21 +567,25 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
                 st_hi[col * 8] = shv;
                 st_lo[col * 8] = slv;
             }
-#ifndef FFB_RNN_FENCE1
+#if !defined(FFB_RNN_FENCE1) && !(FFB_RNN_ABLATE & 8)
             fence_proxy_async_smem();      // staged slice -> visible to the bulk-copy engine
 #endif
             __syncwarp();
             if (lane == 0) mbar_arrive(&staged[g]);
             PROF(11);
+#ifndef FFB_RNN_LATE_PREFETCH
+            // ---- the NEXT step's input projection (x is dead from here on) ----
+            if (s + 1 < Tmax) fetch_x(s + 1, rstep);
+#endif
             // ---- layer output (not on the step's critical path) ----
-            if (cl_dst && s < cl_T) *reinterpret_cast<uint4 *>(cl_dst + (int64_t)cl_row * S) = *cl_src;
+            if (!(FFB_RNN_ABLATE & 4) && cl_dst && s < cl_T) *reinterpret_cast<uint4 *>(cl_dst + (int64_t)cl_row * S) = *cl_src;
             __syncwarp();       // the staging tile has been read (by other lanes than those that rewrite it next step)
-            if (Hout) {
+            if (!(FFB_RNN_ABLATE & 4) && Hout) {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (all || s < cT[i]) __stcs(Hout + (int64_t)orow[i] * S + j, hprev[i]);
             }
-            if (fuse && s > 0) {
+            if (!(FFB_RNN_ABLATE & 4) && fuse && s > 0) {
                 // gate slot 3 = iW_z(next layer) * h_{s-1}: the next layer's z pre-activation of the PREVIOUS time index
                 if (!fuse_ff) {
 #pragma unroll
