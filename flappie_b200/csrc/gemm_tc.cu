@@ -134,9 +134,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     // accumulations into one accumulator cost 1.2e-5 absolute on the pre-activation (2e-4 on `trans` five layers later).
     // So every k-chunk of hi*hi gets its OWN accumulator (4 accumulations each), the cross terms one more, and the
     // epilogue adds them in registers (round-to-nearest): (K/64 + 1) * BN columns, single-buffered.
+    // ACT == 4 (input projection with K > 384, i.e. S = 512): as ACT == 0, but hi*hi is split over the two K-halves into
+    // separate accumulators (3 * BN columns, single-buffered): 32 full-magnitude truncating accumulations in ONE accumulator
+    // put the S = 512 network 1.1e-4 from the oracle on `trans` (tests/test_gpu_hardening.py), 16 + 16 added
+    // round-to-nearest keep it inside the 1e-4 of the smaller sizes.
     constexpr bool PER_CHUNK = (ACT == 3);
-    constexpr int NBUF = PER_CHUNK ? 1 : Cfg::NBUF;
-    constexpr int TCOLS = PER_CHUNK ? 512 : Cfg::TMEM_COLS;
+    constexpr bool KSPLIT = (ACT == 4);
+    constexpr int NBUF = (PER_CHUNK || KSPLIT) ? 1 : Cfg::NBUF;
+    constexpr int TCOLS = (PER_CHUNK || KSPLIT) ? 512 : Cfg::TMEM_COLS;
+    static_assert(!KSPLIT || 3 * BN <= 512, "K-split accumulators");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[Cfg::STAGES], empty_bar[Cfg::STAGES], acc_full[2], acc_empty[2];
@@ -191,8 +197,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 tcgen05_fence_after();
                 const uint32_t d0 = tmem + acc * 2 * BN;
                 const uint32_t dx = PER_CHUNK ? tmem + nk * BN : d0 + BN;
+                const int kh = KSPLIT ? (nk + 1) / 2 : nk;          // K-split: chunks [kh, nk) go to the third accumulator
                 for (int kc = 0; kc < nk; kc++) {
-                    const uint32_t d = PER_CHUNK ? tmem + kc * BN : d0;
+                    const uint32_t d = PER_CHUNK ? tmem + kc * BN : (kc >= kh ? d0 + 2 * BN : d0);
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
@@ -205,7 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         const uint64_t dal = make_smem_desc(a_lo + ko, 16, 1024, LAYOUT_SW128);
                         const uint64_t dbh = make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128);
                         const uint64_t dbl = make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128);
-                        umma_f16(d, dah, dbh, idesc, PER_CHUNK ? (k4 != 0) : ((kc | k4) != 0));    // hi*hi
+                        umma_f16(d, dah, dbh, idesc, PER_CHUNK ? (k4 != 0) : (((kc >= kh ? kc - kh : kc) | k4) != 0));    // hi*hi
                         umma_f16(dx, dah, dbl, idesc, (kc | k4) != 0);   // cross terms
                         umma_f16(dx, dal, dbh, idesc, 1);
                     }
@@ -244,6 +251,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; j++) v[j] += w[j];
                     }
+                } else if constexpr (KSPLIT) {
+                    float w[16];
+                    tmem_ld16(taddr + c, v);
+                    tmem_ld16(taddr + 2 * BN + c, w);
+                    tmem_ld16(taddr + BN + c, vx);
+                    tmem_ld_wait();
+                    if (nk > 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] += w[j];
+                    }
                 } else {
                     tmem_ld16(taddr + c, v);
                     tmem_ld16(taddr + BN + c, vx);
@@ -256,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4 *>(bias + n0 + c + j);
-                        if constexpr (ACT == 0) {
+                        if constexpr (ACT == 0 || ACT == 4) {
                             __stcs(reinterpret_cast<float4 *>(crow + c + j),
                                    make_float4(v[j] + b4.x, v[j + 1] + b4.y, v[j + 2] + b4.z, v[j + 3] + b4.w));
                         } else if constexpr (ACT == 3) {
@@ -761,6 +778,9 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
     if (N % 128 == 0 && K <= ffb::GemmWsCfg384::KMAX && (n0 > 0 || getenv("FFB_GEMM_V1") == nullptr))
         return launch_gemm_ws<ffb::GemmWsCfg384>(Ahi, Alo, Whi, Wlo, bias, C, M, N - n0, K, st, nullptr, nullptr, nullptr, n0, N);
     if (n0 > 0) return -1;
+    // K > 384 (S = 512): hi*hi over two accumulators (accuracy, see gemm_tc_kernel)
+    if (N % 128 == 0 && K > ffb::GemmWsCfg384::KMAX && getenv("FFB_GEMM_NO_KSPLIT") == nullptr)
+        return launch_gemm_tc<128, 4>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 256 == 0) return launch_gemm_tc<256>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 128 == 0) return launch_gemm_tc<128>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     return launch_gemm_tc<64>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);

@@ -151,10 +151,15 @@ __device__ unsigned long long ffb_rnn_prof_dev[16];
 #endif
 // Timing-only ablations (results are garbage): which part of the step bounds the recurrence?  Bit mask, see
 // tools/ablate_timing.py: 1 = cells without MUFU, 2 = a quarter of the MMAs, 4 = no Xin loads / no output stores,
-// 8 = no cross-proxy fence after staging, 16 = no bulk store to the ring, 32 = no tcgen05.ld
+// 8 = no cross-proxy fence after staging, 16 = no bulk store to the ring, 32 = no tcgen05.ld; the parts of 4 one by one:
+// 64 = no Xin loads, 128 = no copy-out of the fp16 planes, 256 = no stores of the fused rows; 512 / 1024 = the fused-row
+// stores / the Xin loads go to a window of 1024 rows (L2-resident: same instructions and requests, no HBM traffic);
+// 2048 / 4096 = the Xin loads / the fused-row stores as 16-byte accesses (a quarter of the instructions, same bytes)
 #ifndef FFB_RNN_ABLATE
 #define FFB_RNN_ABLATE 0
 #endif
+#define XR(r) ((FFB_RNN_ABLATE & 1024) ? ((r) & 1023) : (r))
+#define ZR(r) ((FFB_RNN_ABLATE & 512) ? ((r) & 1023) : (r))
 __device__ __forceinline__ float gate_logistic(float x) {
 #if FFB_RNN_ABLATE & 1
     return fminf(fmaxf(fmaf(x, 0.25f, 0.5f), 0.0f), 1.0f);
@@ -450,21 +455,28 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
         // long-scoreboard stall at the first use of x, on the step's critical path (profiles/r02_rnn_tc_ncu_summary.txt)
         float x[4][NGATE];
         auto fetch_x = [&](int sn, int dr) {
-            if (FFB_RNN_ABLATE & 4) {
+            if (FFB_RNN_ABLATE & (4 | 64)) {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
                     for (int gt = 0; gt < NGATE; gt++) x[i][gt] = 0.01f * (float)(i + gt);
+            } else if (FFB_RNN_ABLATE & 2048) {
+                // the same bytes per thread in NGATE 16-byte loads instead of 4 * NGATE 4-byte loads (wrong elements: timing only)
+#pragma unroll
+                for (int gt = 0; gt < NGATE; gt++) {
+                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(Xin + (int64_t)(orow[gt & 3] + dr) * XROW + gt * S + (j & ~3)));
+                    x[0][gt] = v.x; x[1][gt] = v.y; x[2][gt] = v.z; x[3][gt] = v.w;
+                }
             } else if (sn < Tmin) {                    // warp-uniform
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xj + (int64_t)(orow[i] + dr) * XROW + gt * S);
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = __ldcs(xj + (int64_t)XR(orow[i] + dr) * XROW + gt * S);
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
 #pragma unroll
-                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (sn < cT[i]) ? __ldcs(xj + (int64_t)(orow[i] + dr) * XROW + gt * S) : 0.0f;
+                    for (int gt = 0; gt < NGATE; gt++) x[i][gt] = (sn < cT[i]) ? __ldcs(xj + (int64_t)XR(orow[i] + dr) * XROW + gt * S) : 0.0f;
             }
         };
 #ifndef FFB_RNN_LATE_PREFETCH
@@ -578,19 +590,23 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
             if (s + 1 < Tmax) fetch_x(s + 1, rstep);
 #endif
             // ---- layer output (not on the step's critical path) ----
-            if (!(FFB_RNN_ABLATE & 4) && cl_dst && s < cl_T) *reinterpret_cast<uint4 *>(cl_dst + (int64_t)cl_row * S) = *cl_src;
+            if (!(FFB_RNN_ABLATE & (4 | 128)) && cl_dst && s < cl_T) *reinterpret_cast<uint4 *>(cl_dst + (int64_t)cl_row * S) = *cl_src;
             __syncwarp();       // the staging tile has been read (by other lanes than those that rewrite it next step)
             if (!(FFB_RNN_ABLATE & 4) && Hout) {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (all || s < cT[i]) __stcs(Hout + (int64_t)orow[i] * S + j, hprev[i]);
             }
-            if (!(FFB_RNN_ABLATE & 4) && fuse && s > 0) {
+            if (!(FFB_RNN_ABLATE & (4 | 256)) && fuse && s > 0) {
                 // gate slot 3 = iW_z(next layer) * h_{s-1}: the next layer's z pre-activation of the PREVIOUS time index
-                if (!fuse_ff) {
+                if (!fuse_ff && (FFB_RNN_ABLATE & 4096)) {
+                    // one 16-byte store per thread instead of four 4-byte stores (wrong places: timing only)
+                    if (all || s <= cT[0])
+                        __stcs(reinterpret_cast<float4 *>(xnext + (j & ~3) + (int64_t)(orow[0] - rstep) * next_ld), make_float4(a[0][3] + bz, a[1][3], a[2][3], a[3][3]));
+                } else if (!fuse_ff) {
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        if (all || s <= cT[i]) __stcs(xz + (int64_t)(orow[i] - rstep) * next_ld, a[i][3] + bz);
+                        if (all || s <= cT[i]) __stcs(xz + (int64_t)ZR(orow[i] - rstep) * next_ld, a[i][3] + bz);
                 } else if (j < next_rows) {
 #pragma unroll
                     for (int i = 0; i < 4; i++)

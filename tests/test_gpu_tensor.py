@@ -66,7 +66,8 @@ def gemm(L, A, W, b, mode):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1000, 768, 256), (333, 192, 64), (4097, 1024, 256),
-                                   (700, 1536, 384), (129, 384, 128), (8300, 1536, 384), (65, 128, 320)])
+                                   (700, 1536, 384), (129, 384, 128), (8300, 1536, 384), (65, 128, 320),
+                                   (700, 2048, 512), (129, 1536, 512), (300, 192, 512)])   # K = 512: the K-split accumulators / the plain A-tile kernel
 def test_gemm_tc_matches_fp64(gpu_lib, M, N, K):
     L = _hooks(gpu_lib)
     rng = np.random.default_rng(M + N + K)
