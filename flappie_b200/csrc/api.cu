@@ -132,6 +132,14 @@ struct ffb_model {
     float *d_ffb_s = nullptr; // FF bias zero-padded to S entries
     int tc_max_clusters = 0;
     int layer_in[FFB_NLAYER] = {0};
+    // Head gate (pipelined contexts of one model): the context whose batch most recently ENTERED its last recurrent layer,
+    // and the event it recorded there.  The next batch of another context starts its device work (signal preparation,
+    // convolution, first input projection) behind that event: the last recurrent layer has no streamed GEMM beside it,
+    // so its spare SMs are idle, whereas earlier in the step every SM is taken and the new batch's head kernels would
+    // only push the batch in flight back by their own duration.
+    std::mutex gate_mu;
+    cudaEvent_t gate_ev = nullptr;
+    const struct ffb_ctx *gate_owner = nullptr;
     // conv edge plans, cached per (conv layer, T_in)
     std::mutex mu;
     std::map<std::pair<int, int>, ffb::ConvTail> tail_cache;   // at most FFB_TAIL_CACHE_MAX entries (~0.8 KB each)
@@ -474,6 +482,8 @@ struct ffb_ctx {
     PinArena h_plan, h_raw;
     cudaEvent_t ev_plan = nullptr;    // recorded behind the last copy out of the arenas: the next batch waits for it first
     bool plan_pending = false;
+    cudaEvent_t ev_tail = nullptr;    // recorded when this context's batch enters its last recurrent layer (ffb_model::gate_ev)
+    bool gated = false;               // this batch's device work already waits behind the head gate
     // ffb_submit_raw_begin .. ffb_submit_raw_finish
     bool raw_begun = false;
     ffb_raw_batch raw_rb;
@@ -512,6 +522,7 @@ extern "C" ffb_ctx *ffb_create(ffb_model *m, void *stream) {
     }
     for (auto &e : c->ev) cudaEventCreate(&e);
     cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming);
     return c;
 }
 
@@ -519,6 +530,11 @@ extern "C" void ffb_destroy(ffb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->m->device);
     cudaStreamSynchronize(c->st);
+    {
+        std::lock_guard<std::mutex> lk(c->m->gate_mu);
+        if (c->m->gate_owner == c) { c->m->gate_owner = nullptr; c->m->gate_ev = nullptr; }
+    }
+    if (c->ev_tail) cudaEventDestroy(c->ev_tail);
     DevBuf *all[] = {&c->d_sig, &c->d_c[0], &c->d_c[1], &c->d_act[0], &c->d_act[1], &c->d_xin, &c->d_trans, &c->d_tpost,
                      &c->d_fwd, &c->d_tb, &c->d_path, &c->d_qpath, &c->d_score, &c->d_logz, &c->d_trace, &c->d_blkoff,
                      &c->d_order, &c->d_ahi, &c->d_alo, &c->d_ring, &c->d_xin2, &c->d_work[0], &c->d_work[1], &c->d_progress,
@@ -956,6 +972,31 @@ extern "C" int ffb_reserve(ffb_ctx *c, int64_t n_reads, int64_t samples_per_read
 // Two halves, because the plan needs the trimmed lengths back from the device: `begin` enqueues the raw upload, the chunk
 // MADs, the trim bounds and their copy back, and returns; `finish` waits for the bounds, plans and enqueues the rest.  A host
 // thread can do something useful in between (the command line reads the next window's files).
+// Head gate, see ffb_model.  A scheduling hint only: results do not depend on it (FFB_NO_HEAD_GATE=1 turns it off).
+static bool head_gate_enabled() {
+    static const bool on = getenv("FFB_NO_HEAD_GATE") == nullptr;
+    return on;
+}
+// FFB_HEAD_GATE=conv: only the network waits (the trimming kernels run at once, so the host has the trimmed lengths and
+// the plan early); default: the trimming kernels wait too
+static bool head_gate_prep() {
+    static const bool on = !(getenv("FFB_HEAD_GATE") && strcmp(getenv("FFB_HEAD_GATE"), "conv") == 0);
+    return on;
+}
+static void head_gate_wait(ffb_ctx *c) {
+    if (c->gated || !head_gate_enabled()) return;
+    c->gated = true;
+    std::lock_guard<std::mutex> lk(c->m->gate_mu);      // held across the call: the owner cannot destroy the event under it
+    if (c->m->gate_ev && c->m->gate_owner != c) cudaStreamWaitEvent(c->st, c->m->gate_ev, 0);
+}
+static void head_gate_publish(ffb_ctx *c) {
+    if (!head_gate_enabled() || !c->ev_tail) return;
+    if (cudaEventRecord(c->ev_tail, c->st) != cudaSuccess) { cudaGetLastError(); return; }
+    std::lock_guard<std::mutex> lk(c->m->gate_mu);
+    c->m->gate_ev = c->ev_tail;
+    c->m->gate_owner = c;
+}
+
 static int upload_raw_begin(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch *b) {
     if (!c || !rb || !b || !rb->raw || !rb->raw_off || rb->n_reads < 0 || rb->n_reads != b->n_reads) {
         set_err("ffb_upload_raw: bad arguments");
@@ -997,6 +1038,7 @@ static int upload_raw_begin(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_batch
             CUDA_TRY(cudaMemcpyAsync(c->d_raw.p, rb->raw + rb->raw_off[0], sizeof(float) * (size_t)total_raw, cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
         CUDA_TRY(cudaMemcpyAsync(c->d_rawoff.p, h_roff, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
         CUDA_TRY(cudaMemcpyAsync(c->d_chunkoff.p, h_coff, sizeof(int64_t) * (size_t)(N + 1), cudaMemcpyHostToDevice, st), FFB_ERR_CUDA);
+        if (head_gate_prep()) head_gate_wait(c);   // the copies may run ahead; the kernels wait for the batch in flight to reach its last layer
         LAUNCH_RAW(ffb_launch_chunk_mad(c->d_raw.as<float>(), c->d_rawoff.as<int64_t>(), c->d_chunkoff.as<int64_t>(), (int)N, chunk,
                                         total_chunks, c->d_mad.as<float>(), st));
         LAUNCH_RAW(ffb_launch_trim_bounds(c->d_mad.as<float>(), c->d_rawoff.as<int64_t>(), c->d_chunkoff.as<int64_t>(), (int)N, chunk,
@@ -1066,6 +1108,8 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     cudaStream_t st = c->st;
     if (N == 0 || Tt == 0) return FFB_OK;
     if (N > 0x7fffffff || Tt > 0x7fffffff) return FFB_ERR_ARG;   // kernels index blocks with 32 bits
+    if (!timed) head_gate_wait(c);      // no-op when the raw upload of this batch already waited
+    c->gated = false;
     if (timed) cudaEventRecord(c->ev[0], st);
     // ---- convolutions (features_from_raw folded into the first load) ----
     const float *cur = c->d_sig.as<float>();
@@ -1147,6 +1191,9 @@ static int forward_impl(ffb_ctx *c, bool timed) {
             LAUNCH(ffb_launch_sgemm_bias(in, m->d_iWt[l], m->d_b[l], xin, Tt, G * S, m->layer_in[l], st));
         }
         if (timed) cudaEventRecord(c->ev[6], st);
+        // from here on the SMs beside the recurrence are free: let the next batch's head in.  Only a batch whose recurrence
+        // fills most of the chip gates its successors -- small batches (the per-read drop-ins) gain from plain concurrency.
+        if (last && !timed && tc_rnn && 2 * (sm_count - free_sms) >= sm_count) head_gate_publish(c);
         if (tc_rnn) {
             // the top layer feeds the output layer: fp16 planes for the tensor version, fp32 otherwise
             const bool ff_here = last && fuse_z && m->fuse_ff && tc_ff;     // the top layer writes trans itself
