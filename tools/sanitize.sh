@@ -3,8 +3,8 @@
 out=${1:-gpurun_out}; mkdir -p "$out"
 cd "$(dirname "$0")/.."
 CS=/usr/local/cuda/bin/compute-sanitizer
-for model in r941_native_gru r941_rna002 r941_native r103_native; do
-  for tool in memcheck synccheck racecheck; do
+for model in ${MODELS:-r941_native_gru r941_rna002 r941_native r103_native}; do
+  for tool in ${TOOLS:-memcheck synccheck racecheck}; do
     log="$out/sanitizer_${tool}_${model}.log"
     timeout 420 $CS --tool $tool --print-limit 20 --log-file "$log.raw" python tools/sanitize_run.py $model 32 700 > "$log.stdout" 2>&1
     echo "exit $? tool=$tool model=$model" >> "$log.stdout"
