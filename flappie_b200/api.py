@@ -44,7 +44,7 @@ EXPORTS = [
     "ffb_device_count", "ffb_last_error", "ffb_version", "ffb_model_create", "ffb_model_destroy",
     "ffb_model_size", "ffb_model_nparam", "ffb_model_stride", "ffb_model_nblock", "ffb_register_model",
     "ffb_create", "ffb_destroy", "ffb_basecall_batch", "ffb_upload", "ffb_forward", "ffb_download", "ffb_sync",
-    "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_emit_bases",
+    "ffb_total_blocks", "ffb_launch_count", "ffb_forward_timed", "ffb_debug_fetch", "ffb_debug_group_times", "ffb_emit_bases",
     "ffb_upload_raw", "ffb_basecall_raw_batch", "ffb_submit_batch", "ffb_submit_raw_batch", "ffb_collect",
     "ffb_alloc_pinned", "ffb_free_pinned",
     "decode_crf_runlength", "transpost_crf_runlength", "ffb_emit_runs", "ffb_plan_schedule", "ffb_phred_table",

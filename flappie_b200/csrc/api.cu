@@ -1101,6 +1101,11 @@ extern "C" int ffb_upload_raw(ffb_ctx *c, const ffb_raw_batch *rb, const ffb_bat
         c->launches += n_;                                                   \
     } while (0)
 
+#ifdef FFB_RNN_PROFILE
+static constexpr bool kProfileBuild = true;      // group events are recorded in the ordinary (streamed) schedule too: tools/step_timeline.py
+#else
+static constexpr bool kProfileBuild = false;
+#endif
 static int forward_impl(ffb_ctx *c, bool timed) {
     ffb_model *m = c->m;
     const int64_t N = c->n_reads, Tt = c->total_blocks;
@@ -1110,7 +1115,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
     if (N > 0x7fffffff || Tt > 0x7fffffff) return FFB_ERR_ARG;   // kernels index blocks with 32 bits
     if (!timed) head_gate_wait(c);      // no-op when the raw upload of this batch already waited
     c->gated = false;
-    if (timed) cudaEventRecord(c->ev[0], st);
+    if (timed || kProfileBuild) cudaEventRecord(c->ev[0], st);
     // ---- convolutions (features_from_raw folded into the first load) ----
     const float *cur = c->d_sig.as<float>();
     const bool keep = (c->flags & FFB_FLAG_KEEP_LAYERS) != 0;
@@ -1150,7 +1155,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         cur = out;
     }
     c->last_conv = c->d_act[0].as<float>();
-    if (timed) cudaEventRecord(c->ev[1], st);
+    if (timed || kProfileBuild) cudaEventRecord(c->ev[1], st);
     // ---- five recurrent layers, directions B,F,B,F,B (networks.c:460-483 / :557-580) ----
     RnnBatch rb{c->d_order.as<int32_t>(), c->d_blkoff.as<int64_t>(), c->n_slots, (int)N};
     float gemm_ms = 0.f, rnn_ms = 0.f;
@@ -1232,7 +1237,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         in = out;
     }
     const float *top = in;
-    if (timed) cudaEventRecord(c->ev[2], st);
+    if (timed || kProfileBuild) cudaEventRecord(c->ev[2], st);
     // ---- globalnorm_flipflop (layers.c:1082-1106) ----
     // scale: flip-flop divides tanh by temperature / 5 (layers.c:1087); the run-length head computes 5 tanhf / temperature
     const float ff_scale = m->head ? c->temperature : c->temperature / 5.0f;
@@ -1257,7 +1262,7 @@ static int forward_impl(ffb_ctx *c, bool timed) {
             LAUNCH(ffb_launch_sub_logz(c->d_trans.as<float>(), c->d_blkoff.as<int64_t>(), (int)N, nr, c->d_logz.as<double>(), Tt, st));
         }
     }
-    if (timed) cudaEventRecord(c->ev[3], st);
+    if (timed || kProfileBuild) cudaEventRecord(c->ev[3], st);
     // ---- decoding (flappie.c:277-300 / runnie.c:271-277) ----
     const float *post = c->d_trans.as<float>();
     if (m->head) {
@@ -1289,7 +1294,19 @@ static int forward_impl(ffb_ctx *c, bool timed) {
         cudaEventSynchronize(c->ev[4]);
         c->t_gemm_ms = gemm_ms;
         c->t_rnn_ms = rnn_ms;
+    } else if (kProfileBuild) {
+        cudaEventRecord(c->ev[4], st);
     }
+    return FFB_OK;
+}
+
+// profile build only: the group times of the LAST ordinary ffb_forward (streamed schedule, nothing synchronised in between):
+// ms[0] convolutions, ms[1] input GEMM of layer 1 .. end of the recurrent layers, ms[2] output layer, ms[3] decoding
+extern "C" int ffb_debug_group_times(ffb_ctx *c, float ms[4]) {
+    if (!c || !ms || !kProfileBuild) return FFB_ERR_UNSUPPORTED;
+    if (cudaStreamSynchronize(c->st) != cudaSuccess) return FFB_ERR_CUDA;
+    for (int i = 0; i < 4; i++)
+        if (cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); return FFB_ERR_CUDA; }
     return FFB_OK;
 }
 

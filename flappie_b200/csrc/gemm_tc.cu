@@ -362,6 +362,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 // CTAs are dealt panel = blockIdx % (N/128) with equal strides so the N/128 CTAs working on one
 // activation tile run in step and the tile is read from HBM once.
 #ifdef FFB_RNN_PROFILE
+// per-launch timeline of gemm_ws_kernel: launch k -> [4k] CTA 0 entry, [4k+1] CTA 0 exit, [4k+2] last CTA entry, [4k+3] last CTA exit
+__device__ unsigned long long ffb_gemm_tl[128];
+__device__ unsigned ffb_gemm_tl_n0, ffb_gemm_tl_n1;
+__device__ __forceinline__ unsigned long long ffb_gtime_g() { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); return t_; }
 __device__ unsigned long long ffb_gemm_prof_dev[16];
 #define GPROF_DECL unsigned long long pt_ = clock64(), pa_[8] = {0}
 #define GPROF(i) do { const unsigned long long n_ = clock64(); pa_[i] += n_ - pt_; pt_ = n_; } while (0)
@@ -412,6 +416,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FFB_RNN_PROFILE
+    __shared__ unsigned tl_k;
+    if (threadIdx.x == 0) {
+        tl_k = 0xffffffffu;
+        if (blockIdx.x == 0) { tl_k = atomicAdd(&ffb_gemm_tl_n0, 1u); if (tl_k < 32) ffb_gemm_tl[4 * tl_k] = ffb_gtime_g(); }
+        else if (blockIdx.x == gridDim.x - 1) { tl_k = atomicAdd(&ffb_gemm_tl_n1, 1u); if (tl_k < 32) ffb_gemm_tl[4 * tl_k + 2] = ffb_gtime_g(); }
+    }
+#endif
     const int n_panels = N / Cfg::BF;
     const int panel = blockIdx.x % n_panels;
     const int64_t first = blockIdx.x / n_panels, stride = gridDim.x / n_panels;   // host: gridDim % n_panels == 0
@@ -628,6 +640,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512);
+#ifdef FFB_RNN_PROFILE
+    if (threadIdx.x == 0 && tl_k < 32) ffb_gemm_tl[4 * tl_k + (blockIdx.x == 0 ? 1 : 3)] = ffb_gtime_g();
+#endif
 }
 
 }  // namespace ffb
@@ -742,6 +757,21 @@ static int launch_gemm_ws(const void *Ahi, const void *Alo, const void *Whi, con
     return e == cudaSuccess ? 1 : -1;
 }
 
+int ffb_gemm_tc_timeline(unsigned long long *out, int reset) {     // out[128]; returns the number of gemm_ws launches stamped, -1 without the profile build
+#ifdef FFB_RNN_PROFILE
+    unsigned n = 0;
+    if (cudaMemcpyFromSymbol(&n, ffb::ffb_gemm_tl_n0, sizeof n) != cudaSuccess) return -1;
+    if (out && cudaMemcpyFromSymbol(out, ffb::ffb_gemm_tl, 128 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned z = 0; unsigned long long zz[128] = {0};
+        cudaMemcpyToSymbol(ffb::ffb_gemm_tl_n0, &z, sizeof z); cudaMemcpyToSymbol(ffb::ffb_gemm_tl_n1, &z, sizeof z); cudaMemcpyToSymbol(ffb::ffb_gemm_tl, zz, sizeof zz);
+    }
+    return (int)n;
+#else
+    (void)out; (void)reset;
+    return -1;
+#endif
+}
 int ffb_gemm_tc_prof(unsigned long long *out, int reset) {
 #ifdef FFB_RNN_PROFILE
     if (out && cudaMemcpyFromSymbol(out, ffb::ffb_gemm_prof_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;

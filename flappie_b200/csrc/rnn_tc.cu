@@ -134,6 +134,10 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]
 // Optional phase timing of one control thread and one gate warp (cluster 0, CTA 0, group 0):
 // build with FFB_EXTRA_NVCC_FLAGS=-DFFB_RNN_PROFILE, read with ffb_test_rnn_prof() (testhooks.cu).
 #ifdef FFB_RNN_PROFILE
+// per-launch timeline of the profile build: globaltimer at entry / exit of CTA 0 of launch k at [2k] / [2k + 1] (tools/step_timeline.py)
+__device__ unsigned long long ffb_rnn_tl[64];
+__device__ unsigned ffb_rnn_tl_n;
+__device__ __forceinline__ unsigned long long ffb_gtime() { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); return t_; }
 __device__ unsigned long long ffb_rnn_prof_dev[16];
 #define PROF_DECL unsigned long long pt_ = clock64(), pa_[12] = {0}; const bool prof_ = (blockIdx.x == 0 && g == 0)
 #define PROF(i) do { const unsigned long long n_ = clock64(); pa_[i] += n_ - pt_; pt_ = n_; } while (0)
@@ -199,6 +203,10 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
     const bool fuse = (NGATE == 3) && xnext != nullptr;
     const bool fuse_ff = next_rows > 0;
     extern __shared__ __align__(128) uint8_t smem[];
+#ifdef FFB_RNN_PROFILE
+    __shared__ unsigned tl_k;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tl_k = atomicAdd(&ffb_rnn_tl_n, 1u); if (tl_k < 32) ffb_rnn_tl[2 * tl_k] = ffb_gtime(); }
+#endif
     __shared__ uint64_t h_full[GMAX], h_empty[GMAX], acc_full[GMAX], staged[GMAX];
     __shared__ uint32_t tmem_slot;
 
@@ -667,6 +675,9 @@ rnn_tc_kernel(const float *__restrict__ Xin, const __half *__restrict__ Wimg, fl
 #endif
     cluster_sync_all();
     if (warp == 0) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+#ifdef FFB_RNN_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0 && tl_k < 32) ffb_rnn_tl[2 * tl_k + 1] = ffb_gtime();
+#endif
 }
 
 // two accumulators everywhere TMEM holds both weight planes: four tcgen05.ld instead of six on the step's critical path
@@ -713,6 +724,18 @@ int ffb_rnn_tc_prof(unsigned long long *out, int reset) {
 #else
     (void)out; (void)reset;
     return 0;
+#endif
+}
+int ffb_rnn_tc_timeline(unsigned long long *out, int reset) {      // out[64]; returns the number of launches stamped, -1 without the profile build
+#ifdef FFB_RNN_PROFILE
+    unsigned n = 0;
+    if (cudaMemcpyFromSymbol(&n, ffb::ffb_rnn_tl_n, sizeof n) != cudaSuccess) return -1;
+    if (out && cudaMemcpyFromSymbol(out, ffb::ffb_rnn_tl, 64 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) { unsigned z = 0; unsigned long long zz[64] = {0}; cudaMemcpyToSymbol(ffb::ffb_rnn_tl_n, &z, sizeof z); cudaMemcpyToSymbol(ffb::ffb_rnn_tl, zz, sizeof zz); }
+    return (int)n;
+#else
+    (void)out; (void)reset;
+    return -1;
 #endif
 }
 int ffb_rnn_tc_supported(int kind, int S) { return (kind == 0 || kind == 1) && (S == 256 || S == 384 || S == 512); }

@@ -82,6 +82,15 @@ int ffb_rnn_tc_prof(unsigned long long *out, int reset);
 extern "C" int ffb_test_rnn_prof(unsigned long long *out, int reset) { return ffb_rnn_tc_prof(out, reset); }
 int ffb_gemm_tc_prof(unsigned long long *out, int reset);
 extern "C" int ffb_test_gemm_prof(unsigned long long *out, int reset) { return ffb_gemm_tc_prof(out, reset); }
+// per-launch globaltimer stamps of the recurrent kernel (out_rnn[64]: entry / exit of CTA 0 per launch) and of the W-stationary
+// GEMM (out_gemm[128]: CTA 0 entry / exit, last CTA entry / exit per launch); n[2] = launches stamped; profile build only
+int ffb_rnn_tc_timeline(unsigned long long *out, int reset);
+int ffb_gemm_tc_timeline(unsigned long long *out, int reset);
+extern "C" int ffb_test_timeline(unsigned long long *out_rnn, unsigned long long *out_gemm, int *n, int reset) {
+    const int a = ffb_rnn_tc_timeline(out_rnn, reset), b = ffb_gemm_tc_timeline(out_gemm, reset);
+    if (n) { n[0] = a; n[1] = b; }
+    return (a >= 0 && b >= 0) ? 1 : 0;
+}
 
 
 // im2col-view GEMM probe: x [nx] fp32 (flat activations), W [N][K], bias [N]; row r of A = x[r*hop .. r*hop + K).

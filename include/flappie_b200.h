@@ -270,6 +270,10 @@ int ffb_forward_timed(ffb_ctx *c, float ms[8]);
  * the network reads (concatenated kept ranges).  Copies up to
  * `bytes` to host `dst`; returns bytes copied or negative error. */
 int64_t ffb_debug_fetch(ffb_ctx *c, int what, void *dst, int64_t bytes);
+/* Libraries built with -DFFB_RNN_PROFILE only (FFB_ERR_UNSUPPORTED otherwise): CUDA-event times of the LAST ordinary
+ * ffb_forward on this context, in the schedule as it runs -- ms[0] convolutions, ms[1] first input GEMM .. last recurrent
+ * layer, ms[2] output layer, ms[3] decoding (tools/step_timeline.py). */
+int ffb_debug_group_times(ffb_ctx *c, float ms[4]);
 
 /* The host-side schedule of the tensor recurrent kernel, callable without a device (tests, capacity planning): reads
  * sorted by length form groups of 16; each of the n_clusters x slots slots gets a list of groups, longest first to the
