@@ -361,6 +361,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 //     lanes of a warp write 32 consecutive features of one block row = one full 128-byte line.
 // CTAs are dealt panel = blockIdx % (N/128) with equal strides so the N/128 CTAs working on one
 // activation tile run in step and the tile is read from HBM once.
+#ifndef FFB_GEMM_TICKET_BATCH
+#define FFB_GEMM_TICKET_BATCH 4      // tiles per ticket of the streamed W-stationary GEMM (see its producer)
+#endif
 #ifdef FFB_RNN_PROFILE
 // per-launch timeline of gemm_ws_kernel: launch k -> [4k] CTA 0 entry, [4k+1] CTA 0 exit, [4k+2] last CTA entry, [4k+3] last CTA exit
 __device__ unsigned long long ffb_gemm_tl[128];
@@ -500,30 +503,49 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 if (blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_gemm_prof_dev[12] = t_; ffb_gemm_prof_dev[15] = 0; }
                 if (blockIdx.x == gridDim.x - 1) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ffb_gemm_prof_dev[14] = t_; }
 #endif
-                int64_t ticket = atomicAdd(q, 1);
-                GemmWork w = {};
-                if (ticket < n_tiles) w = work[ticket];
-                while (ticket < n_tiles) {
-                    const int64_t ticket_n = atomicAdd(q, 1);      // next ticket: its latency hides under this tile
+                // Tickets are taken FFB_GEMM_TICKET_BATCH at a time: one round of dependency loads (all in flight together), one
+                // pair of fences and one read of the work list per batch instead of per tile.  Per tile that chain (an L2 round
+                // trip for the counters, the two fences, another round trip for the next work item: ~2800 clk) sat in series with
+                // the issue of the tile's loads -- longer than the 2304 clk of MMAs of a K = 384 tile, so the streamed GEMM of the
+                // LSTM-384 ran at half speed beside the recurrence and finished 1.3 ms after it (profiles/r02_step_timeline_lstm384.txt).
+                constexpr int TB = FFB_GEMM_TICKET_BATCH;
+                int64_t base = atomicAdd(q, TB);
+                while (base < n_tiles) {
+                    const int64_t base_n = atomicAdd(q, TB);       // next batch: its latency hides under this one
                     GPROF(0);
+                    const int nt = (int)((n_tiles - base) < TB ? (n_tiles - base) : TB);
+                    GemmWork w[TB];
 #pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        if (w.idx[d] < 0) continue;
-                        while (true) {
-                            int seen;
-                            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(progress + w.idx[d]) : "memory");
-                            if (seen >= w.cnt[d]) break;
-                            __nanosleep(200);
+                    for (int j = 0; j < TB; j++) w[j] = work[base + (j < nt ? j : 0)];
+                    int seen[TB][3];
+#pragma unroll
+                    for (int j = 0; j < TB; j++)
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            seen[j][d] = 0x7fffffff;
+                            if (j < nt && w[j].idx[d] >= 0)
+                                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen[j][d]) : "l"(progress + w[j].idx[d]) : "memory");
                         }
-                    }
+#pragma unroll
+                    for (int j = 0; j < TB; j++)
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            if (j >= nt || w[j].idx[d] < 0) continue;
+                            while (seen[j][d] < w[j].cnt[d]) {
+                                __nanosleep(200);
+                                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen[j][d]) : "l"(progress + w[j].idx[d]) : "memory");
+                            }
+                        }
                     asm volatile("fence.acq_rel.gpu;" ::: "memory");           // acquire what the counters published
                     asm volatile("fence.proxy.async.global;" ::: "memory");    // ... also for the TMA (async proxy) reads
-                    GemmWork w_n = {};
-                    if (ticket_n < n_tiles) w_n = work[ticket_n];
                     GPROF(1);
-                    announce(w.tile);
-                    load_tile(w.tile);
-                    ticket = ticket_n; w = w_n;
+#pragma unroll
+                    for (int j = 0; j < TB; j++) {
+                        if (j >= nt) break;
+                        announce(w[j].tile);
+                        load_tile(w[j].tile);
+                    }
+                    base = base_n;
                 }
             }
             announce(-1);
