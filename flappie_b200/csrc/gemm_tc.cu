@@ -508,12 +508,19 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 // trip for the counters, the two fences, another round trip for the next work item: ~2800 clk) sat in series with
                 // the issue of the tile's loads -- longer than the 2304 clk of MMAs of a K = 384 tile, so the streamed GEMM of the
                 // LSTM-384 ran at half speed beside the recurrence and finished 1.3 ms after it (profiles/r02_step_timeline_lstm384.txt).
+                // A batch only pays while the GEMM runs BEHIND the recurrence (every tile it asks for is ready).  At the frontier a
+                // CTA that holds four tickets works through them one after the other while its neighbours wait for tiles further
+                // out: on ragged batches (configs[3]: three slots x 15 clusters, 28 SMs for the GEMM) that cost 13 %.  So the batch
+                // size follows what the last batch found: all ready at the first look -> FFB_GEMM_TICKET_BATCH, else one.
                 constexpr int TB = FFB_GEMM_TICKET_BATCH;
-                int64_t base = atomicAdd(q, TB);
+                int nb = 1;                                        // tickets in the batch that starts at `base`
+                bool behind = false;
+                int64_t base = atomicAdd(q, nb);
                 while (base < n_tiles) {
-                    const int64_t base_n = atomicAdd(q, TB);       // next batch: its latency hides under this one
+                    const int nb_n = behind ? TB : 1;
+                    const int64_t base_n = atomicAdd(q, nb_n);     // next batch: its latency hides under this one
                     GPROF(0);
-                    const int nt = (int)((n_tiles - base) < TB ? (n_tiles - base) : TB);
+                    const int nt = (int)((n_tiles - base) < nb ? (n_tiles - base) : nb);
                     GemmWork w[TB];
 #pragma unroll
                     for (int j = 0; j < TB; j++) w[j] = work[base + (j < nt ? j : 0)];
@@ -526,11 +533,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                             if (j < nt && w[j].idx[d] >= 0)
                                 asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen[j][d]) : "l"(progress + w[j].idx[d]) : "memory");
                         }
+                    behind = true;
 #pragma unroll
                     for (int j = 0; j < TB; j++)
 #pragma unroll
                         for (int d = 0; d < 3; d++) {
                             if (j >= nt || w[j].idx[d] < 0) continue;
+                            if (seen[j][d] < w[j].cnt[d]) behind = false;
                             while (seen[j][d] < w[j].cnt[d]) {
                                 __nanosleep(200);
                                 asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(seen[j][d]) : "l"(progress + w[j].idx[d]) : "memory");
@@ -545,7 +554,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         announce(w[j].tile);
                         load_tile(w[j].tile);
                     }
-                    base = base_n;
+                    base = base_n; nb = nb_n;
                 }
             }
             announce(-1);
