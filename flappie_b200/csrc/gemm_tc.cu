@@ -380,27 +380,37 @@ __device__ unsigned long long ffb_gemm_prof_dev[16];
 #endif
 // KMAX = 256 / BB = 128 is the layout the S=256 models run.  S=384 (r941_native at this commit) needs 384 of the 512
 // tensor-memory columns for the panel, which leaves 128 for accumulators: two buffers of BB = 64 blocks.
-template <int KMAX_, int BB_>
+// K = 512 (S = 512, r103_native): the hi plane of a panel alone takes 256 columns, so the lo plane lives in SHARED memory
+// (LO_SMEM: 128 KB, the no-swizzle K-major layout [k-group][128 rows][16 B] that rnn_tc.cu uses for the same purpose; at N = 64
+// an MMA's 32 clk of math cover the 32 clk its A fetch from shared memory takes).  What is left of shared memory holds a hi
+// ring ONE tile deep + three lo slots, and the 256 accumulator columns hold two buffers of TWO accumulators: hi*hi of the second
+// K-half gets its own (KSPLIT) -- 32 full-magnitude truncating accumulations in one accumulator cost 1.1e-4 on `trans`.
+template <int KMAX_, int BB_, bool LO_SMEM_ = false>
 struct GemmWsCfgT {
     static constexpr int BF = 128;                 // features per panel (MMA M)
     static constexpr int BB = BB_;                 // blocks per tile (MMA N)
     static constexpr int BK = 64;                  // K per pipeline stage
     static constexpr int SLOT_BYTES = BB * BK * 2;  // one plane of one k-chunk: [128 blocks][64 halfs]
+    static constexpr bool LO_SMEM = LO_SMEM_, KSPLIT = LO_SMEM_;
+    static constexpr int W_SMEM = LO_SMEM ? BF * KMAX_ * 2 : 0;    // lo plane of the panel
     // Two rings.  The MMAs make two passes over a tile (cross terms first, then hi*hi): the hi plane of a k-chunk
     // is needed in both and is held until pass 2, the lo plane only in pass 1.  The hi ring is two tiles deep so
-    // the next tile loads while this one computes; the lo ring one tile.
-    static constexpr int HI_SLOTS = 2 * (KMAX_ / BK), LO_SLOTS = KMAX_ / BK;
-    static constexpr int SMEM = (HI_SLOTS + LO_SLOTS) * SLOT_BYTES + 1024;
+    // the next tile loads while this one computes; the lo ring one tile.  (LO_SMEM: one tile / three slots.)
+    static constexpr int HI_SLOTS = (LO_SMEM ? 1 : 2) * (KMAX_ / BK), LO_SLOTS = LO_SMEM ? 3 : KMAX_ / BK;
+    static constexpr int SMEM = W_SMEM + (HI_SLOTS + LO_SLOTS) * SLOT_BYTES + 1024;
     static constexpr int EPI_WARPS = 8;            // two per TMEM lane quadrant, BB/2 columns each
     static constexpr int THREADS = 64 + EPI_WARPS * 32;
     static constexpr int KMAX = KMAX_;
-    static constexpr int ACC_COL0 = KMAX;          // W planes: K/2 columns each, at 0 and KMAX/2
-    static constexpr int NACC = 2;                 // accumulator buffers of BB columns
-    static_assert(ACC_COL0 + NACC * BB <= 512, "tensor memory budget");
+    static constexpr int ACC_COL0 = LO_SMEM ? KMAX / 2 : KMAX;     // W planes: K/2 columns each, at 0 and KMAX/2 (LO_SMEM: hi only)
+    static constexpr int NACC = 2;                 // accumulator buffers
+    static constexpr int ACC_W = KSPLIT ? 2 * BB : BB;             // columns of one buffer
+    static_assert(ACC_COL0 + NACC * ACC_W <= 512, "tensor memory budget");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(BB % 64 == 0 && BB <= 128, "epilogue: two column halves of 32 or 64 blocks per quadrant");
 };
 using GemmWsCfg = GemmWsCfgT<256, 128>;
 using GemmWsCfg384 = GemmWsCfgT<384, 64>;
+using GemmWsCfg512 = GemmWsCfgT<512, 64, true>;
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
@@ -451,7 +461,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         const int quad = warp & 3;
         const size_t row = (size_t)n0 + (size_t)panel * Cfg::BF + quad * 32 + lane;
 #pragma unroll 1
-        for (int plane = 0; plane < 2; plane++) {
+        for (int plane = 0; plane < (Cfg::LO_SMEM ? 1 : 2); plane++) {
             const uint4 *src = reinterpret_cast<const uint4 *>((plane ? Wlo : Whi) + row * K);
             const uint32_t tdst = tmem + ((uint32_t)(quad * 32) << 16) + plane * (Cfg::KMAX / 2);
             for (int c = 0; c < K / 2; c += 8) {
@@ -461,6 +471,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             }
         }
         tmem_st_wait();
+        if constexpr (Cfg::LO_SMEM) {
+            // lo plane -> shared memory, k-group kg of row r at (kg * 128 + r) * 16 B: the 32 lanes of a warp write 32
+            // consecutive 16-byte chunks
+            const uint4 *src = reinterpret_cast<const uint4 *>(Wlo + row * K);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem) + (quad * 32 + lane);
+            for (int kg = 0; kg < K / 8; kg++) dst[kg * 128] = src[kg];
+            fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -470,7 +488,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         // ===== TMA producer: activation tiles [128 blocks][64 K] hi / lo =====
         if (elect_one()) {
             int sh = 0, sl = 0; uint32_t ph = 0, pl = 0;     // hi / lo ring positions
-            uint8_t *ring_hi = smem, *ring_lo = smem + Cfg::HI_SLOTS * Cfg::SLOT_BYTES;
+            uint8_t *ring_hi = smem + Cfg::W_SMEM, *ring_lo = ring_hi + Cfg::HI_SLOTS * Cfg::SLOT_BYTES;
             int tcount = 0;
             GPROF_DECL;
             auto announce = [&](int tile) {
@@ -573,7 +591,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             const uint32_t idesc = make_idesc_f16(Cfg::BF, Cfg::BB);
             const uint32_t w_hi = tmem, w_lo = tmem + Cfg::KMAX / 2;
             int sh = 0, sl = 0; uint32_t ph = 0, pl = 0;     // hi / lo ring positions
-            const uint32_t ring_hi = smem_u32(smem), ring_lo = ring_hi + Cfg::HI_SLOTS * Cfg::SLOT_BYTES;
+            const uint32_t ring_hi = smem_u32(smem) + Cfg::W_SMEM, ring_lo = ring_hi + Cfg::HI_SLOTS * Cfg::SLOT_BYTES;
+            const uint64_t dW_lo = make_smem_desc(smem_u32(smem), 128 * 16, 128, LAYOUT_NONE);      // LO_SMEM only
             int acc = 0; uint32_t acc_phase = 0;
             GPROF_DECL;
             for (int tc = 0;; tc++) {
@@ -582,7 +601,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 GPROF(0);
                 tcgen05_fence_after();
-                const uint32_t d = tmem + Cfg::ACC_COL0 + acc * Cfg::BB;
+                const uint32_t d = tmem + Cfg::ACC_COL0 + acc * Cfg::ACC_W;
                 int s1 = sh;
                 for (int kc = 0; kc < nk; kc++) {           // pass 1: cross terms as the k-chunks land
                     mbar_wait(&full_hi[s1], (s1 < sh) ? (ph ^ 1) : ph);   // s1 wrapped past the ring end: next phase
@@ -595,7 +614,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         const uint32_t ko = k4 * 32;   // 16 halfs = 32 bytes along the swizzled row
                         const uint32_t wo = (uint32_t)(kc * Cfg::BK + k4 * 16) / 2;   // TMEM column of these 16 halfs
                         umma_f16_ts(d, w_hi + wo, make_smem_desc(b_lo + ko, 16, 1024, LAYOUT_SW128), idesc, (kc | k4) != 0);
-                        umma_f16_ts(d, w_lo + wo, make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128), idesc, 1);
+                        if constexpr (Cfg::LO_SMEM)
+                            umma_f16(d, dW_lo + (uint64_t)(((kc * (Cfg::BK / 16) + k4) * 2 * 128 * 16) >> 4), make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128), idesc, 1);
+                        else
+                            umma_f16_ts(d, w_lo + wo, make_smem_desc(b_hi + ko, 16, 1024, LAYOUT_SW128), idesc, 1);
                     }
                     umma_commit(&empty_lo[sl]);                // the lo plane is done with
                     if (++sl == Cfg::LO_SLOTS) { sl = 0; pl ^= 1; }
@@ -607,7 +629,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
                     for (int k4 = 0; k4 < Cfg::BK / 16; k4++) {
                         const uint32_t wo = (uint32_t)(kc * Cfg::BK + k4 * 16) / 2;
-                        umma_f16_ts(d, w_hi + wo, make_smem_desc(b_hi + k4 * 32, 16, 1024, LAYOUT_SW128), idesc, 1);
+                        // KSPLIT: the second K-half accumulates into its own columns (first MMA there overwrites)
+                        const bool second = Cfg::KSPLIT && kc >= (nk + 1) / 2;
+                        umma_f16_ts(second ? d + Cfg::BB : d, w_hi + wo, make_smem_desc(b_hi + k4 * 32, 16, 1024, LAYOUT_SW128), idesc,
+                                    !(second && kc == (nk + 1) / 2 && k4 == 0));
                     }
                     umma_commit(&empty_hi[sh]);                // hi slot free once these MMAs retire
                     if (++sh == Cfg::HI_SLOTS) { sh = 0; ph ^= 1; }
@@ -637,7 +662,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #endif
             tcgen05_fence_after();
             const int c0 = half * (Cfg::BB / 2);
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + Cfg::ACC_COL0 + acc * Cfg::BB + c0;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + Cfg::ACC_COL0 + acc * Cfg::ACC_W + c0;
             const int64_t m0 = tile * Cfg::BB + c0;
             float *crow = C + m0 * (int64_t)ldc + n0 + panel * Cfg::BF + f;
             const int nrow = (int)((M - m0 < Cfg::BB / 2) ? (M - m0) : Cfg::BB / 2);   // rows of this half inside the matrix (may be <= 0)
@@ -646,7 +671,18 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                 float v[16], w[16];
                 tmem_ld16(taddr + c, v);
                 tmem_ld16(taddr + c + 16, w);
-                tmem_ld_wait();
+                if constexpr (Cfg::KSPLIT) {
+                    float v2[16], w2[16];
+                    tmem_ld16(taddr + Cfg::BB + c, v2);
+                    tmem_ld16(taddr + Cfg::BB + c + 16, w2);
+                    tmem_ld_wait();
+                    if (nk > 1) {       // a single k-chunk never reaches the second accumulator
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { v[j] += v2[j]; w[j] += w2[j]; }
+                    }
+                } else {
+                    tmem_ld_wait();
+                }
                 if (c + 32 <= nrow) {
 #pragma unroll
                     for (int j = 0; j < 16; j++) __stcs(crow + (int64_t)(c + j) * ldc, acc_comp(v[j]) + b);
@@ -839,7 +875,10 @@ int ffb_launch_gemm_tc(const void *Ahi, const void *Alo, const void *Whi, const 
     if (N % 128 == 0 && K <= ffb::GemmWsCfg384::KMAX && (n0 > 0 || getenv("FFB_GEMM_V1") == nullptr))
         return launch_gemm_ws<ffb::GemmWsCfg384>(Ahi, Alo, Whi, Wlo, bias, C, M, N - n0, K, st, nullptr, nullptr, nullptr, n0, N);
     if (n0 > 0) return -1;
-    // K > 384 (S = 512): hi*hi over two accumulators (accuracy, see gemm_tc_kernel)
+    // K = 385..512 (S = 512): W-stationary with the lo plane in shared memory; FFB_GEMM_NO_WS512=1: the A-tile kernel
+    if (N % 128 == 0 && K <= ffb::GemmWsCfg512::KMAX && getenv("FFB_GEMM_V1") == nullptr && getenv("FFB_GEMM_NO_WS512") == nullptr)
+        return launch_gemm_ws<ffb::GemmWsCfg512>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st, nullptr, nullptr, nullptr, 0, N);
+    // ... on the A-tile kernel: hi*hi over two accumulators (accuracy, see gemm_tc_kernel)
     if (N % 128 == 0 && K > ffb::GemmWsCfg384::KMAX && getenv("FFB_GEMM_NO_KSPLIT") == nullptr)
         return launch_gemm_tc<128, 4>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
     if (N % 256 == 0) return launch_gemm_tc<256>(Ahi, Alo, Whi, Wlo, bias, C, M, N, K, st);
